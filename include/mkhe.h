@@ -1,0 +1,180 @@
+/*
+ * mkhe.h -- C ABI of libmkhe_b200.so: the B200 (sm_100a) backend for the MKHE-KKLSS hot path.
+ *
+ * The reference (SNUCP/MKHE-KKLSS, pure Go) has no FFI seam; this header IS the seam a maintainer
+ * adds under the method bodies of mkrlwe.KeySwitcher / mkbfv.KeySwitcher / mkbfv.FastBasisExtender /
+ * mkckks.Evaluator.Rescale.  Each entry point cites the reference method whose
+ * body it replaces (paths relative to the reference root).  The cgo binding is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative mkhe_status otherwise; mkhe_last_error() gives
+ *     the message.  CUDA failures are sticky on the context.
+ *   - host pointers are borrowed for the duration of the call only (cgo rule): uploads/downloads
+ *     complete before the function returns.  Ops only ENQUEUE work on the context's stream; results
+ *     become visible to the host through *_download / mkhe_sync.
+ *   - a context is not thread safe (neither are the reference's KeySwitcher / Evaluator: shared pools,
+ *     mkrlwe/keyswitch.go:12-15); one context = one CUDA device = one stream.
+ *   - limb  = N little-endian uint64.   poly = [nlimbs][N] (limb-major).
+ *     swk   = [beta_max][nQ+nP][N]: digit-major; Q limbs first, then P limbs (mkrlwe/keys.go:23-25,
+ *     rlwe.PolyQP{Q,P}); always allocated at max level like the reference (keys.go:245-256).
+ *   - ciphertext limbs: coefficient domain, values as the reference stores them (canonical [0,q) except
+ *     the documented lazy forms).  key limbs: NTT domain in lattigo's bit-reversed
+ *     psi ordering, Montgomery form (value * 2^64 mod q) -- exactly the bytes of the Go slices.
+ *   - a ciphertext crosses the ABI as an array of poly handles: element 0 is component "0",
+ *     element 1+t belongs to the t-th party of the accompanying id list (mkrlwe/elements.go:17-33).
+ */
+#ifndef MKHE_H
+#define MKHE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mkhe_ctx mkhe_ctx;
+typedef uint64_t mkhe_poly;   /* device-resident ring.Poly            */
+typedef uint64_t mkhe_swk;    /* device-resident mkrlwe.SwitchingKey / hoisted form */
+
+typedef enum mkhe_status {
+    MKHE_OK = 0,
+    MKHE_ERR_INVALID = -1,      /* bad argument (level mismatch, null handle, ...) */
+    MKHE_ERR_CUDA = -2,         /* CUDA runtime failure (sticky) */
+    MKHE_ERR_NOMEM = -3,
+    MKHE_ERR_UNSUPPORTED = -4,  /* e.g. alpha = #P/gamma != 1, logN out of range */
+    MKHE_ERR_NCCL = -5
+} mkhe_status;
+
+#define MKHE_MAX_PARTIES 64
+
+/* ---- context: replaces mkrlwe.NewParameters + NewKeySwitcher scratch (params.go:16-61, keyswitch.go:33-47) */
+int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int nP, int gamma,
+                    int device, mkhe_ctx **out);
+/* MK-BFV: adds ring QMul (R = Q u QMul) and t (mkbfv/params.go:36-83, mkbfv/basis_extension.go:20-46) */
+int mkhe_ctx_set_bfv(mkhe_ctx *ctx, const uint64_t *QMul, int nQMul, uint64_t T);
+/* optional: lattigo's own ring.Ring tables (public fields NttPsi/NttPsiInv/NttNInv, Montgomery form) for
+ * modulus index m (0..nQ-1 = Q, nQ..nQ+nP-1 = P, then QMul).  Must be called before any op. */
+int mkhe_ctx_set_ntt_tables(mkhe_ctx *ctx, int m, const uint64_t *nttPsi, const uint64_t *nttPsiInv,
+                            uint64_t nttNInv);
+void mkhe_ctx_destroy(mkhe_ctx *ctx);
+const char *mkhe_last_error(const mkhe_ctx *ctx);
+int mkhe_sync(mkhe_ctx *ctx);
+int mkhe_device_count(void);
+
+/* ---- ring.Poly storage (Ciphertext.Value[id], mkrlwe/elements.go:17-62) */
+int mkhe_poly_alloc(mkhe_ctx *ctx, int nlimbs_capacity, mkhe_poly *out);
+int mkhe_poly_free(mkhe_ctx *ctx, mkhe_poly p);
+int mkhe_poly_set_nlimbs(mkhe_ctx *ctx, mkhe_poly p, int nlimbs);   /* DropLevel / Rescale trim: a view, no realloc (mkckks/evaluator.go:106-112,389) */
+int mkhe_poly_get_nlimbs(mkhe_ctx *ctx, mkhe_poly p, int *nlimbs);
+int mkhe_poly_upload_limb(mkhe_ctx *ctx, mkhe_poly p, int limb, const uint64_t *src);     /* Coeffs[limb] */
+int mkhe_poly_download_limb(mkhe_ctx *ctx, mkhe_poly p, int limb, uint64_t *dst);
+int mkhe_poly_upload(mkhe_ctx *ctx, mkhe_poly p, const uint64_t *src, int nlimbs);        /* contiguous [nlimbs][N] */
+int mkhe_poly_download(mkhe_ctx *ctx, mkhe_poly p, uint64_t *dst, int nlimbs);
+int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dst, mkhe_poly src);                          /* ring.Poly.Copy */
+
+/* ---- SwitchingKey / HoistedCiphertext entry storage (mkrlwe/keys.go:23-62, elements.go:5-15) */
+int mkhe_swk_alloc(mkhe_ctx *ctx, mkhe_swk *out);
+int mkhe_swk_free(mkhe_ctx *ctx, mkhe_swk k);
+int mkhe_swk_upload_limb(mkhe_ctx *ctx, mkhe_swk k, int digit, int is_p, int limb, const uint64_t *src);   /* Value[digit].{Q,P}.Coeffs[limb] */
+int mkhe_swk_download_limb(mkhe_ctx *ctx, mkhe_swk k, int digit, int is_p, int limb, uint64_t *dst);
+int mkhe_swk_upload(mkhe_ctx *ctx, mkhe_swk k, const uint64_t *src);      /* contiguous [beta_max][nQ+nP][N] */
+int mkhe_swk_download(mkhe_ctx *ctx, mkhe_swk k, uint64_t *dst);
+
+/* ---- lattigo ring primitives exposed for parity tests (ring.NTTLvl / InvNTTLvl) */
+int mkhe_ntt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out);
+int mkhe_intt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out);
+
+/* ---- mkrlwe.KeySwitcher */
+/* Decompose(levelQ, a, ad)                                   mkrlwe/keyswitch.go:49-73 (= HoistedForm body, mkckks/evaluator.go:543-553) */
+int mkhe_decompose(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk ad);
+/* ExternalProduct(levelQ, a, bg, c)                          mkrlwe/keyswitch.go:79-118 */
+int mkhe_external_product(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk bg, mkhe_poly c);
+/* ExternalProductHoisted(levelQ, aHoisted, bg, c)            mkrlwe/keyswitch_hoisted.go:10-40 */
+int mkhe_external_product_hoisted(mkhe_ctx *ctx, int levelQ, mkhe_swk a_hoisted, mkhe_swk bg, mkhe_poly c);
+/* MulAndRelinHoisted(op0, op1, op0Hoisted, op1Hoisted, rlkSet, ctOut)   mkrlwe/keyswitch_hoisted.go:44-179
+ *   op0[0..n0], op1[0..n1], out[0..nOut]: ciphertext component handles (element 0 = "0").
+ *   h0 / h1: hoisted forms per party, or NULL for the reference's nil branches (:80-85,100-105,148-149,165-166).
+ *   rlk_d[n0], rlk_v[n0] belong to ids0[t]; rlk_b[n1] to ids1[t]  (rlkSet.Value[id].Value[1|2|0]).
+ *   u = params.CRS[-1].  idsOut must be the union of ids0 and ids1; level = ctOut.Level().
+ *   MulAndRelin (mkrlwe/keyswitch.go:122-230) is the same call with h0 = h1 = NULL. */
+int mkhe_mul_relin_hoisted(mkhe_ctx *ctx, int level,
+                           int n0, const int *ids0, const mkhe_poly *op0, const mkhe_swk *h0,
+                           int n1, const int *ids1, const mkhe_poly *op1, const mkhe_swk *h1,
+                           const mkhe_swk *rlk_b, const mkhe_swk *rlk_d, const mkhe_swk *rlk_v, mkhe_swk u,
+                           int nOut, const int *idsOut, const mkhe_poly *out);
+/* RotateHoisted(ctIn, rotidx, ctInHoisted, rkSet, ctOut)     mkrlwe/keyswitch_hoisted.go:183-247
+ *   rk[t] = rkSet.GetRotationKey(id_t, rotidx).Value ; a = params.CRS[rotidx] */
+int mkhe_rotate_hoisted(mkhe_ctx *ctx, int level, int rotidx, int n,
+                        const mkhe_poly *ct_in, const mkhe_swk *hoisted, const mkhe_swk *rk, mkhe_swk a,
+                        const mkhe_poly *ct_out);
+/* Rotate(ctIn, rotidx, rkSet, ctOut)                         mkrlwe/keyswitch.go:234-298 */
+int mkhe_rotate(mkhe_ctx *ctx, int level, int rotidx, int n,
+                const mkhe_poly *ct_in, const mkhe_swk *rk, mkhe_swk a, const mkhe_poly *ct_out);
+/* Conjugate(ctIn, ckSet, ctOut)                              mkrlwe/keyswitch.go:302-332 ; a = CRS[-2] */
+int mkhe_conjugate(mkhe_ctx *ctx, int level, int n,
+                   const mkhe_poly *ct_in, const mkhe_swk *ck, mkhe_swk a, const mkhe_poly *ct_out);
+
+/* ---- mkckks.Evaluator */
+/* ringQ.DivRoundByLastModulusManyLvl(level, nbRescales, in, pool, out) + Coeffs trim   mkckks/evaluator.go:385-390.
+ * Like lattigo it adds (q_l-1)/2 to the INPUT's last limb in place. out view = level+1-nb limbs. */
+int mkhe_rescale(mkhe_ctx *ctx, int level, int nb_rescales, mkhe_poly in, mkhe_poly out);
+/* ringQ.AddLvl / SubLvl(level, a, b, out)                    mkckks/evaluator.go:200-351 call sites */
+int mkhe_poly_add(mkhe_ctx *ctx, int level, mkhe_poly a, mkhe_poly b, mkhe_poly out);
+int mkhe_poly_sub(mkhe_ctx *ctx, int level, mkhe_poly a, mkhe_poly b, mkhe_poly out);
+/* MulRelinNew's device work in one call: hoist both operands (once if same_operand), MulAndRelinHoisted,
+ * Rescale by nb_rescales                                     mkckks/evaluator.go:416-443,558-581
+ * (this is what mkckks_benchmark_test.go:78-82 times).  Hoisting uses context-owned pools, mirroring
+ * rlkSet.HoistPool (mkrlwe/keys.go:53-57). out views are trimmed to level+1-nb_rescales. */
+int mkhe_ckks_mul_relin(mkhe_ctx *ctx, int level, int nb_rescales, int same_operand,
+                        int n0, const int *ids0, const mkhe_poly *op0,
+                        int n1, const int *ids1, const mkhe_poly *op1,
+                        const mkhe_swk *rlk_b, const mkhe_swk *rlk_d, const mkhe_swk *rlk_v, mkhe_swk u,
+                        int nOut, const int *idsOut, const mkhe_poly *out);
+
+/* ---- mkbfv (polys in basis R have 2*nQ limbs: Q limbs then QMul limbs) */
+/* FastBasisExtender.ModUpQtoR(polyQ, polyR)                  mkbfv/basis_extension.go:49-63 */
+int mkhe_bfv_modup_q_to_r(mkhe_ctx *ctx, mkhe_poly polyQ, mkhe_poly polyR);
+/* FastBasisExtender.Rescale(polyQ, polyR)                    mkbfv/basis_extension.go:83-97 */
+int mkhe_bfv_rescale_q_to_r(mkhe_ctx *ctx, mkhe_poly polyQ, mkhe_poly polyR);
+/* FastBasisExtender.Quantize(polyR, polyQ, t)                mkbfv/basis_extension.go:66-80 (polyR in NTT domain) */
+int mkhe_bfv_quantize(mkhe_ctx *ctx, mkhe_poly polyR, mkhe_poly polyQ);
+/* KeySwitcher.DecomposeBFV(levelQ, aR, ad1, ad2)             mkbfv/keyswitch.go:57-81 */
+int mkhe_bfv_decompose(mkhe_ctx *ctx, int levelQ, mkhe_poly aR, mkhe_swk ad1, mkhe_swk ad2);
+/* KeySwitcher.MulAndRelinBFVHoisted(...)                     mkbfv/keyswitch_hoisted.go:39-207
+ *   op0/op1 are R-basis ciphertexts; h*a / h*b the two hoisted halves per party (NULL = nil branches);
+ *   d1,d2,v aligned with ids0 ; b1,b2 aligned with ids1. */
+int mkhe_bfv_mul_relin_hoisted(mkhe_ctx *ctx, int level,
+                               int n0, const int *ids0, const mkhe_poly *op0, const mkhe_swk *h0a, const mkhe_swk *h0b,
+                               int n1, const int *ids1, const mkhe_poly *op1, const mkhe_swk *h1a, const mkhe_swk *h1b,
+                               const mkhe_swk *b1, const mkhe_swk *b2, const mkhe_swk *d1, const mkhe_swk *d2,
+                               const mkhe_swk *v, mkhe_swk u,
+                               int nOut, const int *idsOut, const mkhe_poly *out);
+/* Evaluator.MulRelinNew's device work: ModUpQtoR / Rescale every component, DecomposeBFV, MulAndRelinBFVHoisted
+ *                                                            mkbfv/evaluator.go:84-150 */
+int mkhe_bfv_mul_relin(mkhe_ctx *ctx,
+                       int n0, const int *ids0, const mkhe_poly *ct0,
+                       int n1, const int *ids1, const mkhe_poly *ct1,
+                       const mkhe_swk *b1, const mkhe_swk *b2, const mkhe_swk *d1, const mkhe_swk *d2,
+                       const mkhe_swk *v, mkhe_swk u,
+                       int nOut, const int *idsOut, const mkhe_poly *out);
+
+/* ---- multi-GPU: party-sharded MulRelin; one context per rank, NCCL over NVLink.
+ * unique_id = the 128 bytes of an ncclUniqueId created by rank 0 (mkhe_comm_unique_id) and broadcast by the host. */
+int mkhe_comm_unique_id(uint8_t out[128]);
+int mkhe_comm_init(mkhe_ctx *ctx, int nranks, int rank, const uint8_t unique_id[128]);
+int mkhe_comm_destroy(mkhe_ctx *ctx);
+
+/* ---- measurement helpers (CUDA events on the context's stream) */
+int mkhe_timer_start(mkhe_ctx *ctx);
+int mkhe_timer_stop(mkhe_ctx *ctx, float *elapsed_ms);     /* synchronises */
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t mkhe_launch_count(const mkhe_ctx *ctx);
+/* register-resident Shoup-butterfly throughput microbenchmark: butterflies per second on this device
+ * (the integer-pipe roofline denominator) */
+int mkhe_bench_butterfly_peak(mkhe_ctx *ctx, double *butterflies_per_s);
+const char *mkhe_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MKHE_H */

@@ -1,0 +1,1298 @@
+// mkhe_api.cu -- the C ABI of include/mkhe.h: context, device-resident handles and the op schedules
+// that replace the bodies of mkrlwe.KeySwitcher / mkbfv.KeySwitcher / mkckks.Evaluator.Rescale.
+// No torch types, no exceptions across the boundary, no CPU fallback: every op is a sequence of
+// launches of the kernels in mkhe_kernels.cuh on the context's stream.
+#include "../../include/mkhe.h"
+#include "mkhe_kernels.cuh"
+#include "mkhe_tables.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#ifndef MKHE_EMU
+#ifdef MKHE_WITH_NCCL
+#include <nccl.h>
+#endif
+#endif
+
+using namespace mkhe;
+
+namespace {
+
+enum ObjKind { OBJ_POLY = 1, OBJ_SWK = 2 };
+struct Obj {
+    int kind;
+    u64 *d;
+    int cap_limbs;     // poly: allocated limbs
+    int nlimbs;        // poly: current view
+};
+
+struct Scratch {
+    u64 *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct mkhe_ctx {
+    int logN = 0, N = 0, nQ = 0, nP = 0, nQMul = 0, gamma = 2, device = 0;
+    int S1 = 0, dmax = 0;
+    u64 T = 0;
+    std::vector<u64> mod;                 // Q | P | QMul
+    std::vector<ModTables> tabs;
+    cudaStream_t stream = nullptr;
+    ModC *d_mods = nullptr;
+    ulonglong2 *d_twf = nullptr, *d_twi = nullptr;
+    bool tables_dirty = true;
+    ConvTable *d_conv_PtoQ = nullptr;      // ModDownQPtoQ of the key switch
+    ConvTable *d_conv_QtoQMul = nullptr;   // BFV
+    ConvTable *d_conv_QMultoQ = nullptr;   // BFV
+    std::vector<u64> h_mformQMul;          // MForm(QMul mod q_i)
+    std::unordered_set<Obj *> objs;
+    std::map<std::string, Scratch> scratch;
+    std::string err;
+    int sticky = 0;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void *nccl = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(mkhe_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            ctx->sticky = MKHE_ERR_CUDA;                                                              \
+            return fail(ctx, MKHE_ERR_CUDA, "CUDA error %d (%s) at %s:%d", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                             \
+    } while (0)
+#define CHECK_CTX()                                                                 \
+    do {                                                                            \
+        if (!ctx) return MKHE_ERR_INVALID;                                          \
+        if (ctx->sticky) return ctx->sticky;                                        \
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MKHE_ERR_CUDA, "cudaSetDevice failed"); \
+    } while (0)
+#define TRY(expr)                  \
+    do {                           \
+        int rc_ = (expr);          \
+        if (rc_ != MKHE_OK) return rc_; \
+    } while (0)
+#define LAUNCH(kernel, grid, block, smem, ...)                        \
+    do {                                                              \
+        MKHE_LAUNCH(kernel, grid, block, smem, ctx->stream, __VA_ARGS__); \
+        ctx->launches++;                                              \
+        CU(cudaGetLastError());                                       \
+    } while (0)
+
+Obj *as_obj(mkhe_ctx *ctx, uint64_t h, int kind) {
+    Obj *o = reinterpret_cast<Obj *>(h);
+    if (!o || !ctx->objs.count(o) || o->kind != kind) return nullptr;
+    return o;
+}
+#define POLY(var, h)                                                                     \
+    Obj *var = as_obj(ctx, (h), OBJ_POLY);                                               \
+    if (!var) return fail(ctx, MKHE_ERR_INVALID, "invalid poly handle (%s)", #h)
+#define SWK(var, h)                                                                      \
+    Obj *var = as_obj(ctx, (h), OBJ_SWK);                                                \
+    if (!var) return fail(ctx, MKHE_ERR_INVALID, "invalid switching-key handle (%s)", #h)
+
+size_t swk_elems(const mkhe_ctx *ctx) { return (size_t)ctx->nQ * ctx->dmax * ctx->N; }
+
+int get_scratch(mkhe_ctx *ctx, const std::string &name, size_t bytes, u64 **out) {
+    Scratch &s = ctx->scratch[name];
+    if (s.bytes < bytes) {
+        if (s.p) {
+            CU(cudaStreamSynchronize(ctx->stream));
+            CU(cudaFree(s.p));
+            s.p = nullptr;
+            s.bytes = 0;
+        }
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMalloc(%zu) failed for scratch '%s'", bytes, name.c_str());
+        s.p = (u64 *)p;
+        s.bytes = bytes;
+    }
+    *out = s.p;
+    return MKHE_OK;
+}
+
+int upload_tables(mkhe_ctx *ctx) {
+    if (!ctx->tables_dirty) return MKHE_OK;
+    const size_t nm = ctx->mod.size(), N = ctx->N;
+    if (!ctx->d_mods) {
+        CU(cudaMalloc((void **)&ctx->d_mods, sizeof(ModC) * 64));
+        CU(cudaMalloc((void **)&ctx->d_twf, sizeof(ulonglong2) * 64 * N));
+        CU(cudaMalloc((void **)&ctx->d_twi, sizeof(ulonglong2) * 64 * N));
+    }
+    for (size_t i = 0; i < nm; i++) {
+        CU(cudaMemcpy(ctx->d_mods + i, &ctx->tabs[i].c, sizeof(ModC), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_twf + i * N, ctx->tabs[i].twf.data(), sizeof(ulonglong2) * N, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_twi + i * N, ctx->tabs[i].twi.data(), sizeof(ulonglong2) * N, cudaMemcpyHostToDevice));
+    }
+    ctx->tables_dirty = false;
+    return MKHE_OK;
+}
+
+int upload_conv(mkhe_ctx *ctx, ConvTable **d, const std::vector<int> &src, const std::vector<int> &dst) {
+    if ((int)src.size() > MKHE_CONV_MAX || (int)dst.size() > MKHE_CONV_MAX)
+        return fail(ctx, MKHE_ERR_UNSUPPORTED, "basis conversion with more than %d limbs", MKHE_CONV_MAX);
+    ConvTable *h = new ConvTable();
+    memset(h, 0, sizeof(ConvTable));
+    gen_conv_table(*h, ctx->mod, src, dst);
+    if (!*d) CU(cudaMalloc((void **)d, sizeof(ConvTable)));
+    CU(cudaMemcpy(*d, h, sizeof(ConvTable), cudaMemcpyHostToDevice));
+    delete h;
+    return MKHE_OK;
+}
+
+// limb-slot lists ---------------------------------------------------------------------------------
+struct Slots {
+    int n = 0;
+    int slot[MKHE_MAX_SLOTS];
+    int mod[MKHE_MAX_SLOTS];
+};
+// Q limbs 0..level followed by every P limb: the limbs of a PolyQP at `level` (slot == modulus index)
+Slots qp_slots(const mkhe_ctx *ctx, int level) {
+    Slots s;
+    for (int j = 0; j <= level; j++) { s.slot[s.n] = j; s.mod[s.n++] = j; }
+    for (int j = 0; j < ctx->nP; j++) { s.slot[s.n] = ctx->nQ + j; s.mod[s.n++] = ctx->nQ + j; }
+    return s;
+}
+Slots q_slots(int level) {
+    Slots s;
+    for (int j = 0; j <= level; j++) { s.slot[s.n] = j; s.mod[s.n++] = j; }
+    return s;
+}
+// limbs of a poly in basis R = Q u QMul
+Slots r_slots(const mkhe_ctx *ctx) {
+    Slots s;
+    for (int j = 0; j < ctx->nQ; j++) { s.slot[s.n] = j; s.mod[s.n++] = j; }
+    for (int j = 0; j < ctx->nQMul; j++) { s.slot[s.n] = ctx->nQ + j; s.mod[s.n++] = ctx->nQ + ctx->nP + j; }
+    return s;
+}
+void fill(LimbArgs &a, const Slots &s, int logN) {
+    a.nlimbs = s.n;
+    a.logN = logN;
+    for (int i = 0; i < s.n; i++) { a.slot_of[i] = s.slot[i]; a.mod_of_limb[i] = s.mod[i]; }
+}
+
+template <class F>
+int dispatch_s1(mkhe_ctx *ctx, F &&f) {
+    switch (ctx->S1) {
+        case 3: return f(std::integral_constant<int, 3>());
+        case 4: return f(std::integral_constant<int, 4>());
+        case 5: return f(std::integral_constant<int, 5>());
+        case 6: return f(std::integral_constant<int, 6>());
+        case 7: return f(std::integral_constant<int, 7>());
+    }
+    return fail(ctx, MKHE_ERR_UNSUPPORTED, "logN = %d unsupported (12..16)", ctx->logN);
+}
+
+const size_t SMEM_TILE = MKHE_TILE * 8;
+const size_t SMEM_PASS2 = MKHE_TILE * 8 + (MKHE_TILE - 4) * 16 + 64;
+
+// ---- building blocks ------------------------------------------------------------------------------
+// forward NTT of `npolys` polys over the limb list `s` (out may alias in)
+int ntt_fwd(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *const *out) {
+    const int tiles = ctx->N / MKHE_TILE;
+    for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
+        int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
+        LimbArgs a;
+        fill(a, s, ctx->logN);
+        for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
+        TRY(dispatch_s1(ctx, [&](auto S) -> int {
+            auto kern = k_ntt_pass1<decltype(S)::value>;
+            LAUNCH(kern, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twf);
+            return MKHE_OK;
+        }));
+        Pass2Args b;
+        b.count = 1;
+        b.inst_stride = 0;
+        b.nslots = s.n;
+        b.logN = ctx->logN;
+        for (int i = 0; i < s.n; i++) { b.slots[i] = s.slot[i]; b.mods[i] = s.mod[i]; }
+        for (int i = 0; i < np; i++) b.buf.p[i] = out[p0 + i];
+        LAUNCH(k_ntt_pass2, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf);
+    }
+    return MKHE_OK;
+}
+// inverse pass B over limb list (in place on bufs)
+int intt_passB(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *bufs_in, u64 *const *bufs_out) {
+    const int tiles = ctx->N / MKHE_TILE;
+    for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
+        int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
+        LimbArgs a;
+        fill(a, s, ctx->logN);
+        for (int i = 0; i < np; i++) { a.in.p[i] = bufs_in[p0 + i]; a.out.p[i] = bufs_out[p0 + i]; }
+        TRY(dispatch_s1(ctx, [&](auto S) -> int {
+            auto kern = k_intt_passB<decltype(S)::value>;
+            LAUNCH(kern, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+            return MKHE_OK;
+        }));
+    }
+    return MKHE_OK;
+}
+// full inverse NTT (canonical in, canonical out)
+int ntt_inv(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *const *out) {
+    const int tiles = ctx->N / MKHE_TILE;
+    for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
+        int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
+        InvAArgs a;
+        memset(&a, 0, sizeof a);
+        a.nslots = s.n;
+        a.logN = ctx->logN;
+        for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; a.out_slots[i] = s.slot[i]; }
+        for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
+        LAUNCH(k_intt_passA<false>, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+    }
+    return intt_passB(ctx, s, npolys, out, out);
+}
+
+// Decompose: digits in_limb0 .. in_limb0+beta-1 of each input poly -> swk-shaped outputs (NTT domain)
+int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *const *out, int in_limb0) {
+    const int tiles = ctx->N / MKHE_TILE;
+    const int beta = levelQ + 1;     // alpha = 1
+    Slots s = qp_slots(ctx, levelQ);
+    for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
+        int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
+        BcastArgs a;
+        a.in_limb0 = in_limb0;
+        a.dmax = ctx->dmax;
+        a.nslots = s.n;
+        a.logN = ctx->logN;
+        for (int i = 0; i < s.n; i++) a.slots[i] = s.slot[i];
+        for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
+        TRY(dispatch_s1(ctx, [&](auto S) -> int {
+            auto kern = k_bcast_ntt_pass1<decltype(S)::value>;
+            LAUNCH(kern, dim3(tiles, beta, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twf);
+            return MKHE_OK;
+        }));
+        Pass2Args b;
+        b.count = beta;
+        b.inst_stride = (long)ctx->dmax * ctx->N;
+        b.nslots = s.n;
+        b.logN = ctx->logN;
+        for (int i = 0; i < s.n; i++) { b.slots[i] = s.slot[i]; b.mods[i] = s.mod[i]; }
+        for (int i = 0; i < np; i++) b.buf.p[i] = out[p0 + i];
+        LAUNCH(k_ntt_pass2, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf);
+    }
+    return MKHE_OK;
+}
+
+// batch of external products: for b < nb:  r_b = ModDown(INTT(sum_t sum_i key_t[b][i] (.) hst_t[b][i]))
+//   dst[b] (Q poly) = r_b, or dst[b] = acc[b] + r_b when acc != nullptr.  Batches whose dst aliases
+//   another batch's dst must be issued through `serial` (accumulation into a shared target).
+int ext_products(mkhe_ctx *ctx, int levelQ, int nb, int nsets, u64 *const *key0, u64 *const *hst0, u64 *const *key1,
+                 u64 *const *hst1, u64 *const *dst, u64 *const *acc, bool serial_conv) {
+    if (nb == 0) return MKHE_OK;
+    const int tiles = ctx->N / MKHE_TILE;
+    Slots s = qp_slots(ctx, levelQ);
+    u64 *accqp;
+    const size_t qp = (size_t)ctx->dmax * ctx->N;
+    for (int b0 = 0; b0 < nb; b0 += MKHE_MAX_PARTIES_K) {
+        int n = std::min(MKHE_MAX_PARTIES_K, nb - b0);
+        TRY(get_scratch(ctx, "accqp", qp * 8 * (size_t)std::min(nb, MKHE_MAX_PARTIES_K), &accqp));
+        InvAArgs a;
+        memset(&a, 0, sizeof a);
+        a.nsets = nsets;
+        a.beta = levelQ + 1;
+        a.digit_stride = (long)ctx->dmax * ctx->N;
+        a.nslots = s.n;
+        a.logN = ctx->logN;
+        for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; a.out_slots[i] = s.slot[i]; }
+        std::vector<u64 *> bufs(n);
+        for (int i = 0; i < n; i++) {
+            a.key[0].p[i] = key0[b0 + i];
+            a.hst[0].p[i] = hst0[b0 + i];
+            if (nsets > 1) { a.key[1].p[i] = key1[b0 + i]; a.hst[1].p[i] = hst1[b0 + i]; }
+            bufs[i] = accqp + (size_t)i * qp;
+            a.out.p[i] = bufs[i];
+        }
+        LAUNCH(k_intt_passA<true>, dim3(tiles, s.n, n), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+        TRY(intt_passB(ctx, s, n, bufs.data(), bufs.data()));
+        ConvArgs c;
+        memset(&c, 0, sizeof c);
+        c.src_limb0 = ctx->nQ;
+        c.x_limb0 = 0;
+        c.dst_limb0 = 0;
+        c.n2_used = levelQ + 1;
+        c.has_acc = acc != nullptr;
+        c.logN = ctx->logN;
+        const int cb = (ctx->N + MKHE_THREADS - 1) / MKHE_THREADS;
+        if (!serial_conv) {
+            for (int i = 0; i < n; i++) {
+                c.src.p[i] = bufs[i]; c.x.p[i] = bufs[i]; c.dst.p[i] = dst[b0 + i];
+                c.acc.p[i] = acc ? acc[b0 + i] : nullptr;
+            }
+            LAUNCH(k_conv<CONV_MODDOWN>, dim3(cb, n), dim3(MKHE_THREADS), 0, c, ctx->d_conv_PtoQ, ctx->d_mods);
+        } else {
+            for (int i = 0; i < n; i++) {
+                c.src.p[0] = bufs[i]; c.x.p[0] = bufs[i]; c.dst.p[0] = dst[b0 + i];
+                c.acc.p[0] = acc ? acc[b0 + i] : nullptr;
+                LAUNCH(k_conv<CONV_MODDOWN>, dim3(cb, 1), dim3(MKHE_THREADS), 0, c, ctx->d_conv_PtoQ, ctx->d_mods);
+            }
+        }
+    }
+    return MKHE_OK;
+}
+
+// x_i = MForm(sum_t MRed(key_t[i], hst_t[i]))   (keyswitch_hoisted.go:79-117)
+int mac_parties(mkhe_ctx *ctx, int level, int n, u64 *const *key, u64 *const *hst, u64 *out) {
+    Slots s = qp_slots(ctx, level);
+    if (n > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_UNSUPPORTED, "more than %d parties", MKHE_MAX_PARTIES_K);
+    MacPartiesArgs a;
+    memset(&a, 0, sizeof a);
+    a.out = out;
+    a.nparties = n;
+    a.beta = level + 1;
+    a.dmax = ctx->dmax;
+    a.nslots = s.n;
+    a.logN = ctx->logN;
+    for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; }
+    for (int i = 0; i < n; i++) { a.key.p[i] = key[i]; a.hst.p[i] = hst[i]; }
+    LAUNCH(k_mac_parties, dim3(ctx->N / (2 * MKHE_THREADS), s.n, level + 1), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    return MKHE_OK;
+}
+
+int find_id(int n, const int *ids, int id) {
+    for (int i = 0; i < n; i++) if (ids[i] == id) return i;
+    return -1;
+}
+
+int add_polys(mkhe_ctx *ctx, int level, const u64 *x, const u64 *y, u64 *out, bool sub) {
+    LimbArgs a;
+    fill(a, q_slots(level), ctx->logN);
+    if (sub) LAUNCH(k_addsub<true>, dim3(ctx->N / MKHE_THREADS, level + 1), dim3(MKHE_THREADS), 0, x, y, out, a, ctx->d_mods);
+    else LAUNCH(k_addsub<false>, dim3(ctx->N / MKHE_THREADS, level + 1), dim3(MKHE_THREADS), 0, x, y, out, a, ctx->d_mods);
+    return MKHE_OK;
+}
+
+// resolve arrays of handles
+int polys_of(mkhe_ctx *ctx, int n, const mkhe_poly *h, int min_limbs, std::vector<u64 *> &out, const char *what) {
+    out.resize(n);
+    for (int i = 0; i < n; i++) {
+        Obj *o = as_obj(ctx, h[i], OBJ_POLY);
+        if (!o) return fail(ctx, MKHE_ERR_INVALID, "invalid poly handle in %s[%d]", what, i);
+        if (o->cap_limbs < min_limbs) return fail(ctx, MKHE_ERR_INVALID, "%s[%d] has %d limbs, %d needed", what, i, o->cap_limbs, min_limbs);
+        out[i] = o->d;
+    }
+    return MKHE_OK;
+}
+int swks_of(mkhe_ctx *ctx, int n, const mkhe_swk *h, std::vector<u64 *> &out, const char *what) {
+    out.resize(n);
+    for (int i = 0; i < n; i++) {
+        Obj *o = as_obj(ctx, h[i], OBJ_SWK);
+        if (!o) return fail(ctx, MKHE_ERR_INVALID, "invalid switching-key handle in %s[%d]", what, i);
+        out[i] = o->d;
+    }
+    return MKHE_OK;
+}
+// context-owned swk-shaped scratch pools (mirrors swkPool1..3 / rlkSet.HoistPool)
+int swk_pool(mkhe_ctx *ctx, const char *name, int n, std::vector<u64 *> &out) {
+    u64 *base;
+    TRY(get_scratch(ctx, name, swk_elems(ctx) * 8 * (size_t)std::max(n, 1), &base));
+    out.resize(n);
+    for (int i = 0; i < n; i++) out[i] = base + (size_t)i * swk_elems(ctx);
+    return MKHE_OK;
+}
+int poly_pool(mkhe_ctx *ctx, const char *name, int n, int limbs, std::vector<u64 *> &out) {
+    u64 *base;
+    TRY(get_scratch(ctx, name, (size_t)limbs * ctx->N * 8 * (size_t)std::max(n, 1), &base));
+    out.resize(n);
+    for (int i = 0; i < n; i++) out[i] = base + (size_t)i * limbs * ctx->N;
+    return MKHE_OK;
+}
+
+// MulAndRelinHoisted on raw device pointers (mkrlwe/keyswitch_hoisted.go:44-179)
+int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u64 *const *op0, u64 *const *h0,
+                           int n1, const int *ids1, u64 *const *op1, u64 *const *h1, u64 *const *rlk_b,
+                           u64 *const *rlk_d, u64 *const *rlk_v, u64 *u, int nOut, const int *idsOut, u64 *const *out) {
+    const int N = ctx->N;
+    // steps 2-3 (:79-117): x = MForm(sum d_id (.) h0_id), y = MForm(sum b_id (.) h1_id)
+    std::vector<u64 *> xy;
+    TRY(swk_pool(ctx, "xy", 2, xy));
+    u64 *x = xy[0], *y = xy[1];
+    TRY(mac_parties(ctx, level, n0, rlk_d, h0, x));
+    TRY(mac_parties(ctx, level, n1, rlk_b, h1, y));
+
+    // step 4 (:119-144): tensor product in the NTT domain, then InvNTT of every output component
+    Slots qs = q_slots(level);
+    std::vector<u64 *> tn;
+    TRY(poly_pool(ctx, "tensor_ntt", n0 + n1 + 2, ctx->nQ, tn));
+    std::vector<u64 *> src(n0 + n1 + 2);
+    for (int t = 0; t <= n0; t++) src[t] = op0[t];
+    for (int t = 0; t <= n1; t++) src[n0 + 1 + t] = op1[t];
+    TRY(ntt_fwd(ctx, qs, n0 + n1 + 2, src.data(), tn.data()));
+    if (nOut + 1 > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_UNSUPPORTED, "too many parties");
+    TensorArgs ta;
+    memset(&ta, 0, sizeof ta);
+    ta.A0 = tn[0];
+    ta.B0 = tn[n0 + 1];
+    ta.nout = nOut;
+    ta.nlimbs = level + 1;
+    ta.logN = ctx->logN;
+    for (int i = 0; i <= level; i++) ta.mod_of_limb[i] = i;
+    ta.out.p[0] = out[0];
+    for (int t = 0; t < nOut; t++) {
+        int i0 = find_id(n0, ids0, idsOut[t]), i1 = find_id(n1, ids1, idsOut[t]);
+        ta.A.p[t] = i0 >= 0 ? tn[1 + i0] : nullptr;
+        ta.B.p[t] = i1 >= 0 ? tn[n0 + 2 + i1] : nullptr;
+        ta.out.p[1 + t] = out[1 + t];
+    }
+    LAUNCH(k_tensor, dim3(N / MKHE_THREADS, level + 1), dim3(MKHE_THREADS), 0, ta, ctx->d_mods);
+    TRY(ntt_inv(ctx, qs, nOut + 1, out, out));
+
+    // step 5 (:147-154): c_id += x [.] h1_id
+    {
+        std::vector<u64 *> key(n1, x), dst(n1);
+        for (int t = 0; t < n1; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids1[t])];
+        TRY(ext_products(ctx, level, n1, 1, key.data(), h1, nullptr, nullptr, dst.data(), dst.data(), false));
+    }
+    // step 6 (:161-178): p_id = y [.] h0_id ; Decompose(p_id) ; c_0 += v_id [.] p_id ; c_id += u [.] p_id
+    {
+        std::vector<u64 *> key(n0, y), p, hp;
+        TRY(poly_pool(ctx, "relin_p", n0, ctx->nQ, p));
+        TRY(swk_pool(ctx, "relin_hp", n0, hp));
+        TRY(ext_products(ctx, level, n0, 1, key.data(), h0, nullptr, nullptr, p.data(), nullptr, false));
+        TRY(decompose_impl(ctx, level, n0, p.data(), hp.data(), 0));
+        std::vector<u64 *> ukey(n0, u), dst(n0), c0(n0, out[0]);
+        for (int t = 0; t < n0; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids0[t])];
+        TRY(ext_products(ctx, level, n0, 1, ukey.data(), hp.data(), nullptr, nullptr, dst.data(), dst.data(), false));
+        TRY(ext_products(ctx, level, n0, 1, rlk_v, hp.data(), nullptr, nullptr, c0.data(), c0.data(), true));
+    }
+    return MKHE_OK;
+}
+
+int rescale_impl(mkhe_ctx *ctx, int level, int nb, int npolys, u64 *const *in, u64 *const *out) {
+    if (nb < 0 || nb > level) return fail(ctx, MKHE_ERR_INVALID, "cannot Rescale: nb_rescales = %d at level %d", nb, level);
+    for (int r = 0; r < nb; r++) {
+        const int l = level - r;
+        for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
+            int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
+            RescaleArgs a;
+            memset(&a, 0, sizeof a);
+            a.level = l;
+            a.logN = ctx->logN;
+            const u64 ql = ctx->mod[l], h = (ql - 1) >> 1;
+            for (int i = 0; i < l; i++) {
+                const u64 qi = ctx->mod[i];
+                a.rescale[i] = qi - h_mform(h_invmod(ql % qi, qi), qi);
+                a.halfneg[i] = qi - (h % qi);
+            }
+            for (int i = 0; i < np; i++) { a.in.p[i] = (r == 0) ? in[p0 + i] : out[p0 + i]; a.out.p[i] = out[p0 + i]; }
+            LAUNCH(k_rescale, dim3(ctx->N / MKHE_THREADS, np), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+        }
+    }
+    return MKHE_OK;
+}
+
+int automorph_impl(mkhe_ctx *ctx, int level, u64 galEl, int npolys, u64 *const *in, u64 *const *out) {
+    for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
+        int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
+        LimbArgs a;
+        fill(a, q_slots(level), ctx->logN);
+        for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
+        LAUNCH(k_automorph, dim3(ctx->N / MKHE_THREADS, level + 1, np), dim3(MKHE_THREADS), 0, a, galEl, ctx->d_mods);
+    }
+    return MKHE_OK;
+}
+u64 galois_for_rotation(int logN, int k) {
+    u64 twoN = (u64)1 << (logN + 1), mask = twoN - 1;
+    u64 e = (u64)((long long)k) & mask, r = 1, b = 5;
+    while (e) { if (e & 1) r = (r * b) & mask; b = (b * b) & mask; e >>= 1; }
+    return r;
+}
+
+// RotateHoisted on raw pointers (mkrlwe/keyswitch_hoisted.go:183-247)
+int rotate_hoisted_impl(mkhe_ctx *ctx, int level, int rotidx, int n, u64 *const *ct_in, u64 *const *hoisted,
+                        u64 *const *rk, u64 *a, u64 *const *out) {
+    while (rotidx < 0) rotidx += ctx->N / 2;
+    std::vector<u64 *> tmp;
+    TRY(poly_pool(ctx, "rot_tmp", n + 1, ctx->nQ, tmp));
+    CU(cudaMemcpyAsync(tmp[0], ct_in[0], (size_t)(level + 1) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    std::vector<u64 *> akey(n, a), dst(n), c0(n, tmp[0]);
+    for (int t = 0; t < n; t++) dst[t] = tmp[1 + t];
+    TRY(ext_products(ctx, level, n, 1, akey.data(), hoisted, nullptr, nullptr, dst.data(), nullptr, false));
+    TRY(ext_products(ctx, level, n, 1, rk, hoisted, nullptr, nullptr, c0.data(), c0.data(), true));
+    return automorph_impl(ctx, level, galois_for_rotation(ctx->logN, rotidx), n + 1, tmp.data(), out);
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char *mkhe_version(void) {
+#ifdef MKHE_EMU
+    return "mkhe-b200 0.1 (CPU EMULATION BUILD - development only)";
+#else
+    return "mkhe-b200 0.1 (sm_100a)";
+#endif
+}
+
+int mkhe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int nP, int gamma, int device, mkhe_ctx **out) {
+    if (!out || !Q || !P) return MKHE_ERR_INVALID;
+    *out = nullptr;
+    if (logN < 12 || logN > 16) return MKHE_ERR_UNSUPPORTED;
+    if (gamma <= 0 || nP / gamma != 1) return MKHE_ERR_UNSUPPORTED;      // alpha = #P/gamma must be 1
+    if (nQ < 1 || nQ + nP > MKHE_MAX_SLOTS || nQ > MKHE_CONV_MAX) return MKHE_ERR_UNSUPPORTED;
+    int ndev = mkhe_device_count();
+    if (ndev <= 0 || device < 0 || device >= ndev) return MKHE_ERR_CUDA;   // no GPU: fail loudly, there is no CPU path
+    mkhe_ctx *ctx = new mkhe_ctx();
+    ctx->logN = logN; ctx->N = 1 << logN; ctx->nQ = nQ; ctx->nP = nP; ctx->gamma = gamma; ctx->device = device;
+    ctx->S1 = logN - 9;
+    ctx->dmax = nQ + nP;
+    for (int i = 0; i < nQ; i++) ctx->mod.push_back(Q[i]);
+    for (int i = 0; i < nP; i++) ctx->mod.push_back(P[i]);
+    for (u64 q : ctx->mod) {
+        if (q >= ((u64)1 << 60) || !h_is_prime(q) || (q - 1) % ((u64)2 << logN) != 0) { delete ctx; return MKHE_ERR_UNSUPPORTED; }
+    }
+    ctx->tabs.resize(ctx->mod.size());
+    for (size_t i = 0; i < ctx->mod.size(); i++) gen_mod_tables(ctx->tabs[i], logN, ctx->mod[i]);
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return MKHE_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MKHE_ERR_CUDA; }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+#ifndef MKHE_EMU
+    cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PASS2);
+#endif
+    std::vector<int> src, dst;
+    for (int j = 0; j < nP; j++) src.push_back(nQ + j);
+    for (int j = 0; j < nQ; j++) dst.push_back(j);
+    int rc = upload_conv(ctx, &ctx->d_conv_PtoQ, src, dst);
+    if (rc == MKHE_OK) rc = upload_tables(ctx);
+    if (rc != MKHE_OK) { delete ctx; return rc; }
+    *out = ctx;
+    return MKHE_OK;
+}
+
+int mkhe_ctx_set_bfv(mkhe_ctx *ctx, const uint64_t *QMul, int nQMul, uint64_t T) {
+    CHECK_CTX();
+    if (!QMul || nQMul != ctx->nQ) return fail(ctx, MKHE_ERR_INVALID, "cannot NewParametersFromLiteral: length of Q & QMul is not equal");
+    if (ctx->nQMul) return fail(ctx, MKHE_ERR_INVALID, "BFV parameters already set");
+    for (int i = 0; i < nQMul; i++) {
+        u64 q = QMul[i];
+        if (q >= ((u64)1 << 60) || !h_is_prime(q) || (q - 1) % ((u64)2 << ctx->logN) != 0) return fail(ctx, MKHE_ERR_UNSUPPORTED, "bad QMul prime");
+        ctx->mod.push_back(q);
+        ctx->tabs.emplace_back();
+        gen_mod_tables(ctx->tabs.back(), ctx->logN, q);
+    }
+    ctx->nQMul = nQMul;
+    ctx->T = T;
+    ctx->tables_dirty = true;
+    TRY(upload_tables(ctx));
+    std::vector<int> q, qm;
+    for (int j = 0; j < ctx->nQ; j++) { q.push_back(j); qm.push_back(ctx->nQ + ctx->nP + j); }
+    TRY(upload_conv(ctx, &ctx->d_conv_QtoQMul, q, qm));
+    TRY(upload_conv(ctx, &ctx->d_conv_QMultoQ, qm, q));
+    ctx->h_mformQMul.resize(ctx->nQ);
+    for (int i = 0; i < ctx->nQ; i++) {
+        u64 qi = ctx->mod[i], r = 1;
+        for (int j = 0; j < nQMul; j++) r = h_mulmod(r, QMul[j] % qi, qi);
+        ctx->h_mformQMul[i] = h_mform(r, qi);
+    }
+    return MKHE_OK;
+}
+
+int mkhe_ctx_set_ntt_tables(mkhe_ctx *ctx, int m, const uint64_t *nttPsi, const uint64_t *nttPsiInv, uint64_t nttNInv) {
+    CHECK_CTX();
+    if (m < 0 || m >= (int)ctx->mod.size() || !nttPsi || !nttPsiInv) return fail(ctx, MKHE_ERR_INVALID, "bad modulus index %d", m);
+    set_mod_tables_from_mont(ctx->tabs[m], ctx->logN, ctx->mod[m], (const u64 *)nttPsi, (const u64 *)nttPsiInv, nttNInv);
+    ctx->tables_dirty = true;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return upload_tables(ctx);
+}
+
+void mkhe_ctx_destroy(mkhe_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    mkhe_comm_destroy(ctx);
+    for (Obj *o : ctx->objs) { cudaFree(o->d); delete o; }
+    for (auto &kv : ctx->scratch) cudaFree(kv.second.p);
+    cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi);
+    cudaFree(ctx->d_conv_PtoQ); cudaFree(ctx->d_conv_QtoQMul); cudaFree(ctx->d_conv_QMultoQ);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *mkhe_last_error(const mkhe_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mkhe_sync(mkhe_ctx *ctx) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MKHE_OK;
+}
+
+uint64_t mkhe_launch_count(const mkhe_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- polys ------------------------------------------------------------------------------------------
+int mkhe_poly_alloc(mkhe_ctx *ctx, int nlimbs, mkhe_poly *out) {
+    CHECK_CTX();
+    if (!out || nlimbs < 1 || nlimbs > 64) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
+    void *p = nullptr;
+    size_t bytes = (size_t)nlimbs * ctx->N * 8;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+    CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    Obj *o = new Obj{OBJ_POLY, (u64 *)p, nlimbs, nlimbs};
+    ctx->objs.insert(o);
+    *out = reinterpret_cast<uint64_t>(o);
+    return MKHE_OK;
+}
+int mkhe_poly_free(mkhe_ctx *ctx, mkhe_poly h) {
+    CHECK_CTX();
+    POLY(o, h);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(o->d));
+    ctx->objs.erase(o);
+    delete o;
+    return MKHE_OK;
+}
+int mkhe_poly_set_nlimbs(mkhe_ctx *ctx, mkhe_poly h, int nlimbs) {
+    CHECK_CTX();
+    POLY(o, h);
+    if (nlimbs < 1 || nlimbs > o->cap_limbs) return fail(ctx, MKHE_ERR_INVALID, "view of %d limbs exceeds capacity %d", nlimbs, o->cap_limbs);
+    o->nlimbs = nlimbs;
+    return MKHE_OK;
+}
+int mkhe_poly_get_nlimbs(mkhe_ctx *ctx, mkhe_poly h, int *nlimbs) {
+    CHECK_CTX();
+    POLY(o, h);
+    *nlimbs = o->nlimbs;
+    return MKHE_OK;
+}
+int mkhe_poly_upload_limb(mkhe_ctx *ctx, mkhe_poly h, int limb, const uint64_t *src) {
+    CHECK_CTX();
+    POLY(o, h);
+    if (limb < 0 || limb >= o->cap_limbs || !src) return fail(ctx, MKHE_ERR_INVALID, "limb %d out of range", limb);
+    CU(cudaMemcpyAsync(o->d + (size_t)limb * ctx->N, src, (size_t)ctx->N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MKHE_OK;
+}
+int mkhe_poly_download_limb(mkhe_ctx *ctx, mkhe_poly h, int limb, uint64_t *dst) {
+    CHECK_CTX();
+    POLY(o, h);
+    if (limb < 0 || limb >= o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "limb %d out of range", limb);
+    CU(cudaMemcpyAsync(dst, o->d + (size_t)limb * ctx->N, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MKHE_OK;
+}
+int mkhe_poly_upload(mkhe_ctx *ctx, mkhe_poly h, const uint64_t *src, int nlimbs) {
+    CHECK_CTX();
+    POLY(o, h);
+    if (nlimbs < 1 || nlimbs > o->cap_limbs || !src) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
+    CU(cudaMemcpyAsync(o->d, src, (size_t)nlimbs * ctx->N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MKHE_OK;
+}
+int mkhe_poly_download(mkhe_ctx *ctx, mkhe_poly h, uint64_t *dst, int nlimbs) {
+    CHECK_CTX();
+    POLY(o, h);
+    if (nlimbs < 1 || nlimbs > o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
+    CU(cudaMemcpyAsync(dst, o->d, (size_t)nlimbs * ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MKHE_OK;
+}
+int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dsth, mkhe_poly srch) {
+    CHECK_CTX();
+    POLY(d, dsth);
+    POLY(s, srch);
+    if (d->cap_limbs < s->nlimbs) return fail(ctx, MKHE_ERR_INVALID, "copy: destination too small");
+    CU(cudaMemcpyAsync(d->d, s->d, (size_t)s->nlimbs * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    d->nlimbs = s->nlimbs;
+    return MKHE_OK;
+}
+
+// ---- switching keys ---------------------------------------------------------------------------------
+int mkhe_swk_alloc(mkhe_ctx *ctx, mkhe_swk *out) {
+    CHECK_CTX();
+    if (!out) return MKHE_ERR_INVALID;
+    void *p = nullptr;
+    size_t bytes = swk_elems(ctx) * 8;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+    CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    Obj *o = new Obj{OBJ_SWK, (u64 *)p, 0, 0};
+    ctx->objs.insert(o);
+    *out = reinterpret_cast<uint64_t>(o);
+    return MKHE_OK;
+}
+int mkhe_swk_free(mkhe_ctx *ctx, mkhe_swk h) {
+    CHECK_CTX();
+    SWK(o, h);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(o->d));
+    ctx->objs.erase(o);
+    delete o;
+    return MKHE_OK;
+}
+static int swk_limb_off(mkhe_ctx *ctx, int digit, int is_p, int limb, size_t *off) {
+    if (digit < 0 || digit >= ctx->nQ) return fail(ctx, MKHE_ERR_INVALID, "digit %d out of range", digit);
+    if (limb < 0 || limb >= (is_p ? ctx->nP : ctx->nQ)) return fail(ctx, MKHE_ERR_INVALID, "limb %d out of range", limb);
+    *off = ((size_t)digit * ctx->dmax + (is_p ? ctx->nQ : 0) + limb) * ctx->N;
+    return MKHE_OK;
+}
+int mkhe_swk_upload_limb(mkhe_ctx *ctx, mkhe_swk h, int digit, int is_p, int limb, const uint64_t *src) {
+    CHECK_CTX();
+    SWK(o, h);
+    size_t off;
+    TRY(swk_limb_off(ctx, digit, is_p, limb, &off));
+    CU(cudaMemcpyAsync(o->d + off, src, (size_t)ctx->N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MKHE_OK;
+}
+int mkhe_swk_download_limb(mkhe_ctx *ctx, mkhe_swk h, int digit, int is_p, int limb, uint64_t *dst) {
+    CHECK_CTX();
+    SWK(o, h);
+    size_t off;
+    TRY(swk_limb_off(ctx, digit, is_p, limb, &off));
+    CU(cudaMemcpyAsync(dst, o->d + off, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MKHE_OK;
+}
+int mkhe_swk_upload(mkhe_ctx *ctx, mkhe_swk h, const uint64_t *src) {
+    CHECK_CTX();
+    SWK(o, h);
+    CU(cudaMemcpyAsync(o->d, src, swk_elems(ctx) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MKHE_OK;
+}
+int mkhe_swk_download(mkhe_ctx *ctx, mkhe_swk h, uint64_t *dst) {
+    CHECK_CTX();
+    SWK(o, h);
+    CU(cudaMemcpyAsync(dst, o->d, swk_elems(ctx) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MKHE_OK;
+}
+
+// ---- ring primitives --------------------------------------------------------------------------------
+int mkhe_ntt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out) {
+    CHECK_CTX();
+    POLY(i, in);
+    POLY(o, out);
+    if (level < 0 || level >= i->cap_limbs || level >= o->cap_limbs) return fail(ctx, MKHE_ERR_INVALID, "level %d out of range", level);
+    Slots s = (level >= ctx->nQ) ? r_slots(ctx) : q_slots(level);
+    return ntt_fwd(ctx, s, 1, &i->d, &o->d);
+}
+int mkhe_intt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out) {
+    CHECK_CTX();
+    POLY(i, in);
+    POLY(o, out);
+    if (level < 0 || level >= i->cap_limbs || level >= o->cap_limbs) return fail(ctx, MKHE_ERR_INVALID, "level %d out of range", level);
+    Slots s = (level >= ctx->nQ) ? r_slots(ctx) : q_slots(level);
+    return ntt_inv(ctx, s, 1, &i->d, &o->d);
+}
+
+// ---- KeySwitcher ------------------------------------------------------------------------------------
+static int check_level(mkhe_ctx *ctx, int level) {
+    if (level < 0 || level >= ctx->nQ) return fail(ctx, MKHE_ERR_INVALID, "level %d out of range [0,%d)", level, ctx->nQ);
+    return MKHE_OK;
+}
+
+int mkhe_decompose(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk ad) {
+    CHECK_CTX();
+    TRY(check_level(ctx, levelQ));
+    POLY(p, a);
+    SWK(k, ad);
+    if (p->cap_limbs < levelQ + 1) return fail(ctx, MKHE_ERR_INVALID, "Decompose: poly has %d limbs, level %d", p->cap_limbs, levelQ);
+    return decompose_impl(ctx, levelQ, 1, &p->d, &k->d, 0);
+}
+
+int mkhe_external_product_hoisted(mkhe_ctx *ctx, int levelQ, mkhe_swk a_hoisted, mkhe_swk bg, mkhe_poly c) {
+    CHECK_CTX();
+    TRY(check_level(ctx, levelQ));
+    SWK(h, a_hoisted);
+    SWK(k, bg);
+    POLY(o, c);
+    if (o->cap_limbs < levelQ + 1) return fail(ctx, MKHE_ERR_INVALID, "ExternalProduct: output has %d limbs", o->cap_limbs);
+    return ext_products(ctx, levelQ, 1, 1, &k->d, &h->d, nullptr, nullptr, &o->d, nullptr, false);
+}
+
+int mkhe_external_product(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk bg, mkhe_poly c) {
+    CHECK_CTX();
+    TRY(check_level(ctx, levelQ));
+    POLY(p, a);
+    SWK(k, bg);
+    POLY(o, c);
+    if (p->cap_limbs < levelQ + 1 || o->cap_limbs < levelQ + 1) return fail(ctx, MKHE_ERR_INVALID, "ExternalProduct: too few limbs");
+    std::vector<u64 *> hp;
+    TRY(swk_pool(ctx, "extprod_h", 1, hp));
+    TRY(decompose_impl(ctx, levelQ, 1, &p->d, hp.data(), 0));
+    return ext_products(ctx, levelQ, 1, 1, &k->d, hp.data(), nullptr, nullptr, &o->d, nullptr, false);
+}
+
+static int check_ids(mkhe_ctx *ctx, int n0, const int *ids0, int n1, const int *ids1, int nOut, const int *idsOut) {
+    if (n0 < 0 || n1 < 0 || nOut < 0 || n0 > MKHE_MAX_PARTIES || n1 > MKHE_MAX_PARTIES || nOut > MKHE_MAX_PARTIES)
+        return fail(ctx, MKHE_ERR_INVALID, "party count out of range (max %d)", MKHE_MAX_PARTIES);
+    for (int t = 0; t < n0; t++) if (find_id(nOut, idsOut, ids0[t]) < 0) return fail(ctx, MKHE_ERR_INVALID, "idsOut is not the union of ids0 and ids1");
+    for (int t = 0; t < n1; t++) if (find_id(nOut, idsOut, ids1[t]) < 0) return fail(ctx, MKHE_ERR_INVALID, "idsOut is not the union of ids0 and ids1");
+    for (int t = 0; t < nOut; t++) if (find_id(n0, ids0, idsOut[t]) < 0 && find_id(n1, ids1, idsOut[t]) < 0) return fail(ctx, MKHE_ERR_INVALID, "idsOut is not the union of ids0 and ids1");
+    return MKHE_OK;
+}
+
+int mkhe_mul_relin_hoisted(mkhe_ctx *ctx, int level, int n0, const int *ids0, const mkhe_poly *op0, const mkhe_swk *h0,
+                           int n1, const int *ids1, const mkhe_poly *op1, const mkhe_swk *h1, const mkhe_swk *rlk_b,
+                           const mkhe_swk *rlk_d, const mkhe_swk *rlk_v, mkhe_swk u, int nOut, const int *idsOut,
+                           const mkhe_poly *out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    TRY(check_ids(ctx, n0, ids0, n1, ids1, nOut, idsOut));
+    std::vector<u64 *> p0, p1, po, vh0, vh1, vb, vd, vv;
+    // level checks mirror keyswitch_hoisted.go:48-54
+    for (int t = 0; t <= n0; t++) {
+        Obj *o = as_obj(ctx, op0[t], OBJ_POLY);
+        if (o && o->nlimbs - 1 < level) return fail(ctx, MKHE_ERR_INVALID, "Cannot MulAndRelin: op0 and op1 have different levels");
+    }
+    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0"));
+    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1"));
+    TRY(polys_of(ctx, nOut + 1, out, level + 1, po, "out"));
+    TRY(swks_of(ctx, n1, rlk_b, vb, "rlk_b"));
+    TRY(swks_of(ctx, n0, rlk_d, vd, "rlk_d"));
+    TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v"));
+    SWK(uk, u);
+    if (h0) TRY(swks_of(ctx, n0, h0, vh0, "h0"));
+    else {
+        TRY(swk_pool(ctx, "nil_h0", n0, vh0));
+        TRY(decompose_impl(ctx, level, n0, p0.data() + 1, vh0.data(), 0));
+    }
+    if (h1) TRY(swks_of(ctx, n1, h1, vh1, "h1"));
+    else {
+        TRY(swk_pool(ctx, "nil_h1", n1, vh1));
+        TRY(decompose_impl(ctx, level, n1, p1.data() + 1, vh1.data(), 0));
+    }
+    return mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
+                                  vd.data(), vv.data(), uk->d, nOut, idsOut, po.data());
+}
+
+int mkhe_ckks_mul_relin(mkhe_ctx *ctx, int level, int nb_rescales, int same_operand, int n0, const int *ids0,
+                        const mkhe_poly *op0, int n1, const int *ids1, const mkhe_poly *op1, const mkhe_swk *rlk_b,
+                        const mkhe_swk *rlk_d, const mkhe_swk *rlk_v, mkhe_swk u, int nOut, const int *idsOut,
+                        const mkhe_poly *out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    TRY(check_ids(ctx, n0, ids0, n1, ids1, nOut, idsOut));
+    std::vector<u64 *> p0, p1, po, vh0, vh1, vb, vd, vv;
+    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0"));
+    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1"));
+    TRY(polys_of(ctx, nOut + 1, out, level + 1, po, "out"));
+    TRY(swks_of(ctx, n1, rlk_b, vb, "rlk_b"));
+    TRY(swks_of(ctx, n0, rlk_d, vd, "rlk_d"));
+    TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v"));
+    SWK(uk, u);
+    // hoisting into context pools (rlkSet.HoistPool[0|1], mkckks/evaluator.go:419-441)
+    TRY(swk_pool(ctx, "hoistpool0", n0, vh0));
+    TRY(decompose_impl(ctx, level, n0, p0.data() + 1, vh0.data(), 0));
+    if (same_operand) vh1 = vh0;
+    else {
+        TRY(swk_pool(ctx, "hoistpool1", n1, vh1));
+        TRY(decompose_impl(ctx, level, n1, p1.data() + 1, vh1.data(), 0));
+    }
+    TRY(mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
+                               vd.data(), vv.data(), uk->d, nOut, idsOut, po.data()));
+    TRY(rescale_impl(ctx, level, nb_rescales, nOut + 1, po.data(), po.data()));
+    for (int t = 0; t <= nOut; t++) reinterpret_cast<Obj *>(out[t])->nlimbs = level + 1 - nb_rescales;
+    return MKHE_OK;
+}
+
+int mkhe_rotate_hoisted(mkhe_ctx *ctx, int level, int rotidx, int n, const mkhe_poly *ct_in, const mkhe_swk *hoisted,
+                        const mkhe_swk *rk, mkhe_swk a, const mkhe_poly *ct_out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    if (n < 0 || n > MKHE_MAX_PARTIES) return fail(ctx, MKHE_ERR_INVALID, "party count out of range");
+    for (int t = 0; t <= n; t++) {
+        Obj *o = as_obj(ctx, ct_in[t], OBJ_POLY);
+        if (o && o->nlimbs - 1 < level) return fail(ctx, MKHE_ERR_INVALID, "Cannot Rotate: ctIn and ctOut have different levels");
+    }
+    std::vector<u64 *> pi, po, vh, vrk;
+    TRY(polys_of(ctx, n + 1, ct_in, level + 1, pi, "ct_in"));
+    TRY(polys_of(ctx, n + 1, ct_out, level + 1, po, "ct_out"));
+    TRY(swks_of(ctx, n, hoisted, vh, "hoisted"));
+    TRY(swks_of(ctx, n, rk, vrk, "rk"));
+    SWK(ak, a);
+    return rotate_hoisted_impl(ctx, level, rotidx, n, pi.data(), vh.data(), vrk.data(), ak->d, po.data());
+}
+
+int mkhe_rotate(mkhe_ctx *ctx, int level, int rotidx, int n, const mkhe_poly *ct_in, const mkhe_swk *rk, mkhe_swk a,
+                const mkhe_poly *ct_out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    if (n < 0 || n > MKHE_MAX_PARTIES) return fail(ctx, MKHE_ERR_INVALID, "party count out of range");
+    std::vector<u64 *> pi, po, vh, vrk;
+    TRY(polys_of(ctx, n + 1, ct_in, level + 1, pi, "ct_in"));
+    TRY(polys_of(ctx, n + 1, ct_out, level + 1, po, "ct_out"));
+    TRY(swks_of(ctx, n, rk, vrk, "rk"));
+    SWK(ak, a);
+    TRY(swk_pool(ctx, "rot_h", n, vh));
+    TRY(decompose_impl(ctx, level, n, pi.data() + 1, vh.data(), 0));
+    return rotate_hoisted_impl(ctx, level, rotidx, n, pi.data(), vh.data(), vrk.data(), ak->d, po.data());
+}
+
+int mkhe_conjugate(mkhe_ctx *ctx, int level, int n, const mkhe_poly *ct_in, const mkhe_swk *ck, mkhe_swk a,
+                   const mkhe_poly *ct_out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    if (n < 0 || n > MKHE_MAX_PARTIES) return fail(ctx, MKHE_ERR_INVALID, "party count out of range");
+    std::vector<u64 *> pi, po, vh, vck, tmp;
+    TRY(polys_of(ctx, n + 1, ct_in, level + 1, pi, "ct_in"));
+    TRY(polys_of(ctx, n + 1, ct_out, level + 1, po, "ct_out"));
+    TRY(swks_of(ctx, n, ck, vck, "ck"));
+    SWK(ak, a);
+    // permute first (keyswitch.go:315-317), then key-switch the permuted components (:320-331)
+    TRY(poly_pool(ctx, "conj_tmp", n + 1, ctx->nQ, tmp));
+    TRY(automorph_impl(ctx, level, ((u64)2 << ctx->logN) - 1, n + 1, pi.data(), tmp.data()));
+    TRY(swk_pool(ctx, "rot_h", n, vh));
+    TRY(decompose_impl(ctx, level, n, tmp.data() + 1, vh.data(), 0));
+    CU(cudaMemcpyAsync(po[0], tmp[0], (size_t)(level + 1) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    std::vector<u64 *> akey(n, ak->d), c0(n, po[0]);
+    TRY(ext_products(ctx, level, n, 1, vck.data(), vh.data(), nullptr, nullptr, c0.data(), c0.data(), true));
+    return ext_products(ctx, level, n, 1, akey.data(), vh.data(), nullptr, nullptr, po.data() + 1, nullptr, false);
+}
+
+// ---- mkckks.Evaluator -------------------------------------------------------------------------------
+int mkhe_rescale(mkhe_ctx *ctx, int level, int nb_rescales, mkhe_poly in, mkhe_poly out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    POLY(i, in);
+    POLY(o, out);
+    if (i->cap_limbs < level + 1 || o->cap_limbs < level + 1 - nb_rescales) return fail(ctx, MKHE_ERR_INVALID, "Rescale: too few limbs");
+    if (nb_rescales == 0) {
+        if (i != o) CU(cudaMemcpyAsync(o->d, i->d, (size_t)(level + 1) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        return MKHE_OK;
+    }
+    if (nb_rescales > 1 && i != o) {
+        // lattigo runs the later divisions in a pool, leaving `in` untouched after the first one
+        std::vector<u64 *> tmp;
+        TRY(poly_pool(ctx, "rescale_tmp", 1, ctx->nQ, tmp));
+        TRY(rescale_impl(ctx, level, 1, 1, &i->d, tmp.data()));
+        TRY(rescale_impl(ctx, level - 1, nb_rescales - 1, 1, tmp.data(), tmp.data()));
+        CU(cudaMemcpyAsync(o->d, tmp[0], (size_t)(level + 1 - nb_rescales) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        TRY(rescale_impl(ctx, level, nb_rescales, 1, &i->d, &o->d));
+    }
+    o->nlimbs = level + 1 - nb_rescales;
+    return MKHE_OK;
+}
+int mkhe_poly_add(mkhe_ctx *ctx, int level, mkhe_poly a, mkhe_poly b, mkhe_poly out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    POLY(x, a); POLY(y, b); POLY(o, out);
+    if (x->cap_limbs <= level || y->cap_limbs <= level || o->cap_limbs <= level) return fail(ctx, MKHE_ERR_INVALID, "Add: too few limbs");
+    return add_polys(ctx, level, x->d, y->d, o->d, false);
+}
+int mkhe_poly_sub(mkhe_ctx *ctx, int level, mkhe_poly a, mkhe_poly b, mkhe_poly out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    POLY(x, a); POLY(y, b); POLY(o, out);
+    if (x->cap_limbs <= level || y->cap_limbs <= level || o->cap_limbs <= level) return fail(ctx, MKHE_ERR_INVALID, "Sub: too few limbs");
+    return add_polys(ctx, level, x->d, y->d, o->d, true);
+}
+
+// ---- mkbfv ------------------------------------------------------------------------------------------
+namespace {
+int need_bfv(mkhe_ctx *ctx) {
+    if (!ctx->nQMul) return fail(ctx, MKHE_ERR_INVALID, "BFV parameters not set (mkhe_ctx_set_bfv)");
+    return MKHE_OK;
+}
+int conv_launch(mkhe_ctx *ctx, int mode, const ConvTable *tab, int nb, u64 *const *src, int src_limb0, u64 *const *x,
+                int x_limb0, int x_is_zero, u64 *const *dst, int dst_limb0, int n2) {
+    const int cb = (ctx->N + MKHE_THREADS - 1) / MKHE_THREADS;
+    for (int b0 = 0; b0 < nb; b0 += MKHE_MAX_PARTIES_K) {
+        int n = std::min(MKHE_MAX_PARTIES_K, nb - b0);
+        ConvArgs c;
+        memset(&c, 0, sizeof c);
+        c.src_limb0 = src_limb0; c.x_limb0 = x_limb0; c.dst_limb0 = dst_limb0;
+        c.n2_used = n2; c.x_is_zero = x_is_zero; c.logN = ctx->logN;
+        for (int i = 0; i < n; i++) { c.src.p[i] = src[b0 + i]; c.x.p[i] = x ? x[b0 + i] : nullptr; c.dst.p[i] = dst[b0 + i]; }
+        if (mode == CONV_MODUP) LAUNCH(k_conv<CONV_MODUP>, dim3(cb, n), dim3(MKHE_THREADS), 0, c, tab, ctx->d_mods);
+        else LAUNCH(k_conv<CONV_MODDOWN>, dim3(cb, n), dim3(MKHE_THREADS), 0, c, tab, ctx->d_mods);
+    }
+    return MKHE_OK;
+}
+// ModUpQtoR for a batch (mkbfv/basis_extension.go:49-63)
+int bfv_modup_impl(mkhe_ctx *ctx, int nb, u64 *const *polyQ, u64 *const *polyR) {
+    const size_t qbytes = (size_t)ctx->nQ * ctx->N * 8;
+    for (int i = 0; i < nb; i++) CU(cudaMemcpyAsync(polyR[i], polyQ[i], qbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return conv_launch(ctx, CONV_MODUP, ctx->d_conv_QtoQMul, nb, polyQ, 0, nullptr, 0, 0, polyR, ctx->nQ, ctx->nQ);
+}
+// Rescale Q -> R for a batch (mkbfv/basis_extension.go:83-97)
+int bfv_rescale_impl(mkhe_ctx *ctx, int nb, u64 *const *polyQ, u64 *const *polyR) {
+    std::vector<u64 *> tq;
+    TRY(poly_pool(ctx, "bfv_tq", nb, ctx->nQ, tq));
+    for (int b0 = 0; b0 < nb; b0 += MKHE_MAX_PARTIES_K) {
+        int n = std::min(MKHE_MAX_PARTIES_K, nb - b0);
+        ScaleArgs a;
+        memset(&a, 0, sizeof a);
+        a.nlimbs = ctx->nQ; a.logN = ctx->logN;
+        for (int i = 0; i < ctx->nQ; i++) { a.mod_of_limb[i] = i; a.cmont[i] = ctx->h_mformQMul[i]; }
+        for (int i = 0; i < n; i++) { a.in.p[i] = polyQ[b0 + i]; a.out.p[i] = tq[b0 + i]; }
+        LAUNCH(k_scale, dim3(ctx->N / MKHE_THREADS, ctx->nQ, n), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    }
+    // ModDownQPtoP with a zero P part -> canonical QMul limbs, written straight into R's upper half
+    TRY(conv_launch(ctx, CONV_MODDOWN, ctx->d_conv_QtoQMul, nb, tq.data(), 0, nullptr, 0, 1, polyR, ctx->nQ, ctx->nQ));
+    // ModUpPtoQ: lazy lift of the QMul limbs back to Q -> R's lower half
+    return conv_launch(ctx, CONV_MODUP, ctx->d_conv_QMultoQ, nb, polyR, ctx->nQ, nullptr, 0, 0, polyR, 0, ctx->nQ);
+}
+// Quantize for a batch: polyR (NTT domain, canonical) -> polyQ   (mkbfv/basis_extension.go:66-80)
+int bfv_quantize_impl(mkhe_ctx *ctx, int nb, u64 *const *polyR, u64 *const *polyQ) {
+    std::vector<u64 *> tr;
+    TRY(poly_pool(ctx, "bfv_tr", nb, 2 * ctx->nQ, tr));
+    Slots rs = r_slots(ctx);
+    for (int b0 = 0; b0 < nb; b0 += MKHE_MAX_PARTIES_K) {
+        int n = std::min(MKHE_MAX_PARTIES_K, nb - b0);
+        ScaleArgs a;
+        memset(&a, 0, sizeof a);
+        a.nlimbs = rs.n; a.logN = ctx->logN;
+        for (int i = 0; i < rs.n; i++) { a.mod_of_limb[i] = rs.mod[i]; a.cmont[i] = h_mform(ctx->T % ctx->mod[rs.mod[i]], ctx->mod[rs.mod[i]]); }
+        for (int i = 0; i < n; i++) { a.in.p[i] = polyR[b0 + i]; a.out.p[i] = tr[b0 + i]; }
+        LAUNCH(k_scale, dim3(ctx->N / MKHE_THREADS, rs.n, n), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    }
+    TRY(ntt_inv(ctx, rs, nb, tr.data(), tr.data()));
+    return conv_launch(ctx, CONV_MODDOWN, ctx->d_conv_QMultoQ, nb, tr.data(), ctx->nQ, tr.data(), 0, 0, polyQ, 0, ctx->nQ);
+}
+int bfv_decompose_impl(mkhe_ctx *ctx, int levelQ, int nb, u64 *const *aR, u64 *const *ad1, u64 *const *ad2) {
+    TRY(decompose_impl(ctx, levelQ, nb, aR, ad1, 0));
+    return decompose_impl(ctx, levelQ, nb, aR, ad2, levelQ + 1);
+}
+int mul2(mkhe_ctx *ctx, const Slots &s, const u64 *A, const u64 *B, const u64 *Cc, const u64 *D, u64 *out) {
+    LimbArgs a;
+    fill(a, s, ctx->logN);
+    LAUNCH(k_mul2, dim3(ctx->N / MKHE_THREADS, s.n), dim3(MKHE_THREADS), 0, A, B, Cc, D, out, a, ctx->d_mods);
+    return MKHE_OK;
+}
+// MulAndRelinBFVHoisted on raw pointers (mkbfv/keyswitch_hoisted.go:39-207)
+int bfv_mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u64 *const *op0, u64 *const *h0a,
+                               u64 *const *h0b, int n1, const int *ids1, u64 *const *op1, u64 *const *h1a,
+                               u64 *const *h1b, u64 *const *b1, u64 *const *b2, u64 *const *d1, u64 *const *d2,
+                               u64 *const *v, u64 *u, int nOut, const int *idsOut, u64 *const *out) {
+    std::vector<u64 *> xy;
+    TRY(swk_pool(ctx, "bfv_xy", 4, xy));
+    u64 *x1 = xy[0], *x2 = xy[1], *y1 = xy[2], *y2 = xy[3];
+    TRY(mac_parties(ctx, level, n0, d1, h0a, x1));
+    TRY(mac_parties(ctx, level, n0, d2, h0b, x2));
+    TRY(mac_parties(ctx, level, n1, b1, h1a, y1));
+    TRY(mac_parties(ctx, level, n1, b2, h1b, y2));
+    // tensor product in ring R, each component quantized back to Q (:144-181)
+    Slots rs = r_slots(ctx);
+    std::vector<u64 *> tn, prod, src(n0 + n1 + 2);
+    TRY(poly_pool(ctx, "bfv_tensor_ntt", n0 + n1 + 2, 2 * ctx->nQ, tn));
+    TRY(poly_pool(ctx, "bfv_tensor_prod", nOut + 1, 2 * ctx->nQ, prod));
+    for (int t = 0; t <= n0; t++) src[t] = op0[t];
+    for (int t = 0; t <= n1; t++) src[n0 + 1 + t] = op1[t];
+    TRY(ntt_fwd(ctx, rs, n0 + n1 + 2, src.data(), tn.data()));
+    const u64 *A0 = tn[0], *B0 = tn[n0 + 1];
+    TRY(mul2(ctx, rs, A0, B0, nullptr, nullptr, prod[0]));
+    for (int t = 0; t < nOut; t++) {
+        int i0 = find_id(n0, ids0, idsOut[t]), i1 = find_id(n1, ids1, idsOut[t]);
+        if (i0 >= 0 && i1 < 0) TRY(mul2(ctx, rs, B0, tn[1 + i0], nullptr, nullptr, prod[1 + t]));
+        else if (i0 < 0 && i1 >= 0) TRY(mul2(ctx, rs, A0, tn[n0 + 2 + i1], nullptr, nullptr, prod[1 + t]));
+        else TRY(mul2(ctx, rs, A0, tn[n0 + 2 + i1], B0, tn[1 + i0], prod[1 + t]));
+    }
+    TRY(bfv_quantize_impl(ctx, nOut + 1, prod.data(), out));
+    // c_id += (x1,x2) [.] (h1a,h1b)   (:184-191)
+    {
+        std::vector<u64 *> k1(n1, x1), k2(n1, x2), dst(n1);
+        for (int t = 0; t < n1; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids1[t])];
+        TRY(ext_products(ctx, level, n1, 2, k1.data(), h1a, k2.data(), h1b, dst.data(), dst.data(), false));
+    }
+    // p_id = (y1,y2) [.] (h0a,h0b) ; Decompose ; c_0 += v_id [.] p_id ; c_id += u [.] p_id   (:198-216)
+    {
+        std::vector<u64 *> k1(n0, y1), k2(n0, y2), p, hp;
+        TRY(poly_pool(ctx, "relin_p", n0, ctx->nQ, p));
+        TRY(swk_pool(ctx, "relin_hp", n0, hp));
+        TRY(ext_products(ctx, level, n0, 2, k1.data(), h0a, k2.data(), h0b, p.data(), nullptr, false));
+        TRY(decompose_impl(ctx, level, n0, p.data(), hp.data(), 0));
+        std::vector<u64 *> ukey(n0, u), dst(n0), c0(n0, out[0]);
+        for (int t = 0; t < n0; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids0[t])];
+        TRY(ext_products(ctx, level, n0, 1, ukey.data(), hp.data(), nullptr, nullptr, dst.data(), dst.data(), false));
+        TRY(ext_products(ctx, level, n0, 1, v, hp.data(), nullptr, nullptr, c0.data(), c0.data(), true));
+    }
+    return MKHE_OK;
+}
+}  // namespace
+
+int mkhe_bfv_modup_q_to_r(mkhe_ctx *ctx, mkhe_poly polyQ, mkhe_poly polyR) {
+    CHECK_CTX();
+    TRY(need_bfv(ctx));
+    POLY(q, polyQ); POLY(r, polyR);
+    if (q->cap_limbs < ctx->nQ || r->cap_limbs < 2 * ctx->nQ) return fail(ctx, MKHE_ERR_INVALID, "ModUpQtoR: too few limbs");
+    return bfv_modup_impl(ctx, 1, &q->d, &r->d);
+}
+int mkhe_bfv_rescale_q_to_r(mkhe_ctx *ctx, mkhe_poly polyQ, mkhe_poly polyR) {
+    CHECK_CTX();
+    TRY(need_bfv(ctx));
+    POLY(q, polyQ); POLY(r, polyR);
+    if (q->cap_limbs < ctx->nQ || r->cap_limbs < 2 * ctx->nQ) return fail(ctx, MKHE_ERR_INVALID, "Rescale: too few limbs");
+    return bfv_rescale_impl(ctx, 1, &q->d, &r->d);
+}
+int mkhe_bfv_quantize(mkhe_ctx *ctx, mkhe_poly polyR, mkhe_poly polyQ) {
+    CHECK_CTX();
+    TRY(need_bfv(ctx));
+    POLY(q, polyQ); POLY(r, polyR);
+    if (q->cap_limbs < ctx->nQ || r->cap_limbs < 2 * ctx->nQ) return fail(ctx, MKHE_ERR_INVALID, "Quantize: too few limbs");
+    return bfv_quantize_impl(ctx, 1, &r->d, &q->d);
+}
+int mkhe_bfv_decompose(mkhe_ctx *ctx, int levelQ, mkhe_poly aR, mkhe_swk ad1, mkhe_swk ad2) {
+    CHECK_CTX();
+    TRY(need_bfv(ctx));
+    TRY(check_level(ctx, levelQ));
+    POLY(r, aR); SWK(k1, ad1); SWK(k2, ad2);
+    if (r->cap_limbs < 2 * (levelQ + 1)) return fail(ctx, MKHE_ERR_INVALID, "DecomposeBFV: too few limbs");
+    return bfv_decompose_impl(ctx, levelQ, 1, &r->d, &k1->d, &k2->d);
+}
+int mkhe_bfv_mul_relin_hoisted(mkhe_ctx *ctx, int level, int n0, const int *ids0, const mkhe_poly *op0,
+                               const mkhe_swk *h0a, const mkhe_swk *h0b, int n1, const int *ids1, const mkhe_poly *op1,
+                               const mkhe_swk *h1a, const mkhe_swk *h1b, const mkhe_swk *b1, const mkhe_swk *b2,
+                               const mkhe_swk *d1, const mkhe_swk *d2, const mkhe_swk *v, mkhe_swk u, int nOut,
+                               const int *idsOut, const mkhe_poly *out) {
+    CHECK_CTX();
+    TRY(need_bfv(ctx));
+    TRY(check_level(ctx, level));
+    TRY(check_ids(ctx, n0, ids0, n1, ids1, nOut, idsOut));
+    std::vector<u64 *> p0, p1, po, a0, b0, a1, bb1, vb1, vb2, vd1, vd2, vv;
+    TRY(polys_of(ctx, n0 + 1, op0, 2 * ctx->nQ, p0, "op0"));
+    TRY(polys_of(ctx, n1 + 1, op1, 2 * ctx->nQ, p1, "op1"));
+    TRY(polys_of(ctx, nOut + 1, out, level + 1, po, "out"));
+    TRY(swks_of(ctx, n1, b1, vb1, "b1")); TRY(swks_of(ctx, n1, b2, vb2, "b2"));
+    TRY(swks_of(ctx, n0, d1, vd1, "d1")); TRY(swks_of(ctx, n0, d2, vd2, "d2"));
+    TRY(swks_of(ctx, n0, v, vv, "v"));
+    SWK(uk, u);
+    if (h0a && h0b) { TRY(swks_of(ctx, n0, h0a, a0, "h0a")); TRY(swks_of(ctx, n0, h0b, b0, "h0b")); }
+    else {
+        TRY(swk_pool(ctx, "nil_h0", n0, a0)); TRY(swk_pool(ctx, "nil_h0b", n0, b0));
+        TRY(bfv_decompose_impl(ctx, level, n0, p0.data() + 1, a0.data(), b0.data()));
+    }
+    if (h1a && h1b) { TRY(swks_of(ctx, n1, h1a, a1, "h1a")); TRY(swks_of(ctx, n1, h1b, bb1, "h1b")); }
+    else {
+        TRY(swk_pool(ctx, "nil_h1", n1, a1)); TRY(swk_pool(ctx, "nil_h1b", n1, bb1));
+        TRY(bfv_decompose_impl(ctx, level, n1, p1.data() + 1, a1.data(), bb1.data()));
+    }
+    return bfv_mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), a0.data(), b0.data(), n1, ids1, p1.data(), a1.data(),
+                                      bb1.data(), vb1.data(), vb2.data(), vd1.data(), vd2.data(), vv.data(), uk->d, nOut,
+                                      idsOut, po.data());
+}
+int mkhe_bfv_mul_relin(mkhe_ctx *ctx, int n0, const int *ids0, const mkhe_poly *ct0, int n1, const int *ids1,
+                       const mkhe_poly *ct1, const mkhe_swk *b1, const mkhe_swk *b2, const mkhe_swk *d1,
+                       const mkhe_swk *d2, const mkhe_swk *v, mkhe_swk u, int nOut, const int *idsOut,
+                       const mkhe_poly *out) {
+    CHECK_CTX();
+    TRY(need_bfv(ctx));
+    TRY(check_ids(ctx, n0, ids0, n1, ids1, nOut, idsOut));
+    const int level = ctx->nQ - 1;
+    std::vector<u64 *> p0, p1, po, r0, r1, a0, b0, a1, bb1, vb1, vb2, vd1, vd2, vv;
+    TRY(polys_of(ctx, n0 + 1, ct0, ctx->nQ, p0, "ct0"));
+    TRY(polys_of(ctx, n1 + 1, ct1, ctx->nQ, p1, "ct1"));
+    TRY(polys_of(ctx, nOut + 1, out, ctx->nQ, po, "out"));
+    TRY(swks_of(ctx, n1, b1, vb1, "b1")); TRY(swks_of(ctx, n1, b2, vb2, "b2"));
+    TRY(swks_of(ctx, n0, d1, vd1, "d1")); TRY(swks_of(ctx, n0, d2, vd2, "d2"));
+    TRY(swks_of(ctx, n0, v, vv, "v"));
+    SWK(uk, u);
+    // rlkSet.PolyRPool1/2 and HoistPool1/2 (mkbfv/keys.go:40-68) live in the context
+    TRY(poly_pool(ctx, "bfv_polyR0", n0 + 1, 2 * ctx->nQ, r0));
+    TRY(poly_pool(ctx, "bfv_polyR1", n1 + 1, 2 * ctx->nQ, r1));
+    TRY(bfv_modup_impl(ctx, n0 + 1, p0.data(), r0.data()));
+    TRY(bfv_rescale_impl(ctx, n1 + 1, p1.data(), r1.data()));
+    TRY(swk_pool(ctx, "bfv_h0a", n0, a0)); TRY(swk_pool(ctx, "bfv_h0b", n0, b0));
+    TRY(swk_pool(ctx, "bfv_h1a", n1, a1)); TRY(swk_pool(ctx, "bfv_h1b", n1, bb1));
+    TRY(bfv_decompose_impl(ctx, level, n0, r0.data() + 1, a0.data(), b0.data()));
+    TRY(bfv_decompose_impl(ctx, level, n1, r1.data() + 1, a1.data(), bb1.data()));
+    return bfv_mul_relin_hoisted_impl(ctx, level, n0, ids0, r0.data(), a0.data(), b0.data(), n1, ids1, r1.data(), a1.data(),
+                                      bb1.data(), vb1.data(), vb2.data(), vd1.data(), vd2.data(), vv.data(), uk->d, nOut,
+                                      idsOut, po.data());
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------------
+int mkhe_comm_unique_id(uint8_t out[128]) {
+#if !defined(MKHE_EMU) && defined(MKHE_WITH_NCCL)
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return MKHE_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(out, &id, 128);
+    return MKHE_OK;
+#else
+    memset(out, 0, 128);
+    return MKHE_ERR_UNSUPPORTED;
+#endif
+}
+int mkhe_comm_init(mkhe_ctx *ctx, int nranks, int rank, const uint8_t unique_id[128]) {
+    CHECK_CTX();
+#if !defined(MKHE_EMU) && defined(MKHE_WITH_NCCL)
+    ncclUniqueId id;
+    memcpy(&id, unique_id, 128);
+    ncclComm_t comm;
+    if (ncclCommInitRank(&comm, nranks, id, rank) != ncclSuccess) return fail(ctx, MKHE_ERR_NCCL, "ncclCommInitRank failed");
+    ctx->nccl = comm;
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return MKHE_OK;
+#else
+    (void)nranks; (void)rank; (void)unique_id;
+    return fail(ctx, MKHE_ERR_UNSUPPORTED, "built without NCCL");
+#endif
+}
+int mkhe_comm_destroy(mkhe_ctx *ctx) {
+    if (!ctx) return MKHE_ERR_INVALID;
+#if !defined(MKHE_EMU) && defined(MKHE_WITH_NCCL)
+    if (ctx->nccl) { ncclCommDestroy((ncclComm_t)ctx->nccl); ctx->nccl = nullptr; }
+#endif
+    return MKHE_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------------------
+int mkhe_timer_start(mkhe_ctx *ctx) {
+    CHECK_CTX();
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    return MKHE_OK;
+}
+int mkhe_timer_stop(mkhe_ctx *ctx, float *elapsed_ms) {
+    CHECK_CTX();
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+    return MKHE_OK;
+}
+int mkhe_bench_butterfly_peak(mkhe_ctx *ctx, double *butterflies_per_s) {
+    CHECK_CTX();
+    u64 *sink;
+    TRY(get_scratch(ctx, "sink", 64, &sink));
+    const int iters = 2000, blocks = 148 * 8;
+    ModC m = ctx->tabs[0].c;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        LAUNCH(k_bfly_peak, dim3(blocks), dim3(MKHE_THREADS), 0, sink, m, iters);
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaEventSynchronize(ctx->ev1));
+        float ms;
+        CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *butterflies_per_s = (double)blocks * MKHE_THREADS * 12.0 * iters / (best * 1e-3);
+    return MKHE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,402 @@
+"""Shared parity harness: drives the C ABI (through the reference-shaped host mirror) and the CPU oracle
+on the same seeded inputs and compares every output limb bit for bit.
+
+Used by tests/test_gpu_parity.py (the real CUDA library, `-m gpu`) and by tests/test_emu_kernels.py
+(the same kernel sources compiled for the CPU emulator, development aid).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import oracle as O
+from mkhe_kklss_b200 import mkbfv, mkckks, mkrlwe
+from mkhe_kklss_b200.params import ParamLiteral
+
+
+def assert_same(a, b, what):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        first = tuple(bad[0])
+        raise AssertionError(f"{what}: {len(bad)} of {a.size} words differ; first at {first}: "
+                             f"device={int(a[first])} oracle={int(b[first])}; per-leading-index counts "
+                             f"{np.unique(bad[:, 0], return_counts=True)}")
+
+
+def uniform_poly(prng, ring, level):
+    return prng.uniform(ring, level)
+
+
+def uniform_swk(prng, p: O.MKParams):
+    swk = p.new_swk()
+    for i in range(swk.shape[0]):
+        swk[i, :p.nQ] = prng.uniform(p.ringQ)
+        swk[i, p.nQ:] = prng.uniform(p.ringP)
+    return swk
+
+
+class CKKSWorld:
+    """oracle objects + their device twins for one parameter set with uniform-random key material"""
+
+    def __init__(self, lit: ParamLiteral, nparties, seed=0xB2000001, lib=None, rots=(1, 2), real_keys=False):
+        self.lit = lit
+        self.op = O.MKParams(lit.logN, lit.Q, lit.P, lit.gamma, seed=seed, crs_rots=list(rots))
+        self.prng = O.PRNG(seed ^ 0x5EED)
+        self.dp = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, lib=lib)
+        self.ctx = self.dp.ctx
+        for idx, arr in self.op.CRS.items():
+            self.dp.SetCRS(idx, arr)
+        self.oev = O.CKKSEvaluator(self.op, lit.scale)
+        self.dev = mkckks.Evaluator(self.dp)
+        self.ids = list(range(nparties))
+        self.o_rlk, self.d_rlk = {}, mkrlwe.RelinearizationKeySet()
+        self.o_rk, self.d_rk = {}, mkrlwe.RotationKeySet()
+        self.o_ck, self.d_ck = {}, mkrlwe.ConjugationKeySet()
+        self.sks, self.pks = {}, {}
+        kg = O.KeyGenerator(self.op) if real_keys else None
+        for i in self.ids:
+            if real_keys:
+                sk, r = kg.gen_secret_key(i), kg.gen_secret_key(i)
+                self.sks[i], self.pks[i] = sk, kg.gen_public_key(sk)
+                rl = kg.gen_relin_key(sk, r)
+                rks = {rot: kg.gen_rotation_key(rot, sk) for rot in rots}
+                ck = kg.gen_conjugation_key(sk)
+            else:
+                rl = O.RelinKey(i, uniform_swk(self.prng, self.op), uniform_swk(self.prng, self.op), uniform_swk(self.prng, self.op))
+                rks = {rot: uniform_swk(self.prng, self.op) for rot in rots}
+                ck = uniform_swk(self.prng, self.op)
+            self.o_rlk[i] = rl
+            self.d_rlk.AddRelinearizationKey(mkrlwe.RelinearizationKey(self.ctx, i, rl.b, rl.d, rl.v))
+            self.o_rk[i] = rks
+            for rot, a in rks.items():
+                self.d_rk.AddRotationKey(i, rot, mkrlwe.SwitchingKey(self.ctx, a))
+            self.o_ck[i] = ck
+            self.d_ck.AddConjugationKey(i, mkrlwe.SwitchingKey(self.ctx, ck))
+
+    def random_ct(self, ids, level, scale=None):
+        """uniform-random ciphertext (throughput-style input) on both sides"""
+        scale = self.lit.scale if scale is None else scale
+        val = {"0": uniform_poly(self.prng, self.op.ringQ, level)}
+        for i in ids:
+            val[i] = uniform_poly(self.prng, self.op.ringQ, level)
+        oct_ = O.Ciphertext({k: v.copy() for k, v in val.items()}, scale)
+        dct = mkckks.Ciphertext.from_numpy(self.ctx, val, scale)
+        return oct_, dct
+
+    def compare_ct(self, dct, oct_, what):
+        dv = dct.numpy()
+        assert set(dv) == set(oct_.value), f"{what}: component sets differ {sorted(map(str, dv))} vs {sorted(map(str, oct_.value))}"
+        for k in oct_.value:
+            assert_same(dv[k], oct_.value[k], f"{what}[{k}]")
+
+    def close(self):
+        self.ctx.close()
+
+
+# ---- individual checks (each returns nothing, raises AssertionError on mismatch) -------------------
+def check_ntt(w: CKKSWorld):
+    level = w.op.max_level()
+    a = uniform_poly(w.prng, w.op.ringQ, level)
+    pin = mkrlwe.Poly.from_numpy(w.ctx, a)
+    pout = mkrlwe.Poly(w.ctx, level + 1)
+    w.ctx.ntt(level, pin.h, pout.h)
+    assert_same(pout.numpy(), w.op.ringQ.ntt(a), "NTTLvl")
+    w.ctx.intt(level, pout.h, pin.h)
+    assert_same(pin.numpy(), a, "InvNTTLvl(NTTLvl(a))")
+    b = uniform_poly(w.prng, w.op.ringQ, level)
+    pb = mkrlwe.Poly.from_numpy(w.ctx, b)
+    w.ctx.intt(level, pb.h, pout.h)
+    assert_same(pout.numpy(), w.op.ringQ.intt(b), "InvNTTLvl")
+
+
+def check_decompose(w: CKKSWorld, level=None):
+    level = w.op.max_level() if level is None else level
+    a = uniform_poly(w.prng, w.op.ringQ, level)
+    # non-canonical limbs as produced by the rotation quirk (App. A.3.1): a few coefficients equal to q
+    a[0, :3] = np.uint64(w.op.Q[0])
+    pa = mkrlwe.Poly.from_numpy(w.ctx, a)
+    sk = mkrlwe.SwitchingKey(w.ctx)
+    w.dev.ksw.Decompose(level, pa, sk)
+    ref = w.oev.ksw.decompose(level, a)
+    got = sk.numpy()
+    beta = level + 1
+    assert_same(got[:beta, :level + 1], ref[:beta, :level + 1], f"Decompose(level={level}) Q limbs")
+    assert_same(got[:beta, w.op.nQ:], ref[:beta, w.op.nQ:], f"Decompose(level={level}) P limbs")
+
+
+def check_external_product(w: CKKSWorld, level=None):
+    level = w.op.max_level() if level is None else level
+    a = uniform_poly(w.prng, w.op.ringQ, level)
+    bg = uniform_swk(w.prng, w.op)
+    pa = mkrlwe.Poly.from_numpy(w.ctx, a)
+    dbg = mkrlwe.SwitchingKey(w.ctx, bg)
+    h = mkrlwe.SwitchingKey(w.ctx)
+    w.dev.ksw.Decompose(level, pa, h)
+    pc = mkrlwe.Poly(w.ctx, level + 1)
+    w.dev.ksw.ExternalProductHoisted(level, h, dbg, pc)
+    ref = w.oev.ksw.external_product_hoisted(level, w.oev.ksw.decompose(level, a), bg)
+    assert_same(pc.numpy(), ref, f"ExternalProductHoisted(level={level})")
+    pc2 = mkrlwe.Poly(w.ctx, level + 1)
+    w.dev.ksw.ExternalProduct(level, pa, dbg, pc2)
+    assert_same(pc2.numpy(), w.oev.ksw.external_product(level, a, bg), f"ExternalProduct(level={level})")
+
+
+def check_mul_relin_hoisted(w: CKKSWorld, ids0, ids1, level=None, nil0=False, nil1=False, same=False):
+    level = w.op.max_level() if level is None else level
+    o0, d0 = w.random_ct(ids0, level)
+    if same:
+        o1, d1 = o0, d0
+    else:
+        o1, d1 = w.random_ct(ids1, level)
+    oh0 = None if nil0 else w.oev.hoisted_form(o0)
+    oh1 = None if nil1 else (oh0 if same and not nil0 else w.oev.hoisted_form(o1))
+    dh0 = None if nil0 else w.dev.HoistedForm(d0)
+    dh1 = None if nil1 else (dh0 if same and not nil0 else w.dev.HoistedForm(d1))
+    oout = w.oev._new_binary(o0, o1)
+    w.oev.ksw.mul_and_relin_hoisted(o0, o1, oh0, oh1, w.o_rlk, oout)
+    dout = w.dev.newCiphertextBinary(d0, d1)
+    w.dev.ksw.MulAndRelinHoisted(d0, d1, dh0, dh1, w.d_rlk, dout)
+    w.compare_ct(dout, oout, f"MulAndRelinHoisted(ids0={ids0}, ids1={ids1}, level={level}, nil=({nil0},{nil1}), same={same})")
+
+
+def check_mul_relin_new(w: CKKSWorld, ids0, ids1, level=None, same=False):
+    level = w.op.max_level() if level is None else level
+    o0, d0 = w.random_ct(ids0, level)
+    if same:
+        o1, d1 = o0, d0
+    else:
+        o1, d1 = w.random_ct(ids1, level)
+    oout = w.oev.mul_relin_new(o0, o1, w.o_rlk)
+    dout = w.dev.MulRelinNew(d0, d1, w.d_rlk)
+    assert dout.Level() == oout.level(), (dout.Level(), oout.level())
+    assert dout.Scale == oout.scale, (dout.Scale, oout.scale)
+    w.compare_ct(dout, oout, f"MulRelinNew(ids0={ids0}, ids1={ids1}, level={level}, same={same})")
+    return dout, oout
+
+
+def check_rescale(w: CKKSWorld, level=None, nb=1):
+    level = w.op.max_level() if level is None else level
+    a = uniform_poly(w.prng, w.op.ringQ, level)
+    pin = mkrlwe.Poly.from_numpy(w.ctx, a)
+    pout = mkrlwe.Poly(w.ctx, level + 1)
+    w.ctx.rescale(level, nb, pin.h, pout.h)
+    ain = a.copy()
+    ref = np.zeros_like(a)
+    w.op.ringQ.div_round_by_last_modulus_many(level, nb, ain, ref)
+    assert pout.nlimbs() == level + 1 - nb
+    assert_same(pout.numpy(), ref[:level + 1 - nb], f"DivRoundByLastModulusManyLvl(level={level}, nb={nb})")
+    if nb == 1:
+        # lattigo mutates the input's last limb
+        assert_same(w.ctx.poly_download(pin.h, level + 1), ain, "Rescale input side effect")
+
+
+def check_rotate(w: CKKSWorld, ids, rot, level=None, zero_component=False, hoisted=True):
+    level = w.op.max_level() if level is None else level
+    oct_, dct = w.random_ct(ids, level)
+    if not hoisted:
+        # rot without a CRS entry: RotateNew chains powers of two, RotateHoistedNew panics (mkckks/evaluator.go:615)
+        oo2 = w.oev.rotate_new(oct_, rot, w.o_rk)
+        do2 = w.dev.RotateNew(dct, rot, w.d_rk)
+        w.compare_ct(do2, oo2, f"RotateNew(rot={rot}, chained)")
+        try:
+            w.dev.RotateHoistedNew(dct, rot, w.dev.HoistedForm(dct), w.d_rk)
+        except RuntimeError as e:
+            assert "Hoisted rotation only works for precomputed rotation keys" in str(e)
+        else:
+            raise AssertionError("RotateHoistedNew must panic for a rotation without CRS")
+        return
+    if zero_component:
+        # quirk test: a zero component goes through the permutation as q_j
+        oct_.value["0"][:] = 0
+        w.ctx.poly_upload(dct.Value["0"].h, oct_.value["0"])
+    oh = w.oev.hoisted_form(oct_)
+    dh = w.dev.HoistedForm(dct)
+    oo = w.oev.rotate_hoisted_new(oct_, rot, oh, w.o_rk)
+    do = w.dev.RotateHoistedNew(dct, rot, dh, w.d_rk)
+    w.compare_ct(do, oo, f"RotateHoistedNew(rot={rot}, level={level})")
+    oo2 = w.oev.rotate_new(oct_, rot, w.o_rk)
+    do2 = w.dev.RotateNew(dct, rot, w.d_rk)
+    w.compare_ct(do2, oo2, f"RotateNew(rot={rot}, level={level})")
+
+
+def check_conjugate(w: CKKSWorld, ids, level=None):
+    level = w.op.max_level() if level is None else level
+    oct_, dct = w.random_ct(ids, level)
+    oo = w.oev.conjugate_new(oct_, w.o_ck)
+    do = w.dev.ConjugateNew(dct, w.d_ck)
+    w.compare_ct(do, oo, f"ConjugateNew(level={level})")
+
+
+def check_ckks_semantics(w: CKKSWorld):
+    """T3: decrypt the DEVICE result and apply the reference's own precision threshold
+    (mkckks_test.go:357-358: log2(err) <= -logScale + logSlots + 12)."""
+    assert w.sks, "needs real keys"
+    p, lit = w.op, w.lit
+    n = p.N // 2
+    rng = np.random.default_rng(11)
+    enc, dec = O.Encryptor(p), O.Decryptor(p)
+    k = len(w.ids)
+    msgs, cts = [], []
+    for i in w.ids:
+        m = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)) / k
+        msgs.append(m)
+        cts.append(enc.encrypt(O.ckks_encode(p, m, lit.scale), w.pks[i], i, lit.scale))
+    acc = cts[0]
+    for c in cts[1:]:
+        ids = sorted(set(acc.ids()) | set(c.ids()))
+        nv = {"0": p.ringQ.add(acc.value["0"], c.value["0"])}
+        for i in ids:
+            nv[i] = acc.value[i].copy() if i in acc.value else c.value[i].copy()
+        acc = O.Ciphertext(nv, lit.scale)
+    msum = sum(msgs)
+    dct = mkckks.Ciphertext.from_numpy(w.ctx, acc.value, lit.scale)
+    dres = w.dev.MulRelinNew(dct, dct, w.d_rlk)
+    res = O.Ciphertext(dres.numpy(), dres.Scale)
+    got = O.ckks_decode(p, dec.decrypt(res, w.sks), res.scale)
+    err = np.abs(got - msum * msum).max()
+    bound = 2.0 ** (-np.log2(lit.scale) + np.log2(n) + 12)
+    assert err <= bound, f"MulRelin precision {np.log2(err):.1f} > {np.log2(bound):.1f}"
+    ores = w.oev.mul_relin_new(acc, acc, w.o_rlk)
+    for kk in ores.value:
+        assert_same(res.value[kk], ores.value[kk], f"semantic MulRelinNew[{kk}]")
+    # hoisted rotation by 2 (mkckks_test.go:552-598: +11)
+    dh = w.dev.HoistedForm(dct)
+    drot = w.dev.RotateHoistedNew(dct, 2, dh, w.d_rk)
+    rr = O.Ciphertext(drot.numpy(), drot.Scale)
+    got = O.ckks_decode(p, dec.decrypt(rr, w.sks), rr.scale)
+    err = np.abs(got - np.roll(msum, -2)).max()
+    bound = 2.0 ** (-np.log2(lit.scale) + np.log2(n) + 11)
+    assert err <= bound, f"Rotate precision {np.log2(err):.1f} > {np.log2(bound):.1f}"
+
+
+# ---- BFV --------------------------------------------------------------------------------------------
+class BFVWorld:
+    def __init__(self, lit: ParamLiteral, nparties, seed=0xB2000003, lib=None, real_keys=False):
+        self.lit = lit
+        self.op = O.BFVParams(lit.logN, lit.Q, lit.QMul, lit.P, lit.T, seed=seed)
+        self.prng = O.PRNG(seed ^ 0xBF5EED)
+        self.dp = mkbfv.Parameters(lit.logN, lit.Q, lit.QMul, lit.P, lit.T, lib=lib)
+        self.ctx = self.dp.ctx
+        for idx, arr in self.op.CRS.items():
+            self.dp.SetCRS(idx, arr)
+        self.oev = O.BFVEvaluator(self.op)
+        self.dev = mkbfv.Evaluator(self.dp)
+        self.ids = list(range(nparties))
+        self.o_rlk, self.d_rlk = {}, mkbfv.RelinearizationKeySet()
+        self.sks, self.pks = {}, {}
+        kg = O.BFVKeyGenerator(self.op) if real_keys else None
+        for i in self.ids:
+            if real_keys:
+                sk, r = kg.gen_secret_key(i), kg.gen_secret_key(i)
+                self.sks[i], self.pks[i] = sk, kg.gen_public_key(sk)
+                rl = kg.gen_bfv_relin_key(sk, r)
+            else:
+                u = lambda: uniform_swk(self.prng, self.op)
+                rl = O.BFVRelinKey(i, u(), u(), u(), u(), u())
+            self.o_rlk[i] = rl
+            self.d_rlk.AddRelinearizationKey(mkbfv.RelinearizationKey(self.ctx, i, rl.b1, rl.d1, rl.v, rl.b2, rl.d2))
+
+    def random_ct(self, ids):
+        level = self.op.max_level()
+        val = {"0": uniform_poly(self.prng, self.op.ringQ, level)}
+        for i in ids:
+            val[i] = uniform_poly(self.prng, self.op.ringQ, level)
+        return O.Ciphertext({k: v.copy() for k, v in val.items()}), mkrlwe.Ciphertext.from_numpy(self.ctx, val)
+
+    def close(self):
+        self.ctx.close()
+
+
+def check_bfv_conv(w: BFVWorld):
+    p = w.op
+    a = uniform_poly(w.prng, p.ringQ, p.max_level())
+    pq = mkrlwe.Poly.from_numpy(w.ctx, a)
+    pr = mkrlwe.Poly(w.ctx, 2 * p.nQ)
+    w.dev.conv.ModUpQtoR(pq, pr)
+    refR = w.oev.modup_q_to_r(a)
+    assert_same(pr.numpy(), refR, "ModUpQtoR (lazy multSum limbs must match exactly)")
+    pr2 = mkrlwe.Poly(w.ctx, 2 * p.nQ)
+    w.dev.conv.Rescale(pq, pr2)
+    refR2 = w.oev.rescale_q_to_r(a)
+    assert_same(pr2.numpy(), refR2, "Rescale Q->R")
+    # Quantize takes an NTT-domain R poly
+    r = np.concatenate([uniform_poly(w.prng, p.ringQ, p.max_level()), uniform_poly(w.prng, p.ringQMul, p.max_level())])
+    prn = mkrlwe.Poly.from_numpy(w.ctx, r)
+    pq2 = mkrlwe.Poly(w.ctx, p.nQ)
+    w.dev.conv.Quantize(prn, pq2)
+    assert_same(pq2.numpy(), w.oev.quantize(r), "Quantize")
+    # DecomposeBFV on the lazy R poly
+    h1, h2 = mkrlwe.SwitchingKey(w.ctx), mkrlwe.SwitchingKey(w.ctx)
+    w.dev.ksw.DecomposeBFV(p.max_level(), pr, h1, h2)
+    r1, r2 = w.oev.decompose_bfv(p.max_level(), refR)
+    assert_same(h1.numpy(), r1, "DecomposeBFV ad1")
+    assert_same(h2.numpy(), r2, "DecomposeBFV ad2")
+
+
+def check_bfv_mul_relin(w: BFVWorld, ids0, ids1, same=False):
+    o0, d0 = w.random_ct(ids0)
+    if same:
+        o1, d1 = o0, d0
+    else:
+        o1, d1 = w.random_ct(ids1)
+    oout = w.oev.mul_relin_new(o0, o1, w.o_rlk)
+    dout = w.dev.MulRelinNew(d0, d1, w.d_rlk)
+    dv = dout.numpy()
+    assert set(dv) == set(oout.value)
+    for k in oout.value:
+        assert_same(dv[k], oout.value[k], f"BFV MulRelinNew(ids0={ids0}, ids1={ids1}, same={same})[{k}]")
+    return dout
+
+
+def check_bfv_semantics(w: BFVWorld):
+    """T3: exact plaintext equality after decrypting the DEVICE result (mkbfv_test.go:412)"""
+    p = w.op
+    N, T = p.N, p.T
+    rng = np.random.default_rng(5)
+    enc, dec = O.Encryptor(p), O.Decryptor(p)
+    ms = [rng.integers(0, T, N) for _ in w.ids[:2]]
+    cts = [enc.encrypt(O.bfv_encode(p, ms[j]), w.pks[i], i) for j, i in enumerate(w.ids[:2])]
+    d0 = mkrlwe.Ciphertext.from_numpy(w.ctx, cts[0].value)
+    d1 = mkrlwe.Ciphertext.from_numpy(w.ctx, cts[1].value)
+    dres = w.dev.MulRelinNew(d0, d1, w.d_rlk)
+    got = O.bfv_decode(p, dec.decrypt(O.Ciphertext(dres.numpy()), w.sks))
+    full = np.convolve(np.array([int(x) for x in ms[0]], dtype=object), np.array([int(x) for x in ms[1]], dtype=object))
+    ref = np.zeros(N, dtype=object)
+    for i, v in enumerate(full):
+        if i < N:
+            ref[i] += v
+        else:
+            ref[i - N] -= v
+    ref = np.array([int(v) % T for v in ref], dtype=np.int64)
+    assert np.array_equal(got, ref), "BFV MulRelin: decrypted product differs from the plaintext product"
+
+
+def run_ckks_suite(w: CKKSWorld, quick=False):
+    L = w.op.max_level()
+    check_ntt(w)
+    check_decompose(w)
+    check_decompose(w, level=max(L - 2, 1))
+    check_external_product(w)
+    check_external_product(w, level=1)
+    check_rescale(w)
+    ids = w.ids
+    check_mul_relin_hoisted(w, ids, ids)
+    check_mul_relin_new(w, ids, ids)
+    check_mul_relin_new(w, ids, ids, same=True)
+    check_rotate(w, ids, 2)
+    if quick:
+        return
+    check_rescale(w, nb=2)
+    check_rescale(w, level=1)
+    check_mul_relin_hoisted(w, ids, ids, nil0=True)
+    check_mul_relin_hoisted(w, ids, ids, nil1=True)
+    check_mul_relin_hoisted(w, ids[:1], ids[1:])             # disjoint idsets
+    check_mul_relin_hoisted(w, ids[:1], ids)                 # overlapping idsets
+    check_mul_relin_hoisted(w, ids, ids, level=max(L - 2, 1))
+    check_mul_relin_new(w, ids, ids[:1], level=1)
+    check_rotate(w, ids, 1, level=max(L - 1, 1))
+    check_rotate(w, ids, 3, hoisted=False)                   # rot 3: power-of-two chaining in RotateNew; hoisted panics
+    check_rotate(w, ids, 2, zero_component=True)
+    check_conjugate(w, ids)

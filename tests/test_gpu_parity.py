@@ -1,0 +1,94 @@
+"""-m gpu: the parity tests proper.  Every call goes through the C ABI of libmkhe_b200.so (via the reference-shaped
+host mirror) and is compared bit for bit with the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import parity
+from mkhe_kklss_b200 import params as PR
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("lit,logN,k", [
+    (PR.CKKS_PN14QP439, 12, 2), (PR.CKKS_PN14QP439, 13, 3), (PR.CKKS_PN14QP439, 14, 2),
+    (PR.CNN_PN14QP433, 14, 2), (PR.CKKS_PN15QP880, 12, 4), (PR.CKKS_PN15QP880, 15, 2),
+], ids=lambda x: getattr(x, "name", str(x)))
+def test_ckks_parity(lit, logN, k):
+    w = parity.CKKSWorld(lit.at_logn(logN), k)
+    parity.run_ckks_suite(w, quick=(logN >= 15))
+    w.close()
+
+
+def test_ckks_many_parties():
+    """k = 8 parties (config 2) at a size the oracle finishes in seconds"""
+    w = parity.CKKSWorld(PR.CKKS_PN15QP880.at_logn(12), 8)
+    parity.check_mul_relin_new(w, w.ids, w.ids)
+    parity.check_mul_relin_hoisted(w, w.ids[:5], w.ids[3:])
+    parity.check_rotate(w, w.ids, 1)
+    w.close()
+
+
+def test_ckks_semantics_on_device_outputs():
+    w = parity.CKKSWorld(PR.CKKS_PN14QP439.at_logn(12), 2, real_keys=True)
+    parity.check_ckks_semantics(w)
+    w.close()
+
+
+@pytest.mark.parametrize("logN,k", [(12, 2), (13, 3), (14, 2)])
+def test_bfv_parity(logN, k):
+    w = parity.BFVWorld(PR.BFV_PN14QP439.at_logn(logN), k)
+    parity.check_bfv_conv(w)
+    parity.check_bfv_mul_relin(w, w.ids, w.ids)
+    parity.check_bfv_mul_relin(w, w.ids, w.ids, same=True)
+    parity.check_bfv_mul_relin(w, w.ids[:1], w.ids[1:])
+    parity.check_bfv_mul_relin(w, w.ids[:1], w.ids)
+    w.close()
+
+
+def test_bfv_pn15_primes():
+    w = parity.BFVWorld(PR.BFV_PN15QP880.at_logn(12), 2)
+    parity.check_bfv_conv(w)
+    parity.check_bfv_mul_relin(w, w.ids, w.ids)
+    w.close()
+
+
+def test_bfv_semantics_on_device_outputs():
+    w = parity.BFVWorld(PR.BFV_PN14QP439.at_logn(12), 2, real_keys=True)
+    parity.check_bfv_semantics(w)
+    w.close()
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (PN15QP880, logN = 15, k = 4): size-independent properties instead of the oracle:
+    NTT round trip, MulRelin(op0,op1) == MulRelin(op1,op0), hoisted == non-hoisted, Rotate(r) then Rotate(-r)
+    structure via RotateNew == RotateHoistedNew."""
+    from mkhe_kklss_b200 import mkrlwe
+    w = parity.CKKSWorld(PR.CKKS_PN15QP880, 4)
+    L = w.op.max_level()
+    a = parity.uniform_poly(w.prng, w.op.ringQ, L)
+    pin, pout = mkrlwe.Poly.from_numpy(w.ctx, a), mkrlwe.Poly(w.ctx, L + 1)
+    w.ctx.ntt(L, pin.h, pout.h)
+    w.ctx.intt(L, pout.h, pout.h)
+    parity.assert_same(pout.numpy(), a, "INTT(NTT(a)) at logN=15")
+    _, d0 = w.random_ct(w.ids, L)
+    _, d1 = w.random_ct(w.ids, L)
+    r01 = w.dev.MulRelinNew(d0, d1, w.d_rlk).numpy()
+    h0, h1 = w.dev.HoistedForm(d0), w.dev.HoistedForm(d1)
+    rh = w.dev.MulRelinHoistedNew(d0, d1, h0, h1, w.d_rlk).numpy()
+    for k in r01:
+        parity.assert_same(rh[k], r01[k], f"hoisted vs fused MulRelinNew [{k}]")
+        assert r01[k].shape[0] == L
+        for j, q in enumerate(w.op.Q[:L]):
+            assert int(r01[k][j].max()) < q, "outputs must be canonical"
+    rot_h = w.dev.RotateHoistedNew(d0, 2, h0, w.d_rk).numpy()
+    rot = w.dev.RotateNew(d0, 2, w.d_rk).numpy()
+    for k in rot:
+        parity.assert_same(rot_h[k], rot[k], f"RotateHoistedNew vs RotateNew [{k}]")
+    w.close()
+
+
+def test_full_size_one_party_against_oracle():
+    """one full-size (logN = 15, 14 limbs) MulRelinNew with k = 1 against the oracle (a few seconds of CPU)"""
+    w = parity.CKKSWorld(PR.CKKS_PN15QP880, 1, rots=(1,))
+    parity.check_mul_relin_new(w, [0], [0])
+    w.close()
