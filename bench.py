@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""bench.py -- MK-CKKS MulRelin ops/s (and hoisted Rotate ops/s) at logN=15 on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of the reference's path
+
+A "step" is one `MulRelinNew(ct0, ct1, rlkSet)` exactly as mkckks_benchmark_test.go:78-82 times it: hoist both
+operands, MulAndRelinHoisted, Rescale -- on synthetic uniform-random ciphertexts and keys of the PN15QP880 set
+(mkckks_test.go:51-72), op0 != op1, both with all k party ids, level 13.
+
+  value  : steps/s with ciphertexts and keys already resident in HBM (CUDA events on the library's stream,
+           max over ranks).  N > 1 = independent ciphertext batches per GPU, keys replicated (weak scaling).
+  e2e    : the same call through the host-buffer API: pinned host ciphertexts are uploaded, the op runs, the
+           result ciphertext is downloaded, every step, all inside the timed region.
+Only the cpu_baseline leg and `--impl reference` touch oracle/ (as the thing timed on the CPU, never as
+part of the GPU path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mkhe_kklss_b200 import params as PR  # noqa: E402
+
+METRIC = "MK-CKKS MulRelin ops/s at logN=15 (PN15QP880, level 13)"
+UNIT = "ops/s"
+
+
+# ---------------------------------------------------------------------------------------------------
+def uniform_limbs(rng, moduli, shape_prefix, N):
+    """i.i.d. uniform limbs in [0, q_j) (throughput runs)"""
+    out = np.empty(tuple(shape_prefix) + (len(moduli), N), dtype=np.uint64)
+    for j, q in enumerate(moduli):
+        out[..., j, :] = rng.integers(0, q, size=tuple(shape_prefix) + (N,), dtype=np.uint64)
+    return out
+
+
+def host_keys(lit, k, seed, rots=()):
+    rng = np.random.default_rng(seed)
+    mods = list(lit.Q) + list(lit.P)
+    beta = len(lit.Q)
+    mk = lambda: uniform_limbs(rng, mods, (beta,), lit.N)
+    keys = {"u": mk(), "rlk": [(mk(), mk(), mk()) for _ in range(k)]}
+    keys["a"] = {r: mk() for r in rots}
+    keys["rk"] = [{r: mk() for r in rots} for _ in range(k)]
+    return keys
+
+
+def host_ct(lit, k, level, rng):
+    return {"0" if i < 0 else i: uniform_limbs(rng, lit.Q[:level + 1], (), lit.N) for i in range(-1, k)}
+
+
+def algorithmic_model(k, ell, nP, N):
+    """compulsory bytes / butterflies of one MulRelinNew and the per-kernel algorithmic bytes of
+    the current (materialising) schedule, per step"""
+    D, beta, limb = ell + nP, ell, 8 * N
+    b_mul = (3 * k * beta * D + beta * D + 2 * (k + 1) * ell + (k + 1) * (ell - 1)) * limb
+    logN = N.bit_length() - 1
+    bfly_limb = (N // 2) * logN
+    fwd, inv = 3 * k * beta * D + (2 * k + 2) * ell, (k + 1) * ell + 4 * k * D
+    kern = {
+        "k_bcast_ntt_pass1_": (3 * k * ell + 3 * k * beta * D) * limb,
+        "k_ntt_pass2": 2 * (3 * k * beta * D + (2 * k + 2) * ell) * limb,
+        "k_ntt_pass1_": 2 * (2 * k + 2) * ell * limb,
+        "k_mac_parties": (4 * k * beta * D + 2 * beta * D) * limb,
+        "k_intt_passA<true>": (5 * k * beta * D + 3 * beta * D + 4 * k * D) * limb,
+        "k_intt_passA<false>": 2 * (k + 1) * ell * limb,
+        "k_intt_passB_": 2 * ((k + 1) * ell + 4 * k * D) * limb,
+        "k_conv<CONV_MODDOWN>": 4 * k * (D + 2 * ell) * limb,
+        "k_tensor": (3 * k + 3) * ell * limb,
+        "k_rescale": (k + 1) * (2 * ell - 1) * limb,
+    }
+    s1 = logN - 9
+    bfly = {
+        "k_bcast_ntt_pass1_": 3 * k * beta * D * (N // 2) * s1,
+        "k_ntt_pass2": (3 * k * beta * D + (2 * k + 2) * ell) * (N // 2) * 9,
+        "k_ntt_pass1_": (2 * k + 2) * ell * (N // 2) * s1,
+        "k_intt_passA<true>": 4 * k * D * (N // 2) * 9,
+        "k_intt_passA<false>": (k + 1) * ell * (N // 2) * 9,
+        "k_intt_passB_": ((k + 1) * ell + 4 * k * D) * (N // 2) * s1,
+    }
+    return {"compulsory_bytes": b_mul, "butterflies": (fwd + inv) * bfly_limb, "kernel_bytes": kern, "kernel_butterflies": bfly}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned_like(arr):
+    """copy of arr in pinned host memory (torch is plumbing only)"""
+    try:
+        import torch
+        t = torch.empty(arr.shape, dtype=torch.int64, pin_memory=True)
+        out = t.numpy().view(np.uint64)
+        out[...] = arr
+        return out, t
+    except Exception:
+        return arr.copy(), None
+
+
+# ---------------------------------------------------------------------------------------------------
+class DeviceWorkload:
+    """keys + ciphertext pool of one GPU"""
+
+    def __init__(self, lit, k, device, seed, rots=(2,), npairs=3):
+        from mkhe_kklss_b200 import mkckks, mkrlwe
+        self.lit, self.k, self.rots = lit, k, rots
+        self.level = len(lit.Q) - 1
+        self.params = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, device=device)
+        self.ctx = self.params.ctx
+        self.ev = mkckks.Evaluator(self.params)
+        hk = host_keys(lit, k, seed, rots)
+        self.hk = hk
+        self.params.SetCRS(-1, hk["u"])
+        for r in rots:
+            self.params.SetCRS(r, hk["a"][r])
+        self.rlk = mkrlwe.RelinearizationKeySet()
+        self.rk = mkrlwe.RotationKeySet()
+        for i in range(k):
+            b, d, v = hk["rlk"][i]
+            self.rlk.AddRelinearizationKey(mkrlwe.RelinearizationKey(self.ctx, i, b, d, v))
+            for r in rots:
+                self.rk.AddRotationKey(i, r, mkrlwe.SwitchingKey(self.ctx, hk["rk"][i][r]))
+        rng = np.random.default_rng(seed + 99)
+        self.host_pairs = [(host_ct(lit, k, self.level, rng), host_ct(lit, k, self.level, rng)) for _ in range(npairs)]
+        self.pairs = [(mkckks.Ciphertext.from_numpy(self.ctx, a, lit.scale), mkckks.Ciphertext.from_numpy(self.ctx, b, lit.scale))
+                      for a, b in self.host_pairs]
+        self.ids = list(range(k))
+        self.out = mkckks.Ciphertext.new(self.params, self.ids, self.level, lit.scale)
+        self.nb, self.new_scale = self.ev._nb_rescales(lit.scale * lit.scale, self.level, lit.scale)
+        g = self.rlk.GetRelinearizationKey
+        self.kb = [g(i).Value[0].h for i in self.ids]
+        self.kd = [g(i).Value[1].h for i in self.ids]
+        self.kv = [g(i).Value[2].h for i in self.ids]
+        self.ctx.sync()
+
+    def mul_relin_step(self, i):
+        a, b = self.pairs[i % len(self.pairs)]
+        self.ctx.ckks_mul_relin(self.level, self.nb, False, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
+                                self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, self.out.handles(self.ids))
+
+    def prepare_rotate(self):
+        self.hoisted = [self.ev.HoistedForm(a) for a, _ in self.pairs]
+        self.rot_out = self.out
+        for p in self.rot_out.Value.values():
+            p.set_nlimbs(self.level + 1)
+        self.ctx.sync()
+
+    def rotate_step(self, i, rot=2):
+        j = i % len(self.pairs)
+        a = self.pairs[j][0]
+        self.ctx.rotate_hoisted(self.level, rot, a.handles(self.ids), [self.hoisted[j][t].h for t in self.ids],
+                                [self.rk.GetRotationKey(t, rot).h for t in self.ids], self.params.CRS[rot].h,
+                                self.rot_out.handles(self.ids))
+
+    def timed(self, fn, steps, warmup, barrier=None):
+        """W untimed steps, then exactly K steps between CUDA events on the library's stream"""
+        for i in range(warmup):
+            fn(i)
+        self.ctx.sync()
+        if barrier:
+            barrier()
+        l0 = self.ctx.launch_count()
+        self.ctx.timer_start()
+        for i in range(steps):
+            fn(i)
+        ms = self.ctx.timer_stop()
+        self.last_launches = self.ctx.launch_count() - l0
+        if barrier:
+            barrier()
+        return ms
+
+    # -- end to end through host buffers ------------------------------------------------------------
+    def prepare_e2e(self):
+        self.pin = []
+        self._keep = []
+        for a, b in self.host_pairs:
+            pa, pb = {}, {}
+            for src, dst in ((a, pa), (b, pb)):
+                for kk, arr in src.items():
+                    dst[kk], t = pinned_like(arr)
+                    self._keep.append(t)
+            self.pin.append((pa, pb))
+        self.res_host = {}
+        for kk in ["0"] + self.ids:
+            buf, t = pinned_like(np.zeros((self.level + 1 - self.nb, self.lit.N), dtype=np.uint64))
+            self.res_host[kk] = buf
+            self._keep.append(t)
+        import ctypes as C
+        self._C = C
+
+    def e2e_step(self, i):
+        C = self._C
+        u64p = C.POINTER(C.c_uint64)
+        a, b = self.pairs[i % len(self.pairs)]
+        pa, pb = self.pin[i % len(self.pin)]
+        dll, ptr = self.ctx.dll, self.ctx.ptr
+        h2d = 0
+        for ct, hp in ((a, pa), (b, pb)):
+            for kk, poly in ct.Value.items():
+                arr = hp[kk]
+                self.ctx.check(dll.mkhe_poly_upload(ptr, C.c_uint64(poly.h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
+                h2d += arr.nbytes
+        self.mul_relin_step(i)
+        d2h = 0
+        for kk, poly in self.out.Value.items():
+            arr = self.res_host[kk]
+            self.ctx.check(dll.mkhe_poly_download(ptr, C.c_uint64(poly.h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
+            d2h += arr.nbytes
+        return h2d, d2h
+
+
+def cpu_oracle_run(lit, k, steps, warmup, threads, seed=0xB2000002):
+    """times the oracle port of MulRelinNew on the host cores; returns (ops/s, cores used, seconds per op)"""
+    from oracle import oracle as O
+    cores = O.set_threads(threads)
+    p = O.MKParams(lit.logN, lit.Q, lit.P, 2, seed=seed, crs_rots=[])
+    hk = host_keys(lit, k, seed)
+    p.CRS[-1] = hk["u"]
+    rl = {i: O.RelinKey(i, *hk["rlk"][i]) for i in range(k)}
+    ev = O.CKKSEvaluator(p, lit.scale)
+    rng = np.random.default_rng(seed + 99)
+    level = len(lit.Q) - 1
+    c0 = O.Ciphertext(host_ct(lit, k, level, rng), lit.scale)
+    c1 = O.Ciphertext(host_ct(lit, k, level, rng), lit.scale)
+    for _ in range(warmup):
+        ev.mul_relin_new(c0, c1, rl)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ev.mul_relin_new(c0, c1, rl)
+    dt = time.perf_counter() - t0
+    return steps / dt, cores, dt / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--parties", type=int, default=4)
+    ap.add_argument("--no-extras", action="store_true", help="skip the k=8 / hoisted-Rotate side measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    lit, k = PR.CKKS_PN15QP880, args.parties
+    ell, nP, N = len(lit.Q), len(lit.P), lit.N
+    config = {"workload": f"mkckks MulRelinNew (hoist + MulAndRelinHoisted + Rescale), {lit.name}, logN={lit.logN}, level {ell - 1}, "
+                          f"k={k} parties, op0 != op1",
+              "params": lit.name, "logN": lit.logN, "parties": k, "level": ell - 1,
+              "l2_policy": "inputs larger than L2: every step streams the relinearisation keys "
+                           f"({(3 * k + 1) * ell * (ell + nP) * 8 * N / 2**20:.0f} MiB) and cycles 3 ciphertext pairs"}
+
+    # ---------------- CPU arm ----------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ncpu = os.cpu_count() or 1
+        ops, cores, sec = cpu_oracle_run(lit, k, args.steps, args.warmup, ncpu)
+        line = {"impl": "reference", "metric": METRIC, "value": ops, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": ops, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{args.steps} full MulRelinNew calls (oracle/ C restatement with OpenMP over limbs; the reference itself "
+                                           "is Go + un-vendored lattigo and cannot be built here)"},
+                "e2e": {"value": ops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------- GPU arm ----------------------------------------------------------------------
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def allmax(x):
+        if not dist:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = DeviceWorkload(lit, k, local_rank, seed=0xB2000002 + rank)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms = wl.timed(wl.mul_relin_step, args.steps, warmup, barrier)
+    launches_timed = wl.last_launches
+    clk = clocks.stop()
+    ms = allmax(ms)
+    value = world * args.steps / (ms * 1e-3)
+
+    # end to end through host buffers
+    wl.prepare_e2e()
+    bytes_io = [0, 0]
+
+    def e2e_fn(i):
+        bytes_io[0], bytes_io[1] = wl.e2e_step(i)
+
+    ms_e2e = allmax(wl.timed(e2e_fn, args.steps, warmup, barrier))
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+
+    # per-kernel profile pass (events around every launch; separate from the timed region above)
+    psteps = min(args.steps, 10)
+    wl.ctx.profile_begin()
+    for i in range(psteps):
+        wl.mul_relin_step(i)
+    prof = wl.ctx.profile_end()
+    model = algorithmic_model(k, ell, nP, N)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    bfly_peak = wl.ctx.butterfly_peak()
+    total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
+    kernels = {}
+    for name, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        e = {"launches_per_step": cnt / psteps, "ms_per_step": tms / psteps, "share": tms / total_prof_ms}
+        if name in model["kernel_bytes"]:
+            e["hbm_gbs"] = model["kernel_bytes"][name] / (tms / psteps * 1e-3) / 1e9
+            e["hbm_frac"] = e["hbm_gbs"] / hbm_peak
+        if name in model["kernel_butterflies"]:
+            e["butterflies_per_s"] = model["kernel_butterflies"][name] / (tms / psteps * 1e-3)
+            e["int_frac"] = e["butterflies_per_s"] / bfly_peak
+        kernels[name] = e
+    dom = next(iter(kernels)) if kernels else None
+    roofline = None
+    if dom:
+        d = kernels[dom]
+        per_launch_bytes = model["kernel_bytes"].get(dom, 0) / max(d["launches_per_step"], 1e-9)
+        per_launch_s = d["ms_per_step"] * 1e-3 / max(d["launches_per_step"], 1e-9)
+        ach = per_launch_bytes / per_launch_s / 1e9 if per_launch_s else 0.0
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
+                    "avg_launch_ms": per_launch_s * 1e3,
+                    "integer_pipe": {"achieved_butterflies_per_s": d.get("butterflies_per_s"), "peak_butterflies_per_s": bfly_peak,
+                                     "frac": d.get("int_frac"),
+                                     "peak_source": "register-resident Shoup butterfly loop measured in this run (mkhe_bench_butterfly_peak)"},
+                    "whole_step": {"compulsory_bytes": model["compulsory_bytes"],
+                                   "hbm_frac_of_compulsory": model["compulsory_bytes"] / (ms / args.steps * 1e-3) / 1e9 / hbm_peak,
+                                   "butterflies": model["butterflies"],
+                                   "int_frac": model["butterflies"] / (ms / args.steps * 1e-3) / bfly_peak}}
+
+    extra = {}
+    if not args.no_extras and world == 1:
+        wl.prepare_rotate()
+        ms_rot = wl.timed(wl.rotate_step, args.steps, warmup)
+        extra[f"rotate_hoisted_k{k}_ops_s"] = args.steps / (ms_rot * 1e-3)
+        del wl
+        wl8 = DeviceWorkload(lit, 8, local_rank, seed=0xB2000008)
+        ms8 = wl8.timed(wl8.mul_relin_step, args.steps, warmup)
+        extra["mulrelin_k8_ops_s"] = args.steps / (ms8 * 1e-3)
+        wl8.prepare_rotate()
+        ms_rot8 = wl8.timed(wl8.rotate_step, args.steps, warmup)
+        extra["rotate_hoisted_k8_ops_s"] = args.steps / (ms_rot8 * 1e-3)
+        del wl8
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ops, cores, sec = cpu_oracle_run(lit, k, 3, 1, 1)
+        cpu = {"value": ops, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"3 full MulRelinNew calls after 1 warm-up, same workload ({sec:.2f} s each), single thread like the Go reference; "
+                         "oracle/ C restatement (the Go reference cannot be built here)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic", "config": config,
+                "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io[0], "d2h_bytes_per_step": bytes_io[1],
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches_timed,
+                "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "extra": extra}
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -167,6 +167,10 @@ int mkhe_comm_destroy(mkhe_ctx *ctx);
 /* ---- measurement helpers (CUDA events on the context's stream) */
 int mkhe_timer_start(mkhe_ctx *ctx);
 int mkhe_timer_stop(mkhe_ctx *ctx, float *elapsed_ms);     /* synchronises */
+/* per-kernel timing: between begin and end every launch is bracketed by CUDA events on the context's stream;
+ * end() writes one line "<kernel> <launches> <total_ms>" per kernel into buf.  Not used on the timed path. */
+int mkhe_profile_begin(mkhe_ctx *ctx);
+int mkhe_profile_end(mkhe_ctx *ctx, char *buf, size_t cap);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t mkhe_launch_count(const mkhe_ctx *ctx);
 /* register-resident Shoup-butterfly throughput microbenchmark: butterflies per second on this device

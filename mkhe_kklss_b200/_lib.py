@@ -131,6 +131,19 @@ class Context:
         self.check(self.dll.mkhe_timer_stop(self.ptr, C.byref(ms)))
         return float(ms.value)
 
+    def profile_begin(self):
+        self.check(self.dll.mkhe_profile_begin(self.ptr))
+
+    def profile_end(self) -> dict:
+        """{kernel: (launches, total_ms)} of the launches since profile_begin()"""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.dll.mkhe_profile_end(self.ptr, buf, C.c_size_t(len(buf))))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
+
     def butterfly_peak(self) -> float:
         v = C.c_double()
         self.check(self.dll.mkhe_bench_butterfly_peak(self.ptr, C.byref(v)))

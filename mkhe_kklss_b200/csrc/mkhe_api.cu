@@ -62,6 +62,17 @@ struct mkhe_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void *nccl = nullptr;
     int nranks = 1, rank = 0;
+    // per-kernel CUDA-event profiling (bench.py's roofline leg)
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t prof_event() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
 };
 
 namespace {
@@ -96,8 +107,18 @@ int fail(mkhe_ctx *c, int code, const char *fmt, ...) {
     } while (0)
 #define LAUNCH(kernel, grid, block, smem, ...)                        \
     do {                                                              \
+        cudaEvent_t pa_ = nullptr, pb_ = nullptr;                     \
+        if (ctx->profiling) {                                         \
+            pa_ = ctx->prof_event();                                  \
+            pb_ = ctx->prof_event();                                  \
+            cudaEventRecord(pa_, ctx->stream);                        \
+        }                                                             \
         MKHE_LAUNCH(kernel, grid, block, smem, ctx->stream, __VA_ARGS__); \
         ctx->launches++;                                              \
+        if (ctx->profiling) {                                         \
+            cudaEventRecord(pb_, ctx->stream);                        \
+            ctx->prof.push_back({#kernel, pa_, pb_});                 \
+        }                                                             \
         CU(cudaGetLastError());                                       \
     } while (0)
 
@@ -218,8 +239,8 @@ int ntt_fwd(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
         fill(a, s, ctx->logN);
         for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
         TRY(dispatch_s1(ctx, [&](auto S) -> int {
-            auto kern = k_ntt_pass1<decltype(S)::value>;
-            LAUNCH(kern, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twf);
+            auto k_ntt_pass1_ = k_ntt_pass1<decltype(S)::value>;
+            LAUNCH(k_ntt_pass1_, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twf);
             return MKHE_OK;
         }));
         Pass2Args b;
@@ -242,8 +263,8 @@ int intt_passB(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *bufs_in, u
         fill(a, s, ctx->logN);
         for (int i = 0; i < np; i++) { a.in.p[i] = bufs_in[p0 + i]; a.out.p[i] = bufs_out[p0 + i]; }
         TRY(dispatch_s1(ctx, [&](auto S) -> int {
-            auto kern = k_intt_passB<decltype(S)::value>;
-            LAUNCH(kern, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+            auto k_intt_passB_ = k_intt_passB<decltype(S)::value>;
+            LAUNCH(k_intt_passB_, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
             return MKHE_OK;
         }));
     }
@@ -280,8 +301,8 @@ int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *c
         for (int i = 0; i < s.n; i++) a.slots[i] = s.slot[i];
         for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
         TRY(dispatch_s1(ctx, [&](auto S) -> int {
-            auto kern = k_bcast_ntt_pass1<decltype(S)::value>;
-            LAUNCH(kern, dim3(tiles, beta, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twf);
+            auto k_bcast_ntt_pass1_ = k_bcast_ntt_pass1<decltype(S)::value>;
+            LAUNCH(k_bcast_ntt_pass1_, dim3(tiles, beta, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twf);
             return MKHE_OK;
         }));
         Pass2Args b;
@@ -1273,6 +1294,38 @@ int mkhe_timer_stop(mkhe_ctx *ctx, float *elapsed_ms) {
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaEventSynchronize(ctx->ev1));
     CU(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+    return MKHE_OK;
+}
+int mkhe_profile_begin(mkhe_ctx *ctx) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+    ctx->prof.clear();
+    ctx->profiling = true;
+    return MKHE_OK;
+}
+int mkhe_profile_end(mkhe_ctx *ctx, char *buf, size_t cap) {
+    CHECK_CTX();
+    ctx->profiling = false;
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::map<std::string, std::pair<double, long>> agg;
+    for (auto &r : ctx->prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto &e = agg[r.name];
+        e.first += ms;
+        e.second += 1;
+        ctx->ev_pool.push_back(r.a);
+        ctx->ev_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    std::string out;
+    for (auto &kv : agg) {
+        char line[256];
+        snprintf(line, sizeof line, "%s %ld %.6f\n", kv.first.c_str(), kv.second.second, kv.second.first);
+        out += line;
+    }
+    if (buf && cap) { strncpy(buf, out.c_str(), cap - 1); buf[cap - 1] = 0; }
     return MKHE_OK;
 }
 int mkhe_bench_butterfly_peak(mkhe_ctx *ctx, double *butterflies_per_s) {

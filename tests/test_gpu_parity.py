@@ -92,3 +92,41 @@ def test_full_size_one_party_against_oracle():
     w = parity.CKKSWorld(PR.CKKS_PN15QP880, 1, rots=(1,))
     parity.check_mul_relin_new(w, [0], [0])
     w.close()
+
+
+def test_device_matches_committed_golden_digests():
+    """the committed fixtures (tests/golden/oracle_digests.json, made by tools/gen_golden.py) reproduced on the GPU:
+    same seeds, device results hashed, no oracle call at run time"""
+    import hashlib
+    import json
+    import os
+    from oracle import oracle as O   # PRNG only: regenerates the seeded inputs
+    from mkhe_kklss_b200 import mkckks, mkrlwe
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_digests.json")))
+    dig = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint64).tobytes()).hexdigest()
+    for name, lit, k, same in (("ckks_PN14QP439_logN12_k2", PR.CKKS_PN14QP439.at_logn(12), 2, False),
+                               ("ckks_PN14QP439_logN12_k2_square", PR.CKKS_PN14QP439.at_logn(12), 2, True),
+                               ("ckks_PN15QP880_logN12_k3", PR.CKKS_PN15QP880.at_logn(12), 3, False),
+                               ("cnn_PN14QP433_logN12_k2", PR.CNN_PN14QP433.at_logn(12), 2, False)):
+        p = O.MKParams(lit.logN, lit.Q, lit.P, 2, seed=0xB2000001, crs_rots=[1, 2])
+        prng = O.PRNG(0xB2000001 ^ 0x5EED)
+        dp = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale)
+        for idx, arr in p.CRS.items():
+            dp.SetCRS(idx, arr)
+        rl, rk = mkrlwe.RelinearizationKeySet(), mkrlwe.RotationKeySet()
+        sw = lambda: parity.uniform_swk(prng, p)
+        for i in range(k):
+            rl.AddRelinearizationKey(mkrlwe.RelinearizationKey(dp.ctx, i, sw(), sw(), sw()))
+        for i in range(k):
+            rk.AddRotationKey(i, 2, mkrlwe.SwitchingKey(dp.ctx, sw()))
+        ev = mkckks.Evaluator(dp)
+        L = p.max_level()
+        mk = lambda: {**{"0": prng.uniform(p.ringQ, L)}, **{i: prng.uniform(p.ringQ, L) for i in range(k)}}
+        c0 = mkckks.Ciphertext.from_numpy(dp.ctx, mk(), lit.scale)
+        c1 = c0 if same else mkckks.Ciphertext.from_numpy(dp.ctx, mk(), lit.scale)
+        out = ev.MulRelinNew(c0, c1, rl).numpy()
+        rot = ev.RotateHoistedNew(c0, 2, ev.HoistedForm(c0), rk).numpy()
+        got = {f"mul[{kk}]": dig(v) for kk, v in out.items()}
+        got.update({f"rot[{kk}]": dig(v) for kk, v in rot.items()})
+        assert got == golden[name], name
+        dp.ctx.close()
