@@ -4,9 +4,10 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of the reference's path
 
-A "step" is one `MulRelinNew(ct0, ct1, rlkSet)` exactly as mkckks_benchmark_test.go:78-82 times it: hoist both
-operands, MulAndRelinHoisted, Rescale -- on synthetic uniform-random ciphertexts and keys of the PN15QP880 set
-(mkckks_test.go:51-72), op0 != op1, both with all k party ids, level 13.
+A "step" is one pass over a batch of `--batch` (default 16) ciphertext pairs; each pair is one
+`MulRelinNew(ct0, ct1, rlkSet)` exactly as mkckks_benchmark_test.go:78-82 times it: hoist both operands,
+MulAndRelinHoisted, Rescale -- on synthetic uniform-random ciphertexts and keys of the PN15QP880 set
+(mkckks_test.go:51-72), op0 != op1, both with all k party ids, level 13.  value = MulRelin ops/s.
 
   value  : steps/s with ciphertexts and keys already resident in HBM (CUDA events on the library's stream,
            max over ranks).  N > 1 = independent ciphertext batches per GPU, keys replicated (weak scaling).
@@ -103,7 +104,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -154,9 +155,9 @@ def pinned_like(arr):
 class DeviceWorkload:
     """keys + ciphertext pool of one GPU"""
 
-    def __init__(self, lit, k, device, seed, rots=(2,), npairs=3):
+    def __init__(self, lit, k, device, seed, rots=(2,), npairs=3, batch=16):
         from mkhe_kklss_b200 import mkckks, mkrlwe
-        self.lit, self.k, self.rots = lit, k, rots
+        self.lit, self.k, self.rots, self.batch = lit, k, rots, batch
         self.level = len(lit.Q) - 1
         self.params = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, device=device)
         self.ctx = self.params.ctx
@@ -186,10 +187,14 @@ class DeviceWorkload:
         self.kv = [g(i).Value[2].h for i in self.ids]
         self.ctx.sync()
 
-    def mul_relin_step(self, i):
+    def mul_relin_op(self, i):
         a, b = self.pairs[i % len(self.pairs)]
         self.ctx.ckks_mul_relin(self.level, self.nb, False, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
                                 self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, self.out.handles(self.ids))
+
+    def mul_relin_step(self, i):
+        for j in range(self.batch):
+            self.mul_relin_op(i * self.batch + j)
 
     def prepare_rotate(self):
         self.hoisted = [self.ev.HoistedForm(a) for a, _ in self.pairs]
@@ -199,11 +204,12 @@ class DeviceWorkload:
         self.ctx.sync()
 
     def rotate_step(self, i, rot=2):
-        j = i % len(self.pairs)
-        a = self.pairs[j][0]
-        self.ctx.rotate_hoisted(self.level, rot, a.handles(self.ids), [self.hoisted[j][t].h for t in self.ids],
-                                [self.rk.GetRotationKey(t, rot).h for t in self.ids], self.params.CRS[rot].h,
-                                self.rot_out.handles(self.ids))
+        for b in range(self.batch):
+            j = (i * self.batch + b) % len(self.pairs)
+            a = self.pairs[j][0]
+            self.ctx.rotate_hoisted(self.level, rot, a.handles(self.ids), [self.hoisted[j][t].h for t in self.ids],
+                                    [self.rk.GetRotationKey(t, rot).h for t in self.ids], self.params.CRS[rot].h,
+                                    self.rot_out.handles(self.ids))
 
     def timed(self, fn, steps, warmup, barrier=None):
         """W untimed steps, then exactly K steps between CUDA events on the library's stream"""
@@ -242,23 +248,25 @@ class DeviceWorkload:
         self._C = C
 
     def e2e_step(self, i):
+        """`batch` times: upload both operand ciphertexts from pinned host memory, MulRelinNew, download the result"""
         C = self._C
         u64p = C.POINTER(C.c_uint64)
-        a, b = self.pairs[i % len(self.pairs)]
-        pa, pb = self.pin[i % len(self.pin)]
         dll, ptr = self.ctx.dll, self.ctx.ptr
-        h2d = 0
-        for ct, hp in ((a, pa), (b, pb)):
-            for kk, poly in ct.Value.items():
-                arr = hp[kk]
-                self.ctx.check(dll.mkhe_poly_upload(ptr, C.c_uint64(poly.h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
-                h2d += arr.nbytes
-        self.mul_relin_step(i)
-        d2h = 0
-        for kk, poly in self.out.Value.items():
-            arr = self.res_host[kk]
-            self.ctx.check(dll.mkhe_poly_download(ptr, C.c_uint64(poly.h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
-            d2h += arr.nbytes
+        h2d = d2h = 0
+        for j in range(self.batch):
+            n = i * self.batch + j
+            a, b = self.pairs[n % len(self.pairs)]
+            pa, pb = self.pin[n % len(self.pin)]
+            for ct, hp in ((a, pa), (b, pb)):
+                for kk, poly in ct.Value.items():
+                    arr = hp[kk]
+                    self.ctx.check(dll.mkhe_poly_upload(ptr, C.c_uint64(poly.h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
+                    h2d += arr.nbytes
+            self.mul_relin_op(n)
+            for kk, poly in self.out.Value.items():
+                arr = self.res_host[kk]
+                self.ctx.check(dll.mkhe_poly_download(ptr, C.c_uint64(poly.h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
+                d2h += arr.nbytes
         return h2d, d2h
 
 
@@ -291,6 +299,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--parties", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=16, help="ciphertext pairs (MulRelin ops) per step")
     ap.add_argument("--no-extras", action="store_true", help="skip the k=8 / hoisted-Rotate side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -303,7 +312,7 @@ def main():
     ell, nP, N = len(lit.Q), len(lit.P), lit.N
     config = {"workload": f"mkckks MulRelinNew (hoist + MulAndRelinHoisted + Rescale), {lit.name}, logN={lit.logN}, level {ell - 1}, "
                           f"k={k} parties, op0 != op1",
-              "params": lit.name, "logN": lit.logN, "parties": k, "level": ell - 1,
+              "params": lit.name, "logN": lit.logN, "parties": k, "level": ell - 1, "ops_per_step": args.batch,
               "l2_policy": "inputs larger than L2: every step streams the relinearisation keys "
                            f"({(3 * k + 1) * ell * (ell + nP) * 8 * N / 2**20:.0f} MiB) and cycles 3 ciphertext pairs"}
 
@@ -346,14 +355,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    wl = DeviceWorkload(lit, k, local_rank, seed=0xB2000002 + rank)
+    B = args.batch
+    wl = DeviceWorkload(lit, k, local_rank, seed=0xB2000002 + rank, batch=B)
     clocks = ClockSampler(local_rank)
     clocks.start()
     ms = wl.timed(wl.mul_relin_step, args.steps, warmup, barrier)
     launches_timed = wl.last_launches
     clk = clocks.stop()
     ms = allmax(ms)
-    value = world * args.steps / (ms * 1e-3)
+    value = world * B * args.steps / (ms * 1e-3)
 
     # end to end through host buffers
     wl.prepare_e2e()
@@ -363,13 +373,13 @@ def main():
         bytes_io[0], bytes_io[1] = wl.e2e_step(i)
 
     ms_e2e = allmax(wl.timed(e2e_fn, args.steps, warmup, barrier))
-    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
     # per-kernel profile pass (events around every launch; separate from the timed region above)
-    psteps = min(args.steps, 10)
+    psteps = 8                      # MulRelin ops in the profiled pass
     wl.ctx.profile_begin()
     for i in range(psteps):
-        wl.mul_relin_step(i)
+        wl.mul_relin_op(i)
     prof = wl.ctx.profile_end()
     model = algorithmic_model(k, ell, nP, N)
     peaks = {}
@@ -391,6 +401,11 @@ def main():
             e["butterflies_per_s"] = model["kernel_butterflies"][name] / (tms / psteps * 1e-3)
             e["int_frac"] = e["butterflies_per_s"] / bfly_peak
         kernels[name] = e
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
     dom = next(iter(kernels)) if kernels else None
     roofline = None
     if dom:
@@ -399,28 +414,31 @@ def main():
         per_launch_s = d["ms_per_step"] * 1e-3 / max(d["launches_per_step"], 1e-9)
         ach = per_launch_bytes / per_launch_s / 1e9 if per_launch_s else 0.0
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
+                    "traffic": (traffic.get(dom) or {}).get("dram_bytes_per_launch"),
+                    "traffic_source": (traffic.get(dom) or {}).get("source"), "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
                     "avg_launch_ms": per_launch_s * 1e3,
                     "integer_pipe": {"achieved_butterflies_per_s": d.get("butterflies_per_s"), "peak_butterflies_per_s": bfly_peak,
                                      "frac": d.get("int_frac"),
                                      "peak_source": "register-resident Shoup butterfly loop measured in this run (mkhe_bench_butterfly_peak)"},
                     "whole_step": {"compulsory_bytes": model["compulsory_bytes"],
-                                   "hbm_frac_of_compulsory": model["compulsory_bytes"] / (ms / args.steps * 1e-3) / 1e9 / hbm_peak,
+                                   "hbm_frac_of_compulsory": model["compulsory_bytes"] / (ms / args.steps / B * 1e-3) / 1e9 / hbm_peak,
                                    "butterflies": model["butterflies"],
-                                   "int_frac": model["butterflies"] / (ms / args.steps * 1e-3) / bfly_peak}}
+                                   "int_frac": model["butterflies"] / (ms / args.steps / B * 1e-3) / bfly_peak}}
 
     extra = {}
     if not args.no_extras and world == 1:
         wl.prepare_rotate()
         ms_rot = wl.timed(wl.rotate_step, args.steps, warmup)
-        extra[f"rotate_hoisted_k{k}_ops_s"] = args.steps / (ms_rot * 1e-3)
+        extra[f"rotate_hoisted_k{k}_ops_s"] = B * args.steps / (ms_rot * 1e-3)
+        wl.ctx.close()
         del wl
-        wl8 = DeviceWorkload(lit, 8, local_rank, seed=0xB2000008)
+        wl8 = DeviceWorkload(lit, 8, local_rank, seed=0xB2000008, batch=B)
         ms8 = wl8.timed(wl8.mul_relin_step, args.steps, warmup)
-        extra["mulrelin_k8_ops_s"] = args.steps / (ms8 * 1e-3)
+        extra["mulrelin_k8_ops_s"] = B * args.steps / (ms8 * 1e-3)
         wl8.prepare_rotate()
         ms_rot8 = wl8.timed(wl8.rotate_step, args.steps, warmup)
-        extra["rotate_hoisted_k8_ops_s"] = args.steps / (ms_rot8 * 1e-3)
+        extra["rotate_hoisted_k8_ops_s"] = B * args.steps / (ms_rot8 * 1e-3)
+        wl8.ctx.close()
         del wl8
 
     cpu = None
@@ -432,7 +450,7 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "ms_per_op": ms / args.steps / B, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": config,
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io[0], "d2h_bytes_per_step": bytes_io[1],

@@ -227,7 +227,7 @@ int dispatch_s1(mkhe_ctx *ctx, F &&f) {
 }
 
 const size_t SMEM_TILE = MKHE_TILE * 8;
-const size_t SMEM_PASS2 = MKHE_TILE * 8 + (MKHE_TILE - 4) * 16 + 64;
+const size_t SMEM_PASS2 = MKHE_TILE * 8 + MKHE_TILE * 16;
 
 // ---- building blocks ------------------------------------------------------------------------------
 // forward NTT of `npolys` polys over the limb list `s` (out may alias in)

@@ -40,16 +40,19 @@ struct TwGlobal {
         return tab[(1u << (10 - d + shift)) + ((u32)tile << (10 - d)) + (u32)lg];
     }
 };
-struct TwShared {                  // heap layout minus 4: levels 2^2 .. 2^10 of one pass-2 tile
+// heap layout (levels 2^2 .. 2^10 of one pass-2 tile); entry h lives at h ^ ((h >> 3) & 3) so that the per-thread
+// runs of 2 / 4 consecutive 16-byte entries read in the last round spread over all 8 bank groups
+__device__ __forceinline__ int twz(int h) { return h ^ ((h >> 3) & 3); }
+struct TwShared {
     const ulonglong2 *s;
-    __device__ __forceinline__ ulonglong2 get(int d, int lg) const { return s[(1 << (10 - d)) - 4 + lg]; }
+    __device__ __forceinline__ ulonglong2 get(int d, int lg) const { return s[twz((1 << (10 - d)) + lg)]; }
 };
 __device__ __forceinline__ void load_tile_twiddles(ulonglong2 *s, const ulonglong2 *tab, int S1, int tile) {
-    for (int i = threadIdx.x; i < MKHE_TILE - 4; i += MKHE_THREADS) {
-        u32 h = (u32)i + 4;
+    for (int i = threadIdx.x + 4; i < MKHE_TILE; i += MKHE_THREADS) {
+        u32 h = (u32)i;
         int lv = 31 - mkhe_clz(h);
         u32 lg = h - (1u << lv);
-        s[i] = tab[(1u << (lv + S1 - 2)) + ((u32)tile << lv) + lg];
+        s[twz(i)] = tab[(1u << (lv + S1 - 2)) + ((u32)tile << lv) + lg];
     }
 }
 
