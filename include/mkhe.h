@@ -163,6 +163,17 @@ int mkhe_bfv_mul_relin(mkhe_ctx *ctx,
 int mkhe_comm_unique_id(uint8_t out[128]);
 int mkhe_comm_init(mkhe_ctx *ctx, int nranks, int rank, const uint8_t unique_id[128]);
 int mkhe_comm_destroy(mkhe_ctx *ctx);
+/* party-sharded MulRelinNew: every rank passes the same (replicated) operand ciphertexts and id lists, but only holds
+ * the relinearization keys of the parties in own_ids (other entries of rlk_* may be 0).  Partial x, y and the c_0
+ * contributions are summed with ncclAllReduce(uint64, sum) and reduced mod q -- bit-identical to the single-GPU result
+ * because every accumulation of the reference is an exact modular add.  On return the rank holds component "0" and
+ * the components of its own parties (the others are left incomplete).   mkckks/evaluator.go:416-443 */
+int mkhe_ckks_mul_relin_sharded(mkhe_ctx *ctx, int level, int nb_rescales,
+                                int n0, const int *ids0, const mkhe_poly *op0,
+                                int n1, const int *ids1, const mkhe_poly *op1,
+                                int nown, const int *own_ids,
+                                const mkhe_swk *rlk_b, const mkhe_swk *rlk_d, const mkhe_swk *rlk_v, mkhe_swk u,
+                                int nOut, const int *idsOut, const mkhe_poly *out);
 
 /* ---- measurement helpers (CUDA events on the context's stream) */
 int mkhe_timer_start(mkhe_ctx *ctx);

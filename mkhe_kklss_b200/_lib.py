@@ -269,6 +269,27 @@ class Context:
     def poly_sub(self, level, a, b, out):
         self.check(self.dll.mkhe_poly_sub(self.ptr, C.c_int(level), C.c_uint64(a), C.c_uint64(b), C.c_uint64(out)))
 
+    # multi-GPU (party sharding, NCCL)
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = self.dll.mkhe_comm_unique_id(buf)
+        if rc != OK:
+            raise MkheError(rc, "mkhe_comm_unique_id failed (library built without NCCL?)")
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, uid: bytes):
+        buf = (C.c_uint8 * 128)(*uid)
+        self.check(self.dll.mkhe_comm_init(self.ptr, C.c_int(nranks), C.c_int(rank), buf))
+
+    def ckks_mul_relin_sharded(self, level, nb_rescales, ids0, op0, ids1, op1, own_ids, rlk_b, rlk_d, rlk_v, u, idsOut, out):
+        self.check(self.dll.mkhe_ckks_mul_relin_sharded(
+            self.ptr, C.c_int(level), C.c_int(nb_rescales),
+            C.c_int(len(ids0)), _intarr(ids0), _harr(op0),
+            C.c_int(len(ids1)), _intarr(ids1), _harr(op1),
+            C.c_int(len(own_ids)), _intarr(own_ids),
+            _harr(rlk_b), _harr(rlk_d), _harr(rlk_v), C.c_uint64(u),
+            C.c_int(len(idsOut)), _intarr(idsOut), _harr(out)))
+
     # BFV
     def bfv_modup_q_to_r(self, hq, hr):
         self.check(self.dll.mkhe_bfv_modup_q_to_r(self.ptr, C.c_uint64(hq), C.c_uint64(hr)))

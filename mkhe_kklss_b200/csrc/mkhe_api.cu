@@ -441,17 +441,59 @@ int poly_pool(mkhe_ctx *ctx, const char *name, int n, int limbs, std::vector<u64
     return MKHE_OK;
 }
 
-// MulAndRelinHoisted on raw device pointers (mkrlwe/keyswitch_hoisted.go:44-179)
+// party sharding: which parties this rank owns; inactive = single-GPU behaviour
+struct Shard {
+    bool active = false;
+    std::vector<int> own;
+    bool owns(int id) const { return !active || std::find(own.begin(), own.end(), id) != own.end(); }
+};
+
+int allreduce_mod(mkhe_ctx *ctx, u64 *buf, size_t count, const Slots &s, int nbufs, long buf_stride) {
+#if !defined(MKHE_EMU) && defined(MKHE_WITH_NCCL)
+    if (!ctx->nccl) return fail(ctx, MKHE_ERR_NCCL, "sharded op without mkhe_comm_init");
+    if (ncclAllReduce(buf, buf, count, ncclUint64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream) != ncclSuccess)
+        return fail(ctx, MKHE_ERR_NCCL, "ncclAllReduce failed");
+    if (nbufs > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_UNSUPPORTED, "too many buffers");
+    LimbArgs a;
+    fill(a, s, ctx->logN);
+    for (int i = 0; i < nbufs; i++) { a.in.p[i] = buf + (size_t)i * buf_stride; a.out.p[i] = a.in.p[i]; }
+    LAUNCH(k_reduce, dim3(ctx->N / MKHE_THREADS, s.n, nbufs), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    return MKHE_OK;
+#else
+    (void)buf; (void)count; (void)s; (void)nbufs; (void)buf_stride;
+    return fail(ctx, MKHE_ERR_UNSUPPORTED, "built without NCCL");
+#endif
+}
+
+// MulAndRelinHoisted on raw device pointers (mkrlwe/keyswitch_hoisted.go:44-179).
+// With an active Shard only the owned parties' keys / hoisted forms are touched: the partial x, y and the c_0
+// contributions are summed over ranks (exact: every accumulation of the reference is a modular add, App. A.4);
+// valid outputs on a rank are component "0" and the components of the parties it owns.
 int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u64 *const *op0, u64 *const *h0,
                            int n1, const int *ids1, u64 *const *op1, u64 *const *h1, u64 *const *rlk_b,
-                           u64 *const *rlk_d, u64 *const *rlk_v, u64 *u, int nOut, const int *idsOut, u64 *const *out) {
+                           u64 *const *rlk_d, u64 *const *rlk_v, u64 *u, int nOut, const int *idsOut, u64 *const *out,
+                           const Shard &sh = Shard()) {
     const int N = ctx->N;
+    Slots qps = qp_slots(ctx, level);
+    // owned sub-lists
+    std::vector<int> o0, o1;
+    for (int t = 0; t < n0; t++) if (sh.owns(ids0[t])) o0.push_back(t);
+    for (int t = 0; t < n1; t++) if (sh.owns(ids1[t])) o1.push_back(t);
+    auto pick = [](const std::vector<int> &idx, u64 *const *arr) {
+        std::vector<u64 *> r(idx.size());
+        for (size_t i = 0; i < idx.size(); i++) r[i] = arr[idx[i]];
+        return r;
+    };
+    std::vector<u64 *> d_o = pick(o0, rlk_d), v_o = pick(o0, rlk_v), h0_o = pick(o0, h0), b_o = pick(o1, rlk_b), h1_o = pick(o1, h1);
     // steps 2-3 (:79-117): x = MForm(sum d_id (.) h0_id), y = MForm(sum b_id (.) h1_id)
     std::vector<u64 *> xy;
     TRY(swk_pool(ctx, "xy", 2, xy));
     u64 *x = xy[0], *y = xy[1];
-    TRY(mac_parties(ctx, level, n0, rlk_d, h0, x));
-    TRY(mac_parties(ctx, level, n1, rlk_b, h1, y));
+    if (!o0.empty()) TRY(mac_parties(ctx, level, (int)o0.size(), d_o.data(), h0_o.data(), x));
+    else CU(cudaMemsetAsync(x, 0, swk_elems(ctx) * 8, ctx->stream));
+    if (!o1.empty()) TRY(mac_parties(ctx, level, (int)o1.size(), b_o.data(), h1_o.data(), y));
+    else CU(cudaMemsetAsync(y, 0, swk_elems(ctx) * 8, ctx->stream));
+    if (sh.active) TRY(allreduce_mod(ctx, x, 2 * swk_elems(ctx), qps, 2 * ctx->nQ, (long)ctx->dmax * N));
 
     // step 4 (:119-144): tensor product in the NTT domain, then InvNTT of every output component
     Slots qs = q_slots(level);
@@ -479,25 +521,30 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     }
     LAUNCH(k_tensor, dim3(N / MKHE_THREADS, level + 1), dim3(MKHE_THREADS), 0, ta, ctx->d_mods);
     TRY(ntt_inv(ctx, qs, nOut + 1, out, out));
+    // the tensor term of c_0 is counted once across ranks
+    if (sh.active && ctx->rank != 0) CU(cudaMemsetAsync(out[0], 0, (size_t)(level + 1) * N * 8, ctx->stream));
 
     // step 5 (:147-154): c_id += x [.] h1_id
     {
-        std::vector<u64 *> key(n1, x), dst(n1);
-        for (int t = 0; t < n1; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids1[t])];
-        TRY(ext_products(ctx, level, n1, 1, key.data(), h1, nullptr, nullptr, dst.data(), dst.data(), false));
+        const int m = (int)o1.size();
+        std::vector<u64 *> key(m, x), dst(m);
+        for (int t = 0; t < m; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids1[o1[t]])];
+        TRY(ext_products(ctx, level, m, 1, key.data(), h1_o.data(), nullptr, nullptr, dst.data(), dst.data(), false));
     }
     // step 6 (:161-178): p_id = y [.] h0_id ; Decompose(p_id) ; c_0 += v_id [.] p_id ; c_id += u [.] p_id
     {
-        std::vector<u64 *> key(n0, y), p, hp;
-        TRY(poly_pool(ctx, "relin_p", n0, ctx->nQ, p));
-        TRY(swk_pool(ctx, "relin_hp", n0, hp));
-        TRY(ext_products(ctx, level, n0, 1, key.data(), h0, nullptr, nullptr, p.data(), nullptr, false));
-        TRY(decompose_impl(ctx, level, n0, p.data(), hp.data(), 0));
-        std::vector<u64 *> ukey(n0, u), dst(n0), c0(n0, out[0]);
-        for (int t = 0; t < n0; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids0[t])];
-        TRY(ext_products(ctx, level, n0, 1, ukey.data(), hp.data(), nullptr, nullptr, dst.data(), dst.data(), false));
-        TRY(ext_products(ctx, level, n0, 1, rlk_v, hp.data(), nullptr, nullptr, c0.data(), c0.data(), true));
+        const int m = (int)o0.size();
+        std::vector<u64 *> key(m, y), p, hp;
+        TRY(poly_pool(ctx, "relin_p", m, ctx->nQ, p));
+        TRY(swk_pool(ctx, "relin_hp", m, hp));
+        TRY(ext_products(ctx, level, m, 1, key.data(), h0_o.data(), nullptr, nullptr, p.data(), nullptr, false));
+        TRY(decompose_impl(ctx, level, m, p.data(), hp.data(), 0));
+        std::vector<u64 *> ukey(m, u), dst(m), c0(m, out[0]);
+        for (int t = 0; t < m; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids0[o0[t]])];
+        TRY(ext_products(ctx, level, m, 1, ukey.data(), hp.data(), nullptr, nullptr, dst.data(), dst.data(), false));
+        TRY(ext_products(ctx, level, m, 1, v_o.data(), hp.data(), nullptr, nullptr, c0.data(), c0.data(), true));
     }
+    if (sh.active) TRY(allreduce_mod(ctx, out[0], (size_t)(level + 1) * N, qs, 1, 0));
     return MKHE_OK;
 }
 
@@ -935,6 +982,52 @@ int mkhe_ckks_mul_relin(mkhe_ctx *ctx, int level, int nb_rescales, int same_oper
     }
     TRY(mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
                                vd.data(), vv.data(), uk->d, nOut, idsOut, po.data()));
+    TRY(rescale_impl(ctx, level, nb_rescales, nOut + 1, po.data(), po.data()));
+    for (int t = 0; t <= nOut; t++) reinterpret_cast<Obj *>(out[t])->nlimbs = level + 1 - nb_rescales;
+    return MKHE_OK;
+}
+
+int mkhe_ckks_mul_relin_sharded(mkhe_ctx *ctx, int level, int nb_rescales, int n0, const int *ids0, const mkhe_poly *op0,
+                                int n1, const int *ids1, const mkhe_poly *op1, int nown, const int *own_ids,
+                                const mkhe_swk *rlk_b, const mkhe_swk *rlk_d, const mkhe_swk *rlk_v, mkhe_swk u, int nOut,
+                                const int *idsOut, const mkhe_poly *out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    TRY(check_ids(ctx, n0, ids0, n1, ids1, nOut, idsOut));
+    if (!ctx->nccl) return fail(ctx, MKHE_ERR_NCCL, "mkhe_comm_init has not been called");
+    Shard sh;
+    sh.active = true;
+    sh.own.assign(own_ids, own_ids + nown);
+    std::vector<u64 *> p0, p1, po, vh0(n0, nullptr), vh1(n1, nullptr), vb(n1, nullptr), vd(n0, nullptr), vv(n0, nullptr);
+    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0"));
+    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1"));
+    TRY(polys_of(ctx, nOut + 1, out, level + 1, po, "out"));
+    SWK(uk, u);
+    // keys and hoisting only for the parties this rank owns
+    std::vector<u64 *> in0, in1, hp0, hp1, pool0, pool1;
+    std::vector<int> t0, t1;
+    for (int t = 0; t < n0; t++) if (sh.owns(ids0[t])) t0.push_back(t);
+    for (int t = 0; t < n1; t++) if (sh.owns(ids1[t])) t1.push_back(t);
+    TRY(swk_pool(ctx, "hoistpool0", (int)t0.size(), pool0));
+    TRY(swk_pool(ctx, "hoistpool1", (int)t1.size(), pool1));
+    for (size_t i = 0; i < t0.size(); i++) {
+        int t = t0[i];
+        Obj *d = as_obj(ctx, rlk_d[t], OBJ_SWK), *v = as_obj(ctx, rlk_v[t], OBJ_SWK);
+        if (!d || !v) return fail(ctx, MKHE_ERR_INVALID, "missing relinearization key (d, v) of owned party %d", ids0[t]);
+        vd[t] = d->d; vv[t] = v->d; vh0[t] = pool0[i];
+        in0.push_back(p0[1 + t]);
+    }
+    for (size_t i = 0; i < t1.size(); i++) {
+        int t = t1[i];
+        Obj *b = as_obj(ctx, rlk_b[t], OBJ_SWK);
+        if (!b) return fail(ctx, MKHE_ERR_INVALID, "missing relinearization key (b) of owned party %d", ids1[t]);
+        vb[t] = b->d; vh1[t] = pool1[i];
+        in1.push_back(p1[1 + t]);
+    }
+    TRY(decompose_impl(ctx, level, (int)in0.size(), in0.data(), pool0.data(), 0));
+    TRY(decompose_impl(ctx, level, (int)in1.size(), in1.data(), pool1.data(), 0));
+    TRY(mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
+                               vd.data(), vv.data(), uk->d, nOut, idsOut, po.data(), sh));
     TRY(rescale_impl(ctx, level, nb_rescales, nOut + 1, po.data(), po.data()));
     for (int t = 0; t <= nOut; t++) reinterpret_cast<Obj *>(out[t])->nlimbs = level + 1 - nb_rescales;
     return MKHE_OK;

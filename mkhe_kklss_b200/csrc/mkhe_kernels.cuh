@@ -580,6 +580,15 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_addsub(const u64 *x, const u64
     out[off] = SUB ? csub(x[off] + q - y[off], q) : csub(x[off] + y[off], q);
 }
 
+// x mod q for sums of <= 8 canonical residues (after the party-sharded all-reduce).  grid = (N/256, nlimbs, nbufs)
+__global__ void __launch_bounds__(MKHE_THREADS) k_reduce(LimbArgs a, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const int limb = blockIdx.y, b = blockIdx.z;
+    const ModC m = mods[a.mod_of_limb[limb]];
+    const long off = (long)a.slot_of[limb] * N + (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    a.out.p[b][off] = csub(barrett_lazy(a.in.p[b][off], m.q, m.mu), m.q);
+}
+
 // K6 DivRoundByLastModulusLvl (lattigo ring/scaling.go; call site mkckks/evaluator.go:388).
 //   Writes (x_l + h) mod q_l back into the input's last limb like lattigo does.
 struct RescaleArgs {
