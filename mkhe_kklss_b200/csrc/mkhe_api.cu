@@ -217,17 +217,25 @@ void fill(LimbArgs &a, const Slots &s, int logN) {
 template <class F>
 int dispatch_s1(mkhe_ctx *ctx, F &&f) {
     switch (ctx->S1) {
+        case 1: return f(std::integral_constant<int, 1>());
+        case 2: return f(std::integral_constant<int, 2>());
         case 3: return f(std::integral_constant<int, 3>());
         case 4: return f(std::integral_constant<int, 4>());
         case 5: return f(std::integral_constant<int, 5>());
-        case 6: return f(std::integral_constant<int, 6>());
-        case 7: return f(std::integral_constant<int, 7>());
     }
     return fail(ctx, MKHE_ERR_UNSUPPORTED, "logN = %d unsupported (12..16)", ctx->logN);
 }
 
-const size_t SMEM_TILE = MKHE_TILE * 8;
-const size_t SMEM_PASS2 = MKHE_TILE * 8 + MKHE_TILE * 16;
+const size_t SMEM_TILE = MKHE_XBUF * 8;                      // the padded exchange buffer
+const size_t SMEM_PASS2 = MKHE_XBUF * 8 + MKHE_TILE * 16;    // + the tile's twiddles
+const int COLGROUPS = MKHE_TILE / MKHE_NTT_THREADS;              // CTAs per limb in the column passes
+
+// how many chunks to split `count` looped instances into so that the grid fills the machine (>= ~4 waves of 3 CTAs/SM)
+int pick_chunks(int count, long ctas_per_chunk) {
+    const long want = 148L * 4 * 4;
+    int chunks = (int)std::min<long>(count, std::max<long>(1, (want + ctas_per_chunk - 1) / ctas_per_chunk));
+    return std::max(chunks, 1);
+}
 
 // ---- building blocks ------------------------------------------------------------------------------
 // forward NTT of `npolys` polys over the limb list `s` (out may alias in)
@@ -240,23 +248,23 @@ int ntt_fwd(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
         for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
         TRY(dispatch_s1(ctx, [&](auto S) -> int {
             auto k_ntt_pass1_ = k_ntt_pass1<decltype(S)::value>;
-            LAUNCH(k_ntt_pass1_, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twf);
+            LAUNCH(k_ntt_pass1_, dim3(COLGROUPS, s.n, np), dim3(MKHE_NTT_THREADS), 0, a, ctx->d_mods, ctx->d_twf);
             return MKHE_OK;
         }));
         Pass2Args b;
         b.count = 1;
+        b.chunks = 1;
         b.inst_stride = 0;
         b.nslots = s.n;
         b.logN = ctx->logN;
         for (int i = 0; i < s.n; i++) { b.slots[i] = s.slot[i]; b.mods[i] = s.mod[i]; }
         for (int i = 0; i < np; i++) b.buf.p[i] = out[p0 + i];
-        LAUNCH(k_ntt_pass2, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf);
+        LAUNCH(k_ntt_pass2, dim3(tiles, s.n, np), dim3(MKHE_NTT_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf);
     }
     return MKHE_OK;
 }
 // inverse pass B over limb list (in place on bufs)
 int intt_passB(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *bufs_in, u64 *const *bufs_out) {
-    const int tiles = ctx->N / MKHE_TILE;
     for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
         int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
         LimbArgs a;
@@ -264,7 +272,7 @@ int intt_passB(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *bufs_in, u
         for (int i = 0; i < np; i++) { a.in.p[i] = bufs_in[p0 + i]; a.out.p[i] = bufs_out[p0 + i]; }
         TRY(dispatch_s1(ctx, [&](auto S) -> int {
             auto k_intt_passB_ = k_intt_passB<decltype(S)::value>;
-            LAUNCH(k_intt_passB_, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+            LAUNCH(k_intt_passB_, dim3(COLGROUPS, s.n, np), dim3(MKHE_NTT_THREADS), 0, a, ctx->d_mods, ctx->d_twi);
             return MKHE_OK;
         }));
     }
@@ -281,7 +289,7 @@ int ntt_inv(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
         a.logN = ctx->logN;
         for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; a.out_slots[i] = s.slot[i]; }
         for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
-        LAUNCH(k_intt_passA<false>, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+        LAUNCH(k_intt_passA<false>, dim3(tiles, s.n, np), dim3(MKHE_NTT_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
     }
     return intt_passB(ctx, s, npolys, out, out);
 }
@@ -297,22 +305,24 @@ int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *c
         a.in_limb0 = in_limb0;
         a.dmax = ctx->dmax;
         a.nslots = s.n;
+        a.slot_groups = std::min(s.n, pick_chunks(s.n, (long)COLGROUPS * beta * np));
         a.logN = ctx->logN;
         for (int i = 0; i < s.n; i++) a.slots[i] = s.slot[i];
         for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
         TRY(dispatch_s1(ctx, [&](auto S) -> int {
             auto k_bcast_ntt_pass1_ = k_bcast_ntt_pass1<decltype(S)::value>;
-            LAUNCH(k_bcast_ntt_pass1_, dim3(tiles, beta, np), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twf);
+            LAUNCH(k_bcast_ntt_pass1_, dim3(COLGROUPS * a.slot_groups, beta, np), dim3(MKHE_NTT_THREADS), 0, a, ctx->d_mods, ctx->d_twf);
             return MKHE_OK;
         }));
         Pass2Args b;
         b.count = beta;
+        b.chunks = pick_chunks(beta, (long)tiles * s.n * np);
         b.inst_stride = (long)ctx->dmax * ctx->N;
         b.nslots = s.n;
         b.logN = ctx->logN;
         for (int i = 0; i < s.n; i++) { b.slots[i] = s.slot[i]; b.mods[i] = s.mod[i]; }
         for (int i = 0; i < np; i++) b.buf.p[i] = out[p0 + i];
-        LAUNCH(k_ntt_pass2, dim3(tiles, s.n, np), dim3(MKHE_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf);
+        LAUNCH(k_ntt_pass2, dim3(tiles * b.chunks, s.n, np), dim3(MKHE_NTT_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf);
     }
     return MKHE_OK;
 }
@@ -346,7 +356,7 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nb, int nsets, u64 *const *key0,
             bufs[i] = accqp + (size_t)i * qp;
             a.out.p[i] = bufs[i];
         }
-        LAUNCH(k_intt_passA<true>, dim3(tiles, s.n, n), dim3(MKHE_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+        LAUNCH(k_intt_passA<true>, dim3(tiles, s.n, n), dim3(MKHE_NTT_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
         TRY(intt_passB(ctx, s, n, bufs.data(), bufs.data()));
         ConvArgs c;
         memset(&c, 0, sizeof c);
@@ -633,12 +643,12 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     if (ndev <= 0 || device < 0 || device >= ndev) return MKHE_ERR_CUDA;   // no GPU: fail loudly, there is no CPU path
     mkhe_ctx *ctx = new mkhe_ctx();
     ctx->logN = logN; ctx->N = 1 << logN; ctx->nQ = nQ; ctx->nP = nP; ctx->gamma = gamma; ctx->device = device;
-    ctx->S1 = logN - 9;
+    ctx->S1 = logN - 11;
     ctx->dmax = nQ + nP;
     for (int i = 0; i < nQ; i++) ctx->mod.push_back(Q[i]);
     for (int i = 0; i < nP; i++) ctx->mod.push_back(P[i]);
     for (u64 q : ctx->mod) {
-        if (q >= ((u64)1 << 60) || !h_is_prime(q) || (q - 1) % ((u64)2 << logN) != 0) { delete ctx; return MKHE_ERR_UNSUPPORTED; }
+        if (q >= ((u64)1 << 60) || q < ((u64)1 << 40) || !h_is_prime(q) || (q - 1) % ((u64)2 << logN) != 0) { delete ctx; return MKHE_ERR_UNSUPPORTED; }
     }
     ctx->tabs.resize(ctx->mod.size());
     for (size_t i = 0; i < ctx->mod.size(); i++) gen_mod_tables(ctx->tabs[i], logN, ctx->mod[i]);
@@ -665,7 +675,7 @@ int mkhe_ctx_set_bfv(mkhe_ctx *ctx, const uint64_t *QMul, int nQMul, uint64_t T)
     if (ctx->nQMul) return fail(ctx, MKHE_ERR_INVALID, "BFV parameters already set");
     for (int i = 0; i < nQMul; i++) {
         u64 q = QMul[i];
-        if (q >= ((u64)1 << 60) || !h_is_prime(q) || (q - 1) % ((u64)2 << ctx->logN) != 0) return fail(ctx, MKHE_ERR_UNSUPPORTED, "bad QMul prime");
+        if (q >= ((u64)1 << 60) || q < ((u64)1 << 40) || !h_is_prime(q) || (q - 1) % ((u64)2 << ctx->logN) != 0) return fail(ctx, MKHE_ERR_UNSUPPORTED, "bad QMul prime");
         ctx->mod.push_back(q);
         ctx->tabs.emplace_back();
         gen_mod_tables(ctx->tabs.back(), ctx->logN, q);

@@ -20,6 +20,22 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
+// 16-byte asynchronous global -> shared copy (LDGSTS), 32-byte global store (STG.256, one full sector per lane)
+#ifdef MKHE_EMU
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) { *reinterpret_cast<ulonglong2 *>(smem) = *reinterpret_cast<const ulonglong2 *>(gmem); }
+__device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
+#else
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+#endif
+
 #define MKHE_MAX_PARTIES_K 66     // entries of a kernel-argument pointer list (64 parties + component "0" + 1)
 
 #ifdef MKHE_EMU
@@ -36,7 +52,11 @@ struct ModC {
     u64 ninv, ninv_sh;        // N^-1 mod q as a Shoup pair
     u64 w1ninv, w1ninv_sh;    // psi^-(N/2)... = invtw[1] * N^-1 as a Shoup pair (last inverse stage)
     double qd;                // (double) q, for the fp64 overflow estimate v (basis_extension.go:548)
-    u64 pad;
+    u64 nq;                   // -q mod 2^64
+    u32 big;                  // q >= 2^57: forward butterflies keep values in [0,8q) with a conditional subtraction
+    u32 bshift;               // bitlen(q) - 2                      } canon(): 32-bit Barrett quotient,
+    u32 mu32;                 // floor(2^(bitlen(q)+30) / q)        } valid for any 64-bit input (q >= 2^36)
+    u32 pad;
 };
 
 __device__ __forceinline__ u64 mulhi(u64 a, u64 b) { return __umul64hi(a, b); }
@@ -65,17 +85,80 @@ __device__ __forceinline__ void mac128(u64 &hi, u64 &lo, u64 a, u64 b) {
     hi += ph + (lo < pl ? 1ull : 0ull);
 }
 
-// Harvey forward (Cooley-Tukey) butterfly: X,Y in [0,4q) -> [0,4q)
-__device__ __forceinline__ void bf_fwd(u64 &X, u64 &Y, u64 w, u64 wsh, u64 q, u64 twoq) {
-    u64 x = X >= twoq ? X - twoq : X;
-    u64 t = shoup_lazy(Y, w, wsh, q);
-    X = x + t;
-    Y = x - t + twoq;
+
+// ------------------------------------------------------------------------------------------------
+// 32-bit building blocks.  Measured on B200 (tools/ubench, profiles/r01b_ubench_raw.txt): IMAD.WIDE.U32 and
+// IMAD.HI.U32 occupy the FMA pipe for 4 cycles per warp, a 32-bit IMAD for 2, IADD3/LOP3/SEL run on the ALU pipe
+// (2 cycles) concurrently.  The butterfly below needs 5 wide + 4 narrow multiply-adds = 28 pipe cycles; the
+// compiler's generic 64-bit code (mul.hi.u64 + 2 mul.lo.u64 + a 64-bit compare/select) needs 44.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 lo32(u64 x) { return (u32)x; }
+__device__ __forceinline__ u32 hi32(u64 x) { return (u32)(x >> 32); }
+__device__ __forceinline__ u64 mk64(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+#ifdef MKHE_EMU
+__device__ __forceinline__ u64 mulwide(u32 a, u32 b) { return (u64)a * b; }
+__device__ __forceinline__ u64 madwide(u32 a, u32 b, u64 c) { return (u64)a * b + c; }
+__device__ __forceinline__ u32 madlo(u32 a, u32 b, u32 c) { return a * b + c; }
+__device__ __forceinline__ u32 mulhi32(u32 a, u32 b) { return (u32)(((u64)a * b) >> 32); }
+#else
+__device__ __forceinline__ u64 mulwide(u32 a, u32 b) { u64 r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u64 madwide(u32 a, u32 b, u64 c) { u64 r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r; }
+__device__ __forceinline__ u32 madlo(u32 a, u32 b, u32 c) { u32 r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 mulhi32(u32 a, u32 b) { u32 r; asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+#endif
+
+// x*w mod q for ANY 64-bit x, result in [0,4q):  the Shoup quotient floor(x*wsh / 2^64) is computed without the
+// low x low partial product and without carries between the cross terms, so it is short by at most 2;
+// the remainder x*w - Q*q is evaluated mod 2^64 as x*w + Q*nq with nq = -q (2 wide + 4 narrow multiply-adds).
+__device__ __forceinline__ u64 shoup4(u64 x, u64 w, u64 wsh, u64 nq) {
+    const u32 x0 = lo32(x), x1 = hi32(x), s0 = lo32(wsh), s1 = hi32(wsh);
+    const u64 a = mulwide(x1, s0);
+    const u64 b = mulwide(x0, s1);
+    const u64 h = madwide(x1, s1, (u64)hi32(a)) + hi32(b);
+    u64 t = mulwide(x0, lo32(w));
+    t = madwide(lo32(h), lo32(nq), t);
+    u32 th = hi32(t);
+    th = madlo(x0, hi32(w), th);
+    th = madlo(x1, lo32(w), th);
+    th = madlo(lo32(h), hi32(nq), th);
+    th = madlo(hi32(h), lo32(nq), th);
+    return mk64(lo32(t), th);
 }
-// Harvey inverse (Gentleman-Sande) butterfly: X,Y in [0,2q) -> [0,2q)
-__device__ __forceinline__ void bf_inv(u64 &X, u64 &Y, u64 w, u64 wsh, u64 q, u64 twoq) {
-    u64 s = X + Y;
-    u64 t = X - Y + twoq;
-    X = s >= twoq ? s - twoq : s;
-    Y = shoup_lazy(t, w, wsh, q);
+
+// constants of one modulus as the NTT butterflies use them
+struct NttC {
+    u64 q, nq, fourq;
+};
+__device__ __forceinline__ NttC nttc(const ModC &m) { NttC c; c.q = m.q; c.nq = m.nq; c.fourq = 4 * m.q; return c; }
+
+// forward (Cooley-Tukey) butterfly.
+//   BIG  (2^57 <= q < 2^60): X,Y in [0,8q) -> [0,8q), one conditional subtraction of 4q.
+//   !BIG (q < 2^57):         no reduction at all; every stage adds at most 4q to the magnitude, so inputs below 2^60
+//                            stay below 2^60 + 64q < 2^64 through all (<= 16) stages.
+template <bool BIG>
+__device__ __forceinline__ void bf_fwd(u64 &X, u64 &Y, u64 w, u64 wsh, const NttC &c) {
+    u64 x = X;
+    if (BIG) x = x >= c.fourq ? x - c.fourq : x;
+    const u64 t = shoup4(Y, w, wsh, c.nq);
+    X = x + t;
+    Y = x - t + c.fourq;
+}
+// inverse (Gentleman-Sande) butterfly: X,Y in [0,4q) -> [0,4q)   (8q < 2^63 for every supported q)
+__device__ __forceinline__ void bf_inv(u64 &X, u64 &Y, u64 w, u64 wsh, const NttC &c) {
+    const u64 s = X + Y;
+    const u64 d = X - Y + c.fourq;
+    X = s >= c.fourq ? s - c.fourq : s;
+    Y = shoup4(d, w, wsh, c.nq);
+}
+// any 64-bit v -> canonical [0,q): 32-bit Barrett quotient.  With b = bitlen(q) >= 40: vh = floor(v / 2^(b-2)) < 2^26,
+// mu32 = floor(2^(b+30)/q); the estimate floor(vh*mu32 / 2^32) is never above floor(v/q) and short by at most 1
+// (error terms vh/2^32 + mu32/2^32 < 2^-6 + 1/2), so one conditional subtraction finishes the job.
+__device__ __forceinline__ u64 canon(u64 v, const ModC &m) {
+    const u32 vh = (u32)(v >> m.bshift);
+    const u32 qa = mulhi32(vh, m.mu32);
+    u64 p = mulwide(qa, lo32(m.q));
+    p = mk64(lo32(p), madlo(qa, hi32(m.q), hi32(p)));
+    const u64 r = v - p;
+    const u64 t = r - m.q;
+    return (long long)t < 0 ? r : t;
 }

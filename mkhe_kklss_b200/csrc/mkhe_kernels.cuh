@@ -4,199 +4,183 @@
 // DIT with in-order input and bit-reversed output; stage s (1-based) pairs positions j and
 // j + N/2^s and uses the twiddle psi[2^(s-1) + (j >> (logN-s+1))] (lattigo ring/ntt.go; the tables
 // are public fields read at mkrlwe/basis_extension.go:263-264).  The same dataflow is split into
-//   pass 1: the first S1 = logN-9 stages.  They act on N2 = 512 independent "columns" (positions with
-//           equal j mod 512) and every column uses the same 2^S1-1 twiddles.  A CTA owns a tile of
-//           2^S1 rows x W = 2^(11-S1) adjacent columns (2048 elements, rows are W*8-byte contiguous
-//           segments of HBM).
-//   pass 2: the last 9 stages = 2^S1 independent contiguous blocks of 512 elements, each with its own
-//           511 twiddles.  A CTA owns 4 adjacent blocks (2048 contiguous elements, 16 KiB).
-// Inside a CTA every thread (256 of them) holds 8 elements in registers and performs radix-8 rounds
-// (3 stages, 12 Harvey/Shoup butterflies, values lazily kept in [0,4q)); between rounds the tile is
-// re-distributed through XOR-swizzled shared memory.  The inverse transform mirrors this
-// (Gentleman-Sande, pass A = contiguous, pass B = columns, N^-1 folded into the last stage).
-// Positions are never permuted, so key material in lattigo's ordering is used as uploaded.
+//   pass 1: the first S1 = logN-11 stages.  They act on 2048 independent "columns" (positions with
+//           equal j mod 2048) and every column uses the same 2^S1-1 twiddles.  A thread owns one
+//           column = 2^S1 elements (stride 2048) and does the whole pass in registers: no shared
+//           memory, no barrier; a warp touches 256 contiguous bytes per access.
+//   pass 2: the last 11 stages = N/2048 independent contiguous tiles of 2048 elements, each with its
+//           own 2047 twiddles.  A CTA of 128 threads owns a tile, 16 elements per thread, three
+//           register rounds (4 + 4 + 3 stages) with two XOR-swizzled shared-memory exchanges.
+// The inverse transform mirrors this (Gentleman-Sande, pass A = tiles, pass B = columns with N^-1
+// folded into the last stage).  Positions are never permuted, so key material in lattigo's ordering
+// is used as uploaded.  Butterfly arithmetic: mkhe_arith.cuh.
 #pragma once
 #include "mkhe_arith.cuh"
 
 #define MKHE_TILE 2048
-#define MKHE_THREADS 256
+#define MKHE_NTT_THREADS 128     // NTT kernels: 16 elements per thread
+#define MKHE_THREADS 256         // element-wise kernels
 #define MKHE_MAX_SLOTS 34        // limb slots per launch list (nQ + nP <= 34)
 
-// conflict-free tile addressing: bank bits 0..3 (u64 units) are XORed with index bits 3..6
-__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx >> 3) & 15); }
+// exchange buffer: the three register layouts of a tile (see tile_fwd) meet in one padded buffer with two
+// address maps, so that every access is conflict-free and its address is a per-thread base plus a compile-time offset:
+//   map 1 (layouts A <-> B): element idx at idx + 8*(idx >> 7)        (rows of 128 padded to 136)
+//   map 2 (layouts B <-> C): element idx at idx + (idx >> 4)          (groups of 16 padded to 17)
+// Both maps send the 512 elements [512w, 512w+512) that warp w owns in layouts B and C to the same slots
+// [544w, 544w+544), so the B <-> C exchange only needs a warp-level barrier.
+#define MKHE_XBUF 2176           // u64 slots of the exchange buffer (2048 + 128 padding)
+#ifdef MKHE_EMU
+#define MKHE_SYNCWARP() __syncthreads()
+#else
+#define MKHE_SYNCWARP() __syncwarp()
+#endif
 
 struct PtrList { u64 *p[MKHE_MAX_PARTIES_K]; };
 
 // ------------------------------------------------------------------------------------------------
-// twiddle accessors.  Stage "d" = the butterfly distance is 2^d in tile-local index space (0..10);
-// lg = local group index = local_idx >> (d+1).
-//   pass 1 (columns): table index = 2^(10-d) + lg
-//   pass 2 (contiguous): table index = 2^(S1+8-d) + (tile << (10-d)) + lg
+// twiddles of one pass-2 / pass-A tile in shared memory.  Stage "d" = butterfly distance 2^d in
+// tile-local index space (0..10); level lv = 10-d has 2^lv twiddles, heap index 2^lv + g where
+// g = local_idx >> (d+1).  Global table index = 2^(S1+lv) + (tile << lv) + g.
+//   levels 0..3 (round A, warp-uniform reads): heap order.
+//   levels 4..7 (round B, thread t = hi*8+low reads entries hi*2^(lv-4) + j): stored as [j][hi].
+//   levels 8..10 (round C, thread t reads its private entries t*2^(lv-7) + j): stored as [j][t].
+// so every read is (per-thread base) + (compile-time offset) and a warp reads consecutive 16-byte entries.
 // ------------------------------------------------------------------------------------------------
-struct TwGlobal {
-    const ulonglong2 *tab;
-    int shift, tile;
-    __device__ __forceinline__ ulonglong2 get(int d, int lg) const {
-        return tab[(1u << (10 - d + shift)) + ((u32)tile << (10 - d)) + (u32)lg];
-    }
-};
-// heap layout (levels 2^2 .. 2^10 of one pass-2 tile); entry h lives at h ^ ((h >> 3) & 3) so that the per-thread
-// runs of 2 / 4 consecutive 16-byte entries read in the last round spread over all 8 bank groups
-__device__ __forceinline__ int twz(int h) { return h ^ ((h >> 3) & 3); }
-struct TwShared {
-    const ulonglong2 *s;
-    __device__ __forceinline__ ulonglong2 get(int d, int lg) const { return s[twz((1 << (10 - d)) + lg)]; }
-};
+// asynchronous (LDGSTS): the caller waits with cp_async_wait_all() + a block barrier before the first use.
 __device__ __forceinline__ void load_tile_twiddles(ulonglong2 *s, const ulonglong2 *tab, int S1, int tile) {
-    for (int i = threadIdx.x + 4; i < MKHE_TILE; i += MKHE_THREADS) {
-        u32 h = (u32)i;
-        int lv = 31 - mkhe_clz(h);
-        u32 lg = h - (1u << lv);
-        s[twz(i)] = tab[(1u << (lv + S1 - 2)) + ((u32)tile << lv) + lg];
+#pragma unroll 4
+    for (int h = threadIdx.x; h < MKHE_TILE; h += MKHE_NTT_THREADS) {
+        if (h == 0) continue;
+        const int lv = 31 - mkhe_clz((u32)h);
+        const int g = h - (1 << lv);
+        int pos = h;
+        if (lv >= 8) pos = (1 << lv) + (g & ((1 << (lv - 7)) - 1)) * MKHE_NTT_THREADS + (g >> (lv - 7));
+        else if (lv >= 4) pos = (1 << lv) + (g & ((1 << (lv - 4)) - 1)) * 16 + (g >> (lv - 4));
+        cp_async16(s + pos, tab + ((size_t)1 << (S1 + lv)) + ((size_t)tile << lv) + g);
     }
 }
+struct TwShared {          // accessor used by the tile rounds; b = the register-index bit of the stage
+    const ulonglong2 *sB, *sC, *tab_;   // round A reads its 15 warp-uniform entries straight from the global table (L1 hits)
+    int S1_, tile_;
+    __device__ __forceinline__ TwShared(const ulonglong2 *base, const ulonglong2 *tab, int S1, int tile)
+        : sB(base + (threadIdx.x >> 3)), sC(base + threadIdx.x), tab_(tab), S1_(S1), tile_(tile) {}
+    __device__ __forceinline__ ulonglong2 A(int b, int g) const { return __ldg(tab_ + ((size_t)1 << (S1_ + 3 - b)) + ((size_t)tile_ << (3 - b)) + g); }
+    __device__ __forceinline__ ulonglong2 B(int b, int g) const { return sB[(1 << (7 - b)) + g * 16]; }
+    __device__ __forceinline__ ulonglong2 C(int b, int g) const { return sC[(1 << (10 - b)) + g * MKHE_NTT_THREADS]; }
+};
+struct TwGlobal {          // same interface straight from the global table (single-use tiles)
+    const ulonglong2 *tA, *tB, *tC;
+    int S1, tile;
+    __device__ __forceinline__ TwGlobal(const ulonglong2 *tab, int S1_, int tile_) : tA(tab), tB(tab), tC(tab), S1(S1_), tile(tile_) {}
+    __device__ __forceinline__ ulonglong2 at(int lv, size_t g) const { return __ldg(tA + ((size_t)1 << (S1 + lv)) + ((size_t)tile << lv) + g); }
+    __device__ __forceinline__ ulonglong2 A(int b, int g) const { return at(3 - b, g); }
+    __device__ __forceinline__ ulonglong2 B(int b, int g) const { return at(7 - b, ((size_t)(threadIdx.x >> 3) << (3 - b)) + g); }
+    __device__ __forceinline__ ulonglong2 C(int b, int g) const { return at(10 - b, ((size_t)threadIdx.x << (3 - b)) + g); }
+};
 
 // ------------------------------------------------------------------------------------------------
-// radix-8 register rounds on the window of local index bits [e, e+3); element k of the thread sits
-// at local index (hi << (e+3)) | (k << e) | low.  NS = number of stages performed (the TOP NS bits).
+// tile rounds.  Thread t = hi*8 + low holds 16 elements; their tile-local indices are
+//   layout A:  k*128 + t                 (stages d = 10..7 are register-local, global access coalesced)
+//   layout B:  (hi*16 + k)*8 + low       (stages d = 6..3)
+//   layout C:  t*16 + k                  (stages d = 2..0; 16 contiguous elements per thread)
 // ------------------------------------------------------------------------------------------------
-template <int NS, class TW>
-__device__ __forceinline__ void round_fwd(u64 v[8], int e, int hi, const TW &tw, u64 q, u64 twoq) {
-    {   // distance 2^(e+2)
-        ulonglong2 w = tw.get(e + 2, hi);
-#pragma unroll
-        for (int k = 0; k < 4; k++) bf_fwd(v[k], v[k + 4], w.x, w.y, q, twoq);
+struct XAddr {             // per-thread bases into the exchange buffer
+    u64 *a1, *b1, *c2;
+    __device__ __forceinline__ explicit XAddr(u64 *buf) {
+        const int tid = threadIdx.x, hi = tid >> 3, low = tid & 7;
+        a1 = buf + tid;                    // map 1, layout A: + k*136
+        b1 = buf + hi * 136 + low;         // map 1, layout B: + k*8 ;  map 2, layout B: + k*8 + (k>>1)
+        c2 = buf + tid * 17;               // map 2, layout C: + k
     }
-    if (NS >= 2) {  // distance 2^(e+1)
-#pragma unroll
-        for (int g = 0; g < 2; g++) {
-            ulonglong2 w = tw.get(e + 1, 2 * hi + g);
-            bf_fwd(v[4 * g + 0], v[4 * g + 2], w.x, w.y, q, twoq);
-            bf_fwd(v[4 * g + 1], v[4 * g + 3], w.x, w.y, q, twoq);
-        }
+};
+#define MKHE_STAGE(BF, TWEXPR, NB)                                                                     \
+    _Pragma("unroll") for (int i = 0; i < 8; i++) {                                                    \
+        const int g = i >> b, j = i & ((1 << b) - 1);                                                  \
+        const ulonglong2 w = TWEXPR;                                                                   \
+        BF(v[(g << (b + 1)) + j], v[(g << (b + 1)) + (1 << b) + j], w.x, w.y, c);                      \
     }
-    if (NS >= 3) {  // distance 2^e
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            ulonglong2 w = tw.get(e, 4 * hi + g);
-            bf_fwd(v[2 * g], v[2 * g + 1], w.x, w.y, q, twoq);
-        }
-    }
-}
-// inverse: stages in the opposite order (lowest distance first).  If LAST, the top stage (distance
-// 2^(e+2), which must be the final stage of the whole transform) also multiplies by N^-1.
-template <int NS, bool LAST, class TW>
-__device__ __forceinline__ void round_inv(u64 v[8], int e, int hi, const TW &tw, const ModC &m) {
-    const u64 q = m.q, twoq = 2 * m.q;
-    if (NS >= 3) {
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            ulonglong2 w = tw.get(e, 4 * hi + g);
-            bf_inv(v[2 * g], v[2 * g + 1], w.x, w.y, q, twoq);
-        }
-    }
-    if (NS >= 2) {
-#pragma unroll
-        for (int g = 0; g < 2; g++) {
-            ulonglong2 w = tw.get(e + 1, 2 * hi + g);
-            bf_inv(v[4 * g + 0], v[4 * g + 2], w.x, w.y, q, twoq);
-            bf_inv(v[4 * g + 1], v[4 * g + 3], w.x, w.y, q, twoq);
-        }
-    }
-    if (!LAST) {
-        ulonglong2 w = tw.get(e + 2, hi);
-#pragma unroll
-        for (int k = 0; k < 4; k++) bf_inv(v[k], v[k + 4], w.x, w.y, q, twoq);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            u64 s = v[k] + v[k + 4];
-            u64 t = v[k] - v[k + 4] + twoq;
-            v[k] = csub(shoup_lazy(s, m.ninv, m.ninv_sh, q), q);
-            v[k + 4] = csub(shoup_lazy(t, m.w1ninv, m.w1ninv_sh, q), q);
-        }
-    }
-}
 
-// move the tile from the window-e_from distribution to the window-e_to distribution through smem
-__device__ __forceinline__ void exchange(u64 v[8], u64 *sm, int e_from, int e_to) {
-    const int tid = threadIdx.x;
-    {
-        int low = tid & ((1 << e_from) - 1), hi = tid >> e_from;
-        int base = (hi << (e_from + 3)) | low;
+// the caller guarantees (block barrier) that nobody still reads the buffer when tile_fwd / tile_inv starts
+template <bool BIG, class TW, bool WAIT_ASYNC = false>
+__device__ __forceinline__ void tile_fwd(u64 v[16], const XAddr &x, const TW &tw, const NttC &c) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) sm[swz(base | (k << e_from))] = v[k];
-    }
+    for (int b = 3; b >= 0; b--) { MKHE_STAGE(bf_fwd<BIG>, tw.A(b, g), 0) }
+#pragma unroll
+    for (int k = 0; k < 16; k++) x.a1[k * 136] = v[k];
+    if (WAIT_ASYNC) cp_async_wait_all();      // the staged twiddles of rounds B and C (no-op after the first instance)
     __syncthreads();
-    {
-        int low = tid & ((1 << e_to) - 1), hi = tid >> e_to;
-        int base = (hi << (e_to + 3)) | low;
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = sm[swz(base | (k << e_to))];
-    }
+    for (int k = 0; k < 16; k++) v[k] = x.b1[k * 8];
+#pragma unroll
+    for (int b = 3; b >= 0; b--) { MKHE_STAGE(bf_fwd<BIG>, tw.B(b, g), 0) }
+    MKHE_SYNCWARP();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x.b1[k * 8 + (k >> 1)] = v[k];
+    MKHE_SYNCWARP();
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = x.c2[k];
+#pragma unroll
+    for (int b = 2; b >= 0; b--) { MKHE_STAGE(bf_fwd<BIG>, tw.C(b, g), 0) }
+}
+// inverse: layout C in, layout A out; values stay in [0,4q)
+template <class TW>
+__device__ __forceinline__ void tile_inv(u64 v[16], const XAddr &x, const TW &tw, const NttC &c) {
+#pragma unroll
+    for (int b = 0; b <= 2; b++) { MKHE_STAGE(bf_inv, tw.C(b, g), 0) }
+#pragma unroll
+    for (int k = 0; k < 16; k++) x.c2[k] = v[k];
+    MKHE_SYNCWARP();
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = x.b1[k * 8 + (k >> 1)];
+#pragma unroll
+    for (int b = 0; b <= 3; b++) { MKHE_STAGE(bf_inv, tw.B(b, g), 0) }
+    MKHE_SYNCWARP();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x.b1[k * 8] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = x.a1[k * 136];
+#pragma unroll
+    for (int b = 0; b <= 3; b++) { MKHE_STAGE(bf_inv, tw.A(b, g), 0) }
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass-1 / pass-B tile <-> global index:  local idx = (row << WB) | col,  WB = 11 - S1
+// column stages in registers: a thread owns column `col`, element k at position k*2048 + col,
+// E = 2^S1 elements.  Stage s (1..S1) pairs k and k + E/2^s with twiddle index 2^(s-1) + (k >> (S1-s+1)),
+// the same for every column (warp-uniform loads).
 // ------------------------------------------------------------------------------------------------
-template <int S1>
-__device__ __forceinline__ long col_tile_offset(int idx, int tile) {
-    constexpr int WB = 11 - S1;
-    int row = idx >> WB, col = idx & ((1 << WB) - 1);
-    return (long)row * 512 + ((long)tile << WB) + col;
-}
-
-// forward column stages on registers (+ smem exchanges).  On entry v is in the window-8 distribution,
-// on exit in the window-(11-S1) distribution.
-template <int S1>
-__device__ __forceinline__ void cols_fwd(u64 v[8], u64 *sm, const TwGlobal &tw, u64 q) {
-    constexpr int R = S1 % 3;
-    const int tid = threadIdx.x;
-    const u64 twoq = 2 * q;
-    int e = 8;
-    if (R == 1) round_fwd<1>(v, 8, tid >> 8, tw, q, twoq);
-    else if (R == 2) round_fwd<2>(v, 8, tid >> 8, tw, q, twoq);
-    else round_fwd<3>(v, 8, tid >> 8, tw, q, twoq);
-    int done = (R == 0) ? 3 : R;
+template <int S1, bool BIG>
+__device__ __forceinline__ void cols_fwd(u64 *v, const ulonglong2 *tw, const NttC &c) {
 #pragma unroll
-    for (; done < S1; done += 3) {
-        int en = 11 - done - 3;
-        exchange(v, sm, e, en);
-        e = en;
-        round_fwd<3>(v, e, tid >> e, tw, q, twoq);
-        if (done + 3 < S1) __syncthreads();
+    for (int b = S1 - 1; b >= 0; b--) {
+#pragma unroll
+        for (int i = 0; i < (1 << (S1 - 1)); i++) {
+            const int g = i >> b, j = i & ((1 << b) - 1);
+            const ulonglong2 w = __ldg(tw + (1 << (S1 - 1 - b)) + g);
+            bf_fwd<BIG>(v[(g << (b + 1)) + j], v[(g << (b + 1)) + (1 << b) + j], w.x, w.y, c);
+        }
     }
 }
-// inverse column stages: entry distribution window-(11-S1), exit window-8; final stage applies N^-1
-// and produces canonical values.
+// inverse column stages: inputs in [0,4q); the last stage (twiddle index 1) also multiplies by N^-1
+// and returns canonical values.
 template <int S1>
-__device__ __forceinline__ void cols_inv(u64 v[8], u64 *sm, const TwGlobal &tw, const ModC &m) {
-    constexpr int R = S1 % 3;
-    constexpr int FULL = S1 / 3;               // number of full rounds
-    const int tid = threadIdx.x;
-    int e = 11 - S1;
-    if (R == 0) {
+__device__ __forceinline__ void cols_inv(u64 *v, const ulonglong2 *tw, const NttC &c, const ModC &m) {
 #pragma unroll
-        for (int r = 0; r < FULL; r++) {
-            if (r == FULL - 1) round_inv<3, true>(v, e, tid >> e, tw, m);
-            else {
-                round_inv<3, false>(v, e, tid >> e, tw, m);
-                exchange(v, sm, e, e + 3);
-                __syncthreads();
-                e += 3;
-            }
-        }
-    } else {
+    for (int b = 0; b < S1 - 1; b++) {
 #pragma unroll
-        for (int r = 0; r < FULL; r++) {
-            round_inv<3, false>(v, e, tid >> e, tw, m);
-            int en = (r == FULL - 1) ? 8 : e + 3;
-            exchange(v, sm, e, en);
-            __syncthreads();
-            e = en;
+        for (int i = 0; i < (1 << (S1 - 1)); i++) {
+            const int g = i >> b, j = i & ((1 << b) - 1);
+            const ulonglong2 w = __ldg(tw + (1 << (S1 - 1 - b)) + g);
+            bf_inv(v[(g << (b + 1)) + j], v[(g << (b + 1)) + (1 << b) + j], w.x, w.y, c);
         }
-        if (R == 1) round_inv<1, true>(v, 8, tid >> 8, tw, m);
-        else round_inv<2, true>(v, 8, tid >> 8, tw, m);
+    }
+    constexpr int H = 1 << (S1 - 1);
+#pragma unroll
+    for (int j = 0; j < H; j++) {
+        const u64 s = v[j] + v[j + H];                         // < 8q
+        const u64 d = v[j] - v[j + H] + c.fourq;               // < 8q
+        v[j] = csub(shoup_lazy(s, m.ninv, m.ninv_sh, m.q), m.q);
+        v[j + H] = csub(shoup_lazy(d, m.w1ninv, m.w1ninv_sh, m.q), m.q);
     }
 }
 
@@ -204,8 +188,9 @@ __device__ __forceinline__ void cols_inv(u64 v[8], u64 *sm, const TwGlobal &tw, 
 // K1'  decompose + ModUp (alpha = 1: digit broadcast) + first S1 NTT stages
 //   replaces Decomposer.DecomposeAndSplit copy branch + the head of ringQ/ringP.NTTLvl
 //   (mkrlwe/basis_extension.go:443-451, mkrlwe/keyswitch.go:21-31).
-//   grid = (N/2048 column tiles, ndigits, npolys).  The digit limb is read ONCE and reduced into
-//   every target limb slot (Barrett, then NTT stages), so HBM sees 1 read and D writes per digit.
+//   grid = (2048/128 column groups * slot groups, ndigits, npolys).  The digit limb (values < 2^60) is read
+//   once per slot group and fed UNREDUCED into every target limb: the first butterfly's Shoup product reduces
+//   the multiplied arm, the lazy ranges of bf_fwd absorb the other one, so no Barrett step is needed.
 // ------------------------------------------------------------------------------------------------
 struct BcastArgs {
     PtrList in;            // per poly: coefficient-domain poly
@@ -213,35 +198,42 @@ struct BcastArgs {
     int in_limb0;          // first source limb (BFV's second half uses nQ)
     int dmax;              // limb slots per digit in the output
     int nslots;
+    int slot_groups;       // the slot list is split over blockIdx.x / 16
     int slots[MKHE_MAX_SLOTS];   // modulus index == limb slot of each target limb
     int logN;
 };
 
 template <int S1>
-__global__ void __launch_bounds__(MKHE_THREADS) k_bcast_ntt_pass1(BcastArgs a, const ModC *mods, const ulonglong2 *twf) {
-    MKHE_SMEM(smraw);
-    u64 *sm = reinterpret_cast<u64 *>(smraw);
-    const int tid = threadIdx.x, tile = blockIdx.x, digit = blockIdx.y, poly = blockIdx.z;
+__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_bcast_ntt_pass1(BcastArgs a, const ModC *mods, const ulonglong2 *twf) {
+    constexpr int E = 1 << S1;
+    const int col = (blockIdx.x & 15) * MKHE_NTT_THREADS + threadIdx.x, sg = blockIdx.x >> 4;
+    const int digit = blockIdx.y, poly = blockIdx.z;
     const long N = 1L << a.logN;
-    const u64 *src = a.in.p[poly] + (long)(a.in_limb0 + digit) * N;
-    u64 *dst0 = a.out.p[poly] + (long)digit * a.dmax * N;
-    u64 raw[8];
+    const u64 *src = a.in.p[poly] + (long)(a.in_limb0 + digit) * N + col;
+    u64 *dst0 = a.out.p[poly] + (long)digit * a.dmax * N + col;
+    u64 raw[E];
 #pragma unroll
-    for (int k = 0; k < 8; k++) raw[k] = src[col_tile_offset<S1>((k << 8) | tid, tile)];
-    constexpr int EL = 11 - S1;
-    const int low = tid & ((1 << EL) - 1), hi = tid >> EL;
-    for (int s = 0; s < a.nslots; s++) {
+    for (int k = 0; k < E; k++) raw[k] = src[(long)k * MKHE_TILE];
+    const int per = (a.nslots + a.slot_groups - 1) / a.slot_groups;
+    const int s_end = (sg + 1) * per < a.nslots ? (sg + 1) * per : a.nslots;
+    for (int s = sg * per; s < s_end; s++) {
         const int mi = a.slots[s];
         const ModC m = mods[mi];
-        TwGlobal tw{twf + (long)mi * N, 0, 0};
-        u64 v[8];
+        const NttC c = nttc(m);
+        const ulonglong2 *tw = twf + (long)mi * N;
+        u64 v[E];
+        if (m.big) {       // [0,8q) is required: digits of another limb may exceed it only for lazy 60-bit limbs; reduce to be safe
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = barrett_lazy(raw[k], m.q, m.mu);
-        cols_fwd<S1>(v, sm, tw, m.q);
+            for (int k = 0; k < E; k++) v[k] = barrett_lazy(raw[k], m.q, m.mu);
+            cols_fwd<S1, true>(v, tw, c);
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; k++) v[k] = raw[k];
+            cols_fwd<S1, false>(v, tw, c);
+        }
         u64 *dst = dst0 + (long)mi * N;
 #pragma unroll
-        for (int k = 0; k < 8; k++) dst[col_tile_offset<S1>((hi << (EL + 3)) | (k << EL) | low, tile)] = v[k];
-        if (S1 > 3) __syncthreads();
+        for (int k = 0; k < E; k++) dst[(long)k * MKHE_TILE] = v[k];
     }
 }
 
@@ -256,38 +248,38 @@ struct LimbArgs {
     int logN;
 };
 
-// K1 pass 1 (plain): grid = (tiles, nlimbs, npolys).  Inputs < 4q (canonical, "q" from rotations, or
+// K1 pass 1 (plain): grid = (16, nlimbs, npolys).  Inputs below 2^60 (canonical, "q" from rotations,
 // BFV's lazy multSum limbs) are consumed as they are.
 template <int S1>
-__global__ void __launch_bounds__(MKHE_THREADS) k_ntt_pass1(LimbArgs a, const ModC *mods, const ulonglong2 *twf) {
-    MKHE_SMEM(smraw);
-    u64 *sm = reinterpret_cast<u64 *>(smraw);
-    const int tid = threadIdx.x, tile = blockIdx.x, limb = blockIdx.y, poly = blockIdx.z;
+__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_ntt_pass1(LimbArgs a, const ModC *mods, const ulonglong2 *twf) {
+    constexpr int E = 1 << S1;
+    const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x, limb = blockIdx.y, poly = blockIdx.z;
     const long N = 1L << a.logN;
     const int mi = a.mod_of_limb[limb];
     const ModC m = mods[mi];
-    const u64 *src = a.in.p[poly] + (long)a.slot_of[limb] * N;
-    u64 *dst = a.out.p[poly] + (long)a.slot_of[limb] * N;
-    TwGlobal tw{twf + (long)mi * N, 0, 0};
-    u64 v[8];
+    const NttC c = nttc(m);
+    const u64 *src = a.in.p[poly] + (long)a.slot_of[limb] * N + col;
+    u64 *dst = a.out.p[poly] + (long)a.slot_of[limb] * N + col;
+    u64 v[E];
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = src[col_tile_offset<S1>((k << 8) | tid, tile)];
-    cols_fwd<S1>(v, sm, tw, m.q);
-    constexpr int EL = 11 - S1;
-    const int low = tid & ((1 << EL) - 1), hi = tid >> EL;
+    for (int k = 0; k < E; k++) v[k] = src[(long)k * MKHE_TILE];
+    if (m.big) cols_fwd<S1, true>(v, twf + (long)mi * N, c);
+    else cols_fwd<S1, false>(v, twf + (long)mi * N, c);
 #pragma unroll
-    for (int k = 0; k < 8; k++) dst[col_tile_offset<S1>((hi << (EL + 3)) | (k << EL) | low, tile)] = v[k];
+    for (int k = 0; k < E; k++) dst[(long)k * MKHE_TILE] = v[k];
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1 pass 2: last 9 stages on contiguous tiles, canonical output.
-//   grid = (tiles, nlimbs(slots), npolys); the CTA loops over `count` instances that share the limb
-//   (the digits of a hoisted form) so the tile's 2044 twiddles are staged in shared memory once.
+// K1 pass 2: last 11 stages on contiguous tiles, canonical output.
+//   grid = (tiles * chunks, nslots, npolys); a CTA handles the instances [chunk*per, ...) out of `count`
+//   instances that share the limb (the digits of a hoisted form), so the tile's 2047 twiddles are
+//   staged in shared memory once per CTA.  The next instance's elements are prefetched into registers while
+//   the current one is transformed.
 //   data pointer of instance i = base[poly] + i*inst_stride + slot*N + tile*2048   (in place)
 // ------------------------------------------------------------------------------------------------
 struct Pass2Args {
     PtrList buf;
-    int count;
+    int count, chunks;
     long inst_stride;
     int nslots;
     int slots[MKHE_MAX_SLOTS];       // limb slot (offset slot*N)
@@ -295,63 +287,60 @@ struct Pass2Args {
     int logN;
 };
 
-__device__ __forceinline__ void contig_fwd(u64 v[8], u64 *sm, const TwShared &tw, u64 q) {
+template <bool BIG>
+__device__ __forceinline__ void pass2_body(u64 *base, long inst_stride, int i0, int i1, const XAddr &x, const TwShared &tw,
+                                           const ModC &m) {
     const int tid = threadIdx.x;
-    const u64 twoq = 2 * q;
-    round_fwd<3>(v, 6, tid >> 6, tw, q, twoq);
-    exchange(v, sm, 6, 3);
-    round_fwd<3>(v, 3, tid >> 3, tw, q, twoq);
-    __syncthreads();
-    exchange(v, sm, 3, 0);
-    round_fwd<3>(v, 0, tid, tw, q, twoq);
+    const NttC c = nttc(m);
+    u64 nxt[16];
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = csub(csub(v[k], twoq), q);
-}
-template <class TW>
-__device__ __forceinline__ void contig_inv(u64 v[8], u64 *sm, const TW &tw, const ModC &m) {
-    const int tid = threadIdx.x;
-    round_inv<3, false>(v, 0, tid, tw, m);
-    exchange(v, sm, 0, 3);
-    round_inv<3, false>(v, 3, tid >> 3, tw, m);
-    __syncthreads();
-    exchange(v, sm, 3, 6);
-    round_inv<3, false>(v, 6, tid >> 6, tw, m);
+    for (int k = 0; k < 16; k++) nxt[k] = base[(long)i0 * inst_stride + k * 128 + tid];
+    for (int i = i0; i < i1; i++) {
+        u64 *p = base + (long)i * inst_stride;
+        u64 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = nxt[k];
+        if (i + 1 < i1) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) nxt[k] = p[inst_stride + k * 128 + tid];
+        }
+        if (i > i0) __syncthreads();          // everybody has left the previous instance's exchange buffer
+        tile_fwd<BIG, TwShared, true>(v, x, tw, c);
+        u64 *o = p + tid * 16;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            st_global_v4(o + 4 * k, canon(v[4 * k], m), canon(v[4 * k + 1], m), canon(v[4 * k + 2], m), canon(v[4 * k + 3], m));
+    }
 }
 
-__global__ void __launch_bounds__(MKHE_THREADS) k_ntt_pass2(Pass2Args a, const ModC *mods, const ulonglong2 *twf) {
+__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_ntt_pass2(Pass2Args a, const ModC *mods, const ulonglong2 *twf) {
     MKHE_SMEM(smraw);
-    u64 *sm = reinterpret_cast<u64 *>(smraw);                            // 16 KiB exchange tile
-    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw + MKHE_TILE * 8);   // 32 KiB twiddles
-    const int tid = threadIdx.x, tile = blockIdx.x, poly = blockIdx.z;
-    const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
+    u64 *sm1 = reinterpret_cast<u64 *>(smraw);                                  // 17 KiB exchange buffer
+    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw + MKHE_XBUF * 8);    // 32 KiB twiddles
     const long N = 1L << a.logN;
+    const int ntiles = (int)(N / MKHE_TILE);
+    const int tile = blockIdx.x % ntiles, chunk = blockIdx.x / ntiles, poly = blockIdx.z;
+    const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
     const ModC m = mods[mi];
-    load_tile_twiddles(stw, twf + (long)mi * N, a.logN - 9, tile);
-    __syncthreads();
-    TwShared tw{stw};
+    const int per = (a.count + a.chunks - 1) / a.chunks;
+    const int i0 = chunk * per, i1 = i0 + per < a.count ? i0 + per : a.count;
+    if (i0 >= i1) return;
+    load_tile_twiddles(stw, twf + (long)mi * N, a.logN - 11, tile);     // asynchronous; first needed after round A
+    const TwShared tw(stw, twf + (long)mi * N, a.logN - 11, tile);
+    const XAddr x(sm1);
     u64 *base = a.buf.p[poly] + (long)slot * N + (long)tile * MKHE_TILE;
-    for (int i = 0; i < a.count; i++) {
-        u64 *p = base + (long)i * a.inst_stride;
-        u64 v[8];
-        const int low = tid & 63, hi = tid >> 6;
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = p[(hi << 9) | (k << 6) | low];
-        contig_fwd(v, sm, tw, m.q);
-        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(p + tid * 8);
-#pragma unroll
-        for (int k = 0; k < 4; k++) o[k] = make_ulonglong2(v[2 * k], v[2 * k + 1]);
-        __syncthreads();
-    }
+    if (m.big) pass2_body<true>(base, a.inst_stride, i0, i1, x, tw, m);
+    else pass2_body<false>(base, a.inst_stride, i0, i1, x, tw, m);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2/K3  inverse pass A on contiguous tiles, optionally fed by the key multiply-accumulate
-//   SRC_LOAD: v = in[...]                                     (ringQ.InvNTTLvl head)
+//   SRC_LOAD: v = in[...]  (< 4q)                             (ringQ.InvNTTLvl head)
 //   SRC_MAC : v = sum_t sum_{i<beta} key_t[i] (.) h_t[i]      (MulCoeffsMontgomery[AndAdd]Lvl loops,
 //             mkrlwe/keyswitch_hoisted.go:24-32; nsets = 2 for mkbfv/keyswitch_hoisted.go:20-30)
 //             accumulated in 128 bits, one Montgomery reduction at the end (same canonical value).
-//   grid = (tiles, nslots, nbatch).  Output limb `slot` of out[batch] (coefficient-order positions, still
-//   needing pass B).
+//   grid = (tiles, nslots, nbatch).  Output limb `slot` of out[batch] (coefficient-order positions, values in
+//   [0,4q), still needing pass B).
 // ------------------------------------------------------------------------------------------------
 struct InvAArgs {
     PtrList in;              // SRC_LOAD: per batch input poly
@@ -368,76 +357,77 @@ struct InvAArgs {
 };
 
 template <bool SRC_MAC>
-__global__ void __launch_bounds__(MKHE_THREADS) k_intt_passA(InvAArgs a, const ModC *mods, const ulonglong2 *twi) {
+__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_intt_passA(InvAArgs a, const ModC *mods, const ulonglong2 *twi) {
     MKHE_SMEM(smraw);
-    u64 *sm = reinterpret_cast<u64 *>(smraw);
+    u64 *sm1 = reinterpret_cast<u64 *>(smraw);
     const int tid = threadIdx.x, tile = blockIdx.x, b = blockIdx.z;
     const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y], oslot = a.out_slots[blockIdx.y];
     const long N = 1L << a.logN;
     const ModC m = mods[mi];
-    const long off = (long)slot * N + (long)tile * MKHE_TILE + tid * 8;
-    u64 v[8];
+    const XAddr x(sm1);
+    u64 v[16];
     if (SRC_MAC) {
-        u64 hi[8], lo[8];
+        // the streams are read in layout A (element k*128 + tid: a warp reads 256 contiguous bytes per access), the sums
+        // then move to layout C through the exchange buffer (map 2: idx + (idx >> 4))
+        const long off = (long)slot * N + (long)tile * MKHE_TILE + tid;
+        u64 hi[16], lo[16];
 #pragma unroll
-        for (int k = 0; k < 8; k++) hi[k] = lo[k] = 0;
+        for (int k = 0; k < 16; k++) hi[k] = lo[k] = 0;
         int terms = 0;
         for (int t = 0; t < a.nsets; t++) {
             const u64 *kp = a.key[t].p[b] + off;
             const u64 *hp = a.hst[t].p[b] + off;
             for (int i = 0; i < a.beta; i++) {
-                const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(kp + (long)i * a.digit_stride);
-                const ulonglong2 *h2 = reinterpret_cast<const ulonglong2 *>(hp + (long)i * a.digit_stride);
+                const u64 *k1 = kp + (long)i * a.digit_stride;
+                const u64 *h1 = hp + (long)i * a.digit_stride;
+                u64 kk[16], hh[16];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    ulonglong2 kk = k2[k], hh = h2[k];
-                    mac128(hi[2 * k], lo[2 * k], kk.x, hh.x);
-                    mac128(hi[2 * k + 1], lo[2 * k + 1], kk.y, hh.y);
-                }
+                for (int k = 0; k < 16; k++) { kk[k] = __ldg(k1 + k * 128); hh[k] = __ldg(h1 + k * 128); }
+#pragma unroll
+                for (int k = 0; k < 16; k++) mac128(hi[k], lo[k], kk[k], hh[k]);
                 if ((++terms & 7) == 0) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) hi[k] = csub(barrett_lazy(hi[k], m.q, m.mu), m.q);
+                    for (int k = 0; k < 16; k++) hi[k] = csub(barrett_lazy(hi[k], m.q, m.mu), m.q);
                 }
             }
         }
+        u64 *wr = sm1 + tid + (tid >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 16; k++) {
             u64 h = csub(barrett_lazy(hi[k], m.q, m.mu), m.q);
-            v[k] = mont_reduce(h, lo[k], m.q, m.qinv);
+            wr[k * 136] = mont_reduce(h, lo[k], m.q, m.qinv);         // slot (k*128 + tid) + ((k*128 + tid) >> 4)
         }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = x.c2[k];       // own slots: the next writer of them is this thread (tile_inv)
     } else {
-        const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(a.in.p[b] + off);
+        const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(a.in.p[b] + (long)slot * N + (long)tile * MKHE_TILE + tid * 16);
 #pragma unroll
-        for (int k = 0; k < 4; k++) { ulonglong2 x = p2[k]; v[2 * k] = x.x; v[2 * k + 1] = x.y; }
+        for (int k = 0; k < 8; k++) { ulonglong2 xx = p2[k]; v[2 * k] = xx.x; v[2 * k + 1] = xx.y; }
     }
-    TwGlobal tw{twi + (long)mi * N, a.logN - 9 - 2, tile};
-    contig_inv(v, sm, tw, m);
+    const TwGlobal tw(twi + (long)mi * N, a.logN - 11, tile);
+    tile_inv(v, x, tw, nttc(m));
     u64 *o = a.out.p[b] + (long)oslot * N + (long)tile * MKHE_TILE;
-    const int low = tid & 63, hi6 = tid >> 6;
 #pragma unroll
-    for (int k = 0; k < 8; k++) o[(hi6 << 9) | (k << 6) | low] = v[k];
+    for (int k = 0; k < 16; k++) o[k * 128 + tid] = v[k];
 }
 
-// K2 pass B: remaining S1 inverse stages on columns, N^-1, canonical output (in place capable).
+// K2 pass B: remaining S1 inverse stages on columns, N^-1, canonical output (in place capable).  grid = (16, nlimbs, npolys)
 template <int S1>
-__global__ void __launch_bounds__(MKHE_THREADS) k_intt_passB(LimbArgs a, const ModC *mods, const ulonglong2 *twi) {
-    MKHE_SMEM(smraw);
-    u64 *sm = reinterpret_cast<u64 *>(smraw);
-    const int tid = threadIdx.x, tile = blockIdx.x, limb = blockIdx.y, poly = blockIdx.z;
+__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_intt_passB(LimbArgs a, const ModC *mods, const ulonglong2 *twi) {
+    constexpr int E = 1 << S1;
+    const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x, limb = blockIdx.y, poly = blockIdx.z;
     const long N = 1L << a.logN;
     const int mi = a.mod_of_limb[limb];
     const ModC m = mods[mi];
-    const u64 *src = a.in.p[poly] + (long)a.slot_of[limb] * N;
-    u64 *dst = a.out.p[poly] + (long)a.slot_of[limb] * N;
-    TwGlobal tw{twi + (long)mi * N, 0, 0};
-    constexpr int EL = 11 - S1;
-    const int low = tid & ((1 << EL) - 1), hi = tid >> EL;
-    u64 v[8];
+    const u64 *src = a.in.p[poly] + (long)a.slot_of[limb] * N + col;
+    u64 *dst = a.out.p[poly] + (long)a.slot_of[limb] * N + col;
+    u64 v[E];
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = src[col_tile_offset<S1>((hi << (EL + 3)) | (k << EL) | low, tile)];
-    cols_inv<S1>(v, sm, tw, m);
+    for (int k = 0; k < E; k++) v[k] = src[(long)k * MKHE_TILE];
+    cols_inv<S1>(v, twi + (long)mi * N, nttc(m), m);
 #pragma unroll
-    for (int k = 0; k < 8; k++) dst[col_tile_offset<S1>((k << 8) | tid, tile)] = v[k];
+    for (int k = 0; k < E; k++) dst[(long)k * MKHE_TILE] = v[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -662,14 +652,14 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_bfly_peak(u64 *sink, ModC m, i
 #pragma unroll
     for (int k = 0; k < 8; k++) v[k] = (u64)(threadIdx.x * 8 + k + blockIdx.x) % m.q;
     u64 w = m.ninv, wsh = m.ninv_sh;
-    const u64 q = m.q, twoq = 2 * m.q;
-    for (int it = 0; it < iters; it++) {
+    const NttC c = nttc(m);
+    for (int it = 0; it < iters; it++) {          // throughput probe only: values may wrap, the instruction stream is what counts
 #pragma unroll
-        for (int k = 0; k < 4; k++) bf_fwd(v[k], v[k + 4], w, wsh, q, twoq);
+        for (int k = 0; k < 4; k++) bf_fwd<false>(v[k], v[k + 4], w, wsh, c);
 #pragma unroll
-        for (int g = 0; g < 2; g++) { bf_fwd(v[4 * g], v[4 * g + 2], w, wsh, q, twoq); bf_fwd(v[4 * g + 1], v[4 * g + 3], w, wsh, q, twoq); }
+        for (int g = 0; g < 2; g++) { bf_fwd<false>(v[4 * g], v[4 * g + 2], w, wsh, c); bf_fwd<false>(v[4 * g + 1], v[4 * g + 3], w, wsh, c); }
 #pragma unroll
-        for (int g = 0; g < 4; g++) bf_fwd(v[2 * g], v[2 * g + 1], w, wsh, q, twoq);
+        for (int g = 0; g < 4; g++) bf_fwd<false>(v[2 * g], v[2 * g + 1], w, wsh, c);
     }
     u64 s = 0;
 #pragma unroll

@@ -96,6 +96,12 @@ inline void finish_mod_tables(ModTables &t, int logN, u64 q, const std::vector<u
     t.c.w1ninv = h_mulmod(psiinv[1], ninv, q);
     t.c.w1ninv_sh = h_shoup(t.c.w1ninv, q);
     t.c.qd = (double)q;
+    t.c.nq = 0 - q;
+    t.c.big = q >= ((u64)1 << 57) ? 1u : 0u;
+    int bl = 0;
+    while (bl < 64 && (q >> bl)) bl++;
+    t.c.bshift = (u32)(bl - 2);
+    t.c.mu32 = (u32)((((u128)1) << (bl + 30)) / q);
     t.c.pad = 0;
     t.twf.resize(N);
     t.twi.resize(N);
