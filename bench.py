@@ -70,25 +70,27 @@ def algorithmic_model(k, ell, nP, N):
     bfly_limb = (N // 2) * logN
     fwd, inv = 3 * k * beta * D + (2 * k + 2) * ell, (k + 1) * ell + 4 * k * D
     kern = {
-        "k_bcast_ntt_pass1_": (3 * k * ell + 3 * k * beta * D) * limb,
+        "k_bcast_ntt_pass1": (3 * k * ell + 3 * k * beta * D) * limb,
         "k_ntt_pass2": 2 * (3 * k * beta * D + (2 * k + 2) * ell) * limb,
-        "k_ntt_pass1_": 2 * (2 * k + 2) * ell * limb,
+        "k_ntt_pass1": 2 * (2 * k + 2) * ell * limb,
         "k_mac_parties": (4 * k * beta * D + 2 * beta * D) * limb,
-        "k_intt_passA<true>": (5 * k * beta * D + 3 * beta * D + 4 * k * D) * limb,
-        "k_intt_passA<false>": 2 * (k + 1) * ell * limb,
-        "k_intt_passB_": 2 * ((k + 1) * ell + 4 * k * D) * limb,
-        "k_conv<CONV_MODDOWN>": 4 * k * (D + 2 * ell) * limb,
+        "k_mac_digits": (4 * k * beta * D + 3 * beta * D + 4 * k * D) * limb,
+        "k_intt_passA": 2 * ((k + 1) * ell + 4 * k * D) * limb,
+        "k_intt_passB": 2 * (k + 1) * ell * limb,
+        "k_moddown_P": 4 * k * (2 * nP + 1) * limb,
+        "k_moddown_Q": (4 * k * (ell + nP + 1) + (2 * k + 1) * ell + (3 * k + 1) * ell) * limb,
         "k_tensor": (3 * k + 3) * ell * limb,
         "k_rescale": (k + 1) * (2 * ell - 1) * limb,
     }
-    s1 = logN - 9
+    s1 = logN - 11                 # column stages (pass 1 / pass B); the tile passes do the other 11
     bfly = {
-        "k_bcast_ntt_pass1_": 3 * k * beta * D * (N // 2) * s1,
-        "k_ntt_pass2": (3 * k * beta * D + (2 * k + 2) * ell) * (N // 2) * 9,
-        "k_ntt_pass1_": (2 * k + 2) * ell * (N // 2) * s1,
-        "k_intt_passA<true>": 4 * k * D * (N // 2) * 9,
-        "k_intt_passA<false>": (k + 1) * ell * (N // 2) * 9,
-        "k_intt_passB_": ((k + 1) * ell + 4 * k * D) * (N // 2) * s1,
+        "k_bcast_ntt_pass1": 3 * k * beta * D * (N // 2) * s1,
+        "k_ntt_pass2": (3 * k * beta * D + (2 * k + 2) * ell) * (N // 2) * 11,
+        "k_ntt_pass1": (2 * k + 2) * ell * (N // 2) * s1,
+        "k_intt_passA": ((k + 1) * ell + 4 * k * D) * (N // 2) * 11,
+        "k_intt_passB": (k + 1) * ell * (N // 2) * s1,
+        "k_moddown_P": 4 * k * nP * (N // 2) * s1,
+        "k_moddown_Q": 4 * k * ell * (N // 2) * s1,
     }
     return {"compulsory_bytes": b_mul, "butterflies": (fwd + inv) * bfly_limb, "kernel_bytes": kern, "kernel_butterflies": bfly}
 
@@ -392,7 +394,12 @@ def main():
     bfly_peak = wl.ctx.butterfly_peak()
     total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
     kernels = {}
-    for name, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+    merged = {}
+    for name, (cnt, tms) in prof.items():          # "k_mac_digits<4>", "k_moddown_Q_" ... -> one entry per kernel
+        base = name.split("<")[0].rstrip("_")
+        c0, t0 = merged.get(base, (0, 0.0))
+        merged[base] = (c0 + cnt, t0 + tms)
+    for name, (cnt, tms) in sorted(merged.items(), key=lambda kv: -kv[1][1]):
         e = {"launches_per_step": cnt / psteps, "ms_per_step": tms / psteps, "share": tms / total_prof_ms}
         if name in model["kernel_bytes"]:
             e["hbm_gbs"] = model["kernel_bytes"][name] / (tms / psteps * 1e-3) / 1e9

@@ -287,9 +287,9 @@ int ntt_inv(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
         memset(&a, 0, sizeof a);
         a.nslots = s.n;
         a.logN = ctx->logN;
-        for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; a.out_slots[i] = s.slot[i]; }
+        for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; }
         for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
-        LAUNCH(k_intt_passA<false>, dim3(tiles, s.n, np), dim3(MKHE_NTT_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+        LAUNCH(k_intt_passA, dim3(tiles, s.n, np), dim3(MKHE_NTT_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
     }
     return intt_passB(ctx, s, npolys, out, out);
 }
@@ -327,61 +327,152 @@ int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *c
     return MKHE_OK;
 }
 
-// batch of external products: for b < nb:  r_b = ModDown(INTT(sum_t sum_i key_t[b][i] (.) hst_t[b][i]))
-//   dst[b] (Q poly) = r_b, or dst[b] = acc[b] + r_b when acc != nullptr.  Batches whose dst aliases
-//   another batch's dst must be issued through `serial` (accumulation into a shared target).
-int ext_products(mkhe_ctx *ctx, int levelQ, int nb, int nsets, u64 *const *key0, u64 *const *hst0, u64 *const *key1,
-                 u64 *const *hst1, u64 *const *dst, u64 *const *acc, bool serial_conv) {
+// One external product of a batch:  dst (+)= ModDown(INTT(sum_{set} sum_i key[set][i] (.) hst[set][i]))
+//   (ExternalProductHoisted, mkrlwe/keyswitch_hoisted.go:10-40).  Products that name the same dst are summed
+//   into it (exact modular adds, any order); `add` = start from dst's current contents (ringQ.AddLvl) instead of zero.
+struct Prod {
+    u64 *key[2], *hst[2];
+    u64 *dst;
+    bool add;
+};
+
+int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &prods) {
+    const int nb = (int)prods.size();
     if (nb == 0) return MKHE_OK;
     const int tiles = ctx->N / MKHE_TILE;
-    Slots s = qp_slots(ctx, levelQ);
-    u64 *accqp;
-    const size_t qp = (size_t)ctx->dmax * ctx->N;
-    for (int b0 = 0; b0 < nb; b0 += MKHE_MAX_PARTIES_K) {
-        int n = std::min(MKHE_MAX_PARTIES_K, nb - b0);
-        TRY(get_scratch(ctx, "accqp", qp * 8 * (size_t)std::min(nb, MKHE_MAX_PARTIES_K), &accqp));
-        InvAArgs a;
-        memset(&a, 0, sizeof a);
-        a.nsets = nsets;
-        a.beta = levelQ + 1;
-        a.digit_stride = (long)ctx->dmax * ctx->N;
-        a.nslots = s.n;
-        a.logN = ctx->logN;
-        for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; a.out_slots[i] = s.slot[i]; }
-        std::vector<u64 *> bufs(n);
+    const Slots s = qp_slots(ctx, levelQ);
+    const int vslot = ctx->dmax;                              // spare limb of every accumulator: the overflow estimate v
+    const size_t qp = (size_t)(ctx->dmax + 1) * ctx->N;
+    for (int b0 = 0; b0 < nb; b0 += MKHE_MD_PRODUCTS) {
+        const int n = std::min(MKHE_MD_PRODUCTS, nb - b0);
+        // targets of this chunk; a target must not straddle chunks (its products are summed by one CTA)
+        std::vector<u64 *> tg;
+        std::vector<std::vector<int>> members;
         for (int i = 0; i < n; i++) {
-            a.key[0].p[i] = key0[b0 + i];
-            a.hst[0].p[i] = hst0[b0 + i];
-            if (nsets > 1) { a.key[1].p[i] = key1[b0 + i]; a.hst[1].p[i] = hst1[b0 + i]; }
-            bufs[i] = accqp + (size_t)i * qp;
-            a.out.p[i] = bufs[i];
+            size_t t = std::find(tg.begin(), tg.end(), prods[b0 + i].dst) - tg.begin();
+            if (t == tg.size()) { tg.push_back(prods[b0 + i].dst); members.emplace_back(); }
+            members[t].push_back(i);
         }
-        LAUNCH(k_intt_passA<true>, dim3(tiles, s.n, n), dim3(MKHE_NTT_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
-        TRY(intt_passB(ctx, s, n, bufs.data(), bufs.data()));
-        ConvArgs c;
-        memset(&c, 0, sizeof c);
-        c.src_limb0 = ctx->nQ;
-        c.x_limb0 = 0;
-        c.dst_limb0 = 0;
-        c.n2_used = levelQ + 1;
-        c.has_acc = acc != nullptr;
-        c.logN = ctx->logN;
-        const int cb = (ctx->N + MKHE_THREADS - 1) / MKHE_THREADS;
-        if (!serial_conv) {
-            for (int i = 0; i < n; i++) {
-                c.src.p[i] = bufs[i]; c.x.p[i] = bufs[i]; c.dst.p[i] = dst[b0 + i];
-                c.acc.p[i] = acc ? acc[b0 + i] : nullptr;
+        {   // targets with the most products first: their CTAs run longest
+            std::vector<size_t> ord(tg.size());
+            for (size_t t = 0; t < ord.size(); t++) ord[t] = t;
+            std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return members[a].size() > members[b].size(); });
+            std::vector<u64 *> tg2;
+            std::vector<std::vector<int>> mem2;
+            for (size_t t : ord) { tg2.push_back(tg[t]); mem2.push_back(members[t]); }
+            tg.swap(tg2);
+            members.swap(mem2);
+        }
+        for (int i = b0 + n; i < nb; i++)
+            if (std::find(tg.begin(), tg.end(), prods[i].dst) != tg.end())
+                return fail(ctx, MKHE_ERR_UNSUPPORTED, "more than %d products in one batch with a shared target", MKHE_MD_PRODUCTS);
+        u64 *accqp;
+        TRY(get_scratch(ctx, "accqp", qp * 8 * (size_t)std::min(nb, MKHE_MD_PRODUCTS), &accqp));
+        std::vector<u64 *> bufs(n);
+        for (int i = 0; i < n; i++) bufs[i] = accqp + (size_t)i * qp;
+
+        // ---- multiply-accumulate over the digits; neighbours sharing one operand form a group
+        int i = 0;
+        while (i < n) {
+            for (int G = MKHE_MAC_G; G >= 1; G--) {
+                MacDigitsArgs a;
+                memset(&a, 0, sizeof a);
+                a.nsets = nsets;
+                a.beta = levelQ + 1;
+                a.digit_stride = (long)ctx->dmax * ctx->N;
+                a.nslots = s.n;
+                a.logN = ctx->logN;
+                for (int k = 0; k < s.n; k++) { a.slots[k] = s.slot[k]; a.mods[k] = s.mod[k]; }
+                int ng = 0, j = i;
+                while (j + G <= n && ng < MKHE_MAC_GROUPS) {
+                    const Prod &p0 = prods[b0 + j];
+                    bool sk = true, sh = true;
+                    for (int g = 1; g < G; g++)
+                        for (int t = 0; t < nsets; t++) {
+                            sk = sk && prods[b0 + j + g].key[t] == p0.key[t];
+                            sh = sh && prods[b0 + j + g].hst[t] == p0.hst[t];
+                        }
+                    if (!sk && !sh) break;
+                    for (int t = 0; t < nsets; t++) {
+                        a.shared[t][ng] = sk ? p0.key[t] : p0.hst[t];
+                        for (int g = 0; g < G; g++) a.priv[t][ng * MKHE_MAC_G + g] = sk ? prods[b0 + j + g].hst[t] : prods[b0 + j + g].key[t];
+                    }
+                    for (int g = 0; g < G; g++) a.out[ng * MKHE_MAC_G + g] = bufs[j + g];
+                    ng++;
+                    j += G;
+                }
+                if (ng == 0) continue;
+                const dim3 grid(ctx->N / (2 * MKHE_THREADS), s.n, ng);
+                switch (G) {
+                    case 4: LAUNCH(k_mac_digits<4>, grid, dim3(MKHE_THREADS), 0, a, ctx->d_mods); break;
+                    case 3: LAUNCH(k_mac_digits<3>, grid, dim3(MKHE_THREADS), 0, a, ctx->d_mods); break;
+                    case 2: LAUNCH(k_mac_digits<2>, grid, dim3(MKHE_THREADS), 0, a, ctx->d_mods); break;
+                    default: LAUNCH(k_mac_digits<1>, grid, dim3(MKHE_THREADS), 0, a, ctx->d_mods); break;
+                }
+                i = j;
+                break;
             }
-            LAUNCH(k_conv<CONV_MODDOWN>, dim3(cb, n), dim3(MKHE_THREADS), 0, c, ctx->d_conv_PtoQ, ctx->d_mods);
-        } else {
-            for (int i = 0; i < n; i++) {
-                c.src.p[0] = bufs[i]; c.x.p[0] = bufs[i]; c.dst.p[0] = dst[b0 + i];
-                c.acc.p[0] = acc ? acc[b0 + i] : nullptr;
-                LAUNCH(k_conv<CONV_MODDOWN>, dim3(cb, 1), dim3(MKHE_THREADS), 0, c, ctx->d_conv_PtoQ, ctx->d_mods);
+        }
+        // ---- inverse NTT pass A on every QP accumulator
+        for (int k0 = 0; k0 < n; k0 += MKHE_MAX_PARTIES_K) {
+            const int nk = std::min(MKHE_MAX_PARTIES_K, n - k0);
+            InvAArgs a;
+            memset(&a, 0, sizeof a);
+            a.nslots = s.n;
+            a.logN = ctx->logN;
+            for (int k = 0; k < s.n; k++) { a.slots[k] = s.slot[k]; a.mods[k] = s.mod[k]; }
+            for (int k = 0; k < nk; k++) { a.in.p[k] = bufs[k0 + k]; a.out.p[k] = bufs[k0 + k]; }
+            LAUNCH(k_intt_passA, dim3(tiles, s.n, nk), dim3(MKHE_NTT_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+        }
+        // ---- pass B fused with ModDown and the accumulation
+        ModDownPArgs pa;
+        memset(&pa, 0, sizeof pa);
+        pa.np_limbs = ctx->nP;
+        pa.p_slot0 = ctx->nQ;
+        pa.vslot = vslot;
+        pa.logN = ctx->logN;
+        for (int k = 0; k < n; k++) pa.acc[k] = bufs[k];
+        TRY(dispatch_s1(ctx, [&](auto S) -> int {
+            auto k_moddown_P_ = k_moddown_P<decltype(S)::value>;
+            LAUNCH(k_moddown_P_, dim3(COLGROUPS, n), dim3(MKHE_NTT_THREADS), 0, pa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi);
+            return MKHE_OK;
+        }));
+        for (size_t t0 = 0; t0 < tg.size(); t0 += MKHE_MD_TARGETS) {
+            const int ntg = (int)std::min<size_t>(MKHE_MD_TARGETS, tg.size() - t0);
+            ModDownQArgs qa;
+            memset(&qa, 0, sizeof qa);
+            qa.np_limbs = ctx->nP;
+            qa.p_slot0 = ctx->nQ;
+            qa.vslot = vslot;
+            qa.logN = ctx->logN;
+            int cnt = 0;
+            for (int t = 0; t < ntg; t++) {
+                qa.dst[t] = tg[t0 + t];
+                qa.has_acc[t] = prods[b0 + members[t0 + t][0]].add ? 1 : 0;
+                qa.first[t] = cnt;
+                for (int m : members[t0 + t]) qa.acc[cnt++] = bufs[m];
             }
+            qa.first[ntg] = cnt;
+            TRY(dispatch_s1(ctx, [&](auto S) -> int {
+                auto k_moddown_Q_ = k_moddown_Q<decltype(S)::value>;
+                LAUNCH(k_moddown_Q_, dim3(COLGROUPS, levelQ + 1, ntg), dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi);
+                return MKHE_OK;
+            }));
         }
     }
     return MKHE_OK;
+}
+// array form: product b = (key0[b], hst0[b]) [+ (key1[b], hst1[b])] -> dst[b]; acc is nullptr or == dst
+int ext_products(mkhe_ctx *ctx, int levelQ, int nb, int nsets, u64 *const *key0, u64 *const *hst0, u64 *const *key1,
+                 u64 *const *hst1, u64 *const *dst, u64 *const *acc, bool /*shared_target*/) {
+    std::vector<Prod> v(nb);
+    for (int b = 0; b < nb; b++) {
+        v[b].key[0] = key0[b]; v[b].hst[0] = hst0[b];
+        v[b].key[1] = nsets > 1 ? key1[b] : nullptr; v[b].hst[1] = nsets > 1 ? hst1[b] : nullptr;
+        v[b].dst = dst[b];
+        v[b].add = acc != nullptr;
+    }
+    return ext_products(ctx, levelQ, nsets, v);
 }
 
 // x_i = MForm(sum_t MRed(key_t[i], hst_t[i]))   (keyswitch_hoisted.go:79-117)
@@ -534,25 +625,26 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     // the tensor term of c_0 is counted once across ranks
     if (sh.active && ctx->rank != 0) CU(cudaMemsetAsync(out[0], 0, (size_t)(level + 1) * N * 8, ctx->stream));
 
-    // step 5 (:147-154): c_id += x [.] h1_id
+    // step 5 (:147-154): c_id += x [.] h1_id   and the first half of step 6 (:161-166): p_id = y [.] h0_id, one batch
+    const int m0 = (int)o0.size(), m1 = (int)o1.size();
+    std::vector<u64 *> p, hp;
+    TRY(poly_pool(ctx, "relin_p", m0, ctx->nQ, p));
+    TRY(swk_pool(ctx, "relin_hp", m0, hp));
     {
-        const int m = (int)o1.size();
-        std::vector<u64 *> key(m, x), dst(m);
-        for (int t = 0; t < m; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids1[o1[t]])];
-        TRY(ext_products(ctx, level, m, 1, key.data(), h1_o.data(), nullptr, nullptr, dst.data(), dst.data(), false));
+        std::vector<Prod> pr;
+        for (int t = 0; t < m1; t++) pr.push_back(Prod{{x, nullptr}, {h1_o[t], nullptr}, out[1 + find_id(nOut, idsOut, ids1[o1[t]])], true});
+        for (int t = 0; t < m0; t++) pr.push_back(Prod{{y, nullptr}, {h0_o[t], nullptr}, p[t], false});
+        TRY(ext_products(ctx, level, 1, pr));
     }
-    // step 6 (:161-178): p_id = y [.] h0_id ; Decompose(p_id) ; c_0 += v_id [.] p_id ; c_id += u [.] p_id
-    {
-        const int m = (int)o0.size();
-        std::vector<u64 *> key(m, y), p, hp;
-        TRY(poly_pool(ctx, "relin_p", m, ctx->nQ, p));
-        TRY(swk_pool(ctx, "relin_hp", m, hp));
-        TRY(ext_products(ctx, level, m, 1, key.data(), h0_o.data(), nullptr, nullptr, p.data(), nullptr, false));
-        TRY(decompose_impl(ctx, level, m, p.data(), hp.data(), 0));
-        std::vector<u64 *> ukey(m, u), dst(m), c0(m, out[0]);
-        for (int t = 0; t < m; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids0[o0[t]])];
-        TRY(ext_products(ctx, level, m, 1, ukey.data(), hp.data(), nullptr, nullptr, dst.data(), dst.data(), false));
-        TRY(ext_products(ctx, level, m, 1, v_o.data(), hp.data(), nullptr, nullptr, c0.data(), c0.data(), true));
+    // step 6 (:167-178): Decompose(p_id) ; c_id += u [.] p_id ; c_0 += v_id [.] p_id   (the two products of a party share p_id)
+    if (m0 > 0) {
+        TRY(decompose_impl(ctx, level, m0, p.data(), hp.data(), 0));
+        std::vector<Prod> pr;
+        for (int t = 0; t < m0; t++) {
+            pr.push_back(Prod{{u, nullptr}, {hp[t], nullptr}, out[1 + find_id(nOut, idsOut, ids0[o0[t]])], true});
+            pr.push_back(Prod{{v_o[t], nullptr}, {hp[t], nullptr}, out[0], true});
+        }
+        TRY(ext_products(ctx, level, 1, pr));
     }
     if (sh.active) TRY(allreduce_mod(ctx, out[0], (size_t)(level + 1) * N, qs, 1, 0));
     return MKHE_OK;
@@ -605,10 +697,12 @@ int rotate_hoisted_impl(mkhe_ctx *ctx, int level, int rotidx, int n, u64 *const 
     std::vector<u64 *> tmp;
     TRY(poly_pool(ctx, "rot_tmp", n + 1, ctx->nQ, tmp));
     CU(cudaMemcpyAsync(tmp[0], ct_in[0], (size_t)(level + 1) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    std::vector<u64 *> akey(n, a), dst(n), c0(n, tmp[0]);
-    for (int t = 0; t < n; t++) dst[t] = tmp[1 + t];
-    TRY(ext_products(ctx, level, n, 1, akey.data(), hoisted, nullptr, nullptr, dst.data(), nullptr, false));
-    TRY(ext_products(ctx, level, n, 1, rk, hoisted, nullptr, nullptr, c0.data(), c0.data(), true));
+    std::vector<Prod> pr;
+    for (int t = 0; t < n; t++) {         // the two products of a party share its hoisted form
+        pr.push_back(Prod{{a, nullptr}, {hoisted[t], nullptr}, tmp[1 + t], false});
+        pr.push_back(Prod{{rk[t], nullptr}, {hoisted[t], nullptr}, tmp[0], true});
+    }
+    TRY(ext_products(ctx, level, 1, pr));
     return automorph_impl(ctx, level, galois_for_rotation(ctx->logN, rotidx), n + 1, tmp.data(), out);
 }
 
@@ -1092,9 +1186,12 @@ int mkhe_conjugate(mkhe_ctx *ctx, int level, int n, const mkhe_poly *ct_in, cons
     TRY(swk_pool(ctx, "rot_h", n, vh));
     TRY(decompose_impl(ctx, level, n, tmp.data() + 1, vh.data(), 0));
     CU(cudaMemcpyAsync(po[0], tmp[0], (size_t)(level + 1) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    std::vector<u64 *> akey(n, ak->d), c0(n, po[0]);
-    TRY(ext_products(ctx, level, n, 1, vck.data(), vh.data(), nullptr, nullptr, c0.data(), c0.data(), true));
-    return ext_products(ctx, level, n, 1, akey.data(), vh.data(), nullptr, nullptr, po.data() + 1, nullptr, false);
+    std::vector<Prod> pr;
+    for (int t = 0; t < n; t++) {
+        pr.push_back(Prod{{vck[t], nullptr}, {vh[t], nullptr}, po[0], true});
+        pr.push_back(Prod{{ak->d, nullptr}, {vh[t], nullptr}, po[1 + t], false});
+    }
+    return ext_products(ctx, level, 1, pr);
 }
 
 // ---- mkckks.Evaluator -------------------------------------------------------------------------------
@@ -1237,23 +1334,25 @@ int bfv_mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0
         else TRY(mul2(ctx, rs, A0, tn[n0 + 2 + i1], B0, tn[1 + i0], prod[1 + t]));
     }
     TRY(bfv_quantize_impl(ctx, nOut + 1, prod.data(), out));
-    // c_id += (x1,x2) [.] (h1a,h1b)   (:184-191)
+    // c_id += (x1,x2) [.] (h1a,h1b)   (:184-191)   and   p_id = (y1,y2) [.] (h0a,h0b)   (:198-203), one batch
+    std::vector<u64 *> p, hp;
+    TRY(poly_pool(ctx, "relin_p", n0, ctx->nQ, p));
+    TRY(swk_pool(ctx, "relin_hp", n0, hp));
     {
-        std::vector<u64 *> k1(n1, x1), k2(n1, x2), dst(n1);
-        for (int t = 0; t < n1; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids1[t])];
-        TRY(ext_products(ctx, level, n1, 2, k1.data(), h1a, k2.data(), h1b, dst.data(), dst.data(), false));
+        std::vector<Prod> pr;
+        for (int t = 0; t < n1; t++) pr.push_back(Prod{{x1, x2}, {h1a[t], h1b[t]}, out[1 + find_id(nOut, idsOut, ids1[t])], true});
+        for (int t = 0; t < n0; t++) pr.push_back(Prod{{y1, y2}, {h0a[t], h0b[t]}, p[t], false});
+        TRY(ext_products(ctx, level, 2, pr));
     }
-    // p_id = (y1,y2) [.] (h0a,h0b) ; Decompose ; c_0 += v_id [.] p_id ; c_id += u [.] p_id   (:198-216)
-    {
-        std::vector<u64 *> k1(n0, y1), k2(n0, y2), p, hp;
-        TRY(poly_pool(ctx, "relin_p", n0, ctx->nQ, p));
-        TRY(swk_pool(ctx, "relin_hp", n0, hp));
-        TRY(ext_products(ctx, level, n0, 2, k1.data(), h0a, k2.data(), h0b, p.data(), nullptr, false));
+    // Decompose(p_id) ; c_0 += v_id [.] p_id ; c_id += u [.] p_id   (:204-216)
+    if (n0 > 0) {
         TRY(decompose_impl(ctx, level, n0, p.data(), hp.data(), 0));
-        std::vector<u64 *> ukey(n0, u), dst(n0), c0(n0, out[0]);
-        for (int t = 0; t < n0; t++) dst[t] = out[1 + find_id(nOut, idsOut, ids0[t])];
-        TRY(ext_products(ctx, level, n0, 1, ukey.data(), hp.data(), nullptr, nullptr, dst.data(), dst.data(), false));
-        TRY(ext_products(ctx, level, n0, 1, v, hp.data(), nullptr, nullptr, c0.data(), c0.data(), true));
+        std::vector<Prod> pr;
+        for (int t = 0; t < n0; t++) {
+            pr.push_back(Prod{{u, nullptr}, {hp[t], nullptr}, out[1 + find_id(nOut, idsOut, ids0[t])], true});
+            pr.push_back(Prod{{v[t], nullptr}, {hp[t], nullptr}, out[0], true});
+        }
+        TRY(ext_products(ctx, level, 1, pr));
     }
     return MKHE_OK;
 }

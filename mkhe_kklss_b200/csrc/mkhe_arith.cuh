@@ -24,6 +24,7 @@ typedef unsigned int u32;
 #ifdef MKHE_EMU
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) { *reinterpret_cast<ulonglong2 *>(smem) = *reinterpret_cast<const ulonglong2 *>(gmem); }
 __device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ void prefetch_l2(const void *) {}
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 #else
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -31,6 +32,7 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
@@ -131,17 +133,20 @@ struct NttC {
 };
 __device__ __forceinline__ NttC nttc(const ModC &m) { NttC c; c.q = m.q; c.nq = m.nq; c.fourq = 4 * m.q; return c; }
 
-// forward (Cooley-Tukey) butterfly.
-//   BIG  (2^57 <= q < 2^60): X,Y in [0,8q) -> [0,8q), one conditional subtraction of 4q.
-//   !BIG (q < 2^57):         no reduction at all; every stage adds at most 4q to the magnitude, so inputs below 2^60
-//                            stay below 2^60 + 64q < 2^64 through all (<= 16) stages.
-template <bool BIG>
+// forward (Cooley-Tukey) butterfly without any reduction: the Shoup product lands in [0,4q) for ANY 64-bit Y, so a stage
+// adds at most 4q to the magnitude of both outputs.
+//   q < 2^57        : inputs below 2^60 stay below 2^60 + 64q < 2^64 through all (<= 16) stages.
+//   2^57 <= q < 2^60: the callers keep values below 16q <= 2^64 with fwd_sweep() before every second stage.
 __device__ __forceinline__ void bf_fwd(u64 &X, u64 &Y, u64 w, u64 wsh, const NttC &c) {
-    u64 x = X;
-    if (BIG) x = x >= c.fourq ? x - c.fourq : x;
+    const u64 x = X;
     const u64 t = shoup4(Y, w, wsh, c.nq);
     X = x + t;
     Y = x - t + c.fourq;
+}
+// [0,16q) -> [0,8q)
+__device__ __forceinline__ u64 fwd_sweep(u64 x, const NttC &c) {
+    const u64 e = 2 * c.fourq;
+    return x >= e ? x - e : x;
 }
 // inverse (Gentleman-Sande) butterfly: X,Y in [0,4q) -> [0,4q)   (8q < 2^63 for every supported q)
 __device__ __forceinline__ void bf_inv(u64 &X, u64 &Y, u64 w, u64 wsh, const NttC &c) {

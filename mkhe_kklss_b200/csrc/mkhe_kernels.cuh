@@ -60,11 +60,10 @@ __device__ __forceinline__ void load_tile_twiddles(ulonglong2 *s, const ulonglon
     }
 }
 struct TwShared {          // accessor used by the tile rounds; b = the register-index bit of the stage
-    const ulonglong2 *sB, *sC, *tab_;   // round A reads its 15 warp-uniform entries straight from the global table (L1 hits)
-    int S1_, tile_;
-    __device__ __forceinline__ TwShared(const ulonglong2 *base, const ulonglong2 *tab, int S1, int tile)
-        : sB(base + (threadIdx.x >> 3)), sC(base + threadIdx.x), tab_(tab), S1_(S1), tile_(tile) {}
-    __device__ __forceinline__ ulonglong2 A(int b, int g) const { return __ldg(tab_ + ((size_t)1 << (S1_ + 3 - b)) + ((size_t)tile_ << (3 - b)) + g); }
+    const ulonglong2 *sA, *sB, *sC;     // round A: 15 warp-uniform entries (broadcast reads)
+    __device__ __forceinline__ explicit TwShared(const ulonglong2 *base)
+        : sA(base), sB(base + (threadIdx.x >> 3)), sC(base + threadIdx.x) {}
+    __device__ __forceinline__ ulonglong2 A(int b, int g) const { return sA[(1 << (3 - b)) + g]; }
     __device__ __forceinline__ ulonglong2 B(int b, int g) const { return sB[(1 << (7 - b)) + g * 16]; }
     __device__ __forceinline__ ulonglong2 C(int b, int g) const { return sC[(1 << (10 - b)) + g * MKHE_NTT_THREADS]; }
 };
@@ -99,20 +98,28 @@ struct XAddr {             // per-thread bases into the exchange buffer
         const ulonglong2 w = TWEXPR;                                                                   \
         BF(v[(g << (b + 1)) + j], v[(g << (b + 1)) + (1 << b) + j], w.x, w.y, c);                      \
     }
+#define MKHE_SWEEP16()                                                                                 \
+    if (big) { _Pragma("unroll") for (int k = 0; k < 16; k++) v[k] = fwd_sweep(v[k], c); }
 
-// the caller guarantees (block barrier) that nobody still reads the buffer when tile_fwd / tile_inv starts
-template <bool BIG, class TW, bool WAIT_ASYNC = false>
-__device__ __forceinline__ void tile_fwd(u64 v[16], const XAddr &x, const TW &tw, const NttC &c) {
+// the caller guarantees (block barrier) that nobody still reads the buffer when tile_fwd / tile_inv starts.
+// big (2^57 <= q < 2^60, CTA-uniform): inputs below 16q, a sweep to [0,8q) before every second stage keeps them there.
+template <class TW>
+__device__ __forceinline__ void tile_fwd(u64 v[16], const XAddr &x, const TW &tw, const NttC &c, const bool big) {
 #pragma unroll
-    for (int b = 3; b >= 0; b--) { MKHE_STAGE(bf_fwd<BIG>, tw.A(b, g), 0) }
+    for (int b = 3; b >= 0; b--) {
+        if (b & 1) MKHE_SWEEP16()
+        MKHE_STAGE(bf_fwd, tw.A(b, g), 0)
+    }
 #pragma unroll
     for (int k = 0; k < 16; k++) x.a1[k * 136] = v[k];
-    if (WAIT_ASYNC) cp_async_wait_all();      // the staged twiddles of rounds B and C (no-op after the first instance)
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = x.b1[k * 8];
 #pragma unroll
-    for (int b = 3; b >= 0; b--) { MKHE_STAGE(bf_fwd<BIG>, tw.B(b, g), 0) }
+    for (int b = 3; b >= 0; b--) {
+        if (b & 1) MKHE_SWEEP16()
+        MKHE_STAGE(bf_fwd, tw.B(b, g), 0)
+    }
     MKHE_SYNCWARP();
 #pragma unroll
     for (int k = 0; k < 16; k++) x.b1[k * 8 + (k >> 1)] = v[k];
@@ -120,7 +127,10 @@ __device__ __forceinline__ void tile_fwd(u64 v[16], const XAddr &x, const TW &tw
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = x.c2[k];
 #pragma unroll
-    for (int b = 2; b >= 0; b--) { MKHE_STAGE(bf_fwd<BIG>, tw.C(b, g), 0) }
+    for (int b = 2; b >= 0; b--) {
+        if (!(b & 1)) MKHE_SWEEP16()
+        MKHE_STAGE(bf_fwd, tw.C(b, g), 0)
+    }
 }
 // inverse: layout C in, layout A out; values stay in [0,4q)
 template <class TW>
@@ -149,15 +159,22 @@ __device__ __forceinline__ void tile_inv(u64 v[16], const XAddr &x, const TW &tw
 // E = 2^S1 elements.  Stage s (1..S1) pairs k and k + E/2^s with twiddle index 2^(s-1) + (k >> (S1-s+1)),
 // the same for every column (warp-uniform loads).
 // ------------------------------------------------------------------------------------------------
-template <int S1, bool BIG>
-__device__ __forceinline__ void cols_fwd(u64 *v, const ulonglong2 *tw, const NttC &c) {
+// big: inputs below 8q, outputs below 16q (sweep before the 3rd and 5th stage)
+template <int S1>
+__device__ __forceinline__ void cols_fwd(u64 *v, const ulonglong2 *tw, const NttC &c, const bool big) {
 #pragma unroll
     for (int b = S1 - 1; b >= 0; b--) {
+        if (b < S1 - 1 && ((S1 - 1 - b) & 1) == 0) {
+            if (big) {
+#pragma unroll
+                for (int k = 0; k < (1 << S1); k++) v[k] = fwd_sweep(v[k], c);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < (1 << (S1 - 1)); i++) {
             const int g = i >> b, j = i & ((1 << b) - 1);
             const ulonglong2 w = __ldg(tw + (1 << (S1 - 1 - b)) + g);
-            bf_fwd<BIG>(v[(g << (b + 1)) + j], v[(g << (b + 1)) + (1 << b) + j], w.x, w.y, c);
+            bf_fwd(v[(g << (b + 1)) + j], v[(g << (b + 1)) + (1 << b) + j], w.x, w.y, c);
         }
     }
 }
@@ -225,12 +242,11 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_bcast_ntt_pass1(BcastArgs 
         if (m.big) {       // [0,8q) is required: digits of another limb may exceed it only for lazy 60-bit limbs; reduce to be safe
 #pragma unroll
             for (int k = 0; k < E; k++) v[k] = barrett_lazy(raw[k], m.q, m.mu);
-            cols_fwd<S1, true>(v, tw, c);
         } else {
 #pragma unroll
             for (int k = 0; k < E; k++) v[k] = raw[k];
-            cols_fwd<S1, false>(v, tw, c);
         }
+        cols_fwd<S1>(v, tw, c, m.big != 0);
         u64 *dst = dst0 + (long)mi * N;
 #pragma unroll
         for (int k = 0; k < E; k++) dst[(long)k * MKHE_TILE] = v[k];
@@ -263,8 +279,7 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_ntt_pass1(LimbArgs a, cons
     u64 v[E];
 #pragma unroll
     for (int k = 0; k < E; k++) v[k] = src[(long)k * MKHE_TILE];
-    if (m.big) cols_fwd<S1, true>(v, twf + (long)mi * N, c);
-    else cols_fwd<S1, false>(v, twf + (long)mi * N, c);
+    cols_fwd<S1>(v, twf + (long)mi * N, c, m.big != 0);
 #pragma unroll
     for (int k = 0; k < E; k++) dst[(long)k * MKHE_TILE] = v[k];
 }
@@ -287,25 +302,33 @@ struct Pass2Args {
     int logN;
 };
 
-template <bool BIG>
-__device__ __forceinline__ void pass2_body(u64 *base, long inst_stride, int i0, int i1, const XAddr &x, const TwShared &tw,
-                                           const ModC &m) {
-    const int tid = threadIdx.x;
+__global__ void __launch_bounds__(MKHE_NTT_THREADS, 4) k_ntt_pass2(Pass2Args a, const ModC *mods, const ulonglong2 *twf) {
+    MKHE_SMEM(smraw);
+    u64 *sm1 = reinterpret_cast<u64 *>(smraw);                                  // 17 KiB exchange buffer
+    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw + MKHE_XBUF * 8);    // 32 KiB twiddles
+    const long N = 1L << a.logN;
+    const int ntiles = (int)(N / MKHE_TILE);
+    const int tid = threadIdx.x, tile = blockIdx.x % ntiles, chunk = blockIdx.x / ntiles, poly = blockIdx.z;
+    const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
+    const ModC m = mods[mi];
     const NttC c = nttc(m);
-    u64 nxt[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) nxt[k] = base[(long)i0 * inst_stride + k * 128 + tid];
+    const bool big = m.big != 0;
+    const int per = (a.count + a.chunks - 1) / a.chunks;
+    const int i0 = chunk * per, i1 = i0 + per < a.count ? i0 + per : a.count;
+    if (i0 >= i1) return;
+    load_tile_twiddles(stw, twf + (long)mi * N, a.logN - 11, tile);     // asynchronous (LDGSTS)
+    const TwShared tw(stw);
+    const XAddr x(sm1);
+    u64 *base = a.buf.p[poly] + (long)slot * N + (long)tile * MKHE_TILE;
     for (int i = i0; i < i1; i++) {
-        u64 *p = base + (long)i * inst_stride;
+        u64 *p = base + (long)i * a.inst_stride;
         u64 v[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = nxt[k];
-        if (i + 1 < i1) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) nxt[k] = p[inst_stride + k * 128 + tid];
-        }
-        if (i > i0) __syncthreads();          // everybody has left the previous instance's exchange buffer
-        tile_fwd<BIG, TwShared, true>(v, x, tw, c);
+        for (int k = 0; k < 16; k++) v[k] = p[k * 128 + tid];
+        if (i + 1 < i1) prefetch_l2(p + a.inst_stride + tid * 16);      // the next instance's tile: one 128-byte line per thread
+        if (i == i0) cp_async_wait_all();
+        __syncthreads();          // twiddles staged (first instance) / everybody has left the previous instance's exchange buffer
+        tile_fwd(v, x, tw, c, big);
         u64 *o = p + tid * 16;
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -313,101 +336,92 @@ __device__ __forceinline__ void pass2_body(u64 *base, long inst_stride, int i0, 
     }
 }
 
-__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_ntt_pass2(Pass2Args a, const ModC *mods, const ulonglong2 *twf) {
-    MKHE_SMEM(smraw);
-    u64 *sm1 = reinterpret_cast<u64 *>(smraw);                                  // 17 KiB exchange buffer
-    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw + MKHE_XBUF * 8);    // 32 KiB twiddles
-    const long N = 1L << a.logN;
-    const int ntiles = (int)(N / MKHE_TILE);
-    const int tile = blockIdx.x % ntiles, chunk = blockIdx.x / ntiles, poly = blockIdx.z;
-    const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
-    const ModC m = mods[mi];
-    const int per = (a.count + a.chunks - 1) / a.chunks;
-    const int i0 = chunk * per, i1 = i0 + per < a.count ? i0 + per : a.count;
-    if (i0 >= i1) return;
-    load_tile_twiddles(stw, twf + (long)mi * N, a.logN - 11, tile);     // asynchronous; first needed after round A
-    const TwShared tw(stw, twf + (long)mi * N, a.logN - 11, tile);
-    const XAddr x(sm1);
-    u64 *base = a.buf.p[poly] + (long)slot * N + (long)tile * MKHE_TILE;
-    if (m.big) pass2_body<true>(base, a.inst_stride, i0, i1, x, tw, m);
-    else pass2_body<false>(base, a.inst_stride, i0, i1, x, tw, m);
-}
-
 // ------------------------------------------------------------------------------------------------
-// K2/K3  inverse pass A on contiguous tiles, optionally fed by the key multiply-accumulate
-//   SRC_LOAD: v = in[...]  (< 4q)                             (ringQ.InvNTTLvl head)
-//   SRC_MAC : v = sum_t sum_{i<beta} key_t[i] (.) h_t[i]      (MulCoeffsMontgomery[AndAdd]Lvl loops,
-//             mkrlwe/keyswitch_hoisted.go:24-32; nsets = 2 for mkbfv/keyswitch_hoisted.go:20-30)
-//             accumulated in 128 bits, one Montgomery reduction at the end (same canonical value).
-//   grid = (tiles, nslots, nbatch).  Output limb `slot` of out[batch] (coefficient-order positions, values in
-//   [0,4q), still needing pass B).
+// K3  digit multiply-accumulate, streaming:  O_g = sum_{set} sum_{i<beta} S[set][i] (.) P_g[set][i]
+//   (MulCoeffsMontgomery[AndAdd]Lvl loops of mkrlwe/keyswitch_hoisted.go:24-32; two sets for
+//   mkbfv/keyswitch_hoisted.go:20-30).  A group = one shared swk-shaped operand S (x, y, a hoisted form ...)
+//   against G private ones, so the shared stream is read once for G products.  Raw 128-bit accumulation
+//   (<= 256 terms of < 2^120), one Montgomery reduction at the end: the same canonical value as the reference's
+//   reduce-every-term loop.  Output: limb `slot` of out[g] in NTT order, canonical.
+//   grid = (N/512, nslots, ngroups), 2 adjacent coefficients per thread (16-byte accesses).
 // ------------------------------------------------------------------------------------------------
-struct InvAArgs {
-    PtrList in;              // SRC_LOAD: per batch input poly
-    PtrList key[2];          // SRC_MAC : per batch key   (swk-shaped, Montgomery form)
-    PtrList hst[2];          // SRC_MAC : per batch hoisted (swk-shaped)
-    PtrList out;             // per batch output, limb slots of stride N
+#define MKHE_MAC_GROUPS 16
+#define MKHE_MAC_G 4
+struct MacDigitsArgs {
+    const u64 *shared[2][MKHE_MAC_GROUPS];
+    const u64 *priv[2][MKHE_MAC_GROUPS * MKHE_MAC_G];
+    u64 *out[MKHE_MAC_GROUPS * MKHE_MAC_G];
     int nsets, beta;
     long digit_stride;       // dmax * N
     int nslots;
     int slots[MKHE_MAX_SLOTS];
     int mods[MKHE_MAX_SLOTS];
-    int out_slots[MKHE_MAX_SLOTS];
+    int logN;
+};
+template <int G>
+__global__ void __launch_bounds__(MKHE_THREADS) k_mac_digits(MacDigitsArgs a, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const int grp = blockIdx.z, slot = a.slots[blockIdx.y];
+    const ModC m = mods[a.mods[blockIdx.y]];
+    const long off = (long)slot * N + ((long)blockIdx.x * MKHE_THREADS + threadIdx.x) * 2;
+    u64 hi[G][2], lo[G][2];
+#pragma unroll
+    for (int g = 0; g < G; g++) hi[g][0] = hi[g][1] = lo[g][0] = lo[g][1] = 0;
+    for (int t = 0; t < a.nsets; t++) {
+        const u64 *sp = a.shared[t][grp] + off;
+        const u64 *pp[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) pp[g] = a.priv[t][grp * MKHE_MAC_G + g] + off;
+#pragma unroll 2
+        for (int i = 0; i < a.beta; i++) {
+            const long d = (long)i * a.digit_stride;
+            const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2 *>(sp + d));
+            ulonglong2 p[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) p[g] = __ldg(reinterpret_cast<const ulonglong2 *>(pp[g] + d));
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                mac128(hi[g][0], lo[g][0], s.x, p[g].x);
+                mac128(hi[g][1], lo[g][1], s.y, p[g].y);
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const u64 h0 = csub(barrett_lazy(hi[g][0], m.q, m.mu), m.q), h1 = csub(barrett_lazy(hi[g][1], m.q, m.mu), m.q);
+        *reinterpret_cast<ulonglong2 *>(a.out[grp * MKHE_MAC_G + g] + off) =
+            make_ulonglong2(mont_reduce(h0, lo[g][0], m.q, m.qinv), mont_reduce(h1, lo[g][1], m.q, m.qinv));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  inverse pass A on contiguous tiles (head of ringQ.InvNTT[Lazy]Lvl): inputs < 4q in NTT order, outputs in
+//   [0,4q) still needing pass B.  grid = (tiles, nslots, nbatch).
+// ------------------------------------------------------------------------------------------------
+struct InvAArgs {
+    PtrList in;              // per batch input, limb slots of stride N
+    PtrList out;             // per batch output
+    int nslots;
+    int slots[MKHE_MAX_SLOTS];
+    int mods[MKHE_MAX_SLOTS];
     int logN;
 };
 
-template <bool SRC_MAC>
 __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_intt_passA(InvAArgs a, const ModC *mods, const ulonglong2 *twi) {
     MKHE_SMEM(smraw);
     u64 *sm1 = reinterpret_cast<u64 *>(smraw);
     const int tid = threadIdx.x, tile = blockIdx.x, b = blockIdx.z;
-    const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y], oslot = a.out_slots[blockIdx.y];
+    const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
     const long N = 1L << a.logN;
     const ModC m = mods[mi];
     const XAddr x(sm1);
     u64 v[16];
-    if (SRC_MAC) {
-        // the streams are read in layout A (element k*128 + tid: a warp reads 256 contiguous bytes per access), the sums
-        // then move to layout C through the exchange buffer (map 2: idx + (idx >> 4))
-        const long off = (long)slot * N + (long)tile * MKHE_TILE + tid;
-        u64 hi[16], lo[16];
+    const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(a.in.p[b] + (long)slot * N + (long)tile * MKHE_TILE + tid * 16);
 #pragma unroll
-        for (int k = 0; k < 16; k++) hi[k] = lo[k] = 0;
-        int terms = 0;
-        for (int t = 0; t < a.nsets; t++) {
-            const u64 *kp = a.key[t].p[b] + off;
-            const u64 *hp = a.hst[t].p[b] + off;
-            for (int i = 0; i < a.beta; i++) {
-                const u64 *k1 = kp + (long)i * a.digit_stride;
-                const u64 *h1 = hp + (long)i * a.digit_stride;
-                u64 kk[16], hh[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) { kk[k] = __ldg(k1 + k * 128); hh[k] = __ldg(h1 + k * 128); }
-#pragma unroll
-                for (int k = 0; k < 16; k++) mac128(hi[k], lo[k], kk[k], hh[k]);
-                if ((++terms & 7) == 0) {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) hi[k] = csub(barrett_lazy(hi[k], m.q, m.mu), m.q);
-                }
-            }
-        }
-        u64 *wr = sm1 + tid + (tid >> 4);
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            u64 h = csub(barrett_lazy(hi[k], m.q, m.mu), m.q);
-            wr[k * 136] = mont_reduce(h, lo[k], m.q, m.qinv);         // slot (k*128 + tid) + ((k*128 + tid) >> 4)
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = x.c2[k];       // own slots: the next writer of them is this thread (tile_inv)
-    } else {
-        const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(a.in.p[b] + (long)slot * N + (long)tile * MKHE_TILE + tid * 16);
-#pragma unroll
-        for (int k = 0; k < 8; k++) { ulonglong2 xx = p2[k]; v[2 * k] = xx.x; v[2 * k + 1] = xx.y; }
-    }
+    for (int k = 0; k < 8; k++) { ulonglong2 xx = p2[k]; v[2 * k] = xx.x; v[2 * k + 1] = xx.y; }
     const TwGlobal tw(twi + (long)mi * N, a.logN - 11, tile);
     tile_inv(v, x, tw, nttc(m));
-    u64 *o = a.out.p[b] + (long)oslot * N + (long)tile * MKHE_TILE;
+    u64 *o = a.out.p[b] + (long)slot * N + (long)tile * MKHE_TILE;
 #pragma unroll
     for (int k = 0; k < 16; k++) o[k * 128 + tid] = v[k];
 }
@@ -527,6 +541,103 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_conv(ConvArgs a, const ConvTab
         }
         a.dst.p[b][(long)(a.dst_limb0 + j) * N + x] = res;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2+K4  tail of the key switch: InvNTT pass B fused with ModDownQPtoQ and the accumulation into the target
+//   (mkrlwe/keyswitch_hoisted.go:34-39, basis_extension.go:192-232 with the P -> Q lift of :337-357,537-646).
+//   Works on the per-product QP accumulators after pass A; slot `vslot` of each accumulator is spare.
+//   k_moddown_P : per product, P limbs only: pass B, then y_i = x_i * (P/p_i)^-1 mod p_i in place of limb nQ+i and the
+//                 fp64 overflow estimate v (same operation order as reconstructRNS) into slot `vslot`.
+//                 grid = (16, nproducts)
+//   k_moddown_Q : per target poly and Q limb j: for every product of the target: pass B of limb j, lift of the P part
+//                 (multSum, lazy value reproduced), (lift - x) * -P^-1, exact adds into the target.
+//                 grid = (16, level+1, ntargets)
+// ------------------------------------------------------------------------------------------------
+#define MKHE_MD_TARGETS 66
+#define MKHE_MD_PRODUCTS 132
+struct ModDownPArgs {
+    u64 *acc[MKHE_MD_PRODUCTS];
+    int np_limbs, p_slot0, vslot;
+    int logN;
+};
+template <int S1>
+__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_P(ModDownPArgs a, const ConvTable *tabp, const ModC *mods, const ulonglong2 *twi) {
+    constexpr int E = 1 << S1;
+    const ConvTable &tab = *tabp;
+    const long N = 1L << a.logN;
+    const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x;
+    u64 *base = a.acc[blockIdx.y] + col;
+    double vi[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) vi[k] = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < a.np_limbs; i++) {
+        const int mi = tab.src_mod[i];
+        const ModC m = mods[mi];
+        u64 *p = base + (long)(a.p_slot0 + i) * N;
+        u64 v[E];
+#pragma unroll
+        for (int k = 0; k < E; k++) v[k] = p[(long)k * MKHE_TILE];
+        cols_inv<S1>(v, twi + (long)mi * N, nttc(m), m);
+        const u64 f = tab.qoverqiinvqi[i];
+#pragma unroll
+        for (int k = 0; k < E; k++) {
+            const u64 y = mred(v[k], f, m.q, m.qinv);
+            vi[k] = __dadd_rn(vi[k], __ddiv_rn(__ull2double_rn(y), m.qd));
+            p[(long)k * MKHE_TILE] = y;
+        }
+    }
+    u64 *vp = base + (long)a.vslot * N;
+#pragma unroll
+    for (int k = 0; k < E; k++) vp[(long)k * MKHE_TILE] = __double2ull_rz(vi[k]);
+}
+
+struct ModDownQArgs {
+    u64 *dst[MKHE_MD_TARGETS];
+    int has_acc[MKHE_MD_TARGETS];          // start from the target's current contents (AddLvl) or from zero
+    int first[MKHE_MD_TARGETS + 1];        // products of target t: acc[first[t]] .. acc[first[t+1]-1]
+    const u64 *acc[MKHE_MD_PRODUCTS];
+    int np_limbs, p_slot0, vslot;
+    int logN;
+};
+template <int S1>
+__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_Q(ModDownQArgs a, const ConvTable *tabp, const ModC *mods, const ulonglong2 *twi) {
+    constexpr int E = 1 << S1;
+    const ConvTable &tab = *tabp;
+    const long N = 1L << a.logN;
+    const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x, j = blockIdx.y, t = blockIdx.z;
+    const ModC m = mods[tab.dst_mod[j]];          // == modulus j
+    const NttC c = nttc(m);
+    u64 *dst = a.dst[t] + (long)j * N + col;
+    u64 r[E];
+    if (a.has_acc[t]) {
+#pragma unroll
+        for (int k = 0; k < E; k++) r[k] = dst[(long)k * MKHE_TILE];
+    } else {
+#pragma unroll
+        for (int k = 0; k < E; k++) r[k] = 0;
+    }
+#pragma unroll 1
+    for (int s = a.first[t]; s < a.first[t + 1]; s++) {
+        const u64 *src = a.acc[s] + col;
+        u64 v[E];
+#pragma unroll
+        for (int k = 0; k < E; k++) v[k] = src[(long)j * N + (long)k * MKHE_TILE];
+        cols_inv<S1>(v, twi + (long)tab.dst_mod[j] * N, c, m);
+#pragma unroll
+        for (int k = 0; k < E; k++) {
+            u64 rlo = 0, rhi = 0;
+            for (int i = 0; i < a.np_limbs; i++) mac128(rhi, rlo, src[(long)(a.p_slot0 + i) * N + (long)k * MKHE_TILE], tab.qoverqimodp[j][i]);
+            const u64 ov = src[(long)a.vslot * N + (long)k * MKHE_TILE];
+            const u64 hhi = mulhi(rlo * m.qinv, m.q);
+            const u64 lift = rhi - hhi + m.q + tab.vtimesqmodp[j][ov];       // lazy, exactly multSum's value
+            const u64 d = mred(lift + 2 * m.q - v[k], tab.moddown[j], m.q, m.qinv);
+            r[k] = csub(r[k] + d, m.q);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < E; k++) dst[(long)k * MKHE_TILE] = r[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -655,11 +766,11 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_bfly_peak(u64 *sink, ModC m, i
     const NttC c = nttc(m);
     for (int it = 0; it < iters; it++) {          // throughput probe only: values may wrap, the instruction stream is what counts
 #pragma unroll
-        for (int k = 0; k < 4; k++) bf_fwd<false>(v[k], v[k + 4], w, wsh, c);
+        for (int k = 0; k < 4; k++) bf_fwd(v[k], v[k + 4], w, wsh, c);
 #pragma unroll
-        for (int g = 0; g < 2; g++) { bf_fwd<false>(v[4 * g], v[4 * g + 2], w, wsh, c); bf_fwd<false>(v[4 * g + 1], v[4 * g + 3], w, wsh, c); }
+        for (int g = 0; g < 2; g++) { bf_fwd(v[4 * g], v[4 * g + 2], w, wsh, c); bf_fwd(v[4 * g + 1], v[4 * g + 3], w, wsh, c); }
 #pragma unroll
-        for (int g = 0; g < 4; g++) bf_fwd<false>(v[2 * g], v[2 * g + 1], w, wsh, c);
+        for (int g = 0; g < 4; g++) bf_fwd(v[2 * g], v[2 * g + 1], w, wsh, c);
     }
     u64 s = 0;
 #pragma unroll
