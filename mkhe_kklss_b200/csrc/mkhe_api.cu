@@ -404,10 +404,10 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
                 if (ng == 0) continue;
                 const dim3 grid(ctx->N / (2 * MKHE_THREADS), s.n, ng);
                 switch (G) {
-                    case 4: LAUNCH(k_mac_digits<4>, grid, dim3(MKHE_THREADS), 0, a, ctx->d_mods); break;
-                    case 3: LAUNCH(k_mac_digits<3>, grid, dim3(MKHE_THREADS), 0, a, ctx->d_mods); break;
-                    case 2: LAUNCH(k_mac_digits<2>, grid, dim3(MKHE_THREADS), 0, a, ctx->d_mods); break;
-                    default: LAUNCH(k_mac_digits<1>, grid, dim3(MKHE_THREADS), 0, a, ctx->d_mods); break;
+                    case 4: LAUNCH(k_mac_digits<4>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(4), a, ctx->d_mods); break;
+                    case 3: LAUNCH(k_mac_digits<3>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(3), a, ctx->d_mods); break;
+                    case 2: LAUNCH(k_mac_digits<2>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(2), a, ctx->d_mods); break;
+                    default: LAUNCH(k_mac_digits<1>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(1), a, ctx->d_mods); break;
                 }
                 i = j;
                 break;
@@ -454,8 +454,15 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
             }
             qa.first[ntg] = cnt;
             TRY(dispatch_s1(ctx, [&](auto S) -> int {
-                auto k_moddown_Q_ = k_moddown_Q<decltype(S)::value>;
-                LAUNCH(k_moddown_Q_, dim3(COLGROUPS, levelQ + 1, ntg), dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi);
+                constexpr int s1 = decltype(S)::value;
+                const dim3 grid(COLGROUPS, levelQ + 1, ntg);
+                switch (ctx->nP) {
+                    case 1: { auto k_moddown_Q_ = k_moddown_Q<s1, 1>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 2: { auto k_moddown_Q_ = k_moddown_Q<s1, 2>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 3: { auto k_moddown_Q_ = k_moddown_Q<s1, 3>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 4: { auto k_moddown_Q_ = k_moddown_Q<s1, 4>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    default: return fail(ctx, MKHE_ERR_UNSUPPORTED, "key switch with %d special primes (1..4 supported)", ctx->nP);
+                }
                 return MKHE_OK;
             }));
         }
@@ -752,6 +759,10 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     cudaEventCreate(&ctx->ev1);
 #ifndef MKHE_EMU
     cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PASS2);
+    cudaFuncSetAttribute(k_mac_digits<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(1));
+    cudaFuncSetAttribute(k_mac_digits<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(2));
+    cudaFuncSetAttribute(k_mac_digits<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(3));
+    cudaFuncSetAttribute(k_mac_digits<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(4));
 #endif
     std::vector<int> src, dst;
     for (int j = 0; j < nP; j++) src.push_back(nQ + j);

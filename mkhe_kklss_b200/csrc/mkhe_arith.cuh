@@ -25,6 +25,11 @@ typedef unsigned int u32;
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) { *reinterpret_cast<ulonglong2 *>(smem) = *reinterpret_cast<const ulonglong2 *>(gmem); }
 __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ void prefetch_l2(const void *) {}
+// TMA bulk copies complete at issue under emulation, the barrier operations are no-ops
+__device__ __forceinline__ void mbar_init(u64 *, int) {}
+__device__ __forceinline__ void mbar_expect_tx(u64 *, u32) {}
+__device__ __forceinline__ void mbar_wait(u64 *, u32) {}
+__device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *) { memcpy(smem, gmem, bytes); }
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 #else
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -33,6 +38,33 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// mbarrier + TMA (1-D bulk copy global -> shared, UBLKCP): one thread arms the barrier with the byte count and issues the
+// copies, the consumers wait on the barrier's phase parity.
+__device__ __forceinline__ void mbar_init(u64 *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }

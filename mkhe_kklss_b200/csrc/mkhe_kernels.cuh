@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, 4) k_ntt_pass2(Pass2Args a, 
 //   against G private ones, so the shared stream is read once for G products.  Raw 128-bit accumulation
 //   (<= 256 terms of < 2^120), one Montgomery reduction at the end: the same canonical value as the reference's
 //   reduce-every-term loop.  Output: limb `slot` of out[g] in NTT order, canonical.
-//   grid = (N/512, nslots, ngroups), 2 adjacent coefficients per thread (16-byte accesses).
+//   grid = (N/512, nslots, ngroups), 2 adjacent coefficients per thread; operands staged by TMA bulk copies.
 // ------------------------------------------------------------------------------------------------
 #define MKHE_MAC_GROUPS 16
 #define MKHE_MAC_G 4
@@ -358,38 +358,57 @@ struct MacDigitsArgs {
     int mods[MKHE_MAX_SLOTS];
     int logN;
 };
+#define MKHE_MAC_STAGES 4
+#define MKHE_MAC_TILE (2 * MKHE_THREADS)                       // coefficients per CTA: one 4 KiB TMA box per operand and digit
+#define MKHE_MAC_SMEM(G) (MKHE_MAC_STAGES * ((G) + 1) * MKHE_MAC_TILE * 8 + MKHE_MAC_STAGES * 8)
 template <int G>
 __global__ void __launch_bounds__(MKHE_THREADS) k_mac_digits(MacDigitsArgs a, const ModC *mods) {
+    MKHE_SMEM(smraw);
+    constexpr int BOX = MKHE_MAC_TILE * 8;                     // bytes per operand and stage
+    u64 *bars = reinterpret_cast<u64 *>(smraw + MKHE_MAC_STAGES * (G + 1) * BOX);
     const long N = 1L << a.logN;
-    const int grp = blockIdx.z, slot = a.slots[blockIdx.y];
+    const int tid = threadIdx.x, grp = blockIdx.z, slot = a.slots[blockIdx.y];
     const ModC m = mods[a.mods[blockIdx.y]];
-    const long off = (long)slot * N + ((long)blockIdx.x * MKHE_THREADS + threadIdx.x) * 2;
+    const long off = (long)slot * N + (long)blockIdx.x * MKHE_MAC_TILE;
+    const int nterms = a.nsets * a.beta;
+    // the operand tiles of term (set, digit) arrive by TMA in a ring of MKHE_MAC_STAGES stages
+    auto issue = [&](int term) {
+        const int st = term % MKHE_MAC_STAGES, t = term / a.beta, i = term - t * a.beta;
+        const long d = (long)i * a.digit_stride + off;
+        unsigned char *dst = smraw + st * (G + 1) * BOX;
+        mbar_expect_tx(&bars[st], (G + 1) * BOX);
+        tma_load_1d(dst, a.shared[t][grp] + d, BOX, &bars[st]);
+#pragma unroll
+        for (int g = 0; g < G; g++) tma_load_1d(dst + (1 + g) * BOX, a.priv[t][grp * MKHE_MAC_G + g] + d, BOX, &bars[st]);
+    };
+    if (tid == 0) {
+        for (int st = 0; st < MKHE_MAC_STAGES; st++) mbar_init(&bars[st], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < MKHE_MAC_STAGES && t < nterms; t++) issue(t);
+    }
     u64 hi[G][2], lo[G][2];
 #pragma unroll
     for (int g = 0; g < G; g++) hi[g][0] = hi[g][1] = lo[g][0] = lo[g][1] = 0;
-    for (int t = 0; t < a.nsets; t++) {
-        const u64 *sp = a.shared[t][grp] + off;
-        const u64 *pp[G];
+    for (int term = 0; term < nterms; term++) {
+        const int st = term % MKHE_MAC_STAGES;
+        mbar_wait(&bars[st], (term / MKHE_MAC_STAGES) & 1);
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(smraw + st * (G + 1) * BOX) + tid;
+        const ulonglong2 s = src[0];
 #pragma unroll
-        for (int g = 0; g < G; g++) pp[g] = a.priv[t][grp * MKHE_MAC_G + g] + off;
-#pragma unroll 2
-        for (int i = 0; i < a.beta; i++) {
-            const long d = (long)i * a.digit_stride;
-            const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2 *>(sp + d));
-            ulonglong2 p[G];
-#pragma unroll
-            for (int g = 0; g < G; g++) p[g] = __ldg(reinterpret_cast<const ulonglong2 *>(pp[g] + d));
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                mac128(hi[g][0], lo[g][0], s.x, p[g].x);
-                mac128(hi[g][1], lo[g][1], s.y, p[g].y);
-            }
+        for (int g = 0; g < G; g++) {
+            const ulonglong2 p = src[(1 + g) * MKHE_THREADS];
+            mac128(hi[g][0], lo[g][0], s.x, p.x);
+            mac128(hi[g][1], lo[g][1], s.y, p.y);
         }
+        __syncthreads();                                   // every thread has read stage st
+        if (tid == 0 && term + MKHE_MAC_STAGES < nterms) issue(term + MKHE_MAC_STAGES);
     }
 #pragma unroll
     for (int g = 0; g < G; g++) {
         const u64 h0 = csub(barrett_lazy(hi[g][0], m.q, m.mu), m.q), h1 = csub(barrett_lazy(hi[g][1], m.q, m.mu), m.q);
-        *reinterpret_cast<ulonglong2 *>(a.out[grp * MKHE_MAC_G + g] + off) =
+        *reinterpret_cast<ulonglong2 *>(a.out[grp * MKHE_MAC_G + g] + off + 2 * tid) =
             make_ulonglong2(mont_reduce(h0, lo[g][0], m.q, m.qinv), mont_reduce(h1, lo[g][1], m.q, m.qinv));
     }
 }
@@ -601,14 +620,20 @@ struct ModDownQArgs {
     int np_limbs, p_slot0, vslot;
     int logN;
 };
-template <int S1>
+template <int S1, int NP>
 __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_Q(ModDownQArgs a, const ConvTable *tabp, const ModC *mods, const ulonglong2 *twi) {
-    constexpr int E = 1 << S1;
+    constexpr int E = 1 << S1, HB = E < 8 ? E : 8;
     const ConvTable &tab = *tabp;
     const long N = 1L << a.logN;
     const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x, j = blockIdx.y, t = blockIdx.z;
     const ModC m = mods[tab.dst_mod[j]];          // == modulus j
     const NttC c = nttc(m);
+    u64 cji[NP], vq[NP + 1];
+#pragma unroll
+    for (int i = 0; i < NP; i++) cji[i] = tab.qoverqimodp[j][i];
+#pragma unroll
+    for (int i = 0; i <= NP; i++) vq[i] = tab.vtimesqmodp[j][i];
+    const u64 md = tab.moddown[j];
     u64 *dst = a.dst[t] + (long)j * N + col;
     u64 r[E];
     if (a.has_acc[t]) {
@@ -626,14 +651,27 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_Q(ModDownQArgs a, 
         for (int k = 0; k < E; k++) v[k] = src[(long)j * N + (long)k * MKHE_TILE];
         cols_inv<S1>(v, twi + (long)tab.dst_mod[j] * N, c, m);
 #pragma unroll
-        for (int k = 0; k < E; k++) {
-            u64 rlo = 0, rhi = 0;
-            for (int i = 0; i < a.np_limbs; i++) mac128(rhi, rlo, src[(long)(a.p_slot0 + i) * N + (long)k * MKHE_TILE], tab.qoverqimodp[j][i]);
-            const u64 ov = src[(long)a.vslot * N + (long)k * MKHE_TILE];
-            const u64 hhi = mulhi(rlo * m.qinv, m.q);
-            const u64 lift = rhi - hhi + m.q + tab.vtimesqmodp[j][ov];       // lazy, exactly multSum's value
-            const u64 d = mred(lift + 2 * m.q - v[k], tab.moddown[j], m.q, m.qinv);
-            r[k] = csub(r[k] + d, m.q);
+        for (int h = 0; h < E; h += HB) {
+            u64 y[NP][HB], ov[HB];
+#pragma unroll
+            for (int k = 0; k < HB; k++) {
+#pragma unroll
+                for (int i = 0; i < NP; i++) y[i][k] = src[(long)(a.p_slot0 + i) * N + (long)(h + k) * MKHE_TILE];
+                ov[k] = src[(long)a.vslot * N + (long)(h + k) * MKHE_TILE];
+            }
+#pragma unroll
+            for (int k = 0; k < HB; k++) {
+                u64 rlo = 0, rhi = 0;
+#pragma unroll
+                for (int i = 0; i < NP; i++) mac128(rhi, rlo, y[i][k], cji[i]);
+                u64 vt = vq[0];
+#pragma unroll
+                for (int i = 1; i <= NP; i++) vt = ov[k] == (u64)i ? vq[i] : vt;
+                const u64 hhi = mulhi(rlo * m.qinv, m.q);
+                const u64 lift = rhi - hhi + m.q + vt;                    // lazy, exactly multSum's value
+                const u64 d = mred(lift + 2 * m.q - v[h + k], md, m.q, m.qinv);
+                r[h + k] = csub(r[h + k] + d, m.q);
+            }
         }
     }
 #pragma unroll
