@@ -49,6 +49,7 @@ struct mkhe_ctx {
     cudaStream_t stream = nullptr;
     ModC *d_mods = nullptr;
     ulonglong2 *d_twf = nullptr, *d_twi = nullptr;
+    ulonglong2 *d_twf_tiled = nullptr;      // per (modulus, tile): the staged image pass 2 fetches with one TMA copy
     bool tables_dirty = true;
     ConvTable *d_conv_PtoQ = nullptr;      // ModDownQPtoQ of the key switch
     ConvTable *d_conv_QtoQMul = nullptr;   // BFV
@@ -161,12 +162,16 @@ int upload_tables(mkhe_ctx *ctx) {
         CU(cudaMalloc((void **)&ctx->d_mods, sizeof(ModC) * 64));
         CU(cudaMalloc((void **)&ctx->d_twf, sizeof(ulonglong2) * 64 * N));
         CU(cudaMalloc((void **)&ctx->d_twi, sizeof(ulonglong2) * 64 * N));
+        CU(cudaMalloc((void **)&ctx->d_twf_tiled, sizeof(ulonglong2) * 64 * N));
     }
     for (size_t i = 0; i < nm; i++) {
         CU(cudaMemcpy(ctx->d_mods + i, &ctx->tabs[i].c, sizeof(ModC), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(ctx->d_twf + i * N, ctx->tabs[i].twf.data(), sizeof(ulonglong2) * N, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(ctx->d_twi + i * N, ctx->tabs[i].twi.data(), sizeof(ulonglong2) * N, cudaMemcpyHostToDevice));
     }
+    MKHE_LAUNCH(k_tile_twiddles, dim3(ctx->N / MKHE_TILE, (unsigned)nm), dim3(MKHE_THREADS), 0, ctx->stream, ctx->d_twf, ctx->d_twf_tiled, ctx->logN);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
     ctx->tables_dirty = false;
     return MKHE_OK;
 }
@@ -227,7 +232,7 @@ int dispatch_s1(mkhe_ctx *ctx, F &&f) {
 }
 
 const size_t SMEM_TILE = MKHE_XBUF * 8;                      // the padded exchange buffer
-const size_t SMEM_PASS2 = MKHE_XBUF * 8 + MKHE_TILE * 16;    // + the tile's twiddles
+const size_t SMEM_PASS2 = MKHE_P2_SMEM;                      // twiddles + per group: exchange and landing buffers
 const int COLGROUPS = MKHE_TILE / MKHE_NTT_THREADS;              // CTAs per limb in the column passes
 
 // how many chunks to split `count` looped instances into so that the grid fills the machine (>= ~4 waves of 3 CTAs/SM)
@@ -237,10 +242,35 @@ int pick_chunks(int count, long ctas_per_chunk) {
     return std::max(chunks, 1);
 }
 
+// pass 2: instances per CTA -- even (two groups per CTA), as large as possible while the grid still has >= ~5 waves
+int pick_per(int ninst, long ctas_per_chunk) {
+    const long want = 148L * 2 * 5;
+    const long nchunks = std::max<long>(1, (want + ctas_per_chunk - 1) / ctas_per_chunk);
+    long per = ninst / nchunks;
+    per -= per & 1;
+    per = std::max<long>(per, MKHE_P2_GROUPS);
+    return (int)std::min<long>(per, std::max(ninst, 1));
+}
+int launch_pass2(mkhe_ctx *ctx, const Slots &s, int np, u64 *const *bufs, int count, long inst_stride) {
+    const int tiles = ctx->N / MKHE_TILE;
+    Pass2Args b;
+    memset(&b, 0, sizeof b);
+    b.count = count;
+    b.ninst = np * count;
+    b.per = pick_per(b.ninst, (long)tiles * s.n);
+    b.inst_stride = inst_stride;
+    b.nslots = s.n;
+    b.logN = ctx->logN;
+    for (int i = 0; i < s.n; i++) { b.slots[i] = s.slot[i]; b.mods[i] = s.mod[i]; }
+    for (int i = 0; i < np; i++) b.buf.p[i] = bufs[i];
+    const int nchunks = (b.ninst + b.per - 1) / b.per;
+    LAUNCH(k_ntt_pass2, dim3(tiles * nchunks, s.n), dim3(MKHE_P2_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf_tiled);
+    return MKHE_OK;
+}
+
 // ---- building blocks ------------------------------------------------------------------------------
 // forward NTT of `npolys` polys over the limb list `s` (out may alias in)
 int ntt_fwd(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *const *out) {
-    const int tiles = ctx->N / MKHE_TILE;
     for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
         int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
         LimbArgs a;
@@ -251,15 +281,7 @@ int ntt_fwd(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
             LAUNCH(k_ntt_pass1_, dim3(COLGROUPS, s.n, np), dim3(MKHE_NTT_THREADS), 0, a, ctx->d_mods, ctx->d_twf);
             return MKHE_OK;
         }));
-        Pass2Args b;
-        b.count = 1;
-        b.chunks = 1;
-        b.inst_stride = 0;
-        b.nslots = s.n;
-        b.logN = ctx->logN;
-        for (int i = 0; i < s.n; i++) { b.slots[i] = s.slot[i]; b.mods[i] = s.mod[i]; }
-        for (int i = 0; i < np; i++) b.buf.p[i] = out[p0 + i];
-        LAUNCH(k_ntt_pass2, dim3(tiles, s.n, np), dim3(MKHE_NTT_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf);
+        TRY(launch_pass2(ctx, s, np, out + p0, 1, 0));
     }
     return MKHE_OK;
 }
@@ -296,7 +318,6 @@ int ntt_inv(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
 
 // Decompose: digits in_limb0 .. in_limb0+beta-1 of each input poly -> swk-shaped outputs (NTT domain)
 int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *const *out, int in_limb0) {
-    const int tiles = ctx->N / MKHE_TILE;
     const int beta = levelQ + 1;     // alpha = 1
     Slots s = qp_slots(ctx, levelQ);
     for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
@@ -314,15 +335,7 @@ int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *c
             LAUNCH(k_bcast_ntt_pass1_, dim3(COLGROUPS * a.slot_groups, beta, np), dim3(MKHE_NTT_THREADS), 0, a, ctx->d_mods, ctx->d_twf);
             return MKHE_OK;
         }));
-        Pass2Args b;
-        b.count = beta;
-        b.chunks = pick_chunks(beta, (long)tiles * s.n * np);
-        b.inst_stride = (long)ctx->dmax * ctx->N;
-        b.nslots = s.n;
-        b.logN = ctx->logN;
-        for (int i = 0; i < s.n; i++) { b.slots[i] = s.slot[i]; b.mods[i] = s.mod[i]; }
-        for (int i = 0; i < np; i++) b.buf.p[i] = out[p0 + i];
-        LAUNCH(k_ntt_pass2, dim3(tiles * b.chunks, s.n, np), dim3(MKHE_NTT_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf);
+        TRY(launch_pass2(ctx, s, np, out + p0, beta, (long)ctx->dmax * ctx->N));
     }
     return MKHE_OK;
 }
@@ -818,7 +831,7 @@ void mkhe_ctx_destroy(mkhe_ctx *ctx) {
     mkhe_comm_destroy(ctx);
     for (Obj *o : ctx->objs) { cudaFree(o->d); delete o; }
     for (auto &kv : ctx->scratch) cudaFree(kv.second.p);
-    cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi);
+    cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi); cudaFree(ctx->d_twf_tiled);
     cudaFree(ctx->d_conv_PtoQ); cudaFree(ctx->d_conv_QtoQMul); cudaFree(ctx->d_conv_QMultoQ);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);

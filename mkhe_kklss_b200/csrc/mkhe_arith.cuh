@@ -30,6 +30,7 @@ __device__ __forceinline__ void mbar_init(u64 *, int) {}
 __device__ __forceinline__ void mbar_expect_tx(u64 *, u32) {}
 __device__ __forceinline__ void mbar_wait(u64 *, u32) {}
 __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *) { memcpy(smem, gmem, bytes); }
+__device__ __forceinline__ void named_sync(int, int) { emu_syncthreads(); }      // lock-step rounds: a yield is enough
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 #else
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -59,6 +60,8 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(a), "r"(parity) : "memory");
 }
+// barrier among `nthreads` threads of the CTA (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      (unsigned)__cvta_generic_to_shared(smem)),

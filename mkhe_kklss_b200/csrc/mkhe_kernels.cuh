@@ -46,23 +46,31 @@ struct PtrList { u64 *p[MKHE_MAX_PARTIES_K]; };
 //   levels 8..10 (round C, thread t reads its private entries t*2^(lv-7) + j): stored as [j][t].
 // so every read is (per-thread base) + (compile-time offset) and a warp reads consecutive 16-byte entries.
 // ------------------------------------------------------------------------------------------------
-// asynchronous (LDGSTS): the caller waits with cp_async_wait_all() + a block barrier before the first use.
-__device__ __forceinline__ void load_tile_twiddles(ulonglong2 *s, const ulonglong2 *tab, int S1, int tile) {
-#pragma unroll 4
-    for (int h = threadIdx.x; h < MKHE_TILE; h += MKHE_NTT_THREADS) {
-        if (h == 0) continue;
+// The staged image of every (modulus, tile) is built once per context (k_tile_twiddles) so that a CTA fetches its 32 KiB
+// with ONE TMA bulk copy:  tiled[(mod * ntiles + tile) * 2048 + pos].
+__device__ __forceinline__ int tile_twiddle_pos(int h) {
+    const int lv = 31 - mkhe_clz((u32)h);
+    const int g = h - (1 << lv);
+    if (lv >= 8) return (1 << lv) + (g & ((1 << (lv - 7)) - 1)) * MKHE_NTT_THREADS + (g >> (lv - 7));
+    if (lv >= 4) return (1 << lv) + (g & ((1 << (lv - 4)) - 1)) * 16 + (g >> (lv - 4));
+    return h;
+}
+// grid = (ntiles, nmods), 256 threads
+__global__ void __launch_bounds__(MKHE_THREADS) k_tile_twiddles(const ulonglong2 *tab, ulonglong2 *tiled, int logN) {
+    const long N = 1L << logN;
+    const int S1 = logN - 11, ntiles = (int)(N / MKHE_TILE), tile = blockIdx.x, mi = blockIdx.y;
+    const ulonglong2 *src = tab + (long)mi * N;
+    ulonglong2 *dst = tiled + ((long)mi * ntiles + tile) * MKHE_TILE;
+    for (int h = threadIdx.x; h < MKHE_TILE; h += MKHE_THREADS) {
+        if (h == 0) { dst[0] = make_ulonglong2(0, 0); continue; }
         const int lv = 31 - mkhe_clz((u32)h);
-        const int g = h - (1 << lv);
-        int pos = h;
-        if (lv >= 8) pos = (1 << lv) + (g & ((1 << (lv - 7)) - 1)) * MKHE_NTT_THREADS + (g >> (lv - 7));
-        else if (lv >= 4) pos = (1 << lv) + (g & ((1 << (lv - 4)) - 1)) * 16 + (g >> (lv - 4));
-        cp_async16(s + pos, tab + ((size_t)1 << (S1 + lv)) + ((size_t)tile << lv) + g);
+        dst[tile_twiddle_pos(h)] = src[((size_t)1 << (S1 + lv)) + ((size_t)tile << lv) + (h - (1 << lv))];
     }
 }
 struct TwShared {          // accessor used by the tile rounds; b = the register-index bit of the stage
     const ulonglong2 *sA, *sB, *sC;     // round A: 15 warp-uniform entries (broadcast reads)
-    __device__ __forceinline__ explicit TwShared(const ulonglong2 *base)
-        : sA(base), sB(base + (threadIdx.x >> 3)), sC(base + threadIdx.x) {}
+    __device__ __forceinline__ TwShared(const ulonglong2 *base, int tid)
+        : sA(base), sB(base + (tid >> 3)), sC(base + tid) {}
     __device__ __forceinline__ ulonglong2 A(int b, int g) const { return sA[(1 << (3 - b)) + g]; }
     __device__ __forceinline__ ulonglong2 B(int b, int g) const { return sB[(1 << (7 - b)) + g * 16]; }
     __device__ __forceinline__ ulonglong2 C(int b, int g) const { return sC[(1 << (10 - b)) + g * MKHE_NTT_THREADS]; }
@@ -85,8 +93,8 @@ struct TwGlobal {          // same interface straight from the global table (sin
 // ------------------------------------------------------------------------------------------------
 struct XAddr {             // per-thread bases into the exchange buffer
     u64 *a1, *b1, *c2;
-    __device__ __forceinline__ explicit XAddr(u64 *buf) {
-        const int tid = threadIdx.x, hi = tid >> 3, low = tid & 7;
+    __device__ __forceinline__ XAddr(u64 *buf, int tid) {
+        const int hi = tid >> 3, low = tid & 7;
         a1 = buf + tid;                    // map 1, layout A: + k*136
         b1 = buf + hi * 136 + low;         // map 1, layout B: + k*8 ;  map 2, layout B: + k*8 + (k>>1)
         c2 = buf + tid * 17;               // map 2, layout C: + k
@@ -104,7 +112,7 @@ struct XAddr {             // per-thread bases into the exchange buffer
 // the caller guarantees (block barrier) that nobody still reads the buffer when tile_fwd / tile_inv starts.
 // big (2^57 <= q < 2^60, CTA-uniform): inputs below 16q, a sweep to [0,8q) before every second stage keeps them there.
 template <class TW>
-__device__ __forceinline__ void tile_fwd(u64 v[16], const XAddr &x, const TW &tw, const NttC &c, const bool big) {
+__device__ __forceinline__ void tile_fwd(u64 v[16], const XAddr &x, const TW &tw, const NttC &c, const bool big, const int bar_id) {
 #pragma unroll
     for (int b = 3; b >= 0; b--) {
         if (b & 1) MKHE_SWEEP16()
@@ -112,7 +120,7 @@ __device__ __forceinline__ void tile_fwd(u64 v[16], const XAddr &x, const TW &tw
     }
 #pragma unroll
     for (int k = 0; k < 16; k++) x.a1[k * 136] = v[k];
-    __syncthreads();
+    named_sync(bar_id, MKHE_NTT_THREADS);
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = x.b1[k * 8];
 #pragma unroll
@@ -285,51 +293,72 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_ntt_pass1(LimbArgs a, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1 pass 2: last 11 stages on contiguous tiles, canonical output.
-//   grid = (tiles * chunks, nslots, npolys); a CTA handles the instances [chunk*per, ...) out of `count`
-//   instances that share the limb (the digits of a hoisted form), so the tile's 2047 twiddles are
-//   staged in shared memory once per CTA.  The next instance's elements are prefetched into registers while
-//   the current one is transformed.
-//   data pointer of instance i = base[poly] + i*inst_stride + slot*N + tile*2048   (in place)
-// ------------------------------------------------------------------------------------------------
 struct Pass2Args {
     PtrList buf;
-    int count, chunks;
+    int count;                       // instances per poly (digits); instance i lives at buf[i / count] + (i % count) * inst_stride
+    int ninst;                       // npolys * count
+    int per;                         // instances per CTA (split over the CTA's groups)
     long inst_stride;
     int nslots;
     int slots[MKHE_MAX_SLOTS];       // limb slot (offset slot*N)
     int mods[MKHE_MAX_SLOTS];        // modulus index of that slot
     int logN;
 };
+#define MKHE_P2_GROUPS 2
+#define MKHE_P2_THREADS (MKHE_P2_GROUPS * MKHE_NTT_THREADS)
+#define MKHE_P2_SMEM (MKHE_TILE * 16 + MKHE_P2_GROUPS * (MKHE_XBUF * 8 + MKHE_TILE * 8) + 64)
 
-__global__ void __launch_bounds__(MKHE_NTT_THREADS, 4) k_ntt_pass2(Pass2Args a, const ModC *mods, const ulonglong2 *twf) {
+// K1 pass 2: last 11 stages on contiguous tiles, canonical output, in place.
+//   grid = (tiles * nchunks, nslots).  A CTA owns one (tile, limb) and `per` instances of it (digits x polys): the tile's
+//   2047 twiddles arrive once by TMA, each 128-thread group walks every MKHE_P2_GROUPS-th instance, its 16 KiB input tile
+//   prefetched by TMA into the group's landing buffer while the previous instance is transformed.
+__global__ void __launch_bounds__(MKHE_P2_THREADS, 2) k_ntt_pass2(Pass2Args a, const ModC *mods, const ulonglong2 *tiled) {
     MKHE_SMEM(smraw);
-    u64 *sm1 = reinterpret_cast<u64 *>(smraw);                                  // 17 KiB exchange buffer
-    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw + MKHE_XBUF * 8);    // 32 KiB twiddles
+    const int tid = threadIdx.x & (MKHE_NTT_THREADS - 1), grp = threadIdx.x / MKHE_NTT_THREADS;
+    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw);                                                     // 32 KiB twiddles
+    u64 *xbuf = reinterpret_cast<u64 *>(smraw + MKHE_TILE * 16 + grp * (MKHE_XBUF * 8 + MKHE_TILE * 8));          // 17 KiB exchange
+    u64 *inbuf = xbuf + MKHE_XBUF;                                                                               // 16 KiB landing
+    u64 *bars = reinterpret_cast<u64 *>(smraw + MKHE_TILE * 16 + MKHE_P2_GROUPS * (MKHE_XBUF * 8 + MKHE_TILE * 8));
     const long N = 1L << a.logN;
     const int ntiles = (int)(N / MKHE_TILE);
-    const int tid = threadIdx.x, tile = blockIdx.x % ntiles, chunk = blockIdx.x / ntiles, poly = blockIdx.z;
+    const int tile = blockIdx.x % ntiles, chunk = blockIdx.x / ntiles;
     const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
     const ModC m = mods[mi];
     const NttC c = nttc(m);
     const bool big = m.big != 0;
-    const int per = (a.count + a.chunks - 1) / a.chunks;
-    const int i0 = chunk * per, i1 = i0 + per < a.count ? i0 + per : a.count;
-    if (i0 >= i1) return;
-    load_tile_twiddles(stw, twf + (long)mi * N, a.logN - 11, tile);     // asynchronous (LDGSTS)
-    const TwShared tw(stw);
-    const XAddr x(sm1);
-    u64 *base = a.buf.p[poly] + (long)slot * N + (long)tile * MKHE_TILE;
-    for (int i = i0; i < i1; i++) {
-        u64 *p = base + (long)i * a.inst_stride;
+    const int i0 = chunk * a.per, i1 = i0 + a.per < a.ninst ? i0 + a.per : a.ninst;
+    auto inst_ptr = [&](int i) -> u64 * {
+        const int poly = i / a.count;
+        return a.buf.p[poly] + (long)(i - poly * a.count) * a.inst_stride + (long)slot * N + (long)tile * MKHE_TILE;
+    };
+    if (threadIdx.x == 0) {
+        for (int b = 0; b <= MKHE_P2_GROUPS; b++) mbar_init(&bars[b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bars[0], MKHE_TILE * 16);
+        tma_load_1d(stw, tiled + ((long)mi * ntiles + tile) * MKHE_TILE, MKHE_TILE * 16, &bars[0]);
+    }
+    int i = i0 + grp;
+    if (tid == 0 && i < i1) {
+        mbar_expect_tx(&bars[1 + grp], MKHE_TILE * 8);
+        tma_load_1d(inbuf, inst_ptr(i), MKHE_TILE * 8, &bars[1 + grp]);
+    }
+    const TwShared tw(stw, tid);
+    const XAddr x(xbuf, tid);
+    mbar_wait(&bars[0], 0);
+    for (int n = 0; i < i1; i += MKHE_P2_GROUPS, n++) {
+        mbar_wait(&bars[1 + grp], n & 1);
         u64 v[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = p[k * 128 + tid];
-        if (i + 1 < i1) prefetch_l2(p + a.inst_stride + tid * 16);      // the next instance's tile: one 128-byte line per thread
-        if (i == i0) cp_async_wait_all();
-        __syncthreads();          // twiddles staged (first instance) / everybody has left the previous instance's exchange buffer
-        tile_fwd(v, x, tw, c, big);
-        u64 *o = p + tid * 16;
+        for (int k = 0; k < 16; k++) v[k] = inbuf[k * 128 + tid];
+        named_sync(1 + grp, MKHE_NTT_THREADS);      // the landing buffer is free again; everybody has left the previous instance's exchange buffer
+        if (tid == 0 && i + MKHE_P2_GROUPS < i1) {
+            mbar_expect_tx(&bars[1 + grp], MKHE_TILE * 8);
+            tma_load_1d(inbuf, inst_ptr(i + MKHE_P2_GROUPS), MKHE_TILE * 8, &bars[1 + grp]);
+        }
+        tile_fwd(v, x, tw, c, big, 1 + grp);
+        u64 *o = inst_ptr(i) + tid * 16;
 #pragma unroll
         for (int k = 0; k < 4; k++)
             st_global_v4(o + 4 * k, canon(v[4 * k], m), canon(v[4 * k + 1], m), canon(v[4 * k + 2], m), canon(v[4 * k + 3], m));
@@ -433,7 +462,7 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_intt_passA(InvAArgs a, con
     const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
     const long N = 1L << a.logN;
     const ModC m = mods[mi];
-    const XAddr x(sm1);
+    const XAddr x(sm1, tid);
     u64 v[16];
     const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(a.in.p[b] + (long)slot * N + (long)tile * MKHE_TILE + tid * 16);
 #pragma unroll
