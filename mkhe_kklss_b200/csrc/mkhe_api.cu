@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -46,7 +47,8 @@ struct mkhe_ctx {
     u64 T = 0;
     std::vector<u64> mod;                 // Q | P | QMul
     std::vector<ModTables> tabs;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // the context's stream: every op is ordered on it
+
     ModC *d_mods = nullptr;
     ulonglong2 *d_twf = nullptr, *d_twi = nullptr;
     ulonglong2 *d_twf_tiled = nullptr;      // per (modulus, tile): the staged image pass 2 fetches with one TMA copy
@@ -590,10 +592,12 @@ int allreduce_mod(mkhe_ctx *ctx, u64 *buf, size_t count, const Slots &s, int nbu
 // With an active Shard only the owned parties' keys / hoisted forms are touched: the partial x, y and the c_0
 // contributions are summed over ranks (exact: every accumulation of the reference is a modular add, App. A.4);
 // valid outputs on a rank are component "0" and the components of the parties it owns.
+// hoist0 / hoist1: when set, h0 / h1 are empty pools and the operand is hoisted here (MulRelinNew's implicit hoisting,
+// mkckks/evaluator.go:419-441).
 int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u64 *const *op0, u64 *const *h0,
                            int n1, const int *ids1, u64 *const *op1, u64 *const *h1, u64 *const *rlk_b,
                            u64 *const *rlk_d, u64 *const *rlk_v, u64 *u, int nOut, const int *idsOut, u64 *const *out,
-                           const Shard &sh = Shard()) {
+                           const Shard &sh = Shard(), bool hoist0 = false, bool hoist1 = false) {
     const int N = ctx->N;
     Slots qps = qp_slots(ctx, level);
     // owned sub-lists
@@ -606,50 +610,53 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
         return r;
     };
     std::vector<u64 *> d_o = pick(o0, rlk_d), v_o = pick(o0, rlk_v), h0_o = pick(o0, h0), b_o = pick(o1, rlk_b), h1_o = pick(o1, h1);
-    // steps 2-3 (:79-117): x = MForm(sum d_id (.) h0_id), y = MForm(sum b_id (.) h1_id)
+    const int m0 = (int)o0.size(), m1 = (int)o1.size();
     std::vector<u64 *> xy;
     TRY(swk_pool(ctx, "xy", 2, xy));
     u64 *x = xy[0], *y = xy[1];
-    if (!o0.empty()) TRY(mac_parties(ctx, level, (int)o0.size(), d_o.data(), h0_o.data(), x));
+    std::vector<u64 *> p, hp, tn;
+    TRY(poly_pool(ctx, "relin_p", m0, ctx->nQ, p));
+    TRY(swk_pool(ctx, "relin_hp", m0, hp));
+    TRY(poly_pool(ctx, "tensor_ntt", n0 + n1 + 2, ctx->nQ, tn));
+    if (nOut + 1 > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_UNSUPPORTED, "too many parties");
+
+    if (hoist0) TRY(decompose_impl(ctx, level, n0, op0 + 1, h0, 0));
+    if (hoist1) TRY(decompose_impl(ctx, level, n1, op1 + 1, h1, 0));
+    // steps 2-3 (:79-117): x = MForm(sum d_id (.) h0_id), y = MForm(sum b_id (.) h1_id)
+    if (m0) TRY(mac_parties(ctx, level, m0, d_o.data(), h0_o.data(), x));
     else CU(cudaMemsetAsync(x, 0, swk_elems(ctx) * 8, ctx->stream));
-    if (!o1.empty()) TRY(mac_parties(ctx, level, (int)o1.size(), b_o.data(), h1_o.data(), y));
+    if (m1) TRY(mac_parties(ctx, level, m1, b_o.data(), h1_o.data(), y));
     else CU(cudaMemsetAsync(y, 0, swk_elems(ctx) * 8, ctx->stream));
     if (sh.active) TRY(allreduce_mod(ctx, x, 2 * swk_elems(ctx), qps, 2 * ctx->nQ, (long)ctx->dmax * N));
 
     // step 4 (:119-144): tensor product in the NTT domain, then InvNTT of every output component
-    Slots qs = q_slots(level);
-    std::vector<u64 *> tn;
-    TRY(poly_pool(ctx, "tensor_ntt", n0 + n1 + 2, ctx->nQ, tn));
-    std::vector<u64 *> src(n0 + n1 + 2);
-    for (int t = 0; t <= n0; t++) src[t] = op0[t];
-    for (int t = 0; t <= n1; t++) src[n0 + 1 + t] = op1[t];
-    TRY(ntt_fwd(ctx, qs, n0 + n1 + 2, src.data(), tn.data()));
-    if (nOut + 1 > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_UNSUPPORTED, "too many parties");
-    TensorArgs ta;
-    memset(&ta, 0, sizeof ta);
-    ta.A0 = tn[0];
-    ta.B0 = tn[n0 + 1];
-    ta.nout = nOut;
-    ta.nlimbs = level + 1;
-    ta.logN = ctx->logN;
-    for (int i = 0; i <= level; i++) ta.mod_of_limb[i] = i;
-    ta.out.p[0] = out[0];
-    for (int t = 0; t < nOut; t++) {
-        int i0 = find_id(n0, ids0, idsOut[t]), i1 = find_id(n1, ids1, idsOut[t]);
-        ta.A.p[t] = i0 >= 0 ? tn[1 + i0] : nullptr;
-        ta.B.p[t] = i1 >= 0 ? tn[n0 + 2 + i1] : nullptr;
-        ta.out.p[1 + t] = out[1 + t];
+    {
+        Slots qs = q_slots(level);
+        std::vector<u64 *> src(n0 + n1 + 2);
+        for (int t = 0; t <= n0; t++) src[t] = op0[t];
+        for (int t = 0; t <= n1; t++) src[n0 + 1 + t] = op1[t];
+        TRY(ntt_fwd(ctx, qs, n0 + n1 + 2, src.data(), tn.data()));
+        TensorArgs ta;
+        memset(&ta, 0, sizeof ta);
+        ta.A0 = tn[0];
+        ta.B0 = tn[n0 + 1];
+        ta.nout = nOut;
+        ta.nlimbs = level + 1;
+        ta.logN = ctx->logN;
+        for (int i = 0; i <= level; i++) ta.mod_of_limb[i] = i;
+        ta.out.p[0] = out[0];
+        for (int t = 0; t < nOut; t++) {
+            int i0 = find_id(n0, ids0, idsOut[t]), i1 = find_id(n1, ids1, idsOut[t]);
+            ta.A.p[t] = i0 >= 0 ? tn[1 + i0] : nullptr;
+            ta.B.p[t] = i1 >= 0 ? tn[n0 + 2 + i1] : nullptr;
+            ta.out.p[1 + t] = out[1 + t];
+        }
+        LAUNCH(k_tensor, dim3(N / MKHE_THREADS, level + 1), dim3(MKHE_THREADS), 0, ta, ctx->d_mods);
+        TRY(ntt_inv(ctx, qs, nOut + 1, out, out));
+        // the tensor term of c_0 is counted once across ranks
+        if (sh.active && ctx->rank != 0) CU(cudaMemsetAsync(out[0], 0, (size_t)(level + 1) * N * 8, ctx->stream));
     }
-    LAUNCH(k_tensor, dim3(N / MKHE_THREADS, level + 1), dim3(MKHE_THREADS), 0, ta, ctx->d_mods);
-    TRY(ntt_inv(ctx, qs, nOut + 1, out, out));
-    // the tensor term of c_0 is counted once across ranks
-    if (sh.active && ctx->rank != 0) CU(cudaMemsetAsync(out[0], 0, (size_t)(level + 1) * N * 8, ctx->stream));
-
     // step 5 (:147-154): c_id += x [.] h1_id   and the first half of step 6 (:161-166): p_id = y [.] h0_id, one batch
-    const int m0 = (int)o0.size(), m1 = (int)o1.size();
-    std::vector<u64 *> p, hp;
-    TRY(poly_pool(ctx, "relin_p", m0, ctx->nQ, p));
-    TRY(swk_pool(ctx, "relin_hp", m0, hp));
     {
         std::vector<Prod> pr;
         for (int t = 0; t < m1; t++) pr.push_back(Prod{{x, nullptr}, {h1_o[t], nullptr}, out[1 + find_id(nOut, idsOut, ids1[o1[t]])], true});
@@ -666,7 +673,7 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
         }
         TRY(ext_products(ctx, level, 1, pr));
     }
-    if (sh.active) TRY(allreduce_mod(ctx, out[0], (size_t)(level + 1) * N, qs, 1, 0));
+    if (sh.active) TRY(allreduce_mod(ctx, out[0], (size_t)(level + 1) * N, q_slots(level), 1, 0));
     return MKHE_OK;
 }
 
@@ -1100,16 +1107,12 @@ int mkhe_ckks_mul_relin(mkhe_ctx *ctx, int level, int nb_rescales, int same_oper
     TRY(swks_of(ctx, n0, rlk_d, vd, "rlk_d"));
     TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v"));
     SWK(uk, u);
-    // hoisting into context pools (rlkSet.HoistPool[0|1], mkckks/evaluator.go:419-441)
+    // hoisting into context pools (rlkSet.HoistPool[0|1], mkckks/evaluator.go:419-441), scheduled inside the op
     TRY(swk_pool(ctx, "hoistpool0", n0, vh0));
-    TRY(decompose_impl(ctx, level, n0, p0.data() + 1, vh0.data(), 0));
     if (same_operand) vh1 = vh0;
-    else {
-        TRY(swk_pool(ctx, "hoistpool1", n1, vh1));
-        TRY(decompose_impl(ctx, level, n1, p1.data() + 1, vh1.data(), 0));
-    }
+    else TRY(swk_pool(ctx, "hoistpool1", n1, vh1));
     TRY(mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
-                               vd.data(), vv.data(), uk->d, nOut, idsOut, po.data()));
+                               vd.data(), vv.data(), uk->d, nOut, idsOut, po.data(), Shard(), true, !same_operand));
     TRY(rescale_impl(ctx, level, nb_rescales, nOut + 1, po.data(), po.data()));
     for (int t = 0; t <= nOut; t++) reinterpret_cast<Obj *>(out[t])->nlimbs = level + 1 - nb_rescales;
     return MKHE_OK;

@@ -228,17 +228,17 @@ struct BcastArgs {
     int logN;
 };
 
+#ifndef MKHE_BCAST_MINB
+#define MKHE_BCAST_MINB 5
+#endif
 template <int S1>
-__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_bcast_ntt_pass1(BcastArgs a, const ModC *mods, const ulonglong2 *twf) {
+__global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? MKHE_BCAST_MINB : 2)) k_bcast_ntt_pass1(BcastArgs a, const ModC *mods, const ulonglong2 *twf) {
     constexpr int E = 1 << S1;
     const int col = (blockIdx.x & 15) * MKHE_NTT_THREADS + threadIdx.x, sg = blockIdx.x >> 4;
     const int digit = blockIdx.y, poly = blockIdx.z;
     const long N = 1L << a.logN;
     const u64 *src = a.in.p[poly] + (long)(a.in_limb0 + digit) * N + col;
     u64 *dst0 = a.out.p[poly] + (long)digit * a.dmax * N + col;
-    u64 raw[E];
-#pragma unroll
-    for (int k = 0; k < E; k++) raw[k] = src[(long)k * MKHE_TILE];
     const int per = (a.nslots + a.slot_groups - 1) / a.slot_groups;
     const int s_end = (sg + 1) * per < a.nslots ? (sg + 1) * per : a.nslots;
     for (int s = sg * per; s < s_end; s++) {
@@ -246,13 +246,14 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_bcast_ntt_pass1(BcastArgs 
         const ModC m = mods[mi];
         const NttC c = nttc(m);
         const ulonglong2 *tw = twf + (long)mi * N;
+        // the digit column is re-read for every target limb (L1 hits after the first) instead of being held in registers:
+        // the kernel is integer bound and the registers buy a fifth resident CTA
         u64 v[E];
+#pragma unroll
+        for (int k = 0; k < E; k++) v[k] = __ldg(src + (long)k * MKHE_TILE);
         if (m.big) {       // [0,8q) is required: digits of another limb may exceed it only for lazy 60-bit limbs; reduce to be safe
 #pragma unroll
-            for (int k = 0; k < E; k++) v[k] = barrett_lazy(raw[k], m.q, m.mu);
-        } else {
-#pragma unroll
-            for (int k = 0; k < E; k++) v[k] = raw[k];
+            for (int k = 0; k < E; k++) v[k] = barrett_lazy(v[k], m.q, m.mu);
         }
         cols_fwd<S1>(v, tw, c, m.big != 0);
         u64 *dst = dst0 + (long)mi * N;

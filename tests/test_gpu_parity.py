@@ -130,3 +130,20 @@ def test_device_matches_committed_golden_digests():
         got.update({f"rot[{kk}]": dig(v) for kk, v in rot.items()})
         assert got == golden[name], name
         dp.ctx.close()
+
+
+def test_full_size_repeatability():
+    """logN = 15 (BASELINE size), the same MulRelinNew and hoisted Rotate 25 times against ONE oracle result: an ordering
+    or staging error between kernels (TMA pipelines, scratch reuse) shows up as an intermittent mismatch"""
+    w = parity.CKKSWorld(PR.CKKS_PN15QP880, 2, rots=(2,))
+    level = w.op.max_level()
+    o0, d0 = w.random_ct(w.ids, level)
+    o1, d1 = w.random_ct(w.ids, level)
+    want = w.oev.mul_relin_new(o0, o1, w.o_rlk)
+    for rep in range(25):
+        w.compare_ct(w.dev.MulRelinNew(d0, d1, w.d_rlk), want, f"MulRelinNew repetition {rep}")
+    hd = w.dev.HoistedForm(d0)
+    want_r = w.oev.rotate_hoisted_new(o0, 2, w.oev.hoisted_form(o0), w.o_rk)
+    for rep in range(25):
+        w.compare_ct(w.dev.RotateHoistedNew(d0, 2, hd, w.d_rk), want_r, f"RotateHoistedNew repetition {rep}")
+    w.close()
