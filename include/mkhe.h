@@ -10,8 +10,9 @@
  *   - every function returns 0 on success, a negative mkhe_status otherwise; mkhe_last_error() gives
  *     the message.  CUDA failures are sticky on the context.
  *   - host pointers are borrowed for the duration of the call only (cgo rule): uploads/downloads
- *     complete before the function returns.  Ops only ENQUEUE work on the context's stream; results
- *     become visible to the host through *_download / mkhe_sync.
+ *     complete before the function returns (the *_async pair on library-owned pinned memory is the
+ *     documented exception).  Ops only ENQUEUE work on the context's stream; results become visible
+ *     to the host through *_download / mkhe_sync.
  *   - a context is not thread safe (neither are the reference's KeySwitcher / Evaluator: shared pools,
  *     mkrlwe/keyswitch.go:12-15); one context = one CUDA device = one stream.
  *   - limb  = N little-endian uint64.   poly = [nlimbs][N] (limb-major).
@@ -71,6 +72,15 @@ int mkhe_poly_download_limb(mkhe_ctx *ctx, mkhe_poly p, int limb, uint64_t *dst)
 int mkhe_poly_upload(mkhe_ctx *ctx, mkhe_poly p, const uint64_t *src, int nlimbs);        /* contiguous [nlimbs][N] */
 int mkhe_poly_download(mkhe_ctx *ctx, mkhe_poly p, uint64_t *dst, int nlimbs);
 int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dst, mkhe_poly src);                          /* ring.Poly.Copy */
+/* Asynchronous transfers for pipelines that keep the device busy while ciphertexts stream over PCIe (the Go shim's lazy
+ * syncToDevice / syncToHost, SURVEY 8b "residency model").  The host buffer must be page-locked memory obtained from
+ * mkhe_host_alloc (C-owned, so the cgo pointer rule does not apply) and must stay valid and untouched until mkhe_sync.
+ * Ordering is automatic: the copy starts after every op enqueued so far, and any later op that uses the poly waits for it;
+ * ops that do not touch the poly run concurrently with the copy. */
+int mkhe_host_alloc(mkhe_ctx *ctx, size_t bytes, void **out);
+int mkhe_host_free(mkhe_ctx *ctx, void *p);
+int mkhe_poly_upload_async(mkhe_ctx *ctx, mkhe_poly p, const uint64_t *src, int nlimbs);
+int mkhe_poly_download_async(mkhe_ctx *ctx, mkhe_poly p, uint64_t *dst, int nlimbs);
 
 /* ---- SwitchingKey / HoistedCiphertext entry storage (mkrlwe/keys.go:23-62, elements.go:5-15) */
 int mkhe_swk_alloc(mkhe_ctx *ctx, mkhe_swk *out);

@@ -186,6 +186,31 @@ class Context:
         self.check(self.dll.mkhe_poly_download_limb(self.ptr, C.c_uint64(h), C.c_int(limb), out.ctypes.data_as(u64p)))
         return out
 
+    # -- asynchronous transfers on library-owned pinned memory -----------------------------------
+    def host_alloc(self, shape) -> np.ndarray:
+        """uint64 array of `shape` in page-locked host memory (mkhe_host_alloc); free with host_free(arr)"""
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        self.check(self.dll.mkhe_host_alloc(self.ptr, C.c_size_t(n * 8), C.byref(p)))
+        buf = (C.c_uint64 * n).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint64).reshape(shape)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p.value
+        return arr
+
+    def host_free(self, arr):
+        addr = self._pinned.pop(arr.ctypes.data)
+        self.check(self.dll.mkhe_host_free(self.ptr, C.c_void_p(addr)))
+
+    def poly_upload_async(self, h, arr: np.ndarray):
+        """arr: a (view of a) host_alloc array; must stay untouched until sync()"""
+        assert arr.dtype == np.uint64 and arr.flags.c_contiguous and arr.ndim == 2 and arr.shape[1] == self.N
+        self.check(self.dll.mkhe_poly_upload_async(self.ptr, C.c_uint64(h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
+
+    def poly_download_async(self, h, arr: np.ndarray):
+        assert arr.dtype == np.uint64 and arr.flags.c_contiguous and arr.ndim == 2 and arr.shape[1] == self.N
+        self.check(self.dll.mkhe_poly_download_async(self.ptr, C.c_uint64(h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
+
     def poly_copy(self, dst, src):
         self.check(self.dll.mkhe_poly_copy(self.ptr, C.c_uint64(dst), C.c_uint64(src)))
 

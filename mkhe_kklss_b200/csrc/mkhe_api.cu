@@ -32,6 +32,8 @@ struct Obj {
     u64 *d;
     int cap_limbs;     // poly: allocated limbs
     int nlimbs;        // poly: current view
+    cudaEvent_t xfer = nullptr;     // completion of the last asynchronous transfer touching the object
+    bool xfer_pending = false;      // the context's stream has not been ordered after it yet
 };
 
 struct Scratch {
@@ -48,6 +50,8 @@ struct mkhe_ctx {
     std::vector<u64> mod;                 // Q | P | QMul
     std::vector<ModTables> tabs;
     cudaStream_t stream = nullptr;        // the context's stream: every op is ordered on it
+    cudaStream_t h2d = nullptr, d2h = nullptr;   // copy streams of the asynchronous transfers (one DMA engine per direction)
+    cudaEvent_t ev_compute = nullptr;
 
     ModC *d_mods = nullptr;
     ulonglong2 *d_twf = nullptr, *d_twi = nullptr;
@@ -128,6 +132,10 @@ int fail(mkhe_ctx *c, int code, const char *fmt, ...) {
 Obj *as_obj(mkhe_ctx *ctx, uint64_t h, int kind) {
     Obj *o = reinterpret_cast<Obj *>(h);
     if (!o || !ctx->objs.count(o) || o->kind != kind) return nullptr;
+    if (o->xfer_pending) {          // whatever uses the object next on the context's stream waits for its transfer
+        cudaStreamWaitEvent(ctx->stream, o->xfer, 0);
+        o->xfer_pending = false;
+    }
     return o;
 }
 #define POLY(var, h)                                                                     \
@@ -735,6 +743,21 @@ int rotate_hoisted_impl(mkhe_ctx *ctx, int level, int rotidx, int n, u64 *const 
 
 }  // namespace
 
+namespace {
+// order copy stream `cs` after everything enqueued on the context's stream so far, run `copy` on it, and make the next
+// user of the object on the context's stream wait for the copy
+template <class F>
+int async_transfer(mkhe_ctx *ctx, Obj *o, cudaStream_t cs, F &&copy) {
+    CU(cudaEventRecord(ctx->ev_compute, ctx->stream));
+    CU(cudaStreamWaitEvent(cs, ctx->ev_compute, 0));
+    CU(copy());
+    if (!o->xfer) CU(cudaEventCreate(&o->xfer));
+    CU(cudaEventRecord(o->xfer, cs));
+    o->xfer_pending = true;
+    return MKHE_OK;
+}
+}  // namespace
+
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
@@ -775,6 +798,9 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     for (size_t i = 0; i < ctx->mod.size(); i++) gen_mod_tables(ctx->tabs[i], logN, ctx->mod[i]);
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return MKHE_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MKHE_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MKHE_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MKHE_ERR_CUDA; }
+    cudaEventCreate(&ctx->ev_compute);
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
 #ifndef MKHE_EMU
@@ -835,13 +861,18 @@ void mkhe_ctx_destroy(mkhe_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->h2d);
+    cudaStreamSynchronize(ctx->d2h);
     mkhe_comm_destroy(ctx);
-    for (Obj *o : ctx->objs) { cudaFree(o->d); delete o; }
+    for (Obj *o : ctx->objs) { if (o->xfer) cudaEventDestroy(o->xfer); cudaFree(o->d); delete o; }
     for (auto &kv : ctx->scratch) cudaFree(kv.second.p);
     cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi); cudaFree(ctx->d_twf_tiled);
     cudaFree(ctx->d_conv_PtoQ); cudaFree(ctx->d_conv_QtoQMul); cudaFree(ctx->d_conv_QMultoQ);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_compute);
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->h2d);
+    cudaStreamDestroy(ctx->d2h);
     delete ctx;
 }
 
@@ -850,6 +881,19 @@ const char *mkhe_last_error(const mkhe_ctx *ctx) { return ctx ? ctx->err.c_str()
 int mkhe_sync(mkhe_ctx *ctx) {
     CHECK_CTX();
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->h2d));
+    CU(cudaStreamSynchronize(ctx->d2h));
+    return MKHE_OK;
+}
+int mkhe_host_alloc(mkhe_ctx *ctx, size_t bytes, void **out) {
+    CHECK_CTX();
+    if (!out) return MKHE_ERR_INVALID;
+    if (cudaMallocHost(out, bytes) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes);
+    return MKHE_OK;
+}
+int mkhe_host_free(mkhe_ctx *ctx, void *p) {
+    CHECK_CTX();
+    CU(cudaFreeHost(p));
     return MKHE_OK;
 }
 
@@ -863,7 +907,8 @@ int mkhe_poly_alloc(mkhe_ctx *ctx, int nlimbs, mkhe_poly *out) {
     size_t bytes = (size_t)nlimbs * ctx->N * 8;
     if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
     CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
-    Obj *o = new Obj{OBJ_POLY, (u64 *)p, nlimbs, nlimbs};
+    Obj *o = new Obj();
+    o->kind = OBJ_POLY; o->d = (u64 *)p; o->cap_limbs = nlimbs; o->nlimbs = nlimbs;
     ctx->objs.insert(o);
     *out = reinterpret_cast<uint64_t>(o);
     return MKHE_OK;
@@ -872,6 +917,11 @@ int mkhe_poly_free(mkhe_ctx *ctx, mkhe_poly h) {
     CHECK_CTX();
     POLY(o, h);
     CU(cudaStreamSynchronize(ctx->stream));
+    if (o->xfer) {
+        CU(cudaStreamSynchronize(ctx->h2d));
+        CU(cudaStreamSynchronize(ctx->d2h));
+        cudaEventDestroy(o->xfer);
+    }
     CU(cudaFree(o->d));
     ctx->objs.erase(o);
     delete o;
@@ -922,6 +972,18 @@ int mkhe_poly_download(mkhe_ctx *ctx, mkhe_poly h, uint64_t *dst, int nlimbs) {
     CU(cudaStreamSynchronize(ctx->stream));
     return MKHE_OK;
 }
+int mkhe_poly_upload_async(mkhe_ctx *ctx, mkhe_poly h, const uint64_t *src, int nlimbs) {
+    CHECK_CTX();
+    POLY(o, h);
+    if (nlimbs < 1 || nlimbs > o->cap_limbs || !src) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
+    return async_transfer(ctx, o, ctx->h2d, [&] { return cudaMemcpyAsync(o->d, src, (size_t)nlimbs * ctx->N * 8, cudaMemcpyHostToDevice, ctx->h2d); });
+}
+int mkhe_poly_download_async(mkhe_ctx *ctx, mkhe_poly h, uint64_t *dst, int nlimbs) {
+    CHECK_CTX();
+    POLY(o, h);
+    if (nlimbs < 1 || nlimbs > o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
+    return async_transfer(ctx, o, ctx->d2h, [&] { return cudaMemcpyAsync(dst, o->d, (size_t)nlimbs * ctx->N * 8, cudaMemcpyDeviceToHost, ctx->d2h); });
+}
 int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dsth, mkhe_poly srch) {
     CHECK_CTX();
     POLY(d, dsth);
@@ -940,7 +1002,8 @@ int mkhe_swk_alloc(mkhe_ctx *ctx, mkhe_swk *out) {
     size_t bytes = swk_elems(ctx) * 8;
     if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
     CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
-    Obj *o = new Obj{OBJ_SWK, (u64 *)p, 0, 0};
+    Obj *o = new Obj();
+    o->kind = OBJ_SWK; o->d = (u64 *)p; o->cap_limbs = 0; o->nlimbs = 0;
     ctx->objs.insert(o);
     *out = reinterpret_cast<uint64_t>(o);
     return MKHE_OK;
@@ -949,6 +1012,11 @@ int mkhe_swk_free(mkhe_ctx *ctx, mkhe_swk h) {
     CHECK_CTX();
     SWK(o, h);
     CU(cudaStreamSynchronize(ctx->stream));
+    if (o->xfer) {
+        CU(cudaStreamSynchronize(ctx->h2d));
+        CU(cudaStreamSynchronize(ctx->d2h));
+        cudaEventDestroy(o->xfer);
+    }
     CU(cudaFree(o->d));
     ctx->objs.erase(o);
     delete o;

@@ -147,3 +147,52 @@ def test_full_size_repeatability():
     for rep in range(25):
         w.compare_ct(w.dev.RotateHoistedNew(d0, 2, hd, w.d_rk), want_r, f"RotateHoistedNew repetition {rep}")
     w.close()
+
+
+def test_async_transfers_pipeline():
+    """mkhe_poly_upload_async / _download_async on library-owned pinned memory: a three-deep pipeline of MulRelinNew calls
+    whose operands arrive and whose results leave asynchronously gives the oracle's bits for every op"""
+    w = parity.CKKSWorld(PR.CKKS_PN14QP439, 2)
+    ctx, level = w.ctx, w.op.max_level()
+    ops = []
+    for _ in range(3):
+        o0, _d0 = w.random_ct(w.ids, level)
+        o1, _d1 = w.random_ct(w.ids, level)
+        ops.append((o0, o1, w.oev.mul_relin_new(o0, o1, w.o_rlk)))
+    from mkhe_kklss_b200 import mkckks
+    keys = ["0"] + w.ids
+    dev = [(mkckks.Ciphertext.new(w.dp, w.ids, level, w.lit.scale), mkckks.Ciphertext.new(w.dp, w.ids, level, w.lit.scale)) for _ in range(2)]
+    outs = [mkckks.Ciphertext.new(w.dp, w.ids, level, w.lit.scale) for _ in range(2)]
+    pin_in = [({k: ctx.host_alloc(o0.value[k].shape) for k in keys}, {k: ctx.host_alloc(o1.value[k].shape) for k in keys}) for o0, o1, _ in ops]
+    for (pa, pb), (o0, o1, _) in zip(pin_in, ops):
+        for k in keys:
+            pa[k][...] = o0.value[k]
+            pb[k][...] = o1.value[k]
+    nl = ops[0][2].value["0"].shape[0]
+    pin_out = [{k: ctx.host_alloc((nl, w.lit.N)) for k in keys} for _ in range(6)]
+    g = w.d_rlk.GetRelinearizationKey
+    kb, kd, kv = ([g(i).Value[j].h for i in w.ids] for j in range(3))
+    nb, _ = w.dev._nb_rescales(w.lit.scale * w.lit.scale, level, w.lit.scale)
+
+    def upload(n):
+        a, b = dev[n % 2]
+        pa, pb = pin_in[n % 3]
+        for k in keys:
+            ctx.poly_upload_async(a.Value[k].h, pa[k])
+            ctx.poly_upload_async(b.Value[k].h, pb[k])
+
+    upload(0)
+    for n in range(6):
+        if n + 1 < 6:
+            upload(n + 1)
+        a, b = dev[n % 2]
+        out = outs[n % 2]
+        ctx.ckks_mul_relin(level, nb, False, w.ids, a.handles(w.ids), w.ids, b.handles(w.ids), kb, kd, kv,
+                           w.dp.CRS[-1].h, w.ids, out.handles(w.ids))
+        for k in keys:
+            ctx.poly_download_async(out.Value[k].h, pin_out[n][k])
+    ctx.sync()
+    for n in range(6):
+        for k in keys:
+            parity.assert_same(pin_out[n][k], ops[n % 3][2].value[k], f"pipelined MulRelinNew {n}[{k}]")
+    w.close()
