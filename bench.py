@@ -355,6 +355,7 @@ def main():
     # ---------------- GPU arm ----------------------------------------------------------------------
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MKHE_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)

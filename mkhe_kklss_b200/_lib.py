@@ -85,6 +85,8 @@ class Context:
         self.Q, self.P = [int(x) for x in Q], [int(x) for x in P]
         self.nQ, self.nP = len(self.Q), len(self.P)
         self.D = self.nQ + self.nP
+        self.alpha = max(self.nP // gamma, 1)                       # mkrlwe/params.go:63-65
+        self.beta_max = -(-self.nQ // self.alpha)
         self.QMul = [int(x) for x in (QMul or [])]
         self.T = int(T)
         ptr = C.c_void_p()
@@ -225,11 +227,11 @@ class Context:
 
     def swk_upload(self, h, arr: np.ndarray):
         arr = np.ascontiguousarray(arr, dtype=np.uint64)
-        assert arr.shape == (self.nQ, self.D, self.N), arr.shape
+        assert arr.shape == (self.beta_max, self.D, self.N), arr.shape
         self.check(self.dll.mkhe_swk_upload(self.ptr, C.c_uint64(h), arr.ctypes.data_as(u64p)))
 
     def swk_download(self, h) -> np.ndarray:
-        out = np.empty((self.nQ, self.D, self.N), dtype=np.uint64)
+        out = np.empty((self.beta_max, self.D, self.N), dtype=np.uint64)
         self.check(self.dll.mkhe_swk_download(self.ptr, C.c_uint64(h), out.ctypes.data_as(u64p)))
         return out
 

@@ -46,6 +46,8 @@ struct Scratch {
 struct mkhe_ctx {
     int logN = 0, N = 0, nQ = 0, nP = 0, nQMul = 0, gamma = 2, device = 0;
     int S1 = 0, dmax = 0;
+    int alpha = 1, beta_max = 0;          // alpha = #P/gamma limbs per digit, beta_max = ceil(nQ/alpha) digits (mkrlwe/params.go:63-71)
+    LiftTable *d_lift = nullptr;          // alpha > 1: [beta_max][alpha-1] tables of the Decomposer
     u64 T = 0;
     std::vector<u64> mod;                 // Q | P | QMul
     std::vector<ModTables> tabs;
@@ -145,7 +147,8 @@ Obj *as_obj(mkhe_ctx *ctx, uint64_t h, int kind) {
     Obj *var = as_obj(ctx, (h), OBJ_SWK);                                                \
     if (!var) return fail(ctx, MKHE_ERR_INVALID, "invalid switching-key handle (%s)", #h)
 
-size_t swk_elems(const mkhe_ctx *ctx) { return (size_t)ctx->nQ * ctx->dmax * ctx->N; }
+size_t swk_elems(const mkhe_ctx *ctx) { return (size_t)ctx->beta_max * ctx->dmax * ctx->N; }
+int beta_of(const mkhe_ctx *ctx, int levelQ) { return (levelQ + ctx->alpha) / ctx->alpha; }      // ceil((levelQ+1)/alpha)
 
 int get_scratch(mkhe_ctx *ctx, const std::string &name, size_t bytes, u64 **out) {
     Scratch &s = ctx->scratch[name];
@@ -186,6 +189,20 @@ int upload_tables(mkhe_ctx *ctx) {
     return MKHE_OK;
 }
 
+// alpha > 1: one LiftTable per (digit, nsrc in 2..alpha), index digit*(alpha-1) + nsrc-2 (NewDecomposer's modUpParams)
+int upload_lift_tables(mkhe_ctx *ctx) {
+    const int per = ctx->alpha - 1, n = ctx->beta_max * per;
+    std::vector<LiftTable> h(n);
+    for (int d = 0; d < ctx->beta_max; d++)
+        for (int nsrc = 2; nsrc <= ctx->alpha; nsrc++) {
+            const int src0 = d * ctx->alpha;
+            if (src0 + nsrc > ctx->nQ) { memset(&h[d * per + nsrc - 2], 0, sizeof(LiftTable)); continue; }
+            gen_lift_table(h[d * per + nsrc - 2], ctx->mod, ctx->nQ + ctx->nP, src0, nsrc);
+        }
+    CU(cudaMalloc((void **)&ctx->d_lift, sizeof(LiftTable) * n));
+    CU(cudaMemcpy(ctx->d_lift, h.data(), sizeof(LiftTable) * n, cudaMemcpyHostToDevice));
+    return MKHE_OK;
+}
 int upload_conv(mkhe_ctx *ctx, ConvTable **d, const std::vector<int> &src, const std::vector<int> &dst) {
     if ((int)src.size() > MKHE_CONV_MAX || (int)dst.size() > MKHE_CONV_MAX)
         return fail(ctx, MKHE_ERR_UNSUPPORTED, "basis conversion with more than %d limbs", MKHE_CONV_MAX);
@@ -328,24 +345,56 @@ int ntt_inv(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
 
 // Decompose: digits in_limb0 .. in_limb0+beta-1 of each input poly -> swk-shaped outputs (NTT domain)
 int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *const *out, int in_limb0) {
-    const int beta = levelQ + 1;     // alpha = 1
+    const int alpha = ctx->alpha, beta = beta_of(ctx, levelQ);
+    if (alpha > 1 && in_limb0 != 0) return fail(ctx, MKHE_ERR_UNSUPPORTED, "DecomposeBFV relies on alpha = 1 (mkbfv/keyswitch.go:64-67)");
+    // digits [0, nlift) hold more than one limb and take the exact lift; a last digit of a single limb is a broadcast
+    const int nsrc_last = levelQ + 1 - alpha * (beta - 1);
+    const int nlift = alpha == 1 ? 0 : (nsrc_last == 1 ? beta - 1 : beta);
     Slots s = qp_slots(ctx, levelQ);
+    const long digit_elems = (long)ctx->dmax * ctx->N;
     for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
         int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
-        BcastArgs a;
-        a.in_limb0 = in_limb0;
-        a.dmax = ctx->dmax;
-        a.nslots = s.n;
-        a.slot_groups = std::min(s.n, pick_chunks(s.n, (long)COLGROUPS * beta * np));
-        a.logN = ctx->logN;
-        for (int i = 0; i < s.n; i++) a.slots[i] = s.slot[i];
-        for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
-        TRY(dispatch_s1(ctx, [&](auto S) -> int {
-            auto k_bcast_ntt_pass1_ = k_bcast_ntt_pass1<decltype(S)::value>;
-            LAUNCH(k_bcast_ntt_pass1_, dim3(COLGROUPS * a.slot_groups, beta, np), dim3(MKHE_NTT_THREADS), 0, a, ctx->d_mods, ctx->d_twf);
-            return MKHE_OK;
-        }));
-        TRY(launch_pass2(ctx, s, np, out + p0, beta, (long)ctx->dmax * ctx->N));
+        if (nlift > 0) {
+            LiftArgs a;
+            memset(&a, 0, sizeof a);
+            a.digit0 = 0;
+            a.table_stride = alpha - 1;
+            a.table0 = alpha - 2;
+            a.last_digit = nlift - 1;
+            a.last_table = (nlift - 1) * (alpha - 1) + (nlift == beta ? nsrc_last : alpha) - 2;
+            a.dmax = ctx->dmax;
+            a.nslots = s.n;
+            a.logN = ctx->logN;
+            for (int i = 0; i < s.n; i++) a.slots[i] = s.slot[i];
+            for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
+            LAUNCH(k_decomp_lift, dim3(ctx->N / MKHE_THREADS, nlift, np), dim3(MKHE_THREADS), 0, a, ctx->d_lift, ctx->d_mods);
+            std::vector<u64 *> ent;
+            for (int i = 0; i < np; i++)
+                for (int d = 0; d < nlift; d++) ent.push_back(out[p0 + i] + d * digit_elems);
+            TRY(ntt_fwd(ctx, s, (int)ent.size(), ent.data(), ent.data()));
+        }
+        if (nlift < beta) {
+            const int nd = beta - nlift;
+            BcastArgs a;
+            memset(&a, 0, sizeof a);
+            a.in_limb0 = in_limb0;
+            a.in_limb_stride = alpha;
+            a.digit0 = nlift;
+            a.dmax = ctx->dmax;
+            a.nslots = s.n;
+            a.slot_groups = std::min(s.n, pick_chunks(s.n, (long)COLGROUPS * nd * np));
+            a.logN = ctx->logN;
+            for (int i = 0; i < s.n; i++) a.slots[i] = s.slot[i];
+            for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
+            TRY(dispatch_s1(ctx, [&](auto S) -> int {
+                auto k_bcast_ntt_pass1_ = k_bcast_ntt_pass1<decltype(S)::value>;
+                LAUNCH(k_bcast_ntt_pass1_, dim3(COLGROUPS * a.slot_groups, nd, np), dim3(MKHE_NTT_THREADS), 0, a, ctx->d_mods, ctx->d_twf);
+                return MKHE_OK;
+            }));
+            std::vector<u64 *> bufs(np);
+            for (int i = 0; i < np; i++) bufs[i] = out[p0 + i] + nlift * digit_elems;
+            TRY(launch_pass2(ctx, s, np, bufs.data(), nd, digit_elems));
+        }
     }
     return MKHE_OK;
 }
@@ -401,7 +450,7 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
                 MacDigitsArgs a;
                 memset(&a, 0, sizeof a);
                 a.nsets = nsets;
-                a.beta = levelQ + 1;
+                a.beta = beta_of(ctx, levelQ);
                 a.digit_stride = (long)ctx->dmax * ctx->N;
                 a.nslots = s.n;
                 a.logN = ctx->logN;
@@ -513,13 +562,13 @@ int mac_parties(mkhe_ctx *ctx, int level, int n, u64 *const *key, u64 *const *hs
     memset(&a, 0, sizeof a);
     a.out = out;
     a.nparties = n;
-    a.beta = level + 1;
+    a.beta = beta_of(ctx, level);
     a.dmax = ctx->dmax;
     a.nslots = s.n;
     a.logN = ctx->logN;
     for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; }
     for (int i = 0; i < n; i++) { a.key.p[i] = key[i]; a.hst.p[i] = hst[i]; }
-    LAUNCH(k_mac_parties, dim3(ctx->N / (2 * MKHE_THREADS), s.n, level + 1), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    LAUNCH(k_mac_parties, dim3(ctx->N / (2 * MKHE_THREADS), s.n, a.beta), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
     return MKHE_OK;
 }
 
@@ -635,7 +684,7 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     else CU(cudaMemsetAsync(x, 0, swk_elems(ctx) * 8, ctx->stream));
     if (m1) TRY(mac_parties(ctx, level, m1, b_o.data(), h1_o.data(), y));
     else CU(cudaMemsetAsync(y, 0, swk_elems(ctx) * 8, ctx->stream));
-    if (sh.active) TRY(allreduce_mod(ctx, x, 2 * swk_elems(ctx), qps, 2 * ctx->nQ, (long)ctx->dmax * N));
+    if (sh.active) TRY(allreduce_mod(ctx, x, 2 * swk_elems(ctx), qps, 2 * ctx->beta_max, (long)ctx->dmax * N));
 
     // step 4 (:119-144): tensor product in the NTT domain, then InvNTT of every output component
     {
@@ -781,7 +830,8 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     if (!out || !Q || !P) return MKHE_ERR_INVALID;
     *out = nullptr;
     if (logN < 12 || logN > 16) return MKHE_ERR_UNSUPPORTED;
-    if (gamma <= 0 || nP / gamma != 1) return MKHE_ERR_UNSUPPORTED;      // alpha = #P/gamma must be 1
+    // alpha = #P/gamma limbs per digit (mkrlwe/params.go:63-65); the ModDown kernels are instantiated for 1..4 special primes
+    if (gamma <= 0 || nP < 1 || nP > 4 || nP / gamma < 1 || nP / gamma > MKHE_LIFT_MAX_SRC) return MKHE_ERR_UNSUPPORTED;
     if (nQ < 1 || nQ + nP > MKHE_MAX_SLOTS || nQ > MKHE_CONV_MAX) return MKHE_ERR_UNSUPPORTED;
     int ndev = mkhe_device_count();
     if (ndev <= 0 || device < 0 || device >= ndev) return MKHE_ERR_CUDA;   // no GPU: fail loudly, there is no CPU path
@@ -789,6 +839,8 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     ctx->logN = logN; ctx->N = 1 << logN; ctx->nQ = nQ; ctx->nP = nP; ctx->gamma = gamma; ctx->device = device;
     ctx->S1 = logN - 11;
     ctx->dmax = nQ + nP;
+    ctx->alpha = nP / gamma;
+    ctx->beta_max = (nQ + ctx->alpha - 1) / ctx->alpha;
     for (int i = 0; i < nQ; i++) ctx->mod.push_back(Q[i]);
     for (int i = 0; i < nP; i++) ctx->mod.push_back(P[i]);
     for (u64 q : ctx->mod) {
@@ -815,6 +867,7 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     for (int j = 0; j < nQ; j++) dst.push_back(j);
     int rc = upload_conv(ctx, &ctx->d_conv_PtoQ, src, dst);
     if (rc == MKHE_OK) rc = upload_tables(ctx);
+    if (rc == MKHE_OK && ctx->alpha > 1) rc = upload_lift_tables(ctx);
     if (rc != MKHE_OK) { delete ctx; return rc; }
     *out = ctx;
     return MKHE_OK;
@@ -824,6 +877,8 @@ int mkhe_ctx_set_bfv(mkhe_ctx *ctx, const uint64_t *QMul, int nQMul, uint64_t T)
     CHECK_CTX();
     if (!QMul || nQMul != ctx->nQ) return fail(ctx, MKHE_ERR_INVALID, "cannot NewParametersFromLiteral: length of Q & QMul is not equal");
     if (ctx->nQMul) return fail(ctx, MKHE_ERR_INVALID, "BFV parameters already set");
+    if (ctx->alpha != 1) return fail(ctx, MKHE_ERR_UNSUPPORTED, "mkbfv relies on alpha = #P/gamma = 1 (mkbfv/keyswitch.go:64-67)");
+    if (ctx->mod.size() + (size_t)nQMul > 64) return fail(ctx, MKHE_ERR_UNSUPPORTED, "more than 64 moduli");
     for (int i = 0; i < nQMul; i++) {
         u64 q = QMul[i];
         if (q >= ((u64)1 << 60) || q < ((u64)1 << 40) || !h_is_prime(q) || (q - 1) % ((u64)2 << ctx->logN) != 0) return fail(ctx, MKHE_ERR_UNSUPPORTED, "bad QMul prime");
@@ -867,7 +922,7 @@ void mkhe_ctx_destroy(mkhe_ctx *ctx) {
     for (Obj *o : ctx->objs) { if (o->xfer) cudaEventDestroy(o->xfer); cudaFree(o->d); delete o; }
     for (auto &kv : ctx->scratch) cudaFree(kv.second.p);
     cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi); cudaFree(ctx->d_twf_tiled);
-    cudaFree(ctx->d_conv_PtoQ); cudaFree(ctx->d_conv_QtoQMul); cudaFree(ctx->d_conv_QMultoQ);
+    cudaFree(ctx->d_conv_PtoQ); cudaFree(ctx->d_conv_QtoQMul); cudaFree(ctx->d_conv_QMultoQ); cudaFree(ctx->d_lift);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_compute);
     cudaStreamDestroy(ctx->stream);

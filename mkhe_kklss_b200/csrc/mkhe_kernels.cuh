@@ -20,7 +20,7 @@
 #define MKHE_TILE 2048
 #define MKHE_NTT_THREADS 128     // NTT kernels: 16 elements per thread
 #define MKHE_THREADS 256         // element-wise kernels
-#define MKHE_MAX_SLOTS 34        // limb slots per launch list (nQ + nP <= 34)
+#define MKHE_MAX_SLOTS 40        // limb slots per launch list (nQ + nP <= 40: PN16QP1761 has 34 + 4)
 
 // exchange buffer: the three register layouts of a tile (see tile_fwd) meet in one padded buffer with two
 // address maps, so that every access is conflict-free and its address is a per-thread base plus a compile-time offset:
@@ -220,7 +220,9 @@ __device__ __forceinline__ void cols_inv(u64 *v, const ulonglong2 *tw, const Ntt
 struct BcastArgs {
     PtrList in;            // per poly: coefficient-domain poly
     PtrList out;           // per poly: swk-shaped buffer [digit][Dmax][N]
-    int in_limb0;          // first source limb (BFV's second half uses nQ)
+    int in_limb0;          // source limb of digit d = in_limb0 + d * in_limb_stride (BFV's second half starts at nQ; alpha > 1: stride alpha)
+    int in_limb_stride;
+    int digit0;            // first digit of this launch
     int dmax;              // limb slots per digit in the output
     int nslots;
     int slot_groups;       // the slot list is split over blockIdx.x / 16
@@ -235,9 +237,9 @@ template <int S1>
 __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? MKHE_BCAST_MINB : 2)) k_bcast_ntt_pass1(BcastArgs a, const ModC *mods, const ulonglong2 *twf) {
     constexpr int E = 1 << S1;
     const int col = (blockIdx.x & 15) * MKHE_NTT_THREADS + threadIdx.x, sg = blockIdx.x >> 4;
-    const int digit = blockIdx.y, poly = blockIdx.z;
+    const int digit = a.digit0 + blockIdx.y, poly = blockIdx.z;
     const long N = 1L << a.logN;
-    const u64 *src = a.in.p[poly] + (long)(a.in_limb0 + digit) * N + col;
+    const u64 *src = a.in.p[poly] + (long)(a.in_limb0 + digit * a.in_limb_stride) * N + col;
     u64 *dst0 = a.out.p[poly] + (long)digit * a.dmax * N + col;
     const int per = (a.nslots + a.slot_groups - 1) / a.slot_groups;
     const int s_end = (sg + 1) * per < a.nslots ? (sg + 1) * per : a.nslots;
@@ -259,6 +261,62 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? MKHE_BCAST_MINB :
         u64 *dst = dst0 + (long)mi * N;
 #pragma unroll
         for (int k = 0; k < E; k++) dst[(long)k * MKHE_TILE] = v[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1'' Decomposer.DecomposeAndSplit for alpha > 1 (mkrlwe/basis_extension.go:454-534): the nsrc limbs of digit d are
+//   lifted exactly to every Q limb <= level and every P limb: y_i = x_i (Q_d/q_i)^-1 mod q_i, v = trunc(sum fl(y_i)/fl(q_i))
+//   (fp64, same operation order), out_j = multSum's lazy value.  The reference overwrites the digit's own limbs with their
+//   multSum values as well (:525 starts at alpha*beta); every limb is written the same way here.  Coefficient domain in,
+//   coefficient domain out (the plain forward NTT follows).  grid = (N/256, ndigits, npolys)
+// ------------------------------------------------------------------------------------------------
+#define MKHE_LIFT_MAX_SRC 4
+struct LiftTable {            // constants of one (digit, nsrc) pair; device resident
+    int nsrc, src_limb0;
+    u64 qoverqiinvqi[MKHE_LIFT_MAX_SRC];                       // Montgomery form
+    u64 qoverqimodp[MKHE_MAX_SLOTS][MKHE_LIFT_MAX_SRC];        // [target modulus index][i], Montgomery form
+    u64 vtimesqmodp[MKHE_MAX_SLOTS][MKHE_LIFT_MAX_SRC + 1];
+};
+struct LiftArgs {
+    PtrList in;            // per poly: coefficient-domain poly
+    PtrList out;           // per poly: swk-shaped buffer
+    int digit0;            // first digit of this launch
+    int table0;            // index of digit0's table in the table array; tables of consecutive digits are table_stride apart
+    int table_stride;
+    int last_digit, last_table;      // the (possibly partial) last digit uses table `last_table`
+    int dmax, nslots;
+    int slots[MKHE_MAX_SLOTS];
+    int logN;
+};
+__global__ void __launch_bounds__(MKHE_THREADS) k_decomp_lift(LiftArgs a, const LiftTable *tabs, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const long x = (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    const int digit = a.digit0 + blockIdx.y, poly = blockIdx.z;
+    const LiftTable &tab = tabs[digit == a.last_digit ? a.last_table : a.table0 + (digit - a.digit0) * a.table_stride];
+    u64 y[MKHE_LIFT_MAX_SRC];
+    double vi = 0.0;
+#pragma unroll
+    for (int i = 0; i < MKHE_LIFT_MAX_SRC; i++) {
+        if (i < tab.nsrc) {
+            const ModC &m = mods[tab.src_limb0 + i];
+            y[i] = mred(a.in.p[poly][(long)(tab.src_limb0 + i) * N + x], tab.qoverqiinvqi[i], m.q, m.qinv);
+            vi = __dadd_rn(vi, __ddiv_rn(__ull2double_rn(y[i]), m.qd));
+        } else {
+            y[i] = 0;
+        }
+    }
+    const u64 v = __double2ull_rz(vi);
+    u64 *dst = a.out.p[poly] + (long)digit * a.dmax * N + x;
+    for (int s = 0; s < a.nslots; s++) {
+        const int mi = a.slots[s];
+        const ModC &m = mods[mi];
+        u64 rlo = 0, rhi = 0;
+#pragma unroll
+        for (int i = 0; i < MKHE_LIFT_MAX_SRC; i++)
+            if (i < tab.nsrc) mac128(rhi, rlo, y[i], tab.qoverqimodp[mi][i]);
+        const u64 hhi = mulhi(rlo * m.qinv, m.q);
+        dst[(long)mi * N] = rhi - hhi + m.q + tab.vtimesqmodp[mi][v];
     }
 }
 
@@ -536,7 +594,7 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_mac_parties(MacPartiesArgs a, 
 //   One thread per coefficient.  The fp64 estimate of the overflow count v is reproduced operation by
 //   operation (RN convert, RN divide, RN sequential add, truncate).
 // ------------------------------------------------------------------------------------------------
-#define MKHE_CONV_MAX 16
+#define MKHE_CONV_MAX 40
 struct ConvTable {            // device-resident constants of one (source basis -> target basis) pair
     int n1, n2;
     int src_mod[MKHE_CONV_MAX];             // modulus index of source limb i

@@ -166,4 +166,31 @@ inline void gen_conv_table(ConvTable &c, const std::vector<u64> &mod, const std:
     }
 }
 
+// modUpParams[..][digit][nsrc-2] of NewDecomposer (mkrlwe/basis_extension.go:377-421): basisextenderparameters of the
+// digit's limbs Q[src0 .. src0+nsrc) against every modulus of Q u P (indexed by modulus index)
+inline void gen_lift_table(LiftTable &t, const std::vector<u64> &mod, int nQP, int src0, int nsrc) {
+    memset(&t, 0, sizeof t);
+    t.nsrc = nsrc;
+    t.src_limb0 = src0;
+    for (int i = 0; i < nsrc; i++) {
+        u64 qi = mod[src0 + i];
+        u64 star = 1;
+        for (int j = 0; j < nsrc; j++) if (j != i) star = h_mulmod(star, mod[src0 + j] % qi, qi);
+        t.qoverqiinvqi[i] = h_mform(h_invmod(star, qi), qi);
+    }
+    for (int j = 0; j < nQP; j++) {
+        u64 pj = mod[j];
+        u64 Qmod = 1;
+        for (int i = 0; i < nsrc; i++) {
+            u64 s = 1;
+            for (int u = 0; u < nsrc; u++) if (u != i) s = h_mulmod(s, mod[src0 + u] % pj, pj);
+            t.qoverqimodp[j][i] = h_mform(s, pj);
+            Qmod = h_mulmod(Qmod, mod[src0 + i] % pj, pj);
+        }
+        u64 v = pj - Qmod;
+        t.vtimesqmodp[j][0] = 0;
+        for (int i = 1; i <= nsrc; i++) { u64 w = t.vtimesqmodp[j][i - 1] + v; t.vtimesqmodp[j][i] = w >= pj ? w - pj : w; }
+    }
+}
+
 }  // namespace mkhe

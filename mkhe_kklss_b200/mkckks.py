@@ -8,10 +8,11 @@ from .mkrlwe import IDSet, Poly, SwitchingKey
 
 
 class Parameters(mkrlwe.Parameters):
-    """mkckks.Parameters (mkckks/params.go:9-40): mkrlwe parameters + default scale; gamma fixed to 2 (:20)"""
+    """mkckks.Parameters (mkckks/params.go:9-40): mkrlwe parameters + default scale.  The reference hard-wires gamma = 2
+    (:20); the keyword exists so the tests can reach other digit widths alpha = #P/gamma."""
 
-    def __init__(self, logN, Q, P, scale, device=0, lib=None):
-        super().__init__(logN, Q, P, 2, device, lib=lib)
+    def __init__(self, logN, Q, P, scale, device=0, lib=None, gamma=2):
+        super().__init__(logN, Q, P, gamma, device, lib=lib)
         self.scale = float(scale)
 
     def Scale(self):

@@ -1,6 +1,8 @@
 """Parameter literals of the reference's tests / benchmarks (the reference keeps them as Go literals in
 its test files).  gamma is hard-wired to 2 (mkckks/params.go:20, mkbfv/params.go:77-78),
-so alpha = #P/gamma = 1 and beta(level) = level+1 for every set below.
+so alpha = #P/gamma = 1 and beta(level) = level+1 for every set the reference enables.  PN16QP1761 (four special
+primes, alpha = 2) is the set the reference keeps commented out in mkrlwe_test.go:22-35; it exercises the general
+DecomposeAndSplit branch.
 
 Every prime is = 1 (mod 2^16), so each set can also be instantiated at a smaller logN (used by the
 parity tests to keep the CPU oracle fast).
@@ -79,4 +81,24 @@ BFV_PN14QP439 = ParamLiteral(
     P=(0xffffffffffc0001, 0xfffffffff840001),
     T=65537)
 
-ALL = {p.name: p for p in (CKKS_PN15QP880, CKKS_PN14QP439, CNN_PN14QP433, BFV_PN15QP880, BFV_PN14QP439)}
+# mkrlwe/mkrlwe_test.go:22-35 (commented out there): 55 + 33x45 | 4x55, gamma = 2 -> alpha = 2
+PN16QP1761 = ParamLiteral(
+    "PN16QP1761", 16,
+    Q=(0x80000000080001, 0x2000000a0001, 0x2000000e0001, 0x1fffffc20001,
+       0x200000440001, 0x200000500001, 0x200000620001, 0x1fffff980001,
+       0x2000006a0001, 0x1fffff7e0001, 0x200000860001, 0x200000a60001,
+       0x200000aa0001, 0x200000b20001, 0x200000c80001, 0x1fffff360001,
+       0x200000e20001, 0x1fffff060001, 0x200000fe0001, 0x1ffffede0001,
+       0x1ffffeca0001, 0x1ffffeb40001, 0x200001520001, 0x1ffffe760001,
+       0x2000019a0001, 0x1ffffe640001, 0x200001a00001, 0x1ffffe520001,
+       0x200001e80001, 0x1ffffe0c0001, 0x1ffffdee0001, 0x200002480001,
+       0x1ffffdb60001, 0x200002560001),
+    P=(0x80000000440001, 0x7fffffffba0001, 0x80000000500001, 0x7fffffffaa0001),
+    scale=float(1 << 45))
+# its first 7 Q limbs (odd count: the last digit is a single limb at the top level, partial digits below): test size
+PN16QP1761_Q7 = replace(PN16QP1761, name="PN16QP1761[:7]", Q=PN16QP1761.Q[:7])
+
+# same limbs with gamma = 1: alpha = 4 -> digits of 4 + 3 limbs at the top level, 4 + 2 and 4 + 1 below (partial lifts)
+PN16QP1761_Q7_ALPHA4 = replace(PN16QP1761_Q7, name="PN16QP1761[:7],gamma=1", gamma=1)
+
+ALL = {p.name: p for p in (CKKS_PN15QP880, CKKS_PN14QP439, CNN_PN14QP433, BFV_PN15QP880, BFV_PN14QP439, PN16QP1761)}

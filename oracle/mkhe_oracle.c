@@ -678,7 +678,7 @@ ork_keyswitcher *ork_ks_new(const ork_ring *ringQ, const ork_ring *ringP, int ga
     ks->ringQ = ringQ; ks->ringP = ringP;
     ks->nQ = ringQ->nmod; ks->nP = ringP->nmod; ks->gamma = gamma; ks->N = ringQ->N;
     ks->alpha = ks->nP / gamma;                                    /* params.go:63-65 */
-    if (ks->alpha != 1) { fprintf(stderr, "mkhe_oracle: only alpha = #P/gamma = 1 is restated (SURVEY section 0)\n"); abort(); }
+    if (ks->alpha < 1) { fprintf(stderr, "mkhe_oracle: alpha = #P/gamma must be >= 1\n"); abort(); }
     ks->be = ork_be_new(ringQ, ringP);
     size_t swk = (size_t)ks->nQ * (ks->nQ + ks->nP) * ks->N;       /* beta_max = nQ digits */
     ks->swkPool1 = (uint64_t *)xcalloc(swk, 8);
@@ -713,11 +713,70 @@ void ork_ks_decompose_single_ntt(ork_keyswitcher *ks, int levelQ, const uint64_t
     ork_ntt_lvl(ks->ringQ, levelQ, outQ, outQ);
     ork_ntt_lvl(ks->ringP, levelP, outP, outP);
 }
+/* DecomposeAndSplit, general branch (basis_extension.go:428-535) for digit `beta` when alpha > 1: the digit's limbs
+ * [alpha*beta, alpha*beta + decompLvl + 2) are lifted exactly (reconstructRNS + multSum with the fp64 overflow estimate)
+ * to every Q limb <= levelQ and every P limb.  Like the reference, the loop over "greater" limbs starts at alpha*beta
+ * (:525), so the digit's own limbs are overwritten by their (congruent, lazy) multSum values as well. */
+static void decompose_and_split_general(ork_keyswitcher *ks, int levelQ, int beta, int decompLvl, const uint64_t *a, uint64_t *outQP) {
+    const ork_ring *ringQ = ks->ringQ, *ringP = ks->ringP;
+    int N = ks->N, nQ = ks->nQ, nP = ks->nP, alpha = ks->alpha, levelP = nP - 1;
+    int lvlQStart = beta * alpha, nsrc = decompLvl + 2;
+    /* modUpParams[gamma*alpha-2][beta][decompLvl] = basisextenderparameters(Q[beta*alpha .. +nsrc), Q u P)  (:392-416) */
+    uint64_t *Pi = (uint64_t *)xmalloc(sizeof(uint64_t) * (size_t)(nQ + nP));
+    for (int k = 0; k < nQ; k++) Pi[k] = ringQ->q[k];
+    for (int k = 0; k < nP; k++) Pi[nQ + k] = ringP->q[k];
+    ork_modup_params mp;
+    modup_params_gen(&mp, ringQ->q + lvlQStart, nsrc, Pi, nQ + nP);
+    uint64_t *outQ = outQP, *outP = outQP + (size_t)nQ * N;
+    PAR_FOR
+    for (int x = 0; x < N; x++) {
+        uint64_t y[64];
+        double vi = 0.0;
+        for (int i = 0, j = lvlQStart; i < nsrc; i++, j++) {                 /* :471-503 */
+            uint64_t qi = ringQ->q[j];
+            uint64_t px = a[(size_t)j * N + x];
+            outQ[(size_t)j * N + x] = px;
+            y[i] = mred(px, mp.qoverqiinvqi[i], qi, ringQ->qinv[j]);
+            vi += (double)y[i] / (double)qi;
+        }
+        uint64_t v = (uint64_t)vi;                                           /* :506-513 */
+        for (int u = 0; u < nQ + nP; u++) {
+            int isP = u >= nQ, j = isP ? u - nQ : u;
+            if (!isP && (j > levelQ || (j >= lvlQStart && j < alpha * beta))) continue;   /* :516-527 (second range is empty) */
+            if (isP && j > levelP) continue;
+            uint64_t pj = isP ? ringP->q[j] : ringQ->q[j], qInv = isP ? ringP->qinv[j] : ringQ->qinv[j];
+            const uint64_t *qoq = mp.qoverqimodp + (size_t)u * mp.nq;
+            const uint64_t *vt = mp.vtimesqmodp + (size_t)u * (mp.nq + 1);
+            uint64_t rlo = 0, rhi = 0;
+            for (int i = 0; i < nsrc; i++) {                                 /* multSum :582-646 */
+                u128 m = (u128)y[i] * qoq[i];
+                uint64_t mhi = (uint64_t)(m >> 64), mlo = (uint64_t)m;
+                uint64_t s2 = rlo + mlo;
+                uint64_t c = s2 < rlo;
+                rlo = s2;
+                rhi += mhi + c;
+            }
+            uint64_t hhi = mulhi64(rlo * qInv, pj);
+            (isP ? outP : outQ)[(size_t)j * N + x] = rhi - hhi + pj + vt[v];
+        }
+    }
+    modup_params_free(&mp);
+    free(Pi);
+}
+/* DecomposeSingleNTT keyswitch.go:21-31 for any alpha: `a` is the whole coefficient-domain poly */
+static void decompose_single_ntt_any(ork_keyswitcher *ks, int levelQ, int beta, const uint64_t *a, uint64_t *outQP) {
+    int alpha = ks->alpha, levelP = ks->nP - 1;
+    int decompLvl = levelQ > alpha * (beta + 1) - 1 ? alpha - 2 : (levelQ % alpha) - 1;    /* :435-440 */
+    if (decompLvl == -1) { ork_ks_decompose_single_ntt(ks, levelQ, a + (size_t)beta * alpha * ks->N, outQP); return; }
+    decompose_and_split_general(ks, levelQ, beta, decompLvl, a, outQP);
+    ork_ntt_lvl(ks->ringQ, levelQ, outQP, outQP);
+    ork_ntt_lvl(ks->ringP, levelP, outQP + (size_t)ks->nQ * ks->N, outQP + (size_t)ks->nQ * ks->N);
+}
 /* Decompose keyswitch.go:49-73 (a.IsNTT == false branch: the only one the CKKS/BFV flows take) */
 void ork_ks_decompose(ork_keyswitcher *ks, int levelQ, const uint64_t *a, uint64_t *ad) {
     int beta = ork_ks_beta(ks, levelQ);
     for (int i = 0; i < beta; i++)
-        ork_ks_decompose_single_ntt(ks, levelQ, a + (size_t)i * ks->N, SWK_DIGIT(ks, ad, i));
+        decompose_single_ntt_any(ks, levelQ, i, a, SWK_DIGIT(ks, ad, i));
 }
 static void qp_mul_mont(ork_keyswitcher *ks, int levelQ, int levelP, const uint64_t *a, const uint64_t *b, uint64_t *c, int add) {
     size_t po = (size_t)ks->nQ * ks->N;
@@ -754,7 +813,7 @@ void ork_ks_external_product(ork_keyswitcher *ks, int levelQ, const uint64_t *a,
     int levelP = ks->nP - 1, beta = ork_ks_beta(ks, levelQ);
     uint64_t *c0QP = ks->poolQP0, *c1QP = ks->poolQP1;
     for (int i = 0; i < beta; i++) {
-        ork_ks_decompose_single_ntt(ks, levelQ, a + (size_t)i * ks->N, c0QP);
+        decompose_single_ntt_any(ks, levelQ, i, a, c0QP);
         qp_mul_mont(ks, levelQ, levelP, SWK_DIGIT(ks, bg, i), c0QP, c1QP, i != 0);
     }
     ks_finish_external_product(ks, levelQ, c1QP, c);

@@ -50,8 +50,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()                      # no-op when the library is newer than its sources
         _lib = C.CDLL(_LIB_PATH)
         _lib.ork_ring_new.restype = C.c_void_p
         _lib.ork_be_new.restype = C.c_void_p
@@ -420,7 +419,7 @@ class KeyGenerator:
         return (np.concatenate([outQ, outP]), pk1)
 
     def gen_switching_key(self, sk):
-        """GenSwitchingKey keygen.go:269-327: swk[i] = MForm(NTT(e_i)) ; limb i += P*s (alpha = 1)"""
+        """GenSwitchingKey keygen.go:269-327: swk[i] = MForm(NTT(e_i)) ; limbs [i*alpha, (i+1)*alpha) += P*s"""
         p = self.params
         Pbig = reduce(lambda a, b: a * b, p.P, 1)
         Ps = p.ringQ.mul_bigint(sk.Q, Pbig)                     # :289
@@ -429,9 +428,13 @@ class KeyGenerator:
             e = self.prng.gaussian(p.N, p.sigma, int(6 * p.sigma))
             swk[i, :p.nQ] = p.ringQ.mform(p.ringQ.ntt(p.ringQ.lift_small(e)))
             swk[i, p.nQ:] = p.ringP.mform(p.ringP.ntt(p.ringP.lift_small(e)))
-            q = np.uint64(p.Q[i])
-            t = swk[i, i] + Ps[i]
-            swk[i, i] = np.where(t >= q, t - q, t)             # CRed :320-322
+            for j in range(p.alpha()):                          # :307-323 (limbs of digit i; partial last digit)
+                idx = i * p.alpha() + j
+                if idx >= p.nQ:
+                    break
+                q = np.uint64(p.Q[idx])
+                t = swk[i, idx] + Ps[idx]
+                swk[i, idx] = np.where(t >= q, t - q, t)       # CRed :320-322
         return swk
 
     def _mul_sub_digits(self, a, s, out):

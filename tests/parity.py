@@ -44,7 +44,7 @@ class CKKSWorld:
         self.lit = lit
         self.op = O.MKParams(lit.logN, lit.Q, lit.P, lit.gamma, seed=seed, crs_rots=list(rots))
         self.prng = O.PRNG(seed ^ 0x5EED)
-        self.dp = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, lib=lib)
+        self.dp = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, lib=lib, gamma=lit.gamma)
         self.ctx = self.dp.ctx
         for idx, arr in self.op.CRS.items():
             self.dp.SetCRS(idx, arr)

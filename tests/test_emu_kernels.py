@@ -34,3 +34,25 @@ def test_bfv_kernels_under_emulation(emu):
     parity.check_bfv_mul_relin(w, [0, 1], [0, 1])
     parity.check_bfv_mul_relin(w, [0], [0, 1])
     w.close()
+
+
+@pytest.mark.parametrize("lit", [PR.PN16QP1761_Q7, PR.PN16QP1761_Q7_ALPHA4], ids=lambda l: l.name)
+def test_wide_digits_under_emulation(emu, lit):
+    """four special primes: gamma = 2 -> alpha = 2 (the set the reference keeps commented out, mkrlwe_test.go:22-35),
+    gamma = 1 -> alpha = 4.  Multi-limb digits take the exact lift of DecomposeAndSplit's general branch, a single-limb
+    last digit the broadcast, and the lower levels end in partial digits."""
+    w = parity.CKKSWorld(lit.at_logn(12), 2, lib=emu)
+    parity.run_ckks_suite(w, quick=True)
+    parity.check_decompose(w, level=5)
+    parity.check_decompose(w, level=4)
+    parity.check_mul_relin_new(w, w.ids, w.ids, level=5)
+    w.close()
+
+
+def test_pn16qp1761_full_limb_count_under_emulation(emu):
+    """34 + 4 limbs, 17 two-limb digits"""
+    w = parity.CKKSWorld(PR.PN16QP1761.at_logn(12), 2, lib=emu, rots=(1,))
+    parity.check_decompose(w)
+    parity.check_mul_relin_new(w, w.ids, w.ids)
+    parity.check_rotate(w, w.ids, 1)
+    w.close()

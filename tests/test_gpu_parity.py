@@ -196,3 +196,24 @@ def test_async_transfers_pipeline():
         for k in keys:
             parity.assert_same(pin_out[n][k], ops[n % 3][2].value[k], f"pipelined MulRelinNew {n}[{k}]")
     w.close()
+
+
+@pytest.mark.parametrize("lit,logN", [(PR.PN16QP1761_Q7, 13), (PR.PN16QP1761_Q7_ALPHA4, 12)], ids=lambda x: getattr(x, "name", str(x)))
+def test_wide_digits(lit, logN):
+    """alpha = #P/gamma > 1: DecomposeAndSplit's general branch (mkrlwe/basis_extension.go:454-534), alpha-limb gadget keys"""
+    w = parity.CKKSWorld(lit.at_logn(logN), 2)
+    parity.run_ckks_suite(w, quick=True)
+    parity.check_decompose(w, level=5)
+    parity.check_decompose(w, level=4)
+    parity.check_mul_relin_new(w, w.ids, w.ids, level=5)
+    parity.check_rotate(w, w.ids, 1, level=4)
+    w.close()
+
+
+def test_pn16qp1761_full_limb_count():
+    """the reference's commented-out PN16QP1761 (34 + 4 limbs, alpha = 2, 17 digits) at a size the oracle finishes quickly"""
+    w = parity.CKKSWorld(PR.PN16QP1761.at_logn(12), 2, rots=(1,))
+    parity.check_decompose(w)
+    parity.check_mul_relin_new(w, w.ids, w.ids)
+    parity.check_rotate(w, w.ids, 1)
+    w.close()
