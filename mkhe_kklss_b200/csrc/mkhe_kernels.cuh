@@ -111,13 +111,19 @@ struct XAddr {             // per-thread bases into the exchange buffer
 
 // the caller guarantees (block barrier) that nobody still reads the buffer when tile_fwd / tile_inv starts.
 // big (2^57 <= q < 2^60, CTA-uniform): inputs below 16q, a sweep to [0,8q) before every second stage keeps them there.
+// Round A works on registers only; rounds B and C start with the stores into the exchange buffer, so a caller can put
+// one barrier between the two halves that covers both "everybody has consumed its input" and "everybody has left the
+// previous instance's exchange buffer".
 template <class TW>
-__device__ __forceinline__ void tile_fwd(u64 v[16], const XAddr &x, const TW &tw, const NttC &c, const bool big, const int bar_id) {
+__device__ __forceinline__ void tile_fwd_A(u64 v[16], const TW &tw, const NttC &c, const bool big) {
 #pragma unroll
     for (int b = 3; b >= 0; b--) {
         if (b & 1) MKHE_SWEEP16()
         MKHE_STAGE(bf_fwd, tw.A(b, g), 0)
     }
+}
+template <class TW>
+__device__ __forceinline__ void tile_fwd_BC(u64 v[16], const XAddr &x, const TW &tw, const NttC &c, const bool big, const int bar_id) {
 #pragma unroll
     for (int k = 0; k < 16; k++) x.a1[k * 136] = v[k];
     named_sync(bar_id, MKHE_NTT_THREADS);
@@ -411,12 +417,17 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 2) k_ntt_pass2(Pass2Args a, c
         u64 v[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = inbuf[k * 128 + tid];
-        named_sync(1 + grp, MKHE_NTT_THREADS);      // the landing buffer is free again; everybody has left the previous instance's exchange buffer
+        tile_fwd_A(v, tw, c, big);
+        consume16(v);
+        // Round A has CONSUMED the values read from the landing buffer, so those shared-memory loads have completed: a
+        // barrier alone does not order still-queued generic-proxy loads before the TMA (async-proxy) write that refills
+        // the buffer.  The same barrier tells that everybody has left the previous instance's exchange buffer.
+        named_sync(1 + grp, MKHE_NTT_THREADS);
         if (tid == 0 && i + MKHE_P2_GROUPS < i1) {
             mbar_expect_tx(&bars[1 + grp], MKHE_TILE * 8);
             tma_load_1d(inbuf, inst_ptr(i + MKHE_P2_GROUPS), MKHE_TILE * 8, &bars[1 + grp]);
         }
-        tile_fwd(v, x, tw, c, big, 1 + grp);
+        tile_fwd_BC(v, x, tw, c, big, 1 + grp);
         u64 *o = inst_ptr(i) + tid * 16;
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -484,12 +495,18 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_mac_digits(MacDigitsArgs a, co
         mbar_wait(&bars[st], (term / MKHE_MAC_STAGES) & 1);
         const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(smraw + st * (G + 1) * BOX) + tid;
         const ulonglong2 s = src[0];
+        ulonglong2 p[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) p[g] = src[(1 + g) * MKHE_THREADS];
 #pragma unroll
         for (int g = 0; g < G; g++) {
-            const ulonglong2 p = src[(1 + g) * MKHE_THREADS];
-            mac128(hi[g][0], lo[g][0], s.x, p.x);
-            mac128(hi[g][1], lo[g][1], s.y, p.y);
+            mac128(hi[g][0], lo[g][0], s.x, p[g].x);
+            mac128(hi[g][1], lo[g][1], s.y, p[g].y);
         }
+        // the accumulators depend on every value read from stage st: anchoring them before the barrier guarantees the
+        // shared-memory loads have completed before thread 0 lets the TMA (async proxy) overwrite the stage
+#pragma unroll
+        for (int g = 0; g < G; g++) consume4(hi[g][0], lo[g][0], hi[g][1], lo[g][1]);
         __syncthreads();                                   // every thread has read stage st
         if (tid == 0 && term + MKHE_MAC_STAGES < nterms) issue(term + MKHE_MAC_STAGES);
     }

@@ -132,16 +132,29 @@ def test_device_matches_committed_golden_digests():
         dp.ctx.close()
 
 
-def test_full_size_repeatability():
-    """logN = 15 (BASELINE size), the same MulRelinNew and hoisted Rotate 25 times against ONE oracle result: an ordering
-    or staging error between kernels (TMA pipelines, scratch reuse) shows up as an intermittent mismatch"""
+def test_full_size_back_to_back():
+    """logN = 15 (BASELINE size): MulRelinNew calls enqueued back to back without synchronisation (as bench.py does), every
+    output against ONE oracle result, then the same for hoisted Rotate.  A staging / ordering error between or inside
+    kernels shows up as an intermittent mismatch: this is the test that caught a TMA refill overtaking still-queued
+    shared-memory loads in pass 2 (rate ~1 %, tools/stress_b2b.py)."""
+    from mkhe_kklss_b200 import mkckks
     w = parity.CKKSWorld(PR.CKKS_PN15QP880, 2, rots=(2,))
-    level = w.op.max_level()
-    o0, d0 = w.random_ct(w.ids, level)
-    o1, d1 = w.random_ct(w.ids, level)
+    ids, level = w.ids, w.op.max_level()
+    o0, d0 = w.random_ct(ids, level)
+    o1, d1 = w.random_ct(ids, level)
     want = w.oev.mul_relin_new(o0, o1, w.o_rlk)
-    for rep in range(25):
-        w.compare_ct(w.dev.MulRelinNew(d0, d1, w.d_rlk), want, f"MulRelinNew repetition {rep}")
+    outs = [mkckks.Ciphertext.new(w.dp, ids, level, w.lit.scale) for _ in range(16)]
+    g = w.d_rlk.GetRelinearizationKey
+    kb, kd, kv = ([g(i).Value[j].h for i in ids] for j in range(3))
+    nb, new_scale = w.dev._nb_rescales(w.lit.scale * w.lit.scale, level, w.lit.scale)
+    for rnd in range(12):
+        for out in outs:
+            w.ctx.ckks_mul_relin(level, nb, False, ids, d0.handles(ids), ids, d1.handles(ids), kb, kd, kv, w.dp.CRS[-1].h, ids,
+                                 out.handles(ids))
+        w.ctx.sync()
+        for i, out in enumerate(outs):
+            out.Scale = new_scale
+            w.compare_ct(out, want, f"MulRelinNew round {rnd} op {i}")
     hd = w.dev.HoistedForm(d0)
     want_r = w.oev.rotate_hoisted_new(o0, 2, w.oev.hoisted_form(o0), w.o_rk)
     for rep in range(25):
