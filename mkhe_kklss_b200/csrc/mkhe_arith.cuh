@@ -175,8 +175,10 @@ __device__ __forceinline__ u64 shoup4(u64 x, u64 w, u64 wsh, u64 nq) {
 // constants of one modulus as the NTT butterflies use them
 struct NttC {
     u64 q, nq, fourq;
+    u64 zero;     // 0 at run time, opaque to the compiler: a third addend turns `x + t` into IADD3 / IADD3.X with two carries,
+                  // which ptxas cannot move to the multiplier pipe as IMAD.X (the pipe that bounds the butterflies)
 };
-__device__ __forceinline__ NttC nttc(const ModC &m) { NttC c; c.q = m.q; c.nq = m.nq; c.fourq = 4 * m.q; return c; }
+__device__ __forceinline__ NttC nttc(const ModC &m) { NttC c; c.q = m.q; c.nq = m.nq; c.fourq = 4 * m.q; c.zero = m.pad; return c; }
 
 // forward (Cooley-Tukey) butterfly without any reduction: the Shoup product lands in [0,4q) for ANY 64-bit Y, so a stage
 // adds at most 4q to the magnitude of both outputs.
@@ -185,19 +187,19 @@ __device__ __forceinline__ NttC nttc(const ModC &m) { NttC c; c.q = m.q; c.nq = 
 __device__ __forceinline__ void bf_fwd(u64 &X, u64 &Y, u64 w, u64 wsh, const NttC &c) {
     const u64 x = X;
     const u64 t = shoup4(Y, w, wsh, c.nq);
-    X = x + t;
+    X = x + t + c.zero;
     Y = x - t + c.fourq;
 }
 // [0,16q) -> [0,8q)
 __device__ __forceinline__ u64 fwd_sweep(u64 x, const NttC &c) {
     const u64 e = 2 * c.fourq;
-    return x >= e ? x - e : x;
+    return x - (x >= e ? e : 0ull) + c.zero;
 }
 // inverse (Gentleman-Sande) butterfly: X,Y in [0,4q) -> [0,4q)   (8q < 2^63 for every supported q)
 __device__ __forceinline__ void bf_inv(u64 &X, u64 &Y, u64 w, u64 wsh, const NttC &c) {
-    const u64 s = X + Y;
+    const u64 s = X + Y + c.zero;
     const u64 d = X - Y + c.fourq;
-    X = s >= c.fourq ? s - c.fourq : s;
+    X = s - (s >= c.fourq ? c.fourq : 0ull) + c.zero;
     Y = shoup4(d, w, wsh, c.nq);
 }
 // any 64-bit v -> canonical [0,q): 32-bit Barrett quotient.  With b = bitlen(q) >= 40: vh = floor(v / 2^(b-2)) < 2^26,
