@@ -322,8 +322,12 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="ciphertext pairs (MulRelin ops) per step")
     ap.add_argument("--no-extras", action="store_true", help="skip the k=8 / hoisted-Rotate side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lib", default=None, help="development: load this build of the library instead of the in-tree one")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.lib:
+        from mkhe_kklss_b200 import _lib
+        _lib._default = _lib.Library(os.path.abspath(args.lib))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

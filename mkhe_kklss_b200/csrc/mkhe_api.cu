@@ -46,6 +46,8 @@ struct Scratch {
 struct mkhe_ctx {
     int logN = 0, N = 0, nQ = 0, nP = 0, nQMul = 0, gamma = 2, device = 0;
     int S1 = 0, dmax = 0;
+    int p2_timing_n = 0;
+    int num_sms = 148;                    // persistent kernels size their grids from it
     int alpha = 1, beta_max = 0;          // alpha = #P/gamma limbs per digit, beta_max = ceil(nQ/alpha) digits (mkrlwe/params.go:63-71)
     LiftTable *d_lift = nullptr;          // alpha > 1: [beta_max][alpha-1] tables of the Decomposer
     u64 T = 0;
@@ -269,29 +271,34 @@ int pick_chunks(int count, long ctas_per_chunk) {
     return std::max(chunks, 1);
 }
 
-// pass 2: instances per CTA -- even (two groups per CTA), as large as possible while the grid still has >= ~5 waves
-int pick_per(int ninst, long ctas_per_chunk) {
-    const long want = 148L * 2 * 5;
-    const long nchunks = std::max<long>(1, (want + ctas_per_chunk - 1) / ctas_per_chunk);
-    long per = ninst / nchunks;
-    per -= per & 1;
-    per = std::max<long>(per, MKHE_P2_GROUPS);
-    return (int)std::min<long>(per, std::max(ninst, 1));
-}
+// pass 2 is persistent: the grid is what the device holds at once and every CTA owns an equal-cost stretch of the tile list
+#ifndef MKHE_P2_BIGW
+#define MKHE_P2_BIGW 19          // cost of a tile of a 59/60-bit modulus in sixteenths of a normal one (the sweeps)
+#endif
 int launch_pass2(mkhe_ctx *ctx, const Slots &s, int np, u64 *const *bufs, int count, long inst_stride) {
     const int tiles = ctx->N / MKHE_TILE;
     Pass2Args b;
     memset(&b, 0, sizeof b);
     b.count = count;
     b.ninst = np * count;
-    b.per = pick_per(b.ninst, (long)tiles * s.n);
     b.inst_stride = inst_stride;
     b.nslots = s.n;
     b.logN = ctx->logN;
-    for (int i = 0; i < s.n; i++) { b.slots[i] = s.slot[i]; b.mods[i] = s.mod[i]; }
+    const long per_slot = (long)tiles * b.ninst;
+    for (int i = 0; i < s.n; i++) {
+        b.slots[i] = s.slot[i];
+        b.mods[i] = s.mod[i];
+        b.wslot[i] = ctx->tabs[s.mod[i]].c.big ? MKHE_P2_BIGW : 16;
+        b.wstart[i + 1] = b.wstart[i] + per_slot * b.wslot[i];
+    }
     for (int i = 0; i < np; i++) b.buf.p[i] = bufs[i];
-    const int nchunks = (b.ninst + b.per - 1) / b.per;
-    LAUNCH(k_ntt_pass2, dim3(tiles * nchunks, s.n), dim3(MKHE_P2_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf_tiled);
+    const long ntile_inst = per_slot * s.n;
+    const long grid = std::max<long>(1, std::min<long>(ctx->num_sms, ntile_inst / std::min(b.ninst, MKHE_P2_GROUPS)));
+#ifdef MKHE_P2_TIMING
+    TRY(get_scratch(ctx, "p2timing", 4 * 8 * 4096, &b.timing));
+    ctx->p2_timing_n = (int)grid;
+#endif
+    LAUNCH(k_ntt_pass2, dim3((unsigned)grid), dim3(MKHE_P2_THREADS), SMEM_PASS2, b, ctx->d_mods, ctx->d_twf_tiled);
     return MKHE_OK;
 }
 
@@ -852,6 +859,7 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MKHE_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MKHE_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MKHE_ERR_CUDA; }
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->num_sms = v; }
     cudaEventCreate(&ctx->ev_compute);
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
@@ -1680,6 +1688,17 @@ int mkhe_profile_end(mkhe_ctx *ctx, char *buf, size_t cap) {
     if (buf && cap) { strncpy(buf, out.c_str(), cap - 1); buf[cap - 1] = 0; }
     return MKHE_OK;
 }
+#ifdef MKHE_P2_TIMING
+// development builds only: {start ns, end ns, SM id, tiles} of every CTA of the last pass-2 launch
+int mkhe_debug_p2_timing(mkhe_ctx *ctx, uint64_t *out, int cap, int *n) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n = std::min(cap, ctx->p2_timing_n);
+    CU(cudaMemcpy(out, ctx->scratch["p2timing"].p, (size_t)*n * 32, cudaMemcpyDeviceToHost));
+    return MKHE_OK;
+}
+#endif
+
 int mkhe_bench_butterfly_peak(mkhe_ctx *ctx, double *butterflies_per_s) {
     CHECK_CTX();
     u64 *sink;

@@ -25,12 +25,13 @@ typedef unsigned int u32;
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) { *reinterpret_cast<ulonglong2 *>(smem) = *reinterpret_cast<const ulonglong2 *>(gmem); }
 __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ void prefetch_l2(const void *) {}
-// TMA bulk copies complete at issue under emulation, the barrier operations are no-ops
-__device__ __forceinline__ void mbar_init(u64 *, int) {}
-__device__ __forceinline__ void mbar_expect_tx(u64 *, u32) {}
-__device__ __forceinline__ void mbar_wait(u64 *, u32) {}
-__device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *) { memcpy(smem, gmem, bytes); }
-__device__ __forceinline__ void named_sync(int, int) { emu_syncthreads(); }      // lock-step rounds: a yield is enough
+// TMA bulk copies complete at issue under emulation; the mbarrier keeps its transaction count and phase, so a waiter
+// really waits for the thread that issues the copy
+__device__ __forceinline__ void mbar_init(u64 *bar, int) { emu_mbar_init(bar); }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) { emu_mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { emu_mbar_wait(bar, parity); }
+__device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *bar) { memcpy(smem, gmem, bytes); emu_mbar_complete_tx(bar, bytes); }
+__device__ __forceinline__ void named_sync(int id, int nthreads) { emu_barrier(id, nthreads); }
 __device__ __forceinline__ void consume16(const u64 *) {}
 __device__ __forceinline__ void consume4(u64, u64, u64, u64) {}
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }

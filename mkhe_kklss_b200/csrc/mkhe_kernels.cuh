@@ -30,7 +30,7 @@
 // [544w, 544w+544), so the B <-> C exchange only needs a warp-level barrier.
 #define MKHE_XBUF 2176           // u64 slots of the exchange buffer (2048 + 128 padding)
 #ifdef MKHE_EMU
-#define MKHE_SYNCWARP() __syncthreads()
+#define MKHE_SYNCWARP() emu_syncwarp()
 #else
 #define MKHE_SYNCWARP() __syncwarp()
 #endif
@@ -362,77 +362,151 @@ struct Pass2Args {
     PtrList buf;
     int count;                       // instances per poly (digits); instance i lives at buf[i / count] + (i % count) * inst_stride
     int ninst;                       // npolys * count
-    int per;                         // instances per CTA (split over the CTA's groups)
     long inst_stride;
     int nslots;
     int slots[MKHE_MAX_SLOTS];       // limb slot (offset slot*N)
     int mods[MKHE_MAX_SLOTS];        // modulus index of that slot
+    int wslot[MKHE_MAX_SLOTS];       // cost of one tile of that slot (16 = a modulus below 2^57; the 59/60-bit ones sweep and cost more)
+    long wstart[MKHE_MAX_SLOTS + 1]; // cumulative cost before slot s; wstart[nslots] = total
     int logN;
+#ifdef MKHE_P2_TIMING
+    u64 *timing;                     // development builds: per CTA {start ns, end ns, SM id, tiles}
+#endif
 };
-#define MKHE_P2_GROUPS 2
+#ifndef MKHE_P2_GROUPS
+#define MKHE_P2_GROUPS 4
+#endif
 #define MKHE_P2_THREADS (MKHE_P2_GROUPS * MKHE_NTT_THREADS)
-#define MKHE_P2_SMEM (MKHE_TILE * 16 + MKHE_P2_GROUPS * (MKHE_XBUF * 8 + MKHE_TILE * 8) + 64)
+#define MKHE_P2_GROUP_BYTES (MKHE_XBUF * 8 + MKHE_TILE * 8)
+#define MKHE_P2_SMEM (MKHE_TILE * 16 + MKHE_P2_GROUPS * MKHE_P2_GROUP_BYTES + 8 * (1 + MKHE_P2_GROUPS) + 16 + 16 * MKHE_P2_GROUPS)
+
+// the work of a launch is the list of tiles (slot, tile, instance), instance fastest; CTA c of G owns the stretch whose cumulative
+// cost lies in [c, c+1) * total / G.  The boundary is the first list index whose cumulative cost reaches the target.
+__device__ __forceinline__ long p2_boundary(const Pass2Args &a, long target, long per_slot) {
+    int s = 0;
+    while (s + 1 < a.nslots && a.wstart[s + 1] <= target) s++;
+    long o = (target - a.wstart[s] + a.wslot[s] - 1) / a.wslot[s];
+    if (o > per_slot) o = per_slot;
+    return (long)s * per_slot + o;
+}
+struct P2Mail { int off, pad; u64 *ptr; };       // a group's next tile, published by its thread 0
 
 // K1 pass 2: last 11 stages on contiguous tiles, canonical output, in place.
-//   grid = (tiles * nchunks, nslots).  A CTA owns one (tile, limb) and `per` instances of it (digits x polys): the tile's
-//   2047 twiddles arrive once by TMA, each 128-thread group walks every MKHE_P2_GROUPS-th instance, its 16 KiB input tile
-//   prefetched by TMA into the group's landing buffer while the previous instance is transformed.
-__global__ void __launch_bounds__(MKHE_P2_THREADS, 2) k_ntt_pass2(Pass2Args a, const ModC *mods, const ulonglong2 *tiled) {
+//   Persistent: ONE CTA per SM (two co-resident CTAs do not share an SM fairly: the older one is served first, measured
+//   2.9 vs 4.0 us per tile, and the SM is half empty once it leaves), MKHE_P2_GROUPS groups of 128 threads.  Every CTA owns an
+//   equal-cost stretch of the tile list, so there is no tail across SMs and the start-up is paid once.  Within the stretch the
+//   groups take tiles from a shared counter (a group that the warp schedulers favour simply transforms more tiles).  The tiles
+//   of one (slot, tile) pair are consecutive: the pair's 2047 twiddles arrive once by TMA; a group's next 16 KiB input tile is
+//   prefetched by TMA into its landing buffer while the current one is transformed.
+__global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(Pass2Args a, const ModC *mods, const ulonglong2 *tiled) {
     MKHE_SMEM(smraw);
     const int tid = threadIdx.x & (MKHE_NTT_THREADS - 1), grp = threadIdx.x / MKHE_NTT_THREADS;
-    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw);                                                     // 32 KiB twiddles
-    u64 *xbuf = reinterpret_cast<u64 *>(smraw + MKHE_TILE * 16 + grp * (MKHE_XBUF * 8 + MKHE_TILE * 8));          // 17 KiB exchange
-    u64 *inbuf = xbuf + MKHE_XBUF;                                                                               // 16 KiB landing
-    u64 *bars = reinterpret_cast<u64 *>(smraw + MKHE_TILE * 16 + MKHE_P2_GROUPS * (MKHE_XBUF * 8 + MKHE_TILE * 8));
+    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw);                                          // 32 KiB twiddles
+    u64 *xbuf = reinterpret_cast<u64 *>(smraw + MKHE_TILE * 16 + grp * MKHE_P2_GROUP_BYTES);           // 17 KiB exchange
+    u64 *inbuf = xbuf + MKHE_XBUF;                                                                    // 16 KiB landing
+    unsigned char *tail = smraw + MKHE_TILE * 16 + MKHE_P2_GROUPS * MKHE_P2_GROUP_BYTES;
+    u64 *bars = reinterpret_cast<u64 *>(tail);
+    int *ctr = reinterpret_cast<int *>(tail + 8 * (1 + MKHE_P2_GROUPS));
+    P2Mail *mail = reinterpret_cast<P2Mail *>(tail + 8 * (1 + MKHE_P2_GROUPS) + 16);
     const long N = 1L << a.logN;
     const int ntiles = (int)(N / MKHE_TILE);
-    const int tile = blockIdx.x % ntiles, chunk = blockIdx.x / ntiles;
-    const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
-    const ModC m = mods[mi];
-    const NttC c = nttc(m);
-    const bool big = m.big != 0;
-    const int i0 = chunk * a.per, i1 = i0 + a.per < a.ninst ? i0 + a.per : a.ninst;
-    auto inst_ptr = [&](int i) -> u64 * {
-        const int poly = i / a.count;
-        return a.buf.p[poly] + (long)(i - poly * a.count) * a.inst_stride + (long)slot * N + (long)tile * MKHE_TILE;
+    const int per_slot = ntiles * a.ninst;          // the tile list has at most 40 * 32 * 64 * 40 entries: 32-bit indices (no 64-bit divisions)
+    const long total = a.wstart[a.nslots];
+    const int w_begin = (int)p2_boundary(a, total * blockIdx.x / gridDim.x, per_slot);
+    const int w_end = (int)p2_boundary(a, total * (blockIdx.x + 1) / gridDim.x, per_slot);
+    const int nwork = w_end - w_begin;
+    auto tile_ptr = [&](int w) -> u64 * {
+        const unsigned sidx = (unsigned)w / (unsigned)per_slot;
+        const unsigned r = (unsigned)w - sidx * (unsigned)per_slot;
+        const unsigned tile = r / (unsigned)a.ninst, inst = r - tile * (unsigned)a.ninst;
+        const unsigned poly = inst / (unsigned)a.count;
+        return a.buf.p[poly] + (long)(inst - poly * a.count) * a.inst_stride + (long)a.slots[sidx] * N + (long)tile * MKHE_TILE;
     };
     if (threadIdx.x == 0) {
         for (int b = 0; b <= MKHE_P2_GROUPS; b++) mbar_init(&bars[b], 1);
+        *ctr = MKHE_P2_GROUPS;                      // group g starts with tile g of the stretch
     }
+#ifdef MKHE_P2_TIMING
+    if (threadIdx.x == 0 && a.timing) {
+        u64 t; u32 sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        a.timing[4 * blockIdx.x] = t; a.timing[4 * blockIdx.x + 2] = sm; a.timing[4 * blockIdx.x + 3] = (u64)nwork;
+    }
+#endif
     __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&bars[0], MKHE_TILE * 16);
-        tma_load_1d(stw, tiled + ((long)mi * ntiles + tile) * MKHE_TILE, MKHE_TILE * 16, &bars[0]);
-    }
-    int i = i0 + grp;
-    if (tid == 0 && i < i1) {
-        mbar_expect_tx(&bars[1 + grp], MKHE_TILE * 8);
-        tma_load_1d(inbuf, inst_ptr(i), MKHE_TILE * 8, &bars[1 + grp]);
+    int cur = grp;                                  // offset of the group's current tile within the stretch
+    u64 *cur_ptr = nullptr;
+    if (cur < nwork) {
+        cur_ptr = tile_ptr(w_begin + cur);
+        if (tid == 0) {
+            mbar_expect_tx(&bars[1 + grp], MKHE_TILE * 8);
+            tma_load_1d(inbuf, cur_ptr, MKHE_TILE * 8, &bars[1 + grp]);
+        }
     }
     const TwShared tw(stw, tid);
     const XAddr x(xbuf, tid);
-    mbar_wait(&bars[0], 0);
-    for (int n = 0; i < i1; i += MKHE_P2_GROUPS, n++) {
-        mbar_wait(&bars[1 + grp], n & 1);
-        u64 v[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = inbuf[k * 128 + tid];
-        tile_fwd_A(v, tw, c, big);
-        consume16(v);
-        // Round A has CONSUMED the values read from the landing buffer, so those shared-memory loads have completed: a
-        // barrier alone does not order still-queued generic-proxy loads before the TMA (async-proxy) write that refills
-        // the buffer.  The same barrier tells that everybody has left the previous instance's exchange buffer.
-        named_sync(1 + grp, MKHE_NTT_THREADS);
-        if (tid == 0 && i + MKHE_P2_GROUPS < i1) {
-            mbar_expect_tx(&bars[1 + grp], MKHE_TILE * 8);
-            tma_load_1d(inbuf, inst_ptr(i + MKHE_P2_GROUPS), MKHE_TILE * 8, &bars[1 + grp]);
+    u32 tw_phase = 0, in_phase = 0;
+    bool first = true;
+    for (int seg = w_begin; seg < w_end;) {         // CTA-uniform walk over the (slot, tile) pairs of the stretch
+        const int sidx = seg / per_slot;
+        const int tile = (seg - sidx * per_slot) / a.ninst;
+        const int pair_end = sidx * per_slot + (tile + 1) * a.ninst;
+        seg = pair_end < w_end ? pair_end : w_end;
+        const int seg_end = seg - w_begin;
+        const int mi = a.mods[sidx];
+        const ModC m = mods[mi];
+        const NttC c = nttc(m);
+        const bool big = m.big != 0;
+        // every group has left the previous pair (its twiddles are about to be overwritten)
+        if (!first) __syncthreads();
+        first = false;
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bars[0], MKHE_TILE * 16);
+            tma_load_1d(stw, tiled + ((long)mi * ntiles + tile) * MKHE_TILE, MKHE_TILE * 16, &bars[0]);
         }
-        tile_fwd_BC(v, x, tw, c, big, 1 + grp);
-        u64 *o = inst_ptr(i) + tid * 16;
+        mbar_wait(&bars[0], tw_phase);
+        tw_phase ^= 1;
+        while (cur < seg_end) {
+            mbar_wait(&bars[1 + grp], in_phase);
+            in_phase ^= 1;
+            u64 v[16];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            st_global_v4(o + 4 * k, canon(v[4 * k], m), canon(v[4 * k + 1], m), canon(v[4 * k + 2], m), canon(v[4 * k + 3], m));
+            for (int k = 0; k < 16; k++) v[k] = inbuf[k * 128 + tid];
+            tile_fwd_A(v, tw, c, big);
+            consume16(v);
+            // Round A has CONSUMED the values read from the landing buffer, so those shared-memory loads have completed: a
+            // barrier alone does not order still-queued generic-proxy loads before the TMA (async-proxy) write that refills
+            // the buffer.  The same barrier tells that everybody has left the previous tile's exchange buffer and mail slot.
+            named_sync(1 + grp, MKHE_NTT_THREADS);
+            if (tid == 0) {
+                const int nxt = atomicAdd(ctr, 1);
+                u64 *np = nullptr;
+                if (nxt < nwork) {                  // the next tile may belong to the next pair: its data does not depend on twiddles
+                    np = tile_ptr(w_begin + nxt);
+                    mbar_expect_tx(&bars[1 + grp], MKHE_TILE * 8);
+                    tma_load_1d(inbuf, np, MKHE_TILE * 8, &bars[1 + grp]);
+                }
+                mail[grp].off = nxt;
+                mail[grp].ptr = np;
+            }
+            tile_fwd_BC(v, x, tw, c, big, 1 + grp);         // its barrier publishes the mail slot
+            u64 *o = cur_ptr + tid * 16;
+            cur = mail[grp].off;
+            cur_ptr = mail[grp].ptr;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                st_global_v4(o + 4 * k, canon(v[4 * k], m), canon(v[4 * k + 1], m), canon(v[4 * k + 2], m), canon(v[4 * k + 3], m));
+        }
     }
+#ifdef MKHE_P2_TIMING
+    __syncthreads();
+    if (threadIdx.x == 0 && a.timing) {
+        u64 t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.timing[4 * blockIdx.x + 1] = t;
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -21,6 +21,8 @@ struct Worker {
     int current = -1;
     const std::function<void()> *body = nullptr;
     std::vector<unsigned char> smem;
+    int nthreads = 0;
+    unsigned bar_cnt[64] = {0}, bar_gen[64] = {0};      // 0..15: bar.sync ids, 16..: one per warp (__syncwarp)
 };
 thread_local Worker *tl_worker = nullptr;
 
@@ -32,10 +34,37 @@ void fiber_entry() {
 }
 }  // namespace
 
-void emu_syncthreads() {
+static void emu_yield() {
     Worker *w = tl_worker;
     swapcontext(&w->fibers[w->current].ctx, &w->sched);
     threadIdx = w->fibers[w->current].tid;
+}
+// a real counting barrier: groups of a CTA may pass different numbers of barriers (persistent kernels)
+void emu_barrier(int id, int nthreads) {
+    Worker *w = tl_worker;
+    const unsigned gen = w->bar_gen[id];
+    if (++w->bar_cnt[id] == (unsigned)nthreads) {
+        w->bar_cnt[id] = 0;
+        w->bar_gen[id]++;
+        return;
+    }
+    while (w->bar_gen[id] == gen) emu_yield();
+}
+void emu_syncthreads() { emu_barrier(0, tl_worker->nthreads); }
+void emu_syncwarp() {
+    Worker *w = tl_worker;
+    const int warp = w->current / 32, lanes = w->nthreads - warp * 32 < 32 ? w->nthreads - warp * 32 : 32;
+    emu_barrier(16 + warp, lanes);
+}
+// mbarrier with transaction count: low 32 bits = bytes still expected, high 32 bits = completed phases
+void emu_mbar_init(unsigned long long *bar) { *bar = 0; }
+void emu_mbar_expect_tx(unsigned long long *bar, unsigned bytes) { *bar += bytes; }
+void emu_mbar_complete_tx(unsigned long long *bar, unsigned bytes) {
+    *bar -= bytes;
+    if ((unsigned)(*bar & 0xffffffffull) == 0) *bar += 1ull << 32;
+}
+void emu_mbar_wait(unsigned long long *bar, unsigned parity) {
+    while ((((unsigned)(*bar >> 32)) & 1u) == parity) emu_yield();
 }
 
 double emu_now_ms() {
@@ -51,6 +80,7 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> 
         Worker w;
         tl_worker = &w;
         w.body = &body;
+        w.nthreads = nthreads;
         w.fibers.resize(nthreads);
         for (auto &f : w.fibers) f.stack = (unsigned char *)malloc(kStack);
         w.smem.assign(smem + 64, 0);
@@ -74,6 +104,7 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> 
                 f.ctx.uc_link = nullptr;
                 makecontext(&f.ctx, (void (*)())fiber_entry, 0);
             }
+            memset(w.bar_cnt, 0, sizeof w.bar_cnt);
             int remaining = nthreads;
             while (remaining > 0) {
                 for (int t = 0; t < nthreads; t++) {

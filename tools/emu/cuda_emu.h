@@ -31,6 +31,12 @@ extern thread_local uint3_emu threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
 extern thread_local unsigned char *emu_smem;           // dynamic shared memory of the running block
 void emu_syncthreads();
+void emu_syncwarp();
+void emu_barrier(int id, int nthreads);
+void emu_mbar_init(unsigned long long *bar);
+void emu_mbar_expect_tx(unsigned long long *bar, unsigned bytes);
+void emu_mbar_complete_tx(unsigned long long *bar, unsigned bytes);
+void emu_mbar_wait(unsigned long long *bar, unsigned parity);
 
 #define __global__
 #define __device__
@@ -50,6 +56,7 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline unsigned long long __double2ull_rz(double x) { return (unsigned long long)x; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }      // fibers are cooperative
 
 // ---- runtime API subset -------------------------------------------------------------------------
 typedef int cudaError_t;
@@ -63,6 +70,8 @@ static inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 6; return 0; }    // a small "device": persistent grids stay cheap to emulate
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }

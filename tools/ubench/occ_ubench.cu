@@ -8,6 +8,44 @@
 #include "mkhe_arith.cuh"
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
+// EXTRA independent ALU instructions (LOP3 / IADD3 alternating) per butterfly: do ALU-pipe instructions delay the multiplier pipe?
+template <int EXTRA>
+__global__ void __launch_bounds__(128, 4) k_extra(u64 *sink, ModC m, const ulonglong2 *tw, int iters) {
+    extern __shared__ unsigned char sm[];
+    u64 v[16];
+    u32 e[8];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = (u64)(threadIdx.x * 16 + k + blockIdx.x) % m.q;
+#pragma unroll
+    for (int k = 0; k < 8; k++) e[k] = threadIdx.x * 7 + k;
+    const NttC c = nttc(m);
+    ulonglong2 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) w[k] = tw[k];
+    const u32 z = (u32)m.q;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int b = 3; b >= 0; b--) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int g = i >> b, j = i & ((1 << b) - 1);
+                bf_fwd(v[(g << (b + 1)) + j], v[(g << (b + 1)) + (1 << b) + j], w[b].x, w[b].y, c);
+#pragma unroll
+                for (int x = 0; x < EXTRA; x++) {
+                    if (x & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(e[(i + x) & 7]) : "r"(z), "r"(e[(i + x + 3) & 7]));
+                    else asm volatile("add.u32 %0, %0, %1;" : "+r"(e[(i + x) & 7]) : "r"(z));
+                }
+            }
+        }
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s ^= v[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= e[k];
+    if (s == 0x123456789abcdefull) sink[0] = s + sm[0];
+}
+
 template <int MAXREG_CTAS>
 __global__ void __launch_bounds__(128, MAXREG_CTAS) k_round(u64 *sink, ModC m, const ulonglong2 *tw, int iters) {
     extern __shared__ unsigned char sm[];
@@ -71,5 +109,13 @@ int main() {
         const double cyc = best * 1e-3 * (clk_khz * 1e3) * sms * 4 / (bfs / 32);
         printf("minb%d  %d CTAs/SM = %2d warps/SM: %8.3f ms  %.3e bf/s  %6.2f SMSP-cycles per warp-butterfly\n", variant ? 8 : 4, ctas, ctas * 4, best, bfs / (best * 1e-3), cyc);
     }
+#define RUN_EXTRA(E) { \
+        const int blocks = sms * 16; float best = 1e30f; \
+        for (int rep = 0; rep < 4; rep++) { CK(cudaEventRecord(e0)); k_extra<E><<<blocks, 128, 48 * 1024>>>(sink, m, tw, iters); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep && ms < best) best = ms; } \
+        CK(cudaGetLastError()); \
+        const double bfs = (double)blocks * 128 * iters * 32.0; \
+        printf("extra ALU ops per butterfly %2d: %6.2f SMSP-cycles per warp-butterfly (16 warps/SM)\n", E, best * 1e-3 * (clk_khz * 1e3) * sms * 4 / (bfs / 32)); }
+    RUN_EXTRA(0) RUN_EXTRA(1) RUN_EXTRA(2) RUN_EXTRA(4) RUN_EXTRA(6) RUN_EXTRA(8) RUN_EXTRA(12)
     return 0;
 }
