@@ -146,7 +146,7 @@ class ClockSampler:
 class DeviceWorkload:
     """keys + ciphertext pool of one GPU"""
 
-    def __init__(self, lit, k, device, seed, rots=(2,), npairs=3, batch=16):
+    def __init__(self, lit, k, device, seed, rots=(2,), npairs=4, batch=16, lanes=2):
         from mkhe_kklss_b200 import mkckks, mkrlwe
         self.lit, self.k, self.rots, self.batch = lit, k, rots, batch
         self.level = len(lit.Q) - 1
@@ -170,7 +170,11 @@ class DeviceWorkload:
         self.pairs = [(mkckks.Ciphertext.from_numpy(self.ctx, a, lit.scale), mkckks.Ciphertext.from_numpy(self.ctx, b, lit.scale))
                       for a, b in self.host_pairs]
         self.ids = list(range(k))
-        self.out = mkckks.Ciphertext.new(self.params, self.ids, self.level, lit.scale)
+        # lanes: forks of the context (mkhe_ctx_fork) -- same keys and ciphertext handles, own stream and scratch pools; op n
+        # runs on lane n % lanes, so the bandwidth-bound stages of one op overlap the integer-bound ones of its neighbour
+        self.lanes = [self.ctx] + [self.ctx.fork() for _ in range(lanes - 1)]
+        self.outs = [mkckks.Ciphertext.new(self.params, self.ids, self.level, lit.scale) for _ in self.lanes]
+        self.out = self.outs[0]
         self.nb, self.new_scale = self.ev._nb_rescales(lit.scale * lit.scale, self.level, lit.scale)
         g = self.rlk.GetRelinearizationKey
         self.kb = [g(i).Value[0].h for i in self.ids]
@@ -178,52 +182,65 @@ class DeviceWorkload:
         self.kv = [g(i).Value[2].h for i in self.ids]
         self.ctx.sync()
 
-    def mul_relin_op(self, i):
+    def mul_relin_op(self, i, lane=None):
         a, b = self.pairs[i % len(self.pairs)]
-        self.ctx.ckks_mul_relin(self.level, self.nb, False, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
-                                self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, self.out.handles(self.ids))
+        ln = i % len(self.lanes) if lane is None else lane
+        self.lanes[ln].ckks_mul_relin(self.level, self.nb, False, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
+                                      self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, self.outs[ln].handles(self.ids))
 
     def mul_relin_step(self, i):
         for j in range(self.batch):
             self.mul_relin_op(i * self.batch + j)
 
+    def sync(self):
+        for ln in self.lanes:
+            ln.sync()
+
+    def launch_count(self):
+        return sum(ln.launch_count() for ln in self.lanes)
+
     def prepare_rotate(self):
         self.hoisted = [self.ev.HoistedForm(a) for a, _ in self.pairs]
-        self.rot_out = self.out
-        for p in self.rot_out.Value.values():
-            p.set_nlimbs(self.level + 1)
-        self.ctx.sync()
+        for o in self.outs:
+            for p in o.Value.values():
+                p.set_nlimbs(self.level + 1)
+        self.sync()
 
     def rotate_step(self, i, rot=2):
         for b in range(self.batch):
-            j = (i * self.batch + b) % len(self.pairs)
+            n = i * self.batch + b
+            j, ln = n % len(self.pairs), n % len(self.lanes)
             a = self.pairs[j][0]
-            self.ctx.rotate_hoisted(self.level, rot, a.handles(self.ids), [self.hoisted[j][t].h for t in self.ids],
-                                    [self.rk.GetRotationKey(t, rot).h for t in self.ids], self.params.CRS[rot].h,
-                                    self.rot_out.handles(self.ids))
+            self.lanes[ln].rotate_hoisted(self.level, rot, a.handles(self.ids), [self.hoisted[j][t].h for t in self.ids],
+                                          [self.rk.GetRotationKey(t, rot).h for t in self.ids], self.params.CRS[rot].h,
+                                          self.outs[ln].handles(self.ids))
 
     def timed(self, fn, steps, warmup, barrier=None):
-        """W untimed steps, then exactly K steps between CUDA events on the library's stream"""
+        """W untimed steps, then exactly K steps between CUDA events on the root lane's stream: the other lanes start after
+        the first event (mkhe_ctx_wait) and the root lane waits for them before the second one"""
         for i in range(warmup):
             fn(i)
-        self.ctx.sync()
+        self.sync()
         if barrier:
             barrier()
-        l0 = self.ctx.launch_count()
+        l0 = self.launch_count()
         self.ctx.timer_start()
+        for ln in self.lanes[1:]:
+            ln.wait(self.ctx)
         for i in range(steps):
             fn(i)
+        for ln in self.lanes[1:]:
+            self.ctx.wait(ln)
         ms = self.ctx.timer_stop()
-        self.last_launches = self.ctx.launch_count() - l0
+        self.last_launches = self.launch_count() - l0
         if barrier:
             barrier()
         return ms
 
     # -- end to end through host buffers ------------------------------------------------------------
     def prepare_e2e(self):
-        """page-locked host copies of the operand ciphertexts (library-owned, mkhe_host_alloc), two result ciphertexts on
-        the device and their host landing buffers"""
-        from mkhe_kklss_b200 import mkckks
+        """page-locked host copies of the operand ciphertexts (library-owned, mkhe_host_alloc), one result ciphertext per lane
+        on the device and its host landing buffer"""
         self.pin = []
         for a, b in self.host_pairs:
             pa, pb = {}, {}
@@ -232,42 +249,52 @@ class DeviceWorkload:
                     dst[kk] = self.ctx.host_alloc(arr.shape)
                     dst[kk][...] = arr
             self.pin.append((pa, pb))
-        self.outs = [self.out, mkckks.Ciphertext.new(self.params, self.ids, self.level, self.lit.scale)]
+        from mkhe_kklss_b200 import mkckks
         nl = self.level + 1 - self.nb
-        self.res_host = [{kk: self.ctx.host_alloc((nl, self.lit.N)) for kk in ["0"] + self.ids} for _ in self.outs]
+        # two result ciphertexts (and host landing buffers) per lane: op n+lanes writes one while result n streams back from the other
+        self.e2e_outs = [[self.outs[ln], mkckks.Ciphertext.new(self.params, self.ids, self.level, self.lit.scale)] for ln in range(len(self.lanes))]
+        self.res_host = [[{kk: self.ctx.host_alloc((nl, self.lit.N)) for kk in ["0"] + self.ids} for _ in range(2)] for _ in self.lanes]
         self.e2e_n = 0
         self.e2e_primed = False
 
     def _upload_pair(self, n):
-        """asynchronous upload of host pair n into device pair n (both modulo the pool size)"""
+        """asynchronous upload of host pair n into device slot n (both modulo the pool size) on op n's lane"""
+        lane = self.lanes[n % len(self.lanes)]
         a, b = self.pairs[n % len(self.pairs)]
         pa, pb = self.pin[n % len(self.pin)]
         nbytes = 0
         for ct, hp in ((a, pa), (b, pb)):
             for kk, poly in ct.Value.items():
-                self.ctx.poly_upload_async(poly.h, hp[kk])
+                lane.poly_upload_async(poly.h, hp[kk])
                 nbytes += hp[kk].nbytes
         return nbytes
 
     def e2e_step(self, i):
         """`batch` times through the C ABI with HOST buffers: upload both operand ciphertexts, MulRelinNew, download the
-        result ciphertext.  The transfers are asynchronous (mkhe_poly_upload_async / _download_async on pinned memory): the
-        upload of operand pair n+1 and the download of result n-1 overlap MulRelin n; every op still waits for its own
-        operands, and the whole region ends with mkhe_sync."""
+        result ciphertext -- all three on the op's lane (op n runs on lane n % lanes).  The transfers are asynchronous
+        (mkhe_poly_upload_async / _download_async on pinned memory, every lane has its own copy streams): the operands of a
+        lane's NEXT op are uploaded while its current op runs, results stream back behind the compute, and the copies of one
+        lane overlap the compute of the other.  Every op waits for its own operands; a device slot is not overwritten before
+        its last reader has finished (the library orders uses of one object); the region ends with mkhe_sync on every lane."""
         h2d = d2h = 0
+        L = len(self.lanes)
         if not self.e2e_primed:
-            self._upload_pair(self.e2e_n)          # pipeline prologue (first call only, inside the warm-up)
+            for j in range(L):
+                self._upload_pair(self.e2e_n + j)          # pipeline prologue (first call only, inside the warm-up)
             self.e2e_primed = True
         for _ in range(self.batch):
             n = self.e2e_n
-            h2d += self._upload_pair(n + 1)        # next op's operands: runs beside op n
+            ln = n % L
+            lane = self.lanes[ln]
+            h2d += self._upload_pair(n + L)                # the lane's next operands: copied beside op n
             a, b = self.pairs[n % len(self.pairs)]
-            out = self.outs[n % 2]
-            self.ctx.ckks_mul_relin(self.level, self.nb, False, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
-                                    self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, out.handles(self.ids))
+            par = (n // L) % 2
+            out = self.e2e_outs[ln][par]
+            lane.ckks_mul_relin(self.level, self.nb, False, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
+                                self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, out.handles(self.ids))
             for kk, poly in out.Value.items():
-                dst = self.res_host[n % 2][kk]
-                self.ctx.poly_download_async(poly.h, dst)
+                dst = self.res_host[ln][par][kk]
+                lane.poly_download_async(poly.h, dst)
                 d2h += dst.nbytes
             self.e2e_n += 1
         return h2d, d2h
@@ -277,13 +304,13 @@ class DeviceWorkload:
         synchronisations (mkhe_sync waits for the context's stream and both copy streams)"""
         for i in range(warmup):
             fn(i)
-        self.ctx.sync()
+        self.sync()
         if barrier:
             barrier()
         t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
-        self.ctx.sync()
+        self.sync()
         ms = (time.perf_counter() - t0) * 1e3
         if barrier:
             barrier()
@@ -320,6 +347,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--parties", type=int, default=4)
     ap.add_argument("--batch", type=int, default=16, help="ciphertext pairs (MulRelin ops) per step")
+    ap.add_argument("--lanes", type=int, default=2, help="lanes (mkhe_ctx_fork) the ops of a step are spread over, per GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the k=8 / hoisted-Rotate side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lib", default=None, help="development: load this build of the library instead of the in-tree one")
@@ -337,6 +365,7 @@ def main():
     config = {"workload": f"mkckks MulRelinNew (hoist + MulAndRelinHoisted + Rescale), {lit.name}, logN={lit.logN}, level {ell - 1}, "
                           f"k={k} parties, op0 != op1",
               "params": lit.name, "logN": lit.logN, "parties": k, "level": ell - 1, "ops_per_step": args.batch,
+              "lanes_per_gpu": args.lanes,
               "l2_policy": "inputs larger than L2: every step streams the relinearisation keys "
                            f"({(3 * k + 1) * ell * (ell + nP) * 8 * N / 2**20:.0f} MiB) and cycles 3 ciphertext pairs"}
 
@@ -381,7 +410,7 @@ def main():
         return float(t.item())
 
     B = args.batch
-    wl = DeviceWorkload(lit, k, local_rank, seed=0xB2000002 + rank, batch=B)
+    wl = DeviceWorkload(lit, k, local_rank, seed=0xB2000002 + rank, batch=B, lanes=args.lanes)
     clocks = ClockSampler(local_rank)
     clocks.start()
     ms = wl.timed(wl.mul_relin_step, args.steps, warmup, barrier)
@@ -404,7 +433,7 @@ def main():
     psteps = 8                      # MulRelin ops in the profiled pass
     wl.ctx.profile_begin()
     for i in range(psteps):
-        wl.mul_relin_op(i)
+        wl.mul_relin_op(i, lane=0)         # one lane only: the per-kernel times are those of kernels running alone
     prof = wl.ctx.profile_end()
     model = algorithmic_model(k, ell, nP, N)
     peaks = {}
@@ -462,7 +491,7 @@ def main():
         extra[f"rotate_hoisted_k{k}_ops_s"] = B * args.steps / (ms_rot * 1e-3)
         wl.ctx.close()
         del wl
-        wl8 = DeviceWorkload(lit, 8, local_rank, seed=0xB2000008, batch=B)
+        wl8 = DeviceWorkload(lit, 8, local_rank, seed=0xB2000008, batch=B, lanes=args.lanes)
         ms8 = wl8.timed(wl8.mul_relin_step, args.steps, warmup)
         extra["mulrelin_k8_ops_s"] = B * args.steps / (ms8 * 1e-3)
         wl8.prepare_rotate()

@@ -57,6 +57,17 @@ int mkhe_ctx_set_bfv(mkhe_ctx *ctx, const uint64_t *QMul, int nQMul, uint64_t T)
  * modulus index m (0..nQ-1 = Q, nQ..nQ+nP-1 = P, then QMul).  Must be called before any op. */
 int mkhe_ctx_set_ntt_tables(mkhe_ctx *ctx, int m, const uint64_t *nttPsi, const uint64_t *nttPsiInv,
                             uint64_t nttNInv);
+/* A lane: a second evaluator over the same parameters, keys and ciphertexts -- what constructing another mkrlwe.KeySwitcher
+ * over one Parameters value is in the reference (private pools, shared read-only tables: mkrlwe/keyswitch.go:33-47, and
+ * FastBasisExtender.ShallowCopy, mkrlwe/basis_extension.go:155-175).  The fork shares every handle of its root (polys, switching
+ * keys, hoisted forms) and owns a CUDA stream, two copy streams and its scratch pools, so independent ops issued on different
+ * lanes overlap on the device (the bandwidth-bound multiply-accumulates of one beside the integer-bound transforms of the
+ * other).  Uses of ONE object on different lanes are ordered automatically with events (a reader waits for the last writer, a
+ * writer for every earlier user).  A root and its forks are driven from one host thread at a time; at most 3 forks per root;
+ * mkhe_ctx_set_bfv / mkhe_ctx_set_ntt_tables come first.  Destroying the root destroys its forks. */
+int mkhe_ctx_fork(mkhe_ctx *ctx, mkhe_ctx **out);
+/* ctx's stream waits for everything enqueued so far on `other` (a lane of the same root): joins lanes without blocking the host */
+int mkhe_ctx_wait(mkhe_ctx *ctx, mkhe_ctx *other);
 void mkhe_ctx_destroy(mkhe_ctx *ctx);
 const char *mkhe_last_error(const mkhe_ctx *ctx);
 int mkhe_sync(mkhe_ctx *ctx);

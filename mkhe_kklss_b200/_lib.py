@@ -99,14 +99,35 @@ class Context:
             self.check(self.dll.mkhe_ctx_set_bfv(self.ptr, _u64arr(self.QMul), C.c_int(len(self.QMul)), C.c_uint64(self.T)))
 
     # -- plumbing -----------------------------------------------------------------------------
+    def fork(self) -> "Context":
+        """a lane of this context (mkhe_ctx_fork): same handles, own stream and scratch pools"""
+        import copy
+        f = copy.copy(self)
+        ptr = C.c_void_p()
+        self.check(self.dll.mkhe_ctx_fork(self.ptr, C.byref(ptr)))
+        f.ptr = ptr
+        f.parent = self
+        f._forks = []
+        self.__dict__.setdefault("_forks", []).append(f)
+        return f
+
+    def wait(self, other: "Context"):
+        """this lane's stream waits for everything enqueued so far on `other`"""
+        self.check(self.dll.mkhe_ctx_wait(self.ptr, other.ptr))
+
     def check(self, rc):
         if rc != OK:
             raise MkheError(rc, self.dll.mkhe_last_error(self.ptr).decode())
 
     def close(self):
         if getattr(self, "ptr", None):
+            for f in self.__dict__.get("_forks", []):      # mkhe_ctx_destroy(root) destroys the forks
+                f.ptr = None
             self.dll.mkhe_ctx_destroy(self.ptr)
             self.ptr = None
+            parent = self.__dict__.get("parent")
+            if parent is not None and self in parent.__dict__.get("_forks", []):
+                parent._forks.remove(self)
 
     def __del__(self):
         try:

@@ -26,6 +26,8 @@ using namespace mkhe;
 
 namespace {
 
+#define MKHE_MAX_LANES 4
+#define MKHE_LANE_EVENTS 64
 enum ObjKind { OBJ_POLY = 1, OBJ_SWK = 2 };
 struct Obj {
     int kind;
@@ -34,7 +36,12 @@ struct Obj {
     int nlimbs;        // poly: current view
     cudaEvent_t xfer = nullptr;     // completion of the last asynchronous transfer touching the object
     bool xfer_pending = false;      // the context's stream has not been ordered after it yet
+    // forked contexts (lanes): the last op of every lane that touched the object, so that a use on another lane is ordered
+    // after it (read-after-write, write-after-read, write-after-write).  Unused while the root has no forks.
+    struct Use { cudaEvent_t ev = nullptr; bool valid = false, wrote = false; };
+    Use use[MKHE_MAX_LANES];
 };
+enum AccessMode { ACC_WRITE = 0, ACC_READ = 1 };       // the default is the conservative one
 
 struct Scratch {
     u64 *p = nullptr;
@@ -65,7 +72,19 @@ struct mkhe_ctx {
     ConvTable *d_conv_QtoQMul = nullptr;   // BFV
     ConvTable *d_conv_QMultoQ = nullptr;   // BFV
     std::vector<u64> h_mformQMul;          // MForm(QMul mod q_i)
-    std::unordered_set<Obj *> objs;
+    std::unordered_set<Obj *> objs;       // the ROOT's registry; forks resolve handles through root->objs
+    // lanes: a fork shares the root's tables, keys and ciphertext objects and owns its stream, copy streams and scratch pools
+    // (another KeySwitcher over the same Parameters, mkrlwe/keyswitch.go:33-47; cf. FastBasisExtender.ShallowCopy,
+    // mkrlwe/basis_extension.go:155-175)
+    mkhe_ctx *root = nullptr;
+    int lane = 0;
+    std::vector<mkhe_ctx *> lanes;        // root only: [0] = root, then the live forks (nullptr = destroyed)
+    struct Touched { Obj *o; bool write; };
+    std::vector<Touched> touched;         // objects of the op being enqueued
+    cudaEvent_t lane_ev[MKHE_LANE_EVENTS] = {nullptr};
+    unsigned lane_ev_next = 0;
+    cudaEvent_t override_ev = nullptr;    // an asynchronous transfer completes on a copy stream: its event stands for the op
+    bool multi() const { return root->lanes.size() > 1; }
     std::map<std::string, Scratch> scratch;
     std::string err;
     int sticky = 0;
@@ -105,12 +124,37 @@ int fail(mkhe_ctx *c, int code, const char *fmt, ...) {
             return fail(ctx, MKHE_ERR_CUDA, "CUDA error %d (%s) at %s:%d", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
         }                                                                                             \
     } while (0)
-#define CHECK_CTX()                                                                 \
-    do {                                                                            \
-        if (!ctx) return MKHE_ERR_INVALID;                                          \
-        if (ctx->sticky) return ctx->sticky;                                        \
-        if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MKHE_ERR_CUDA, "cudaSetDevice failed"); \
-    } while (0)
+// every entry point: validate, select the device, and open the scope that publishes the op's completion event to the
+// objects it touched (only when the root has forks)
+struct OpScope {
+    mkhe_ctx *c;
+    explicit OpScope(mkhe_ctx *ctx) : c(ctx) {}
+    ~OpScope() {
+        if (c->touched.empty()) { c->override_ev = nullptr; return; }
+        if (c->multi()) {
+            cudaEvent_t ev = c->override_ev;
+            if (!ev) {
+                cudaEvent_t &slot = c->lane_ev[c->lane_ev_next++ % MKHE_LANE_EVENTS];
+                if (!slot) cudaEventCreateWithFlags(&slot, cudaEventDisableTiming);
+                cudaEventRecord(slot, c->stream);       // a recycled slot only makes a later waiter wait longer
+                ev = slot;
+            }
+            for (auto &t : c->touched) {
+                Obj::Use &u = t.o->use[c->lane];
+                u.wrote = (u.valid && u.wrote) || t.write;
+                u.valid = true;
+                u.ev = ev;
+            }
+        }
+        c->touched.clear();
+        c->override_ev = nullptr;
+    }
+};
+#define CHECK_CTX()                                                                                             \
+    if (!ctx) return MKHE_ERR_INVALID;                                                                          \
+    if (ctx->sticky) return ctx->sticky;                                                                        \
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MKHE_ERR_CUDA, "cudaSetDevice failed");      \
+    OpScope op_scope_(ctx)
 #define TRY(expr)                  \
     do {                           \
         int rc_ = (expr);          \
@@ -133,21 +177,36 @@ int fail(mkhe_ctx *c, int code, const char *fmt, ...) {
         CU(cudaGetLastError());                                       \
     } while (0)
 
-Obj *as_obj(mkhe_ctx *ctx, uint64_t h, int kind) {
+Obj *as_obj(mkhe_ctx *ctx, uint64_t h, int kind, int mode = ACC_WRITE) {
     Obj *o = reinterpret_cast<Obj *>(h);
-    if (!o || !ctx->objs.count(o) || o->kind != kind) return nullptr;
+    if (!o || !ctx->root->objs.count(o) || o->kind != kind) return nullptr;
+    const bool multi = ctx->multi();
     if (o->xfer_pending) {          // whatever uses the object next on the context's stream waits for its transfer
         cudaStreamWaitEvent(ctx->stream, o->xfer, 0);
-        o->xfer_pending = false;
+        if (!multi) o->xfer_pending = false;        // with forks every lane has to see it: kept until the next transfer replaces it
+    }
+    if (multi) {
+        const bool write = mode == ACC_WRITE;
+        for (int l = 0; l < MKHE_MAX_LANES; l++) {
+            if (l == ctx->lane) continue;
+            Obj::Use &u = o->use[l];
+            if (u.valid && (u.wrote || write)) cudaStreamWaitEvent(ctx->stream, u.ev, 0);
+            if (write) u.valid = false;             // ordered before this op; later users wait for this lane instead
+        }
+        ctx->touched.push_back({o, write});
     }
     return o;
 }
-#define POLY(var, h)                                                                     \
-    Obj *var = as_obj(ctx, (h), OBJ_POLY);                                               \
+#define POLY_M(var, h, mode)                                                             \
+    Obj *var = as_obj(ctx, (h), OBJ_POLY, (mode));                                       \
     if (!var) return fail(ctx, MKHE_ERR_INVALID, "invalid poly handle (%s)", #h)
-#define SWK(var, h)                                                                      \
-    Obj *var = as_obj(ctx, (h), OBJ_SWK);                                                \
+#define SWK_M(var, h, mode)                                                              \
+    Obj *var = as_obj(ctx, (h), OBJ_SWK, (mode));                                        \
     if (!var) return fail(ctx, MKHE_ERR_INVALID, "invalid switching-key handle (%s)", #h)
+#define POLY(var, h) POLY_M(var, h, ACC_WRITE)
+#define SWK(var, h) SWK_M(var, h, ACC_WRITE)
+#define POLY_R(var, h) POLY_M(var, h, ACC_READ)
+#define SWK_R(var, h) SWK_M(var, h, ACC_READ)
 
 size_t swk_elems(const mkhe_ctx *ctx) { return (size_t)ctx->beta_max * ctx->dmax * ctx->N; }
 int beta_of(const mkhe_ctx *ctx, int levelQ) { return (levelQ + ctx->alpha) / ctx->alpha; }      // ceil((levelQ+1)/alpha)
@@ -593,20 +652,20 @@ int add_polys(mkhe_ctx *ctx, int level, const u64 *x, const u64 *y, u64 *out, bo
 }
 
 // resolve arrays of handles
-int polys_of(mkhe_ctx *ctx, int n, const mkhe_poly *h, int min_limbs, std::vector<u64 *> &out, const char *what) {
+int polys_of(mkhe_ctx *ctx, int n, const mkhe_poly *h, int min_limbs, std::vector<u64 *> &out, const char *what, int mode = ACC_WRITE) {
     out.resize(n);
     for (int i = 0; i < n; i++) {
-        Obj *o = as_obj(ctx, h[i], OBJ_POLY);
+        Obj *o = as_obj(ctx, h[i], OBJ_POLY, mode);
         if (!o) return fail(ctx, MKHE_ERR_INVALID, "invalid poly handle in %s[%d]", what, i);
         if (o->cap_limbs < min_limbs) return fail(ctx, MKHE_ERR_INVALID, "%s[%d] has %d limbs, %d needed", what, i, o->cap_limbs, min_limbs);
         out[i] = o->d;
     }
     return MKHE_OK;
 }
-int swks_of(mkhe_ctx *ctx, int n, const mkhe_swk *h, std::vector<u64 *> &out, const char *what) {
+int swks_of(mkhe_ctx *ctx, int n, const mkhe_swk *h, std::vector<u64 *> &out, const char *what, int mode = ACC_WRITE) {
     out.resize(n);
     for (int i = 0; i < n; i++) {
-        Obj *o = as_obj(ctx, h[i], OBJ_SWK);
+        Obj *o = as_obj(ctx, h[i], OBJ_SWK, mode);
         if (!o) return fail(ctx, MKHE_ERR_INVALID, "invalid switching-key handle in %s[%d]", what, i);
         out[i] = o->d;
     }
@@ -800,6 +859,19 @@ int rotate_hoisted_impl(mkhe_ctx *ctx, int level, int rotidx, int n, u64 *const 
 }  // namespace
 
 namespace {
+// before an object is freed: every lane that may still use it has drained
+int sync_all_users(mkhe_ctx *ctx, Obj *o) {
+    for (mkhe_ctx *l : ctx->root->lanes) {
+        if (!l) continue;
+        if (l != ctx && !o->use[l->lane].valid && !o->xfer) continue;
+        CU(cudaStreamSynchronize(l->stream));
+        if (o->xfer) {
+            CU(cudaStreamSynchronize(l->h2d));
+            CU(cudaStreamSynchronize(l->d2h));
+        }
+    }
+    return MKHE_OK;
+}
 // order copy stream `cs` after everything enqueued on the context's stream so far, run `copy` on it, and make the next
 // user of the object on the context's stream wait for the copy
 template <class F>
@@ -810,6 +882,7 @@ int async_transfer(mkhe_ctx *ctx, Obj *o, cudaStream_t cs, F &&copy) {
     if (!o->xfer) CU(cudaEventCreate(&o->xfer));
     CU(cudaEventRecord(o->xfer, cs));
     o->xfer_pending = true;
+    ctx->override_ev = o->xfer;          // other lanes order themselves after the COPY, not after the call
     return MKHE_OK;
 }
 }  // namespace
@@ -843,6 +916,8 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     int ndev = mkhe_device_count();
     if (ndev <= 0 || device < 0 || device >= ndev) return MKHE_ERR_CUDA;   // no GPU: fail loudly, there is no CPU path
     mkhe_ctx *ctx = new mkhe_ctx();
+    ctx->root = ctx;
+    ctx->lanes.push_back(ctx);
     ctx->logN = logN; ctx->N = 1 << logN; ctx->nQ = nQ; ctx->nP = nP; ctx->gamma = gamma; ctx->device = device;
     ctx->S1 = logN - 11;
     ctx->dmax = nQ + nP;
@@ -881,10 +956,55 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     return MKHE_OK;
 }
 
+// a lane: shares the root's moduli, tables, keys and ciphertext objects (handles are valid on every lane), owns its stream,
+// copy streams and scratch pools.  Ops on different lanes run concurrently on the device; uses of one object on different lanes
+// are ordered automatically (events).  A context and its forks are driven from one host thread at a time.
+int mkhe_ctx_fork(mkhe_ctx *parent, mkhe_ctx **out) {
+    mkhe_ctx *ctx = parent;
+    CHECK_CTX();
+    if (!out) return MKHE_ERR_INVALID;
+    mkhe_ctx *root = parent->root;
+    int lane = -1;
+    for (int l = 1; l < MKHE_MAX_LANES; l++)
+        if (l >= (int)root->lanes.size() || !root->lanes[l]) { lane = l; break; }
+    if (lane < 0) return fail(parent, MKHE_ERR_UNSUPPORTED, "at most %d lanes per root context", MKHE_MAX_LANES);
+    TRY(upload_tables(root));
+    mkhe_ctx *f = new mkhe_ctx();
+    f->logN = root->logN; f->N = root->N; f->nQ = root->nQ; f->nP = root->nP; f->nQMul = root->nQMul; f->gamma = root->gamma;
+    f->device = root->device; f->num_sms = root->num_sms; f->S1 = root->S1; f->dmax = root->dmax; f->alpha = root->alpha;
+    f->beta_max = root->beta_max; f->d_lift = root->d_lift; f->T = root->T; f->mod = root->mod; f->tabs = root->tabs;
+    f->d_mods = root->d_mods; f->d_twf = root->d_twf; f->d_twi = root->d_twi; f->d_twf_tiled = root->d_twf_tiled;
+    f->tables_dirty = false;
+    f->d_conv_PtoQ = root->d_conv_PtoQ; f->d_conv_QtoQMul = root->d_conv_QtoQMul; f->d_conv_QMultoQ = root->d_conv_QMultoQ;
+    f->h_mformQMul = root->h_mformQMul;
+    f->root = root;
+    f->lane = lane;
+    if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&f->h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&f->d2h, cudaStreamNonBlocking) != cudaSuccess) { delete f; return fail(parent, MKHE_ERR_CUDA, "stream creation failed"); }
+    cudaEventCreate(&f->ev_compute);
+    cudaEventCreate(&f->ev0);
+    cudaEventCreate(&f->ev1);
+    if ((int)root->lanes.size() <= lane) root->lanes.resize(lane + 1, nullptr);
+    root->lanes[lane] = f;
+    *out = f;
+    return MKHE_OK;
+}
+// ctx's stream waits for everything enqueued so far on other's stream (both lanes of one root)
+int mkhe_ctx_wait(mkhe_ctx *ctx, mkhe_ctx *other) {
+    CHECK_CTX();
+    if (!other || other->root != ctx->root) return fail(ctx, MKHE_ERR_INVALID, "mkhe_ctx_wait: not lanes of one root context");
+    if (other == ctx) return MKHE_OK;
+    CU(cudaEventRecord(other->ev_compute, other->stream));
+    CU(cudaStreamWaitEvent(ctx->stream, other->ev_compute, 0));
+    return MKHE_OK;
+}
+
 int mkhe_ctx_set_bfv(mkhe_ctx *ctx, const uint64_t *QMul, int nQMul, uint64_t T) {
     CHECK_CTX();
     if (!QMul || nQMul != ctx->nQ) return fail(ctx, MKHE_ERR_INVALID, "cannot NewParametersFromLiteral: length of Q & QMul is not equal");
     if (ctx->nQMul) return fail(ctx, MKHE_ERR_INVALID, "BFV parameters already set");
+    if (ctx->root != ctx || ctx->multi()) return fail(ctx, MKHE_ERR_INVALID, "mkhe_ctx_set_bfv must precede mkhe_ctx_fork");
     if (ctx->alpha != 1) return fail(ctx, MKHE_ERR_UNSUPPORTED, "mkbfv relies on alpha = #P/gamma = 1 (mkbfv/keyswitch.go:64-67)");
     if (ctx->mod.size() + (size_t)nQMul > 64) return fail(ctx, MKHE_ERR_UNSUPPORTED, "more than 64 moduli");
     for (int i = 0; i < nQMul; i++) {
@@ -914,6 +1034,7 @@ int mkhe_ctx_set_bfv(mkhe_ctx *ctx, const uint64_t *QMul, int nQMul, uint64_t T)
 int mkhe_ctx_set_ntt_tables(mkhe_ctx *ctx, int m, const uint64_t *nttPsi, const uint64_t *nttPsiInv, uint64_t nttNInv) {
     CHECK_CTX();
     if (m < 0 || m >= (int)ctx->mod.size() || !nttPsi || !nttPsiInv) return fail(ctx, MKHE_ERR_INVALID, "bad modulus index %d", m);
+    if (ctx->root != ctx || ctx->multi()) return fail(ctx, MKHE_ERR_INVALID, "mkhe_ctx_set_ntt_tables must precede mkhe_ctx_fork");
     set_mod_tables_from_mont(ctx->tabs[m], ctx->logN, ctx->mod[m], (const u64 *)nttPsi, (const u64 *)nttPsiInv, nttNInv);
     ctx->tables_dirty = true;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -923,14 +1044,26 @@ int mkhe_ctx_set_ntt_tables(mkhe_ctx *ctx, int m, const uint64_t *nttPsi, const 
 void mkhe_ctx_destroy(mkhe_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->root == ctx) {                                  // the root takes its forks with it
+        for (size_t l = 1; l < ctx->lanes.size(); l++)
+            if (ctx->lanes[l]) mkhe_ctx_destroy(ctx->lanes[l]);
+    }
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->h2d);
     cudaStreamSynchronize(ctx->d2h);
     mkhe_comm_destroy(ctx);
-    for (Obj *o : ctx->objs) { if (o->xfer) cudaEventDestroy(o->xfer); cudaFree(o->d); delete o; }
     for (auto &kv : ctx->scratch) cudaFree(kv.second.p);
-    cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi); cudaFree(ctx->d_twf_tiled);
-    cudaFree(ctx->d_conv_PtoQ); cudaFree(ctx->d_conv_QtoQMul); cudaFree(ctx->d_conv_QMultoQ); cudaFree(ctx->d_lift);
+    for (cudaEvent_t e : ctx->lane_ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->root == ctx) {
+        for (Obj *o : ctx->objs) { if (o->xfer) cudaEventDestroy(o->xfer); cudaFree(o->d); delete o; }
+        cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi); cudaFree(ctx->d_twf_tiled);
+        cudaFree(ctx->d_conv_PtoQ); cudaFree(ctx->d_conv_QtoQMul); cudaFree(ctx->d_conv_QMultoQ); cudaFree(ctx->d_lift);
+    } else {
+        for (Obj *o : ctx->root->objs) o->use[ctx->lane] = Obj::Use();       // the lane's work has completed (synchronised above)
+        ctx->root->lanes[ctx->lane] = nullptr;
+        while (!ctx->root->lanes.empty() && !ctx->root->lanes.back()) ctx->root->lanes.pop_back();
+    }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_compute);
     cudaStreamDestroy(ctx->stream);
@@ -972,21 +1105,19 @@ int mkhe_poly_alloc(mkhe_ctx *ctx, int nlimbs, mkhe_poly *out) {
     CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
     Obj *o = new Obj();
     o->kind = OBJ_POLY; o->d = (u64 *)p; o->cap_limbs = nlimbs; o->nlimbs = nlimbs;
-    ctx->objs.insert(o);
+    ctx->root->objs.insert(o);
+    if (ctx->multi()) ctx->touched.push_back({o, true});        // the memset above runs on this lane
     *out = reinterpret_cast<uint64_t>(o);
     return MKHE_OK;
 }
 int mkhe_poly_free(mkhe_ctx *ctx, mkhe_poly h) {
     CHECK_CTX();
     POLY(o, h);
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (o->xfer) {
-        CU(cudaStreamSynchronize(ctx->h2d));
-        CU(cudaStreamSynchronize(ctx->d2h));
-        cudaEventDestroy(o->xfer);
-    }
+    TRY(sync_all_users(ctx, o));
+    if (o->xfer) cudaEventDestroy(o->xfer);
     CU(cudaFree(o->d));
-    ctx->objs.erase(o);
+    ctx->root->objs.erase(o);
+    ctx->touched.clear();
     delete o;
     return MKHE_OK;
 }
@@ -999,7 +1130,7 @@ int mkhe_poly_set_nlimbs(mkhe_ctx *ctx, mkhe_poly h, int nlimbs) {
 }
 int mkhe_poly_get_nlimbs(mkhe_ctx *ctx, mkhe_poly h, int *nlimbs) {
     CHECK_CTX();
-    POLY(o, h);
+    POLY_R(o, h);
     *nlimbs = o->nlimbs;
     return MKHE_OK;
 }
@@ -1013,7 +1144,7 @@ int mkhe_poly_upload_limb(mkhe_ctx *ctx, mkhe_poly h, int limb, const uint64_t *
 }
 int mkhe_poly_download_limb(mkhe_ctx *ctx, mkhe_poly h, int limb, uint64_t *dst) {
     CHECK_CTX();
-    POLY(o, h);
+    POLY_R(o, h);
     if (limb < 0 || limb >= o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "limb %d out of range", limb);
     CU(cudaMemcpyAsync(dst, o->d + (size_t)limb * ctx->N, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1029,7 +1160,7 @@ int mkhe_poly_upload(mkhe_ctx *ctx, mkhe_poly h, const uint64_t *src, int nlimbs
 }
 int mkhe_poly_download(mkhe_ctx *ctx, mkhe_poly h, uint64_t *dst, int nlimbs) {
     CHECK_CTX();
-    POLY(o, h);
+    POLY_R(o, h);
     if (nlimbs < 1 || nlimbs > o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
     CU(cudaMemcpyAsync(dst, o->d, (size_t)nlimbs * ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1043,14 +1174,14 @@ int mkhe_poly_upload_async(mkhe_ctx *ctx, mkhe_poly h, const uint64_t *src, int 
 }
 int mkhe_poly_download_async(mkhe_ctx *ctx, mkhe_poly h, uint64_t *dst, int nlimbs) {
     CHECK_CTX();
-    POLY(o, h);
+    POLY_R(o, h);
     if (nlimbs < 1 || nlimbs > o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
     return async_transfer(ctx, o, ctx->d2h, [&] { return cudaMemcpyAsync(dst, o->d, (size_t)nlimbs * ctx->N * 8, cudaMemcpyDeviceToHost, ctx->d2h); });
 }
 int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dsth, mkhe_poly srch) {
     CHECK_CTX();
     POLY(d, dsth);
-    POLY(s, srch);
+    POLY_R(s, srch);
     if (d->cap_limbs < s->nlimbs) return fail(ctx, MKHE_ERR_INVALID, "copy: destination too small");
     CU(cudaMemcpyAsync(d->d, s->d, (size_t)s->nlimbs * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     d->nlimbs = s->nlimbs;
@@ -1067,21 +1198,19 @@ int mkhe_swk_alloc(mkhe_ctx *ctx, mkhe_swk *out) {
     CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
     Obj *o = new Obj();
     o->kind = OBJ_SWK; o->d = (u64 *)p; o->cap_limbs = 0; o->nlimbs = 0;
-    ctx->objs.insert(o);
+    ctx->root->objs.insert(o);
+    if (ctx->multi()) ctx->touched.push_back({o, true});
     *out = reinterpret_cast<uint64_t>(o);
     return MKHE_OK;
 }
 int mkhe_swk_free(mkhe_ctx *ctx, mkhe_swk h) {
     CHECK_CTX();
     SWK(o, h);
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (o->xfer) {
-        CU(cudaStreamSynchronize(ctx->h2d));
-        CU(cudaStreamSynchronize(ctx->d2h));
-        cudaEventDestroy(o->xfer);
-    }
+    TRY(sync_all_users(ctx, o));
+    if (o->xfer) cudaEventDestroy(o->xfer);
     CU(cudaFree(o->d));
-    ctx->objs.erase(o);
+    ctx->root->objs.erase(o);
+    ctx->touched.clear();
     delete o;
     return MKHE_OK;
 }
@@ -1102,7 +1231,7 @@ int mkhe_swk_upload_limb(mkhe_ctx *ctx, mkhe_swk h, int digit, int is_p, int lim
 }
 int mkhe_swk_download_limb(mkhe_ctx *ctx, mkhe_swk h, int digit, int is_p, int limb, uint64_t *dst) {
     CHECK_CTX();
-    SWK(o, h);
+    SWK_R(o, h);
     size_t off;
     TRY(swk_limb_off(ctx, digit, is_p, limb, &off));
     CU(cudaMemcpyAsync(dst, o->d + off, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1118,7 +1247,7 @@ int mkhe_swk_upload(mkhe_ctx *ctx, mkhe_swk h, const uint64_t *src) {
 }
 int mkhe_swk_download(mkhe_ctx *ctx, mkhe_swk h, uint64_t *dst) {
     CHECK_CTX();
-    SWK(o, h);
+    SWK_R(o, h);
     CU(cudaMemcpyAsync(dst, o->d, swk_elems(ctx) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return MKHE_OK;
@@ -1127,7 +1256,7 @@ int mkhe_swk_download(mkhe_ctx *ctx, mkhe_swk h, uint64_t *dst) {
 // ---- ring primitives --------------------------------------------------------------------------------
 int mkhe_ntt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out) {
     CHECK_CTX();
-    POLY(i, in);
+    POLY_R(i, in);
     POLY(o, out);
     if (level < 0 || level >= i->cap_limbs || level >= o->cap_limbs) return fail(ctx, MKHE_ERR_INVALID, "level %d out of range", level);
     Slots s = (level >= ctx->nQ) ? r_slots(ctx) : q_slots(level);
@@ -1135,7 +1264,7 @@ int mkhe_ntt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out) {
 }
 int mkhe_intt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out) {
     CHECK_CTX();
-    POLY(i, in);
+    POLY_R(i, in);
     POLY(o, out);
     if (level < 0 || level >= i->cap_limbs || level >= o->cap_limbs) return fail(ctx, MKHE_ERR_INVALID, "level %d out of range", level);
     Slots s = (level >= ctx->nQ) ? r_slots(ctx) : q_slots(level);
@@ -1151,7 +1280,7 @@ static int check_level(mkhe_ctx *ctx, int level) {
 int mkhe_decompose(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk ad) {
     CHECK_CTX();
     TRY(check_level(ctx, levelQ));
-    POLY(p, a);
+    POLY_R(p, a);
     SWK(k, ad);
     if (p->cap_limbs < levelQ + 1) return fail(ctx, MKHE_ERR_INVALID, "Decompose: poly has %d limbs, level %d", p->cap_limbs, levelQ);
     return decompose_impl(ctx, levelQ, 1, &p->d, &k->d, 0);
@@ -1160,8 +1289,8 @@ int mkhe_decompose(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk ad) {
 int mkhe_external_product_hoisted(mkhe_ctx *ctx, int levelQ, mkhe_swk a_hoisted, mkhe_swk bg, mkhe_poly c) {
     CHECK_CTX();
     TRY(check_level(ctx, levelQ));
-    SWK(h, a_hoisted);
-    SWK(k, bg);
+    SWK_R(h, a_hoisted);
+    SWK_R(k, bg);
     POLY(o, c);
     if (o->cap_limbs < levelQ + 1) return fail(ctx, MKHE_ERR_INVALID, "ExternalProduct: output has %d limbs", o->cap_limbs);
     return ext_products(ctx, levelQ, 1, 1, &k->d, &h->d, nullptr, nullptr, &o->d, nullptr, false);
@@ -1170,8 +1299,8 @@ int mkhe_external_product_hoisted(mkhe_ctx *ctx, int levelQ, mkhe_swk a_hoisted,
 int mkhe_external_product(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk bg, mkhe_poly c) {
     CHECK_CTX();
     TRY(check_level(ctx, levelQ));
-    POLY(p, a);
-    SWK(k, bg);
+    POLY_R(p, a);
+    SWK_R(k, bg);
     POLY(o, c);
     if (p->cap_limbs < levelQ + 1 || o->cap_limbs < levelQ + 1) return fail(ctx, MKHE_ERR_INVALID, "ExternalProduct: too few limbs");
     std::vector<u64 *> hp;
@@ -1199,22 +1328,22 @@ int mkhe_mul_relin_hoisted(mkhe_ctx *ctx, int level, int n0, const int *ids0, co
     std::vector<u64 *> p0, p1, po, vh0, vh1, vb, vd, vv;
     // level checks mirror keyswitch_hoisted.go:48-54
     for (int t = 0; t <= n0; t++) {
-        Obj *o = as_obj(ctx, op0[t], OBJ_POLY);
+        Obj *o = as_obj(ctx, op0[t], OBJ_POLY, ACC_READ);
         if (o && o->nlimbs - 1 < level) return fail(ctx, MKHE_ERR_INVALID, "Cannot MulAndRelin: op0 and op1 have different levels");
     }
-    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0"));
-    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1"));
+    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0", ACC_READ));
+    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1", ACC_READ));
     TRY(polys_of(ctx, nOut + 1, out, level + 1, po, "out"));
-    TRY(swks_of(ctx, n1, rlk_b, vb, "rlk_b"));
-    TRY(swks_of(ctx, n0, rlk_d, vd, "rlk_d"));
-    TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v"));
-    SWK(uk, u);
-    if (h0) TRY(swks_of(ctx, n0, h0, vh0, "h0"));
+    TRY(swks_of(ctx, n1, rlk_b, vb, "rlk_b", ACC_READ));
+    TRY(swks_of(ctx, n0, rlk_d, vd, "rlk_d", ACC_READ));
+    TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v", ACC_READ));
+    SWK_R(uk, u);
+    if (h0) TRY(swks_of(ctx, n0, h0, vh0, "h0", ACC_READ));
     else {
         TRY(swk_pool(ctx, "nil_h0", n0, vh0));
         TRY(decompose_impl(ctx, level, n0, p0.data() + 1, vh0.data(), 0));
     }
-    if (h1) TRY(swks_of(ctx, n1, h1, vh1, "h1"));
+    if (h1) TRY(swks_of(ctx, n1, h1, vh1, "h1", ACC_READ));
     else {
         TRY(swk_pool(ctx, "nil_h1", n1, vh1));
         TRY(decompose_impl(ctx, level, n1, p1.data() + 1, vh1.data(), 0));
@@ -1231,13 +1360,13 @@ int mkhe_ckks_mul_relin(mkhe_ctx *ctx, int level, int nb_rescales, int same_oper
     TRY(check_level(ctx, level));
     TRY(check_ids(ctx, n0, ids0, n1, ids1, nOut, idsOut));
     std::vector<u64 *> p0, p1, po, vh0, vh1, vb, vd, vv;
-    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0"));
-    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1"));
+    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0", ACC_READ));
+    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1", ACC_READ));
     TRY(polys_of(ctx, nOut + 1, out, level + 1, po, "out"));
-    TRY(swks_of(ctx, n1, rlk_b, vb, "rlk_b"));
-    TRY(swks_of(ctx, n0, rlk_d, vd, "rlk_d"));
-    TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v"));
-    SWK(uk, u);
+    TRY(swks_of(ctx, n1, rlk_b, vb, "rlk_b", ACC_READ));
+    TRY(swks_of(ctx, n0, rlk_d, vd, "rlk_d", ACC_READ));
+    TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v", ACC_READ));
+    SWK_R(uk, u);
     // hoisting into context pools (rlkSet.HoistPool[0|1], mkckks/evaluator.go:419-441), scheduled inside the op
     TRY(swk_pool(ctx, "hoistpool0", n0, vh0));
     if (same_operand) vh1 = vh0;
@@ -1261,10 +1390,10 @@ int mkhe_ckks_mul_relin_sharded(mkhe_ctx *ctx, int level, int nb_rescales, int n
     sh.active = true;
     sh.own.assign(own_ids, own_ids + nown);
     std::vector<u64 *> p0, p1, po, vh0(n0, nullptr), vh1(n1, nullptr), vb(n1, nullptr), vd(n0, nullptr), vv(n0, nullptr);
-    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0"));
-    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1"));
+    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0", ACC_READ));
+    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1", ACC_READ));
     TRY(polys_of(ctx, nOut + 1, out, level + 1, po, "out"));
-    SWK(uk, u);
+    SWK_R(uk, u);
     // keys and hoisting only for the parties this rank owns
     std::vector<u64 *> in0, in1, hp0, hp1, pool0, pool1;
     std::vector<int> t0, t1;
@@ -1274,14 +1403,14 @@ int mkhe_ckks_mul_relin_sharded(mkhe_ctx *ctx, int level, int nb_rescales, int n
     TRY(swk_pool(ctx, "hoistpool1", (int)t1.size(), pool1));
     for (size_t i = 0; i < t0.size(); i++) {
         int t = t0[i];
-        Obj *d = as_obj(ctx, rlk_d[t], OBJ_SWK), *v = as_obj(ctx, rlk_v[t], OBJ_SWK);
+        Obj *d = as_obj(ctx, rlk_d[t], OBJ_SWK, ACC_READ), *v = as_obj(ctx, rlk_v[t], OBJ_SWK, ACC_READ);
         if (!d || !v) return fail(ctx, MKHE_ERR_INVALID, "missing relinearization key (d, v) of owned party %d", ids0[t]);
         vd[t] = d->d; vv[t] = v->d; vh0[t] = pool0[i];
         in0.push_back(p0[1 + t]);
     }
     for (size_t i = 0; i < t1.size(); i++) {
         int t = t1[i];
-        Obj *b = as_obj(ctx, rlk_b[t], OBJ_SWK);
+        Obj *b = as_obj(ctx, rlk_b[t], OBJ_SWK, ACC_READ);
         if (!b) return fail(ctx, MKHE_ERR_INVALID, "missing relinearization key (b) of owned party %d", ids1[t]);
         vb[t] = b->d; vh1[t] = pool1[i];
         in1.push_back(p1[1 + t]);
@@ -1301,15 +1430,15 @@ int mkhe_rotate_hoisted(mkhe_ctx *ctx, int level, int rotidx, int n, const mkhe_
     TRY(check_level(ctx, level));
     if (n < 0 || n > MKHE_MAX_PARTIES) return fail(ctx, MKHE_ERR_INVALID, "party count out of range");
     for (int t = 0; t <= n; t++) {
-        Obj *o = as_obj(ctx, ct_in[t], OBJ_POLY);
+        Obj *o = as_obj(ctx, ct_in[t], OBJ_POLY, ACC_READ);
         if (o && o->nlimbs - 1 < level) return fail(ctx, MKHE_ERR_INVALID, "Cannot Rotate: ctIn and ctOut have different levels");
     }
     std::vector<u64 *> pi, po, vh, vrk;
-    TRY(polys_of(ctx, n + 1, ct_in, level + 1, pi, "ct_in"));
+    TRY(polys_of(ctx, n + 1, ct_in, level + 1, pi, "ct_in", ACC_READ));
     TRY(polys_of(ctx, n + 1, ct_out, level + 1, po, "ct_out"));
-    TRY(swks_of(ctx, n, hoisted, vh, "hoisted"));
-    TRY(swks_of(ctx, n, rk, vrk, "rk"));
-    SWK(ak, a);
+    TRY(swks_of(ctx, n, hoisted, vh, "hoisted", ACC_READ));
+    TRY(swks_of(ctx, n, rk, vrk, "rk", ACC_READ));
+    SWK_R(ak, a);
     return rotate_hoisted_impl(ctx, level, rotidx, n, pi.data(), vh.data(), vrk.data(), ak->d, po.data());
 }
 
@@ -1319,10 +1448,10 @@ int mkhe_rotate(mkhe_ctx *ctx, int level, int rotidx, int n, const mkhe_poly *ct
     TRY(check_level(ctx, level));
     if (n < 0 || n > MKHE_MAX_PARTIES) return fail(ctx, MKHE_ERR_INVALID, "party count out of range");
     std::vector<u64 *> pi, po, vh, vrk;
-    TRY(polys_of(ctx, n + 1, ct_in, level + 1, pi, "ct_in"));
+    TRY(polys_of(ctx, n + 1, ct_in, level + 1, pi, "ct_in", ACC_READ));
     TRY(polys_of(ctx, n + 1, ct_out, level + 1, po, "ct_out"));
-    TRY(swks_of(ctx, n, rk, vrk, "rk"));
-    SWK(ak, a);
+    TRY(swks_of(ctx, n, rk, vrk, "rk", ACC_READ));
+    SWK_R(ak, a);
     TRY(swk_pool(ctx, "rot_h", n, vh));
     TRY(decompose_impl(ctx, level, n, pi.data() + 1, vh.data(), 0));
     return rotate_hoisted_impl(ctx, level, rotidx, n, pi.data(), vh.data(), vrk.data(), ak->d, po.data());
@@ -1334,10 +1463,10 @@ int mkhe_conjugate(mkhe_ctx *ctx, int level, int n, const mkhe_poly *ct_in, cons
     TRY(check_level(ctx, level));
     if (n < 0 || n > MKHE_MAX_PARTIES) return fail(ctx, MKHE_ERR_INVALID, "party count out of range");
     std::vector<u64 *> pi, po, vh, vck, tmp;
-    TRY(polys_of(ctx, n + 1, ct_in, level + 1, pi, "ct_in"));
+    TRY(polys_of(ctx, n + 1, ct_in, level + 1, pi, "ct_in", ACC_READ));
     TRY(polys_of(ctx, n + 1, ct_out, level + 1, po, "ct_out"));
-    TRY(swks_of(ctx, n, ck, vck, "ck"));
-    SWK(ak, a);
+    TRY(swks_of(ctx, n, ck, vck, "ck", ACC_READ));
+    SWK_R(ak, a);
     // permute first (keyswitch.go:315-317), then key-switch the permuted components (:320-331)
     TRY(poly_pool(ctx, "conj_tmp", n + 1, ctx->nQ, tmp));
     TRY(automorph_impl(ctx, level, ((u64)2 << ctx->logN) - 1, n + 1, pi.data(), tmp.data()));
@@ -1379,14 +1508,14 @@ int mkhe_rescale(mkhe_ctx *ctx, int level, int nb_rescales, mkhe_poly in, mkhe_p
 int mkhe_poly_add(mkhe_ctx *ctx, int level, mkhe_poly a, mkhe_poly b, mkhe_poly out) {
     CHECK_CTX();
     TRY(check_level(ctx, level));
-    POLY(x, a); POLY(y, b); POLY(o, out);
+    POLY_R(x, a); POLY_R(y, b); POLY(o, out);
     if (x->cap_limbs <= level || y->cap_limbs <= level || o->cap_limbs <= level) return fail(ctx, MKHE_ERR_INVALID, "Add: too few limbs");
     return add_polys(ctx, level, x->d, y->d, o->d, false);
 }
 int mkhe_poly_sub(mkhe_ctx *ctx, int level, mkhe_poly a, mkhe_poly b, mkhe_poly out) {
     CHECK_CTX();
     TRY(check_level(ctx, level));
-    POLY(x, a); POLY(y, b); POLY(o, out);
+    POLY_R(x, a); POLY_R(y, b); POLY(o, out);
     if (x->cap_limbs <= level || y->cap_limbs <= level || o->cap_limbs <= level) return fail(ctx, MKHE_ERR_INVALID, "Sub: too few limbs");
     return add_polys(ctx, level, x->d, y->d, o->d, true);
 }
@@ -1541,7 +1670,7 @@ int mkhe_bfv_decompose(mkhe_ctx *ctx, int levelQ, mkhe_poly aR, mkhe_swk ad1, mk
     CHECK_CTX();
     TRY(need_bfv(ctx));
     TRY(check_level(ctx, levelQ));
-    POLY(r, aR); SWK(k1, ad1); SWK(k2, ad2);
+    POLY_R(r, aR); SWK(k1, ad1); SWK(k2, ad2);
     if (r->cap_limbs < 2 * (levelQ + 1)) return fail(ctx, MKHE_ERR_INVALID, "DecomposeBFV: too few limbs");
     return bfv_decompose_impl(ctx, levelQ, 1, &r->d, &k1->d, &k2->d);
 }
@@ -1555,19 +1684,19 @@ int mkhe_bfv_mul_relin_hoisted(mkhe_ctx *ctx, int level, int n0, const int *ids0
     TRY(check_level(ctx, level));
     TRY(check_ids(ctx, n0, ids0, n1, ids1, nOut, idsOut));
     std::vector<u64 *> p0, p1, po, a0, b0, a1, bb1, vb1, vb2, vd1, vd2, vv;
-    TRY(polys_of(ctx, n0 + 1, op0, 2 * ctx->nQ, p0, "op0"));
-    TRY(polys_of(ctx, n1 + 1, op1, 2 * ctx->nQ, p1, "op1"));
+    TRY(polys_of(ctx, n0 + 1, op0, 2 * ctx->nQ, p0, "op0", ACC_READ));
+    TRY(polys_of(ctx, n1 + 1, op1, 2 * ctx->nQ, p1, "op1", ACC_READ));
     TRY(polys_of(ctx, nOut + 1, out, level + 1, po, "out"));
-    TRY(swks_of(ctx, n1, b1, vb1, "b1")); TRY(swks_of(ctx, n1, b2, vb2, "b2"));
-    TRY(swks_of(ctx, n0, d1, vd1, "d1")); TRY(swks_of(ctx, n0, d2, vd2, "d2"));
-    TRY(swks_of(ctx, n0, v, vv, "v"));
-    SWK(uk, u);
-    if (h0a && h0b) { TRY(swks_of(ctx, n0, h0a, a0, "h0a")); TRY(swks_of(ctx, n0, h0b, b0, "h0b")); }
+    TRY(swks_of(ctx, n1, b1, vb1, "b1", ACC_READ)); TRY(swks_of(ctx, n1, b2, vb2, "b2", ACC_READ));
+    TRY(swks_of(ctx, n0, d1, vd1, "d1", ACC_READ)); TRY(swks_of(ctx, n0, d2, vd2, "d2", ACC_READ));
+    TRY(swks_of(ctx, n0, v, vv, "v", ACC_READ));
+    SWK_R(uk, u);
+    if (h0a && h0b) { TRY(swks_of(ctx, n0, h0a, a0, "h0a", ACC_READ)); TRY(swks_of(ctx, n0, h0b, b0, "h0b", ACC_READ)); }
     else {
         TRY(swk_pool(ctx, "nil_h0", n0, a0)); TRY(swk_pool(ctx, "nil_h0b", n0, b0));
         TRY(bfv_decompose_impl(ctx, level, n0, p0.data() + 1, a0.data(), b0.data()));
     }
-    if (h1a && h1b) { TRY(swks_of(ctx, n1, h1a, a1, "h1a")); TRY(swks_of(ctx, n1, h1b, bb1, "h1b")); }
+    if (h1a && h1b) { TRY(swks_of(ctx, n1, h1a, a1, "h1a", ACC_READ)); TRY(swks_of(ctx, n1, h1b, bb1, "h1b", ACC_READ)); }
     else {
         TRY(swk_pool(ctx, "nil_h1", n1, a1)); TRY(swk_pool(ctx, "nil_h1b", n1, bb1));
         TRY(bfv_decompose_impl(ctx, level, n1, p1.data() + 1, a1.data(), bb1.data()));
@@ -1585,13 +1714,13 @@ int mkhe_bfv_mul_relin(mkhe_ctx *ctx, int n0, const int *ids0, const mkhe_poly *
     TRY(check_ids(ctx, n0, ids0, n1, ids1, nOut, idsOut));
     const int level = ctx->nQ - 1;
     std::vector<u64 *> p0, p1, po, r0, r1, a0, b0, a1, bb1, vb1, vb2, vd1, vd2, vv;
-    TRY(polys_of(ctx, n0 + 1, ct0, ctx->nQ, p0, "ct0"));
-    TRY(polys_of(ctx, n1 + 1, ct1, ctx->nQ, p1, "ct1"));
+    TRY(polys_of(ctx, n0 + 1, ct0, ctx->nQ, p0, "ct0", ACC_READ));
+    TRY(polys_of(ctx, n1 + 1, ct1, ctx->nQ, p1, "ct1", ACC_READ));
     TRY(polys_of(ctx, nOut + 1, out, ctx->nQ, po, "out"));
-    TRY(swks_of(ctx, n1, b1, vb1, "b1")); TRY(swks_of(ctx, n1, b2, vb2, "b2"));
-    TRY(swks_of(ctx, n0, d1, vd1, "d1")); TRY(swks_of(ctx, n0, d2, vd2, "d2"));
-    TRY(swks_of(ctx, n0, v, vv, "v"));
-    SWK(uk, u);
+    TRY(swks_of(ctx, n1, b1, vb1, "b1", ACC_READ)); TRY(swks_of(ctx, n1, b2, vb2, "b2", ACC_READ));
+    TRY(swks_of(ctx, n0, d1, vd1, "d1", ACC_READ)); TRY(swks_of(ctx, n0, d2, vd2, "d2", ACC_READ));
+    TRY(swks_of(ctx, n0, v, vv, "v", ACC_READ));
+    SWK_R(uk, u);
     // rlkSet.PolyRPool1/2 and HoistPool1/2 (mkbfv/keys.go:40-68) live in the context
     TRY(poly_pool(ctx, "bfv_polyR0", n0 + 1, 2 * ctx->nQ, r0));
     TRY(poly_pool(ctx, "bfv_polyR1", n1 + 1, 2 * ctx->nQ, r1));

@@ -398,7 +398,12 @@ struct P2Mail { int off, pad; u64 *ptr; };       // a group's next tile, publish
 //   groups take tiles from a shared counter (a group that the warp schedulers favour simply transforms more tiles).  The tiles
 //   of one (slot, tile) pair are consecutive: the pair's 2047 twiddles arrive once by TMA; a group's next 16 KiB input tile is
 //   prefetched by TMA into its landing buffer while the current one is transformed.
-__global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(Pass2Args a, const ModC *mods, const ulonglong2 *tiled) {
+#ifdef MKHE_P2_MAXNREG
+__global__ void __maxnreg__(MKHE_P2_MAXNREG) k_ntt_pass2(
+#else
+__global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
+#endif
+    Pass2Args a, const ModC *mods, const ulonglong2 *tiled) {
     MKHE_SMEM(smraw);
     const int tid = threadIdx.x & (MKHE_NTT_THREADS - 1), grp = threadIdx.x / MKHE_NTT_THREADS;
     ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw);                                          // 32 KiB twiddles

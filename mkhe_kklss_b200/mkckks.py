@@ -48,6 +48,17 @@ class Evaluator:
         self.ctx = params.ctx
         self.ksw = mkrlwe.KeySwitcher(params)
 
+    def ShallowCopy(self):
+        """a second evaluator over the same parameters, keys and ciphertexts whose ops run on their own lane of the device
+        (mkhe_ctx_fork): what another NewEvaluator / NewKeySwitcher over one Parameters value is in the reference
+        (mkrlwe/keyswitch.go:33-47: private pools, shared tables; cf. FastBasisExtender.ShallowCopy,
+        mkrlwe/basis_extension.go:155-175).  Independent ops issued on the two evaluators overlap on the GPU; uses of one
+        ciphertext on both are ordered by the library."""
+        import copy
+        p2 = copy.copy(self.params)
+        p2.ctx = self.params.ctx.fork()
+        return Evaluator(p2)
+
     # -- helpers ------------------------------------------------------------------------------
     def newCiphertextBinary(self, op0, op1):
         """evaluator.go:306-316: union idset, min level, max scale"""

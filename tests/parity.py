@@ -221,6 +221,39 @@ def check_rotate(w: CKKSWorld, ids, rot, level=None, zero_component=False, hoist
     w.compare_ct(do2, oo2, f"RotateNew(rot={rot}, level={level})")
 
 
+def check_lanes(w: CKKSWorld, rounds=3, level=None):
+    """two evaluators on two lanes of one context (mkhe_ctx_fork): independent ops interleaved, then chains whose operands
+    cross lanes -- read-after-write (a product made on one lane is rotated and squared on the other), write-after-read (an
+    operand still being read on one lane is overwritten from the other) -- everything compared with the oracle"""
+    level = w.op.max_level() if level is None else level
+    ev = [w.dev, w.dev.ShallowCopy()]
+    ids = w.ids
+    rot = sorted(r for r in w.op.CRS if r > 0)[0]
+    pend = []
+    for r in range(rounds):
+        for lane in (0, 1):
+            o0, d0 = w.random_ct(ids, level)
+            o1, d1 = w.random_ct(ids, level)
+            dout = ev[lane].MulRelinNew(d0, d1, w.d_rlk)                 # independent ops, alternating lanes
+            other = ev[1 - lane]
+            drot = other.RotateNew(dout, rot, w.d_rk)                   # consumer on the OTHER lane (RAW)
+            dsq = other.MulRelinNew(dout, dout, w.d_rlk) if dout.Level() > 0 else None
+            # WAR: overwrite one operand from the other lane while the first product may still be reading it
+            o2, _ = w.random_ct(ids, level)
+            for kk, poly in d0.Value.items():
+                other.ctx.poly_upload(poly.h, o2.value[kk])
+            drot2 = other.RotateNew(d0, rot, w.d_rk)
+            pend.append((o0, o1, o2, dout, drot, dsq, drot2))
+    for n, (o0, o1, o2, dout, drot, dsq, drot2) in enumerate(pend):
+        oout = w.oev.mul_relin_new(o0, o1, w.o_rlk)
+        w.compare_ct(dout, oout, f"lanes[{n}] MulRelinNew")
+        w.compare_ct(drot, w.oev.rotate_new(oout, rot, w.o_rk), f"lanes[{n}] RotateNew of the other lane's product")
+        if dsq is not None:
+            w.compare_ct(dsq, w.oev.mul_relin_new(oout, oout, w.o_rlk), f"lanes[{n}] square of the other lane's product")
+        w.compare_ct(drot2, w.oev.rotate_new(o2, rot, w.o_rk), f"lanes[{n}] RotateNew after a cross-lane overwrite")
+    ev[1].ctx.close()
+
+
 def check_conjugate(w: CKKSWorld, ids, level=None):
     level = w.op.max_level() if level is None else level
     oct_, dct = w.random_ct(ids, level)

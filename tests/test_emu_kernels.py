@@ -21,6 +21,14 @@ def test_ckks_kernels_under_emulation(emu, logN):
     w.close()
 
 
+def test_lanes_under_emulation(emu):
+    """forked contexts: shared handles, private pools, the cross-lane bookkeeping (host logic; the emulator is synchronous)"""
+    w = parity.CKKSWorld(PR.CKKS_PN14QP439.at_logn(12), 2, lib=emu)
+    parity.check_lanes(w, rounds=1)
+    parity.check_mul_relin_new(w, w.ids, w.ids)          # the root is intact after its fork is gone
+    w.close()
+
+
 def test_cnn_parameter_set_under_emulation(emu):
     """48-bit primes with a 58-bit q0: digits far above the target modulus"""
     w = parity.CKKSWorld(PR.CNN_PN14QP433.at_logn(12), 2, lib=emu)

@@ -28,6 +28,14 @@ def test_ckks_many_parties():
     w.close()
 
 
+@pytest.mark.parametrize("logN,k,rounds", [(12, 2, 6), (14, 2, 3), (15, 4, 2)])
+def test_lanes(logN, k, rounds):
+    """two lanes of one context: concurrent independent ops and cross-lane read-after-write / write-after-read chains"""
+    w = parity.CKKSWorld(PR.CKKS_PN15QP880.at_logn(logN), k, rots=(1,))
+    parity.check_lanes(w, rounds=rounds, level=None if logN < 15 else 3)
+    w.close()
+
+
 def test_ckks_semantics_on_device_outputs():
     w = parity.CKKSWorld(PR.CKKS_PN14QP439.at_logn(12), 2, real_keys=True)
     parity.check_ckks_semantics(w)

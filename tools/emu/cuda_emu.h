@@ -85,6 +85,8 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 double emu_now_ms();
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event{0}; return 0; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new emu_event{0}; return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = emu_now_ms(); return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
