@@ -83,6 +83,7 @@ int mkhe_poly_download_limb(mkhe_ctx *ctx, mkhe_poly p, int limb, uint64_t *dst)
 int mkhe_poly_upload(mkhe_ctx *ctx, mkhe_poly p, const uint64_t *src, int nlimbs);        /* contiguous [nlimbs][N] */
 int mkhe_poly_download(mkhe_ctx *ctx, mkhe_poly p, uint64_t *dst, int nlimbs);
 int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dst, mkhe_poly src);                          /* ring.Poly.Copy */
+int mkhe_poly_copy_lvl(mkhe_ctx *ctx, int level, mkhe_poly dst, mkhe_poly src);           /* ring.CopyValuesLvl (mkckks/evaluator.go:297-301): limbs 0..level, views unchanged */
 /* Asynchronous transfers for pipelines that keep the device busy while ciphertexts stream over PCIe (the Go shim's lazy
  * syncToDevice / syncToHost, SURVEY 8b "residency model").  The host buffer must be page-locked memory obtained from
  * mkhe_host_alloc (C-owned, so the cgo pointer rule does not apply) and must stay valid and untouched until mkhe_sync.
@@ -142,6 +143,18 @@ int mkhe_rescale(mkhe_ctx *ctx, int level, int nb_rescales, mkhe_poly in, mkhe_p
 /* ringQ.AddLvl / SubLvl(level, a, b, out)                    mkckks/evaluator.go:200-351 call sites */
 int mkhe_poly_add(mkhe_ctx *ctx, int level, mkhe_poly a, mkhe_poly b, mkhe_poly out);
 int mkhe_poly_sub(mkhe_ctx *ctx, int level, mkhe_poly a, mkhe_poly b, mkhe_poly out);
+/* ringQ.NegLvl(level, a, out): q - x, unreduced (0 is stored as q)       mkckks/evaluator.go:340 (Sub's negation) */
+int mkhe_poly_neg(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out);
+/* MultByConst(ct0, constant, ctOut)                          mkckks/evaluator.go:117-198
+ *   c_real, c_imag, scale: what getConstAndScale (:39-93, host bookkeeping) returns for the constant.  The library derives the
+ *   per-limb multipliers exactly like the reference (scaleUpExact, mkckks/utils.go:59-86; MRed by NttPsi[i][1] for the imaginary
+ *   part) and multiplies coefficients [0, N/2) and [N/2, N) of every limb <= level by the first / second one.  in[t] -> out[t]
+ *   for the n components of ct0 (out may alias in).  ctOut.Scale = ct0.Scale * scale stays on the host. */
+int mkhe_ckks_mult_by_const(mkhe_ctx *ctx, int level, int n, const mkhe_poly *in, const mkhe_poly *out,
+                            double c_real, double c_imag, double scale);
+/* MulPtxtNew's device work before its Rescale                mkckks/evaluator.go:465-478
+ *   pt = ckks.Plaintext.Value (coefficient domain): NTT + MForm once, then per component NTT, MulCoeffsMontgomery, InvNTT. */
+int mkhe_ckks_mul_ptxt(mkhe_ctx *ctx, int level, mkhe_poly pt, int n, const mkhe_poly *in, const mkhe_poly *out);
 /* MulRelinNew's device work in one call: hoist both operands (once if same_operand), MulAndRelinHoisted,
  * Rescale by nb_rescales                                     mkckks/evaluator.go:416-443,558-581
  * (this is what mkckks_benchmark_test.go:78-82 times).  Hoisting uses context-owned pools, mirroring

@@ -237,6 +237,9 @@ class Context:
     def poly_copy(self, dst, src):
         self.check(self.dll.mkhe_poly_copy(self.ptr, C.c_uint64(dst), C.c_uint64(src)))
 
+    def poly_copy_lvl(self, level, dst, src):
+        self.check(self.dll.mkhe_poly_copy_lvl(self.ptr, C.c_int(level), C.c_uint64(dst), C.c_uint64(src)))
+
     # -- switching keys ---------------------------------------------------------------------------
     def swk_alloc(self) -> int:
         h = C.c_uint64()
@@ -316,6 +319,16 @@ class Context:
 
     def poly_sub(self, level, a, b, out):
         self.check(self.dll.mkhe_poly_sub(self.ptr, C.c_int(level), C.c_uint64(a), C.c_uint64(b), C.c_uint64(out)))
+
+    def poly_neg(self, level, a, out):
+        self.check(self.dll.mkhe_poly_neg(self.ptr, C.c_int(level), C.c_uint64(a), C.c_uint64(out)))
+
+    def ckks_mult_by_const(self, level, hin, hout, c_real, c_imag, scale):
+        self.check(self.dll.mkhe_ckks_mult_by_const(self.ptr, C.c_int(level), C.c_int(len(hin)), _harr(hin), _harr(hout),
+                                                    C.c_double(c_real), C.c_double(c_imag), C.c_double(scale)))
+
+    def ckks_mul_ptxt(self, level, pt, hin, hout):
+        self.check(self.dll.mkhe_ckks_mul_ptxt(self.ptr, C.c_int(level), C.c_uint64(pt), C.c_int(len(hin)), _harr(hin), _harr(hout)))
 
     # multi-GPU (party sharding, NCCL)
     def comm_unique_id(self) -> bytes:

@@ -651,6 +651,14 @@ int add_polys(mkhe_ctx *ctx, int level, const u64 *x, const u64 *y, u64 *out, bo
     return MKHE_OK;
 }
 
+// out = MForm(A) (.) B [+ MForm(C) (.) D]  (MFormLvl + MulCoeffsMontgomery[AndAdd]Lvl)
+int mul2(mkhe_ctx *ctx, const Slots &s, const u64 *A, const u64 *B, const u64 *Cc, const u64 *D, u64 *out) {
+    LimbArgs a;
+    fill(a, s, ctx->logN);
+    LAUNCH(k_mul2, dim3(ctx->N / MKHE_THREADS, s.n), dim3(MKHE_THREADS), 0, A, B, Cc, D, out, a, ctx->d_mods);
+    return MKHE_OK;
+}
+
 // resolve arrays of handles
 int polys_of(mkhe_ctx *ctx, int n, const mkhe_poly *h, int min_limbs, std::vector<u64 *> &out, const char *what, int mode = ACC_WRITE) {
     out.resize(n);
@@ -1188,6 +1196,15 @@ int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dsth, mkhe_poly srch) {
     return MKHE_OK;
 }
 
+int mkhe_poly_copy_lvl(mkhe_ctx *ctx, int level, mkhe_poly dsth, mkhe_poly srch) {
+    CHECK_CTX();
+    POLY(d, dsth);
+    POLY_R(s, srch);
+    if (level < 0 || d->cap_limbs < level + 1 || s->cap_limbs < level + 1) return fail(ctx, MKHE_ERR_INVALID, "copy: level %d out of range", level);
+    CU(cudaMemcpyAsync(d->d, s->d, (size_t)(level + 1) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return MKHE_OK;
+}
+
 // ---- switching keys ---------------------------------------------------------------------------------
 int mkhe_swk_alloc(mkhe_ctx *ctx, mkhe_swk *out) {
     CHECK_CTX();
@@ -1520,6 +1537,80 @@ int mkhe_poly_sub(mkhe_ctx *ctx, int level, mkhe_poly a, mkhe_poly b, mkhe_poly 
     return add_polys(ctx, level, x->d, y->d, o->d, true);
 }
 
+/* scaleUpExact (mkckks/utils.go:59-86): big.NewFloat(n*value) carries 53 bits, so the product and the + 0.5 are float64
+ * operations; Int() truncates; mod q; a negative value gives q - res (q, not 0, for a multiple of q) */
+static u64 scale_up_exact(double value, double n, u64 q) {
+    const bool neg = value < 0;
+    volatile double x = neg ? -n * value : n * value;
+    x = x + 0.5;
+    u64 res;
+    if (x < 18446744073709551616.0) res = (u64)x % q;
+    else res = (u64)(((unsigned __int128)x) % q);
+    return neg ? q - res : res;
+}
+int mkhe_ckks_mult_by_const(mkhe_ctx *ctx, int level, int n, const mkhe_poly *in, const mkhe_poly *out, double c_real, double c_imag,
+                            double scale) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    if (n < 1 || n > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_INVALID, "MultByConst: bad component count %d", n);
+    std::vector<u64 *> pi, po;
+    TRY(polys_of(ctx, n, in, level + 1, pi, "in", ACC_READ));
+    TRY(polys_of(ctx, n, out, level + 1, po, "out"));
+    ConstArgs a;
+    memset(&a, 0, sizeof a);
+    a.nlimbs = level + 1;
+    a.logN = ctx->logN;
+    for (int i = 0; i <= level; i++) {
+        const u64 qi = ctx->mod[i];
+        a.mod_of_limb[i] = i;
+        u64 sReal = 0, sImag = 0, sc = 0;
+        if (c_real != 0) { sReal = scale_up_exact(c_real, scale, qi); sc = sReal; }
+        if (c_imag != 0) {
+            sImag = scale_up_exact(c_imag, scale, qi);
+            sImag = h_mulmod(sImag % qi, ctx->tabs[i].twf[1].x, qi);          // MRed(., NttPsi[i][1])
+            sc = sc + sImag;
+            if (sc >= qi) sc -= qi;                                            // CRed
+        }
+        a.c_first[i] = h_mform(sc % qi, qi);
+        if (c_imag != 0) {
+            sc = sReal + (qi - sImag);
+            if (sc >= qi) sc -= qi;
+        }
+        a.c_second[i] = h_mform(sc % qi, qi);
+    }
+    for (int i = 0; i < n; i++) { a.in.p[i] = pi[i]; a.out.p[i] = po[i]; }
+    LAUNCH(k_mul_const, dim3(ctx->N / MKHE_THREADS, level + 1, n), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    return MKHE_OK;
+}
+int mkhe_poly_neg(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    POLY_R(i, in); POLY(o, out);
+    if (i->cap_limbs < level + 1 || o->cap_limbs < level + 1) return fail(ctx, MKHE_ERR_INVALID, "neg: too few limbs");
+    LimbArgs a;
+    fill(a, q_slots(level), ctx->logN);
+    a.in.p[0] = i->d; a.out.p[0] = o->d;
+    LAUNCH(k_neg, dim3(ctx->N / MKHE_THREADS, level + 1, 1), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    return MKHE_OK;
+}
+int mkhe_ckks_mul_ptxt(mkhe_ctx *ctx, int level, mkhe_poly pt, int n, const mkhe_poly *in, const mkhe_poly *out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    if (n < 1 || n + 1 > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_INVALID, "MulPtxt: bad component count %d", n);
+    POLY_R(p, pt);
+    if (p->cap_limbs < level + 1) return fail(ctx, MKHE_ERR_INVALID, "MulPtxt: plaintext has too few limbs");
+    std::vector<u64 *> pi, po, tn;
+    TRY(polys_of(ctx, n, in, level + 1, pi, "in", ACC_READ));
+    TRY(polys_of(ctx, n, out, level + 1, po, "out"));
+    TRY(poly_pool(ctx, "mulptxt_ntt", n + 1, ctx->nQ, tn));
+    const Slots qs = q_slots(level);
+    std::vector<u64 *> src(pi);
+    src.push_back(p->d);
+    TRY(ntt_fwd(ctx, qs, n + 1, src.data(), tn.data()));
+    for (int t = 0; t < n; t++) TRY(mul2(ctx, qs, tn[n], tn[t], nullptr, nullptr, tn[t]));   // MForm(pt) (.) ct, Montgomery
+    return ntt_inv(ctx, qs, n, tn.data(), po.data());
+}
+
 // ---- mkbfv ------------------------------------------------------------------------------------------
 namespace {
 int need_bfv(mkhe_ctx *ctx) {
@@ -1585,12 +1676,6 @@ int bfv_quantize_impl(mkhe_ctx *ctx, int nb, u64 *const *polyR, u64 *const *poly
 int bfv_decompose_impl(mkhe_ctx *ctx, int levelQ, int nb, u64 *const *aR, u64 *const *ad1, u64 *const *ad2) {
     TRY(decompose_impl(ctx, levelQ, nb, aR, ad1, 0));
     return decompose_impl(ctx, levelQ, nb, aR, ad2, levelQ + 1);
-}
-int mul2(mkhe_ctx *ctx, const Slots &s, const u64 *A, const u64 *B, const u64 *Cc, const u64 *D, u64 *out) {
-    LimbArgs a;
-    fill(a, s, ctx->logN);
-    LAUNCH(k_mul2, dim3(ctx->N / MKHE_THREADS, s.n), dim3(MKHE_THREADS), 0, A, B, Cc, D, out, a, ctx->d_mods);
-    return MKHE_OK;
 }
 // MulAndRelinBFVHoisted on raw pointers (mkbfv/keyswitch_hoisted.go:39-207)
 int bfv_mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u64 *const *op0, u64 *const *h0a,

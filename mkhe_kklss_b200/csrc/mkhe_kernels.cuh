@@ -967,6 +967,31 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_scale(ScaleArgs a, const ModC 
     a.out.p[b][off] = mred(a.in.p[b][off], a.cmont[limb], m.q, m.qinv);
 }
 
+// MultByConst (mkckks/evaluator.go:117-198): coefficients [0, N/2) times c_first, [N/2, N) times c_second (Montgomery form);
+// ringQ.NegLvl: q - x, unreduced (0 -> q).  grid = (N/256, nlimbs, npolys)
+struct ConstArgs {
+    PtrList in, out;
+    int nlimbs;
+    int mod_of_limb[MKHE_MAX_SLOTS];
+    u64 c_first[MKHE_MAX_SLOTS], c_second[MKHE_MAX_SLOTS];
+    int logN;
+};
+__global__ void __launch_bounds__(MKHE_THREADS) k_mul_const(ConstArgs a, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const int limb = blockIdx.y, b = blockIdx.z;
+    const ModC m = mods[a.mod_of_limb[limb]];
+    const long j = (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    const long off = (long)limb * N + j;
+    a.out.p[b][off] = mred(a.in.p[b][off], j < (N >> 1) ? a.c_first[limb] : a.c_second[limb], m.q, m.qinv);
+}
+__global__ void __launch_bounds__(MKHE_THREADS) k_neg(LimbArgs a, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const int limb = blockIdx.y, b = blockIdx.z;
+    const u64 q = mods[a.mod_of_limb[limb]].q;
+    const long off = (long)a.slot_of[limb] * N + (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    a.out.p[b][off] = q - a.in.p[b][off];
+}
+
 // BFV tensor products in ring R (mkbfv/keyswitch_hoisted.go:144-181): out = A*B (+ C*D), operands may be lazy (<4q)
 __global__ void __launch_bounds__(MKHE_THREADS) k_mul2(const u64 *A, const u64 *B, const u64 *Cc, const u64 *D, u64 *out,
                                                         LimbArgs a, const ModC *mods) {

@@ -186,32 +186,82 @@ class Evaluator:
         self.ksw.Conjugate(ct0, ckSet, ctOut)
         return ctOut
 
+    def CopyNew(self, ct):
+        """Ciphertext.CopyNew (mkckks/elements.go)"""
+        return self._copy(ct)
+
+    def DropLevelNew(self, ct0, levels):
+        """evaluator.go:98-102"""
+        out = self._copy(ct0)
+        self.DropLevel(out, levels)
+        return out
+
+    def getConstAndScale(self, level, constant):
+        """evaluator.go:39-93: a float / complex constant with a fractional part is scaled by q_level"""
+        scale = 1.0
+        if isinstance(constant, complex):
+            cReal, cImag = constant.real, constant.imag
+        else:
+            cReal, cImag = float(constant), 0.0
+        if isinstance(constant, (float, complex)):
+            for c in (cReal, cImag):
+                if c != 0 and c - float(int(c)) != 0:
+                    scale = float(self.params.Q[level])
+        return cReal, cImag, scale
+
+    def MultByConst(self, ct0, constant, ctOut):
+        """evaluator.go:117-198 (ctOut may be ct0): the per-limb multipliers are derived on the library side exactly like the
+        reference; only the components of ct0 are written"""
+        level = min(ct0.Level(), ctOut.Level())
+        cReal, cImag, scale = self.getConstAndScale(level, constant)
+        ks = list(ct0.Value)
+        self.ctx.ckks_mult_by_const(level, [ct0.Value[k].h for k in ks], [ctOut.Value[k].h for k in ks], cReal, cImag, scale)
+        ctOut.Scale = ct0.Scale * scale
+
+    def MulPtxtNew(self, ct, ptValue, ptScale):
+        """evaluator.go:465-481; ptValue = ckks.Plaintext.Value as a device Poly (coefficient domain), ptScale its Scale"""
+        ctOut = Ciphertext.new(self.params, ct.IDSet(), ct.Level(), ct.Scale * ptScale)
+        ks = list(ct.Value)
+        self.ctx.ckks_mul_ptxt(ct.Level(), ptValue.h, [ct.Value[k].h for k in ks], [ctOut.Value[k].h for k in ks])
+        self.Rescale(ctOut, self.params.Scale(), ctOut)
+        return ctOut
+
     def AddNew(self, op0, op1):
-        """evaluator.go:200-250 restricted to equal scales (scale alignment via MultByConst is host-side 'next' work)"""
-        return self._addsub(op0, op1, False)
+        """evaluator.go:319-330 = newCiphertextBinary + evaluateInPlace (:200-304)"""
+        return self._evaluate_new(op0, op1, False)
 
     def SubNew(self, op0, op1):
-        return self._addsub(op0, op1, True)
+        """evaluator.go:332-357: evaluateInPlace with SubLvl, then NegLvl (q - x, unreduced) of the components missing from op0"""
+        return self._evaluate_new(op0, op1, True)
 
-    def _addsub(self, op0, op1, sub):
-        if op0.Scale != op1.Scale:
-            raise RuntimeError("AddNew/SubNew: scale alignment is not on the device path yet")
+    def _evaluate_new(self, op0, op1, sub):
+        """evaluateInPlace's third branch (ctOut is a fresh element): the operand with the smaller scale is first multiplied
+        by floor(ratio) when that exceeds 1 (into a pool ciphertext, evaluator.go:274-292), components held by one operand
+        only are copied (:297-303)"""
+        import math
         ctOut = self.newCiphertextBinary(op0, op1)
-        level = ctOut.Level()
+        level = min(op0.Level(), op1.Level(), ctOut.Level())
+        s0, s1 = op0.ScalingFactor(), op1.ScalingFactor()
+        t0, t1, pool = op0, op1, None
+        if s1 > s0 and math.floor(s1 / s0) > 1:
+            pool = t0 = Ciphertext.new(self.params, op0.IDSet(), op0.Level(), ctOut.Scale)
+            self.MultByConst(op0, float(math.floor(s1 / s0)), t0)
+            t0.Scale = ctOut.Scale
+        elif s0 > s1 and math.floor(s0 / s1) > 1:
+            pool = t1 = Ciphertext.new(self.params, op1.IDSet(), op1.Level(), ctOut.Scale)
+            self.MultByConst(op1, float(math.floor(s0 / s1)), t1)
+            t1.Scale = ctOut.Scale
         for k in ctOut.Value:
             in0, in1 = k in op0.Value, k in op1.Value
             o = ctOut.Value[k].h
             if in0 and in1:
-                (self.ctx.poly_sub if sub else self.ctx.poly_add)(level, op0.Value[k].h, op1.Value[k].h, o)
+                (self.ctx.poly_sub if sub else self.ctx.poly_add)(level, t0.Value[k].h, t1.Value[k].h, o)
             elif in0:
-                self.ctx.poly_copy(o, op0.Value[k].h)
-                self.ctx.poly_set_nlimbs(o, level + 1)
+                self.ctx.poly_copy_lvl(level, o, t0.Value[k].h)
+            elif sub:
+                self.ctx.poly_neg(level, t1.Value[k].h, o)
             else:
-                if sub:
-                    zero = Poly(self.ctx, level + 1)
-                    self.ctx.poly_sub(level, zero.h, op1.Value[k].h, o)
-                    zero.free()
-                else:
-                    self.ctx.poly_copy(o, op1.Value[k].h)
-                    self.ctx.poly_set_nlimbs(o, level + 1)
+                self.ctx.poly_copy_lvl(level, o, t1.Value[k].h)
+        if pool is not None:
+            pool.free()
         return ctOut

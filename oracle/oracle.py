@@ -24,6 +24,8 @@ import subprocess
 from dataclasses import dataclass, field
 from functools import reduce
 
+import math
+
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -739,6 +741,125 @@ class CKKSEvaluator:
         out = self.new_ciphertext(ct.ids(), ct.level(), ct.scale)
         self.ksw.conjugate(ct, cks, out)
         return out
+
+    # ---- element-wise evaluator ops either side of the key switches ---------------------------
+    def get_const_and_scale(self, level, constant):
+        """getConstAndScale mkckks/evaluator.go:39-93: a constant with a fractional part is scaled by q_level"""
+        scale = 1.0
+        if isinstance(constant, complex):
+            cReal, cImag = constant.real, constant.imag
+        else:
+            cReal, cImag = float(constant), 0.0
+        if isinstance(constant, (float, complex)):
+            for c in (cReal, cImag):
+                if c != 0 and c - float(int(c)) != 0:
+                    scale = float(self.params.Q[level])
+        return cReal, cImag, scale
+
+    @staticmethod
+    def scale_up_exact(value, n, q):
+        """scaleUpExact mkckks/utils.go:59-86: big.NewFloat(n*value) has 53 bits of precision, so the product and the
+        + 0.5 are float64 operations (round to nearest even), Int() truncates, then mod q; negative values give q - res
+        (so -0.0... never; a negative multiple of q gives q, not 0)"""
+        neg = value < 0
+        x = (-n * value) if neg else (n * value)
+        x = x + 0.5
+        res = int(x) % q
+        return q - res if neg else res
+
+    def const_residues(self, level, constant):
+        """the two per-limb multipliers of MultByConst (evaluator.go:117-198): coefficients [0, N/2) are multiplied by
+        a + b*psi^(N/2)... (NttPsi[i][1]), coefficients [N/2, N) by a - b*(...) -- the reference applies the NTT-domain formula
+        to whatever domain the ciphertext is in; reproduced as written.  Returns (first[], second[], scale), plain residues."""
+        cReal, cImag, scale = self.get_const_and_scale(level, constant)
+        first, second = [], []
+        ring = self.params.ringQ
+        for i in range(level + 1):
+            qi = ring.moduli[i]
+            sReal = self.scale_up_exact(cReal, scale, qi) if cReal != 0 else 0
+            sc = sReal
+            sImag = 0
+            if cImag != 0:
+                sImag = self.scale_up_exact(cImag, scale, qi)
+                psi1 = int(ring.tables(i)[0][1])                       # NttPsi[i][1], Montgomery form
+                sImag = (sImag * psi1 * pow(1 << 64, -1, qi)) % qi     # MRed
+                sc = sc + sImag
+                if sc >= qi:
+                    sc -= qi                                           # CRed
+            first.append(sc % qi)                                      # MForm reduces
+            if cImag != 0:
+                sc = sReal + (qi - sImag)
+                if sc >= qi:
+                    sc -= qi
+            second.append(sc % qi)
+        return first, second, scale
+
+    def mult_by_const(self, ct0, constant, ctOut):
+        """MultByConst evaluator.go:117-198; ctOut may be ct0.  Only the components of ct0 and the limbs <= min level are
+        written, like the reference."""
+        level = min(ct0.level(), ctOut.level())
+        first, second, scale = self.const_residues(level, constant)
+        ring = self.params.ringQ
+        h = self.params.N // 2
+        for u in ct0.value:
+            a = ct0.value[u][:level + 1]
+            lo = ring.mul_residues(np.ascontiguousarray(a), first, level)
+            hi = ring.mul_residues(np.ascontiguousarray(a), second, level)
+            lo[:, h:] = hi[:, h:]
+            ctOut.value[u][:level + 1] = lo
+        ctOut.scale = ct0.scale * scale
+
+    def _evaluate_new(self, c0, c1, sub):
+        """AddNew / SubNew = newCiphertextBinary + evaluateInPlace's third branch (ctOut is neither input), evaluator.go:
+        200-351: the operand with the smaller scale is multiplied by floor(ratio) when that exceeds 1, components present
+        in one operand only are copied, and Sub negates (q - x, unreduced) the ones missing from op0."""
+        ctOut = self._new_binary(c0, c1)
+        level = min(c0.level(), c1.level(), ctOut.level())
+        ring = self.params.ringQ
+        s0, s1 = c0.scale, c1.scale
+        t0, t1 = c0, c1
+        if s1 > s0 and math.floor(s1 / s0) > 1:
+            t0 = self.new_ciphertext(c0.ids(), c0.level(), ctOut.scale)
+            self.mult_by_const(c0, float(math.floor(s1 / s0)), t0)
+        elif s0 > s1 and math.floor(s0 / s1) > 1:
+            t1 = self.new_ciphertext(c1.ids(), c1.level(), ctOut.scale)
+            self.mult_by_const(c1, float(math.floor(s0 / s1)), t1)
+        fn = ring.sub if sub else ring.add
+        for k in ctOut.value:
+            in0, in1 = k in c0.value, k in c1.value
+            if in0 and in1:
+                ctOut.value[k] = fn(np.ascontiguousarray(t0.value[k][:level + 1]), np.ascontiguousarray(t1.value[k][:level + 1]), level)
+            elif in0:
+                ctOut.value[k] = t0.value[k][:level + 1].copy()
+            else:
+                v = t1.value[k][:level + 1].copy()
+                ctOut.value[k] = ring.neg(np.ascontiguousarray(v), level) if sub else v
+        return ctOut
+
+    def add_new(self, c0, c1):
+        return self._evaluate_new(c0, c1, False)
+
+    def sub_new(self, c0, c1):
+        return self._evaluate_new(c0, c1, True)
+
+    def mul_ptxt_new(self, ct, pt_value, pt_scale):
+        """MulPtxtNew evaluator.go:465-481: NTT(pt) in Montgomery form, per component NTT, MulCoeffsMontgomery, InvNTT;
+        then Rescale to the default scale"""
+        level = ct.level()
+        ring = self.params.ringQ
+        out = self.new_ciphertext(ct.ids(), level, ct.scale * pt_scale)
+        ptn = ring.mform(ring.ntt(np.ascontiguousarray(pt_value[:level + 1]), level), level)
+        for k in ct.value:
+            t = ring.ntt(np.ascontiguousarray(ct.value[k][:level + 1]), level)
+            t = ring.mul_mont(t, ptn, level)
+            out.value[k] = ring.intt(t, level)
+        self.rescale(out, self.scale, out)
+        return out
+
+    def drop_level(self, ct, levels):
+        level = ct.level()
+        for k in ct.value:
+            ct.value[k] = np.ascontiguousarray(ct.value[k][:level + 1 - levels])
 
 
 # --------------------------------------------------------------------------------------------

@@ -254,6 +254,70 @@ def check_lanes(w: CKKSWorld, rounds=3, level=None):
     ev[1].ctx.close()
 
 
+def check_elementwise(w: CKKSWorld):
+    """the evaluator ops either side of the key switches: AddNew / SubNew over different id sets, levels
+    and scales (scale alignment through MultByConst), MultByConst with integer / fractional / negative / complex constants,
+    MulPtxtNew, DropLevelNew -- bit for bit against the oracle"""
+    L = w.op.max_level()
+    ids = w.ids
+    cases = [(ids, ids, L, L, 1.0, 1.0), (ids[:1], ids[1:], L, L, 1.0, 1.0), (ids[:1], ids, L, L - 1, 1.0, 1.0),
+             (ids, ids[1:], L - 1, L, 1.0, 1.0), (ids, ids, L, L, 1.0, 7.3), (ids[:1], ids, L, L, 5.0, 1.0),
+             (ids, ids, L, L, 1.0, 1.9)]
+    for n, (i0, i1, l0, l1, f0, f1) in enumerate(cases):
+        o0, d0 = w.random_ct(i0, l0, w.lit.scale * f0)
+        o1, d1 = w.random_ct(i1, l1, w.lit.scale * f1)
+        if n == 0:      # non-canonical inputs as rotations produce them (q stored for a negated zero)
+            o0.value["0"][:, :7] = np.array(w.op.Q[:l0 + 1], dtype=np.uint64)[:, None]
+            w.ctx.poly_upload(d0.Value["0"].h, o0.value["0"])
+        for sub in (False, True):
+            oo = (w.oev.sub_new if sub else w.oev.add_new)(o0, o1)
+            do = (w.dev.SubNew if sub else w.dev.AddNew)(d0, d1)
+            assert do.Level() == oo.level() and do.Scale == oo.scale, (n, sub, do.Level(), oo.level(), do.Scale, oo.scale)
+            w.compare_ct(do, oo, f"{'SubNew' if sub else 'AddNew'} case {n}")
+    for const in (3, -5, 2.5, -0.37, 1e-3, complex(0.5, -1.25), complex(0, 2), float(2 ** 40) + 0.5, 0):
+        o0, d0 = w.random_ct(ids, L)
+        oo = w.oev.new_ciphertext(ids, L, 0.0)
+        do = mkckks.Ciphertext.new(w.dp, ids, L, 0.0)
+        w.oev.mult_by_const(o0, const, oo)
+        w.dev.MultByConst(d0, const, do)
+        assert do.Scale == oo.scale, (const, do.Scale, oo.scale)
+        w.compare_ct(do, oo, f"MultByConst({const})")
+    w.oev.mult_by_const(o0, -7, o0)                      # in place
+    w.dev.MultByConst(d0, -7, d0)
+    w.compare_ct(d0, o0, "MultByConst in place")
+    for lvl in (L, 1):
+        o0, d0 = w.random_ct(ids, lvl)
+        pt = uniform_poly(w.prng, w.op.ringQ, lvl)
+        dpt = mkrlwe.Poly.from_numpy(w.ctx, pt)
+        oo = w.oev.mul_ptxt_new(o0, pt, w.lit.scale)
+        do = w.dev.MulPtxtNew(d0, dpt, w.lit.scale)
+        assert do.Level() == oo.level() and do.Scale == oo.scale
+        w.compare_ct(do, oo, f"MulPtxtNew(level={lvl})")
+    o0, d0 = w.random_ct(ids, L)
+    dd = w.dev.DropLevelNew(d0, 2)
+    w.oev.drop_level(o0, 2)
+    w.compare_ct(dd, o0, "DropLevelNew")
+
+
+def check_cnn_flow(lit, lib=None):
+    """the reference's encrypted-CNN op sequence (tests/cnn_flow.py) on the oracle and on the device, compared bit for bit"""
+    import cnn_flow as F
+    inp = F.make_inputs(lit)
+    oout, omid = F.run_oracle(lit, inp)
+    dout, dmid, fac, ctx = F.run_device(lit, inp, lib)
+    for name in omid:
+        for k in omid[name].value:
+            assert_same(dmid[name].numpy()[k], omid[name].value[k], f"cnn {name}[{k}]")
+    assert dout.Level() == oout.level() == 0 and dout.Scale == oout.scale, (dout.Level(), oout.level(), dout.Scale, oout.scale)
+    dv = dout.numpy()
+    assert set(dv) == set(oout.value)
+    for k in oout.value:
+        assert_same(dv[k], oout.value[k], f"cnn fc2Out[{k}]")
+    assert fac.counts == {"HoistedForm": 27, "MulRelinHoistedNew": 14, "MulRelinNew": 1, "RotateHoistedNew": 11, "RotateNew": 19,
+                          "AddNew": 31, "MulPtxtNew": 1}, fac.counts
+    ctx.close()
+
+
 def check_conjugate(w: CKKSWorld, ids, level=None):
     level = w.op.max_level() if level is None else level
     oct_, dct = w.random_ct(ids, level)
@@ -302,6 +366,37 @@ def check_ckks_semantics(w: CKKSWorld):
     err = np.abs(got - np.roll(msum, -2)).max()
     bound = 2.0 ** (-np.log2(lit.scale) + np.log2(n) + 11)
     assert err <= bound, f"Rotate precision {np.log2(err):.1f} > {np.log2(bound):.1f}"
+    # element-wise ops on device outputs, the reference's thresholds (mkckks_test.go:228-318: Add / Sub +11; the product
+    # thresholds +12 for the plaintext product and the constant multiples)
+    bound = 2.0 ** (-np.log2(lit.scale) + np.log2(n) + 12)
+
+    def dec_dev(dc):
+        r = O.Ciphertext(dc.numpy(), dc.Scale)
+        return O.ckks_decode(p, dec.decrypt(r, w.sks), r.scale)
+
+    d0 = mkckks.Ciphertext.from_numpy(w.ctx, cts[0].value, lit.scale)
+    d1 = mkckks.Ciphertext.from_numpy(w.ctx, cts[-1].value, lit.scale)
+    assert np.abs(dec_dev(w.dev.AddNew(d0, d1)) - (msgs[0] + msgs[-1])).max() <= bound, "AddNew precision"
+    assert np.abs(dec_dev(w.dev.SubNew(d0, d1)) - (msgs[0] - msgs[-1])).max() <= bound, "SubNew precision"
+    # real constants only: for a complex one the reference applies lattigo's NTT-domain formula (first / second half of the
+    # SLOTS) to a coefficient-domain ciphertext (evaluator.go:123-127 vs the InvNTT'd ciphertexts of this library), which is
+    # reproduced bit for bit (check_elementwise) but is not a multiplication by that constant
+    for const in (3, -2.5):
+        dm = mkckks.Ciphertext.new(w.dp, d0.IDSet(), d0.Level(), 0.0)
+        w.dev.MultByConst(d0, const, dm)
+        if dm.Scale > lit.scale * 2:                       # a scaled constant: bring the scale back like a caller would
+            assert w.dev.Rescale(dm, lit.scale, dm) is None
+        assert np.abs(dec_dev(dm) - const * msgs[0]).max() <= bound * 8, f"MultByConst({const}) precision"
+    # scale alignment: the product (scale ~ Delta after Rescale... here: not rescaled, Delta^2) plus a fresh ciphertext
+    big = mkckks.Ciphertext.new(w.dp, d0.IDSet(), d0.Level(), 0.0)
+    w.dev.MultByConst(d0, 1000, big)                       # same scale, message * 1000
+    big.Scale = lit.scale * 1000                           # ... reinterpreted: message at scale 1000 * Delta
+    aligned = w.dev.AddNew(big, d1)                        # d1 is multiplied by floor(1000) first
+    assert aligned.Scale == lit.scale * 1000
+    assert np.abs(dec_dev(aligned) - (msgs[0] + msgs[-1])).max() <= bound, "AddNew with scale alignment"
+    mp = rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)
+    dpt = mkrlwe.Poly.from_numpy(w.ctx, O.ckks_encode(p, mp, lit.scale))
+    assert np.abs(dec_dev(w.dev.MulPtxtNew(d0, dpt, lit.scale)) - mp * msgs[0]).max() <= bound, "MulPtxtNew precision"
 
 
 # ---- BFV --------------------------------------------------------------------------------------------
@@ -407,6 +502,8 @@ def check_bfv_semantics(w: BFVWorld):
 
 
 def run_ckks_suite(w: CKKSWorld, quick=False):
+    if len(w.ids) >= 2 and w.op.max_level() >= 2:
+        check_elementwise(w)
     L = w.op.max_level()
     check_ntt(w)
     check_decompose(w)

@@ -64,3 +64,16 @@ def test_pn16qp1761_full_limb_count_under_emulation(emu):
     parity.check_mul_relin_new(w, w.ids, w.ids)
     parity.check_rotate(w, w.ids, 1)
     w.close()
+
+
+def test_elementwise_semantics_under_emulation(emu):
+    """AddNew / SubNew / MultByConst / MulPtxtNew on real encryptions: decrypted results against the plain computation, with
+    the reference's precision thresholds (pins what the element-wise ops MEAN, not only that oracle and device agree)"""
+    w = parity.CKKSWorld(PR.CKKS_PN14QP439.at_logn(12), 2, lib=emu, real_keys=True)
+    parity.check_ckks_semantics(w)
+    w.close()
+
+
+def test_cnn_flow_under_emulation(emu):
+    """the reference's CNN op sequence at logN = 12 (rotations beyond N/2 wrap, the ones without a key chain powers of two)"""
+    parity.check_cnn_flow(PR.CNN_PN14QP433.at_logn(12), lib=emu)

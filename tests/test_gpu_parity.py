@@ -36,6 +36,14 @@ def test_lanes(logN, k, rounds):
     w.close()
 
 
+def test_cnn_inference_flow():
+    """BASELINE config 5: the whole encrypted-CNN op sequence of the reference (cnn/cnn.go + cnn/cnn_test.go:121-162) at its own
+    parameter set PN14QP433 / logN = 14, two parties (model owner, data owner), 24 rotation keys per party: 15 MulRelin, 11
+    hoisted + 19 plain rotations, 27 HoistedForm, 31 AddNew, 1 MulPtxtNew, levels 6 -> 0.  Every intermediate ciphertext of
+    the device is the oracle's, bit for bit."""
+    parity.check_cnn_flow(PR.CNN_PN14QP433)
+
+
 def test_ckks_semantics_on_device_outputs():
     w = parity.CKKSWorld(PR.CKKS_PN14QP439.at_logn(12), 2, real_keys=True)
     parity.check_ckks_semantics(w)
@@ -138,6 +146,15 @@ def test_device_matches_committed_golden_digests():
         got.update({f"rot[{kk}]": dig(v) for kk, v in rot.items()})
         assert got == golden[name], name
         dp.ctx.close()
+    # the reference's CNN op sequence at logN = 12: device result and intermediates hashed against the committed digests
+    import cnn_flow as F
+    lit = PR.CNN_PN14QP433.at_logn(12)
+    out, mid, _, ctx = F.run_device(lit, F.make_inputs(lit))
+    got = {f"fc2Out[{kk}]": dig(v) for kk, v in out.numpy().items()}
+    for nm, ct in mid.items():
+        got.update({f"{nm}[{kk}]": dig(v) for kk, v in ct.numpy().items()})
+    assert got == golden["cnn_flow_PN14QP433_logN12"]
+    ctx.close()
 
 
 def test_full_size_back_to_back():

@@ -59,7 +59,35 @@ def golden_cases():
         res["rescale"] = ev.rescale_q_to_r(c0.value["0"])
         return res
 
+    def cnn_flow_case(lit):
+        import cnn_flow as F
+        out, mid = F.run_oracle(lit)
+        res = {f"fc2Out[{kk}]": v for kk, v in out.value.items()}
+        for name, ct in mid.items():
+            res.update({f"{name}[{kk}]": v for kk, v in ct.value.items()})
+        return res
+
+    def elementwise_case(lit):
+        p = O.MKParams(lit.logN, lit.Q, lit.P, 2, seed=0xB2000006, crs_rots=[])
+        prng = O.PRNG(0xB2000006 ^ 0x5EED)
+        ev = O.CKKSEvaluator(p, lit.scale)
+        L = p.max_level()
+        mk = lambda ids, lvl, sc: O.Ciphertext({**{"0": prng.uniform(p.ringQ, lvl)}, **{i: prng.uniform(p.ringQ, lvl) for i in ids}}, sc)
+        a, b, c = mk([0, 1], L, lit.scale), mk([1, 2], L - 1, lit.scale * 7.3), mk([0], L, lit.scale)
+        res = {}
+        for nm, ct in (("add", ev.add_new(a, b)), ("sub", ev.sub_new(a, b)), ("sub2", ev.sub_new(c, b))):
+            res.update({f"{nm}[{kk}]": v for kk, v in ct.value.items()})
+        for n, const in enumerate((3, -2.5, complex(0.5, -1.25))):
+            o = ev.new_ciphertext([0, 1], L, 0.0)
+            ev.mult_by_const(a, const, o)
+            res.update({f"const{n}[{kk}]": v for kk, v in o.value.items()})
+        pt = prng.uniform(p.ringQ, L)
+        res.update({f"mulptxt[{kk}]": v for kk, v in ev.mul_ptxt_new(a, pt, lit.scale).value.items()})
+        return res
+
     return [
+        ("cnn_flow_PN14QP433_logN12", lambda: cnn_flow_case(PR.CNN_PN14QP433.at_logn(12))),
+        ("elementwise_PN14QP439_logN12", lambda: elementwise_case(PR.CKKS_PN14QP439.at_logn(12))),
         ("ckks_PN14QP439_logN12_k2", lambda: ckks_case(PR.CKKS_PN14QP439.at_logn(12), 2, False)),
         ("ckks_PN14QP439_logN12_k2_square", lambda: ckks_case(PR.CKKS_PN14QP439.at_logn(12), 2, True)),
         ("ckks_PN15QP880_logN12_k3", lambda: ckks_case(PR.CKKS_PN15QP880.at_logn(12), 3, False)),
