@@ -72,8 +72,9 @@ def algorithmic_model(k, ell, nP, N):
     fwd, inv = 3 * k * beta * D + (2 * k + 2) * ell, (k + 1) * ell + 4 * k * D
     kern = {
         "k_bcast_ntt_pass1": (3 * k * ell + 3 * k * beta * D) * limb,
-        "k_ntt_pass2": 2 * (3 * k * beta * D + (2 * k + 2) * ell) * limb,
-        "k_ntt_pass1": 2 * (2 * k + 2) * ell * limb,
+        # the tensor step transforms only the two "0" components: NTT(op_id) is read from the diagonal of the hoisted forms
+        "k_ntt_pass2": 2 * (3 * k * beta * D + 2 * ell) * limb,
+        "k_ntt_pass1": 2 * 2 * ell * limb,
         "k_mac_parties": (4 * k * beta * D + 2 * beta * D) * limb,
         "k_mac_digits": (4 * k * beta * D + 3 * beta * D + 4 * k * D) * limb,
         "k_intt_passA": 2 * ((k + 1) * ell + 4 * k * D) * limb,
@@ -86,8 +87,8 @@ def algorithmic_model(k, ell, nP, N):
     s1 = logN - 11                 # column stages (pass 1 / pass B); the tile passes do the other 11
     bfly = {
         "k_bcast_ntt_pass1": 3 * k * beta * D * (N // 2) * s1,
-        "k_ntt_pass2": (3 * k * beta * D + (2 * k + 2) * ell) * (N // 2) * 11,
-        "k_ntt_pass1": (2 * k + 2) * ell * (N // 2) * s1,
+        "k_ntt_pass2": (3 * k * beta * D + 2 * ell) * (N // 2) * 11,
+        "k_ntt_pass1": 2 * ell * (N // 2) * s1,
         "k_intt_passA": ((k + 1) * ell + 4 * k * D) * (N // 2) * 11,
         "k_intt_passB": (k + 1) * ell * (N // 2) * s1,
         "k_moddown_P": 4 * k * nP * (N // 2) * s1,
@@ -317,6 +318,55 @@ class DeviceWorkload:
         return ms
 
 
+def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dist, barrier, allmax):
+    """BASELINE config 4: ONE MulRelinNew whose per-party key switches are sharded over the ranks (mkhe_ckks_mul_relin_sharded:
+    rank g holds the relinearisation keys of its parties only, the partial x, y and the c_0 contributions are summed with
+    ncclAllReduce over NVLink and reduced mod q).  Operand ciphertexts are replicated (they are small); every rank issues the
+    same ops.  Returns ops/s of the whole group (strong scaling: total work fixed) -- CUDA events, max over ranks."""
+    from mkhe_kklss_b200 import mkckks, mkrlwe, sharding
+    level = len(lit.Q) - 1
+    params = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, device=local_rank)
+    ctx = params.ctx
+    uid = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(world, rank, uid[0])
+    mods, beta = list(lit.Q) + list(lit.P), len(lit.Q)
+    mk = lambda rng: uniform_limbs(rng, mods, (beta,), lit.N)
+    params.SetCRS(-1, mk(np.random.default_rng(0xB2000040)))            # the CRS is common to all ranks
+    ids = list(range(k))
+    own = sharding.owned_parties(ids, world, rank)
+    rlk = mkrlwe.RelinearizationKeySet()
+    for i in own:
+        rng = np.random.default_rng(0xB2000041 + i)
+        rlk.AddRelinearizationKey(mkrlwe.RelinearizationKey(ctx, i, mk(rng), mk(rng), mk(rng)))
+    rng = np.random.default_rng(0xB2000042)                             # replicated operands: same seed on every rank
+    pairs = [(mkckks.Ciphertext.from_numpy(ctx, host_ct(lit, k, level, rng), lit.scale),
+              mkckks.Ciphertext.from_numpy(ctx, host_ct(lit, k, level, rng), lit.scale)) for _ in range(2)]
+    out = mkckks.Ciphertext.new(params, ids, level, lit.scale)
+    ev = mkckks.Evaluator(params)
+    nb, _ = ev._nb_rescales(lit.scale * lit.scale, level, lit.scale)
+    key = lambda i, j: rlk.Value[i].Value[j].h if i in rlk.Value else 0
+    kb, kd, kv = [key(i, 0) for i in ids], [key(i, 1) for i in ids], [key(i, 2) for i in ids]
+
+    def step(i):
+        for j in range(batch):
+            a, b = pairs[(i * batch + j) % len(pairs)]
+            ctx.ckks_mul_relin_sharded(level, nb, ids, a.handles(ids), ids, b.handles(ids), own, kb, kd, kv,
+                                       params.CRS[-1].h, ids, out.handles(ids))
+
+    for i in range(warmup):
+        step(i)
+    ctx.sync()
+    barrier()
+    ctx.timer_start()
+    for i in range(steps):
+        step(i)
+    ms = allmax(ctx.timer_stop())
+    barrier()
+    ctx.close()
+    return batch * steps / (ms * 1e-3)
+
+
 def cpu_oracle_run(lit, k, steps, warmup, threads, seed=0xB2000002):
     """times the oracle port of MulRelinNew on the host cores; returns (ops/s, cores used, seconds per op)"""
     from oracle import oracle as O
@@ -388,7 +438,9 @@ def main():
     # ---------------- GPU arm ----------------------------------------------------------------------
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MKHE_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: whatever NCCL has to say (its version banner included) goes to a file
+        os.environ["NCCL_DEBUG"] = os.environ.get("MKHE_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mkhe_nccl.%h.%p.log")
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
@@ -499,6 +551,17 @@ def main():
         extra["rotate_hoisted_k8_ops_s"] = B * args.steps / (ms_rot8 * 1e-3)
         wl8.ctx.close()
         del wl8
+
+    if not args.no_extras and world > 1:
+        # party-sharded MulRelin over NCCL (strong scaling of ONE op; the headline above is weak scaling over independent batches)
+        for ks in sorted({8, max(world, 2) * 2}):
+            if ks < world:
+                continue
+            try:
+                extra[f"sharded_mulrelin_k{ks}_ops_s"] = sharded_mul_relin(lit, ks, rank, world, local_rank, max(args.steps // 4, 2), warmup,
+                                                                           4, dist, barrier, allmax)
+            except Exception as e:      # a missing NCCL build must not take the headline down with it
+                extra[f"sharded_mulrelin_k{ks}_error"] = str(e)[:200]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -728,7 +728,9 @@ int allreduce_mod(mkhe_ctx *ctx, u64 *buf, size_t count, const Slots &s, int nbu
 int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u64 *const *op0, u64 *const *h0,
                            int n1, const int *ids1, u64 *const *op1, u64 *const *h1, u64 *const *rlk_b,
                            u64 *const *rlk_d, u64 *const *rlk_v, u64 *u, int nOut, const int *idsOut, u64 *const *out,
-                           const Shard &sh = Shard(), bool hoist0 = false, bool hoist1 = false) {
+                           const Shard &sh = Shard(), bool hoist0 = false, bool hoist1 = false, bool fresh0 = false, bool fresh1 = false) {
+    fresh0 = fresh0 || hoist0;          // hoisted in this call: the form is Decompose(op) by construction
+    fresh1 = fresh1 || hoist1;
     const int N = ctx->N;
     Slots qps = qp_slots(ctx, level);
     // owned sub-lists
@@ -760,17 +762,25 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     else CU(cudaMemsetAsync(y, 0, swk_elems(ctx) * 8, ctx->stream));
     if (sh.active) TRY(allreduce_mod(ctx, x, 2 * swk_elems(ctx), qps, 2 * ctx->beta_max, (long)ctx->dmax * N));
 
-    // step 4 (:119-144): tensor product in the NTT domain, then InvNTT of every output component
+    // step 4 (:119-144): tensor product in the NTT domain, then InvNTT of every output component.
+    // With alpha = 1, digit i of a hoisted form is limb i of the poly broadcast to every modulus, so its limb i IS
+    // NTT_{q_i}(poly limb i): when the library has just hoisted the operand itself (fresh0 / fresh1), NTT(op_id) is read from the
+    // diagonal of h_id instead of being transformed again -- the same kernel produced it from the same input, bit for bit.
     {
         Slots qs = q_slots(level);
-        std::vector<u64 *> src(n0 + n1 + 2);
-        for (int t = 0; t <= n0; t++) src[t] = op0[t];
-        for (int t = 0; t <= n1; t++) src[n0 + 1 + t] = op1[t];
-        TRY(ntt_fwd(ctx, qs, n0 + n1 + 2, src.data(), tn.data()));
+        const bool dg0 = fresh0 && ctx->alpha == 1, dg1 = fresh1 && ctx->alpha == 1;
+        std::vector<u64 *> src, dst;
+        src.push_back(op0[0]); dst.push_back(tn[0]);
+        src.push_back(op1[0]); dst.push_back(tn[n0 + 1]);
+        if (!dg0) for (int t = 1; t <= n0; t++) { src.push_back(op0[t]); dst.push_back(tn[t]); }
+        if (!dg1) for (int t = 1; t <= n1; t++) { src.push_back(op1[t]); dst.push_back(tn[n0 + 1 + t]); }
+        TRY(ntt_fwd(ctx, qs, (int)src.size(), src.data(), dst.data()));
         TensorArgs ta;
         memset(&ta, 0, sizeof ta);
         ta.A0 = tn[0];
         ta.B0 = tn[n0 + 1];
+        ta.strideA = dg0 ? (long)(ctx->dmax + 1) * N : N;
+        ta.strideB = dg1 ? (long)(ctx->dmax + 1) * N : N;
         ta.nout = nOut;
         ta.nlimbs = level + 1;
         ta.logN = ctx->logN;
@@ -778,8 +788,8 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
         ta.out.p[0] = out[0];
         for (int t = 0; t < nOut; t++) {
             int i0 = find_id(n0, ids0, idsOut[t]), i1 = find_id(n1, ids1, idsOut[t]);
-            ta.A.p[t] = i0 >= 0 ? tn[1 + i0] : nullptr;
-            ta.B.p[t] = i1 >= 0 ? tn[n0 + 2 + i1] : nullptr;
+            ta.A.p[t] = i0 >= 0 ? (dg0 ? h0[i0] : tn[1 + i0]) : nullptr;
+            ta.B.p[t] = i1 >= 0 ? (dg1 ? h1[i1] : tn[n0 + 2 + i1]) : nullptr;
             ta.out.p[1 + t] = out[1 + t];
         }
         LAUNCH(k_tensor, dim3(N / MKHE_THREADS, level + 1), dim3(MKHE_THREADS), 0, ta, ctx->d_mods);
@@ -1389,7 +1399,7 @@ int mkhe_ckks_mul_relin(mkhe_ctx *ctx, int level, int nb_rescales, int same_oper
     if (same_operand) vh1 = vh0;
     else TRY(swk_pool(ctx, "hoistpool1", n1, vh1));
     TRY(mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
-                               vd.data(), vv.data(), uk->d, nOut, idsOut, po.data(), Shard(), true, !same_operand));
+                               vd.data(), vv.data(), uk->d, nOut, idsOut, po.data(), Shard(), true, !same_operand, true, true));
     TRY(rescale_impl(ctx, level, nb_rescales, nOut + 1, po.data(), po.data()));
     for (int t = 0; t <= nOut; t++) reinterpret_cast<Obj *>(out[t])->nlimbs = level + 1 - nb_rescales;
     return MKHE_OK;

@@ -871,6 +871,8 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_Q(ModDownQArgs a, 
 struct TensorArgs {
     const u64 *A0, *B0;           // NTT(op0_0), NTT(op1_0)
     PtrList A, B;                 // per output party: NTT(op0_id) / NTT(op1_id) or nullptr
+    long strideA, strideB;        // distance between consecutive limbs of A.p[t] / B.p[t]: N for a poly, (dmax + 1) * N when the
+                                  // operand is read from the diagonal of the party's freshly hoisted form (digit i, limb i)
     PtrList out;                  // [0] = component "0", [1+t]
     int nout;                     // parties in the output
     int nlimbs;
@@ -881,14 +883,16 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_tensor(TensorArgs a, const Mod
     const long N = 1L << a.logN;
     const int limb = blockIdx.y;
     const ModC m = mods[a.mod_of_limb[limb]];
-    const long off = (long)limb * N + (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    const long x = (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    const long off = (long)limb * N + x;
+    const long offA = (long)limb * a.strideA + x, offB = (long)limb * a.strideB + x;
     const u64 a0 = mred(a.A0[off], m.r2, m.q, m.qinv);      // MForm
     const u64 b0 = mred(a.B0[off], m.r2, m.q, m.qinv);
     a.out.p[0][off] = mred(a0, a.B0[off], m.q, m.qinv);
     for (int t = 0; t < a.nout; t++) {
         u64 r = 0;
-        if (a.A.p[t]) r = mred(b0, a.A.p[t][off], m.q, m.qinv);
-        if (a.B.p[t]) r = csub(r + mred(a0, a.B.p[t][off], m.q, m.qinv), m.q);
+        if (a.A.p[t]) r = mred(b0, a.A.p[t][offA], m.q, m.qinv);
+        if (a.B.p[t]) r = csub(r + mred(a0, a.B.p[t][offB], m.q, m.qinv), m.q);
         a.out.p[1 + t][off] = r;
     }
 }
