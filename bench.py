@@ -401,6 +401,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the k=8 / hoisted-Rotate side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lib", default=None, help="development: load this build of the library instead of the in-tree one")
+    ap.add_argument("--sweep", default=None, help="party-count sweep (BASELINE config 4), e.g. 2,4,8,16,32: prints one JSON line "
+                                                  "with MulRelin and hoisted-Rotate ops/s per k instead of the headline run")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.lib:
@@ -433,6 +435,25 @@ def main():
                                            "is Go + un-vendored lattigo and cannot be built here)"},
                 "e2e": {"value": ops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
+        return
+
+    # ---------------- party-count sweep (single GPU) -----------------------------------------------
+    if args.sweep:
+        res = {}
+        for ks in [int(x) for x in args.sweep.split(",")]:
+            w = DeviceWorkload(lit, ks, local_rank, seed=0xB2000100 + ks, batch=8, lanes=args.lanes)
+            ms = w.timed(w.mul_relin_step, max(args.steps // 2, 2), warmup)
+            mul = w.batch * max(args.steps // 2, 2) / (ms * 1e-3)
+            w.prepare_rotate()
+            ms = w.timed(w.rotate_step, max(args.steps // 2, 2), warmup)
+            rot = w.batch * max(args.steps // 2, 2) / (ms * 1e-3)
+            m = algorithmic_model(ks, ell, nP, N)
+            res[str(ks)] = {"mulrelin_ops_s": mul, "rotate_hoisted_ops_s": rot,
+                            "mulrelin_int_frac": m["butterflies"] * mul / w.ctx.butterfly_peak(),
+                            "mulrelin_hbm_frac_of_compulsory": m["compulsory_bytes"] * mul / 1e9 / 6549.4}
+            w.ctx.close()
+            del w
+        print(json.dumps({"metric": "party-count sweep, " + METRIC, "unit": UNIT, "lanes_per_gpu": args.lanes, "by_parties": res}))
         return
 
     # ---------------- GPU arm ----------------------------------------------------------------------
