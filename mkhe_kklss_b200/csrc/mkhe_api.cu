@@ -67,6 +67,7 @@ struct mkhe_ctx {
     ModC *d_mods = nullptr;
     ulonglong2 *d_twf = nullptr, *d_twi = nullptr;
     ulonglong2 *d_twf_tiled = nullptr;      // per (modulus, tile): the staged image pass 2 fetches with one TMA copy
+    ulonglong2 *d_twi_tiled = nullptr;      // the same for the inverse pass A
     bool tables_dirty = true;
     ConvTable *d_conv_PtoQ = nullptr;      // ModDownQPtoQ of the key switch
     ConvTable *d_conv_QtoQMul = nullptr;   // BFV
@@ -237,6 +238,7 @@ int upload_tables(mkhe_ctx *ctx) {
         CU(cudaMalloc((void **)&ctx->d_twf, sizeof(ulonglong2) * 64 * N));
         CU(cudaMalloc((void **)&ctx->d_twi, sizeof(ulonglong2) * 64 * N));
         CU(cudaMalloc((void **)&ctx->d_twf_tiled, sizeof(ulonglong2) * 64 * N));
+        CU(cudaMalloc((void **)&ctx->d_twi_tiled, sizeof(ulonglong2) * 64 * N));
     }
     for (size_t i = 0; i < nm; i++) {
         CU(cudaMemcpy(ctx->d_mods + i, &ctx->tabs[i].c, sizeof(ModC), cudaMemcpyHostToDevice));
@@ -244,6 +246,7 @@ int upload_tables(mkhe_ctx *ctx) {
         CU(cudaMemcpy(ctx->d_twi + i * N, ctx->tabs[i].twi.data(), sizeof(ulonglong2) * N, cudaMemcpyHostToDevice));
     }
     MKHE_LAUNCH(k_tile_twiddles, dim3(ctx->N / MKHE_TILE, (unsigned)nm), dim3(MKHE_THREADS), 0, ctx->stream, ctx->d_twf, ctx->d_twf_tiled, ctx->logN);
+    MKHE_LAUNCH(k_tile_twiddles, dim3(ctx->N / MKHE_TILE, (unsigned)nm), dim3(MKHE_THREADS), 0, ctx->stream, ctx->d_twi, ctx->d_twi_tiled, ctx->logN);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->tables_dirty = false;
@@ -402,9 +405,10 @@ int ntt_inv(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
         memset(&a, 0, sizeof a);
         a.nslots = s.n;
         a.logN = ctx->logN;
+        a.nbatch = np;
         for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; }
         for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
-        LAUNCH(k_intt_passA, dim3(tiles, s.n, np), dim3(MKHE_NTT_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+        LAUNCH(k_intt_passA, dim3(tiles, s.n, (np + MKHE_PA_GROUPS - 1) / MKHE_PA_GROUPS), dim3(MKHE_PA_THREADS), MKHE_PA_SMEM, a, ctx->d_mods, ctx->d_twi_tiled);
     }
     return intt_passB(ctx, s, npolys, out, out);
 }
@@ -558,9 +562,10 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
             memset(&a, 0, sizeof a);
             a.nslots = s.n;
             a.logN = ctx->logN;
+            a.nbatch = nk;
             for (int k = 0; k < s.n; k++) { a.slots[k] = s.slot[k]; a.mods[k] = s.mod[k]; }
             for (int k = 0; k < nk; k++) { a.in.p[k] = bufs[k0 + k]; a.out.p[k] = bufs[k0 + k]; }
-            LAUNCH(k_intt_passA, dim3(tiles, s.n, nk), dim3(MKHE_NTT_THREADS), SMEM_TILE, a, ctx->d_mods, ctx->d_twi);
+            LAUNCH(k_intt_passA, dim3(tiles, s.n, (nk + MKHE_PA_GROUPS - 1) / MKHE_PA_GROUPS), dim3(MKHE_PA_THREADS), MKHE_PA_SMEM, a, ctx->d_mods, ctx->d_twi_tiled);
         }
         // ---- pass B fused with ModDown and the accumulation
         ModDownPArgs pa;
@@ -958,6 +963,7 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     cudaEventCreate(&ctx->ev1);
 #ifndef MKHE_EMU
     cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PASS2);
+    cudaFuncSetAttribute(k_intt_passA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_PA_SMEM);
     cudaFuncSetAttribute(k_mac_digits<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(1));
     cudaFuncSetAttribute(k_mac_digits<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(2));
     cudaFuncSetAttribute(k_mac_digits<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(3));
@@ -991,7 +997,7 @@ int mkhe_ctx_fork(mkhe_ctx *parent, mkhe_ctx **out) {
     f->logN = root->logN; f->N = root->N; f->nQ = root->nQ; f->nP = root->nP; f->nQMul = root->nQMul; f->gamma = root->gamma;
     f->device = root->device; f->num_sms = root->num_sms; f->S1 = root->S1; f->dmax = root->dmax; f->alpha = root->alpha;
     f->beta_max = root->beta_max; f->d_lift = root->d_lift; f->T = root->T; f->mod = root->mod; f->tabs = root->tabs;
-    f->d_mods = root->d_mods; f->d_twf = root->d_twf; f->d_twi = root->d_twi; f->d_twf_tiled = root->d_twf_tiled;
+    f->d_mods = root->d_mods; f->d_twf = root->d_twf; f->d_twi = root->d_twi; f->d_twf_tiled = root->d_twf_tiled; f->d_twi_tiled = root->d_twi_tiled;
     f->tables_dirty = false;
     f->d_conv_PtoQ = root->d_conv_PtoQ; f->d_conv_QtoQMul = root->d_conv_QtoQMul; f->d_conv_QMultoQ = root->d_conv_QMultoQ;
     f->h_mformQMul = root->h_mformQMul;
@@ -1075,7 +1081,7 @@ void mkhe_ctx_destroy(mkhe_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->root == ctx) {
         for (Obj *o : ctx->objs) { if (o->xfer) cudaEventDestroy(o->xfer); cudaFree(o->d); delete o; }
-        cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi); cudaFree(ctx->d_twf_tiled);
+        cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi); cudaFree(ctx->d_twf_tiled); cudaFree(ctx->d_twi_tiled);
         cudaFree(ctx->d_conv_PtoQ); cudaFree(ctx->d_conv_QtoQMul); cudaFree(ctx->d_conv_QMultoQ); cudaFree(ctx->d_lift);
     } else {
         for (Obj *o : ctx->root->objs) o->use[ctx->lane] = Obj::Use();       // the lane's work has completed (synchronised above)

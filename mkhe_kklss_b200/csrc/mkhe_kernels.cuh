@@ -148,7 +148,7 @@ __device__ __forceinline__ void tile_fwd_BC(u64 v[16], const XAddr &x, const TW 
 }
 // inverse: layout C in, layout A out; values stay in [0,4q)
 template <class TW>
-__device__ __forceinline__ void tile_inv(u64 v[16], const XAddr &x, const TW &tw, const NttC &c) {
+__device__ __forceinline__ void tile_inv(u64 v[16], const XAddr &x, const TW &tw, const NttC &c, const int bar_id) {
 #pragma unroll
     for (int b = 0; b <= 2; b++) { MKHE_STAGE(bf_inv, tw.C(b, g), 0) }
 #pragma unroll
@@ -161,7 +161,7 @@ __device__ __forceinline__ void tile_inv(u64 v[16], const XAddr &x, const TW &tw
     MKHE_SYNCWARP();
 #pragma unroll
     for (int k = 0; k < 16; k++) x.b1[k * 8] = v[k];
-    __syncthreads();
+    named_sync(bar_id, MKHE_NTT_THREADS);
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = x.a1[k * 136];
 #pragma unroll
@@ -604,26 +604,44 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_mac_digits(MacDigitsArgs a, co
 struct InvAArgs {
     PtrList in;              // per batch input, limb slots of stride N
     PtrList out;             // per batch output
+    int nbatch;
     int nslots;
     int slots[MKHE_MAX_SLOTS];
     int mods[MKHE_MAX_SLOTS];
     int logN;
 };
+#define MKHE_PA_GROUPS 2
+#define MKHE_PA_THREADS (MKHE_PA_GROUPS * MKHE_NTT_THREADS)
+#define MKHE_PA_SMEM (MKHE_TILE * 16 + MKHE_PA_GROUPS * MKHE_XBUF * 8 + 16)
 
-__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_intt_passA(InvAArgs a, const ModC *mods, const ulonglong2 *twi) {
+// grid = (tiles, nslots, ceil(nbatch / 2)).  A CTA owns one (tile, limb) and two batch entries, one per 128-thread group: the
+// tile's 2047 inverse twiddles arrive by ONE TMA bulk copy (shared by both groups) while the inputs are read from global memory.
+__global__ void __launch_bounds__(MKHE_PA_THREADS, 3) k_intt_passA(InvAArgs a, const ModC *mods, const ulonglong2 *tiled_inv) {
     MKHE_SMEM(smraw);
-    u64 *sm1 = reinterpret_cast<u64 *>(smraw);
-    const int tid = threadIdx.x, tile = blockIdx.x, b = blockIdx.z;
+    const int tid = threadIdx.x & (MKHE_NTT_THREADS - 1), grp = threadIdx.x / MKHE_NTT_THREADS;
+    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw);
+    u64 *xbuf = reinterpret_cast<u64 *>(smraw + MKHE_TILE * 16 + grp * MKHE_XBUF * 8);
+    u64 *bar = reinterpret_cast<u64 *>(smraw + MKHE_TILE * 16 + MKHE_PA_GROUPS * MKHE_XBUF * 8);
+    const int tile = blockIdx.x, b = blockIdx.z * MKHE_PA_GROUPS + grp;
     const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
     const long N = 1L << a.logN;
+    const int ntiles = (int)(N / MKHE_TILE);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, MKHE_TILE * 16);
+        tma_load_1d(stw, tiled_inv + ((long)mi * ntiles + tile) * MKHE_TILE, MKHE_TILE * 16, bar);
+    }
+    if (b >= a.nbatch) return;
     const ModC m = mods[mi];
-    const XAddr x(sm1, tid);
+    const XAddr x(xbuf, tid);
     u64 v[16];
     const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(a.in.p[b] + (long)slot * N + (long)tile * MKHE_TILE + tid * 16);
 #pragma unroll
     for (int k = 0; k < 8; k++) { ulonglong2 xx = p2[k]; v[2 * k] = xx.x; v[2 * k + 1] = xx.y; }
-    const TwGlobal tw(twi + (long)mi * N, a.logN - 11, tile);
-    tile_inv(v, x, tw, nttc(m));
+    const TwShared tw(stw, tid);
+    mbar_wait(bar, 0);
+    tile_inv(v, x, tw, nttc(m), 1 + grp);
     u64 *o = a.out.p[b] + (long)slot * N + (long)tile * MKHE_TILE;
 #pragma unroll
     for (int k = 0; k < 16; k++) o[k * 128 + tid] = v[k];
