@@ -318,7 +318,7 @@ class DeviceWorkload:
         return ms
 
 
-def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dist, barrier, allmax):
+def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dist, barrier, allmax, nlanes=2):
     """BASELINE config 4: ONE MulRelinNew whose per-party key switches are sharded over the ranks (mkhe_ckks_mul_relin_sharded:
     rank g holds the relinearisation keys of its parties only, the partial x, y and the c_0 contributions are summed with
     ncclAllReduce over NVLink and reduced mod q).  Operand ciphertexts are replicated (they are small); every rank issues the
@@ -342,25 +342,41 @@ def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dis
     rng = np.random.default_rng(0xB2000042)                             # replicated operands: same seed on every rank
     pairs = [(mkckks.Ciphertext.from_numpy(ctx, host_ct(lit, k, level, rng), lit.scale),
               mkckks.Ciphertext.from_numpy(ctx, host_ct(lit, k, level, rng), lit.scale)) for _ in range(2)]
-    out = mkckks.Ciphertext.new(params, ids, level, lit.scale)
     ev = mkckks.Evaluator(params)
     nb, _ = ev._nb_rescales(lit.scale * lit.scale, level, lit.scale)
     key = lambda i, j: rlk.Value[i].Value[j].h if i in rlk.Value else 0
     kb, kd, kv = [key(i, 0) for i in ids], [key(i, 1) for i in ids], [key(i, 2) for i in ids]
+    # two lanes, each with its own NCCL communicator: the all-reduce of one op runs beside the transforms of the next one
+    # (every rank issues op n on lane n % 2, so the collectives of each communicator are issued in the same order everywhere)
+    lanes = [ctx]
+    for _ in range(nlanes - 1):
+        ln = ctx.fork()
+        uid = [ln.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ln.comm_init(world, rank, uid[0])
+        lanes.append(ln)
+    outs = [mkckks.Ciphertext.new(params, ids, level, lit.scale) for _ in lanes]
 
     def step(i):
         for j in range(batch):
-            a, b = pairs[(i * batch + j) % len(pairs)]
-            ctx.ckks_mul_relin_sharded(level, nb, ids, a.handles(ids), ids, b.handles(ids), own, kb, kd, kv,
-                                       params.CRS[-1].h, ids, out.handles(ids))
+            n = i * batch + j
+            a, b = pairs[n % len(pairs)]
+            ln = n % len(lanes)
+            lanes[ln].ckks_mul_relin_sharded(level, nb, ids, a.handles(ids), ids, b.handles(ids), own, kb, kd, kv,
+                                             params.CRS[-1].h, ids, outs[ln].handles(ids))
 
     for i in range(warmup):
         step(i)
-    ctx.sync()
+    for ln in lanes:
+        ln.sync()
     barrier()
     ctx.timer_start()
+    for ln in lanes[1:]:
+        ln.wait(ctx)
     for i in range(steps):
         step(i)
+    for ln in lanes[1:]:
+        ctx.wait(ln)
     ms = allmax(ctx.timer_stop())
     barrier()
     ctx.close()
@@ -580,7 +596,10 @@ def main():
                 continue
             try:
                 extra[f"sharded_mulrelin_k{ks}_ops_s"] = sharded_mul_relin(lit, ks, rank, world, local_rank, max(args.steps // 4, 2), warmup,
-                                                                           4, dist, barrier, allmax)
+                                                                           4, dist, barrier, allmax, nlanes=args.lanes)
+                if args.lanes > 1:
+                    extra[f"sharded_mulrelin_k{ks}_one_lane_ops_s"] = sharded_mul_relin(lit, ks, rank, world, local_rank, max(args.steps // 4, 2),
+                                                                                        warmup, 4, dist, barrier, allmax, nlanes=1)
             except Exception as e:      # a missing NCCL build must not take the headline down with it
                 extra[f"sharded_mulrelin_k{ks}_error"] = str(e)[:200]
 
