@@ -383,6 +383,53 @@ def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dis
     return batch * steps / (ms * 1e-3)
 
 
+def bfv_mul_relin_ops(lit, k, device, steps, warmup, batch, nlanes):
+    """BASELINE config 3: mkbfv MulRelinNew (ModUpQtoR / Rescale to R, DecomposeBFV, MulAndRelinBFVHoisted, Quantize), uniform
+    keys and ciphertexts, ops spread over the lanes"""
+    from mkhe_kklss_b200 import mkbfv, mkrlwe
+    params = mkbfv.Parameters(lit.logN, lit.Q, lit.QMul, lit.P, lit.T, device=device)
+    ctx = params.ctx
+    rng = np.random.default_rng(0xB2000300)
+    mods, beta = list(lit.Q) + list(lit.P), len(lit.Q)
+    mk = lambda: uniform_limbs(rng, mods, (beta,), lit.N)
+    params.SetCRS(-1, mk())
+    rlk = mkbfv.RelinearizationKeySet()
+    for i in range(k):
+        rlk.AddRelinearizationKey(mkbfv.RelinearizationKey(ctx, i, mk(), mk(), mk(), mk(), mk()))
+    level = len(lit.Q) - 1
+    ids = list(range(k))
+    pairs = [(mkrlwe.Ciphertext.from_numpy(ctx, host_ct(lit, k, level, rng)), mkrlwe.Ciphertext.from_numpy(ctx, host_ct(lit, k, level, rng)))
+             for _ in range(2)]
+    lanes = [ctx] + [ctx.fork() for _ in range(nlanes - 1)]
+    outs = [mkrlwe.Ciphertext.new(ctx, ids, level) for _ in lanes]
+    g = rlk.GetRelinearizationKey
+    kb1, kb2 = [g(i).b1.h for i in ids], [g(i).b2.h for i in ids]
+    kd1, kd2, kv = [g(i).d1.h for i in ids], [g(i).d2.h for i in ids], [g(i).v.h for i in ids]
+
+    def step(i):
+        for j in range(batch):
+            n = i * batch + j
+            a, b = pairs[n % 2]
+            ln = n % len(lanes)
+            lanes[ln].bfv_mul_relin(ids, a.handles(ids), ids, b.handles(ids), kb1, kb2, kd1, kd2, kv, params.CRS[-1].h, ids,
+                                    outs[ln].handles(ids))
+
+    for i in range(warmup):
+        step(i)
+    for ln in lanes:
+        ln.sync()
+    ctx.timer_start()
+    for ln in lanes[1:]:
+        ln.wait(ctx)
+    for i in range(steps):
+        step(i)
+    for ln in lanes[1:]:
+        ctx.wait(ln)
+    ms = ctx.timer_stop()
+    ctx.close()
+    return batch * steps / (ms * 1e-3)
+
+
 def cpu_oracle_run(lit, k, steps, warmup, threads, seed=0xB2000002):
     """times the oracle port of MulRelinNew on the host cores; returns (ops/s, cores used, seconds per op)"""
     from oracle import oracle as O
@@ -435,7 +482,7 @@ def main():
               "params": lit.name, "logN": lit.logN, "parties": k, "level": ell - 1, "ops_per_step": args.batch,
               "lanes_per_gpu": args.lanes,
               "l2_policy": "inputs larger than L2: every step streams the relinearisation keys "
-                           f"({(3 * k + 1) * ell * (ell + nP) * 8 * N / 2**20:.0f} MiB) and cycles 3 ciphertext pairs"}
+                           f"({(3 * k + 1) * ell * (ell + nP) * 8 * N / 2**20:.0f} MiB) and cycles 4 ciphertext pairs"}
 
     # ---------------- CPU arm ----------------------------------------------------------------------
     if args.impl == "reference":
@@ -588,6 +635,14 @@ def main():
         extra["rotate_hoisted_k8_ops_s"] = B * args.steps / (ms_rot8 * 1e-3)
         wl8.ctx.close()
         del wl8
+        # the other BASELINE configs as side measurements: config 1 (PN14QP439, k = 2, the reference's CPU-runnable case) and
+        # config 3 (mkbfv MulRelinNew, PN15QP880 primes, k = 4)
+        wl14 = DeviceWorkload(PR.CKKS_PN14QP439, 2, local_rank, seed=0xB2000014, batch=B, lanes=args.lanes)
+        ms14 = wl14.timed(wl14.mul_relin_step, args.steps, warmup)
+        extra["mulrelin_PN14QP439_k2_ops_s"] = B * args.steps / (ms14 * 1e-3)
+        wl14.ctx.close()
+        del wl14
+        extra["bfv_mulrelin_PN15QP880_k4_ops_s"] = bfv_mul_relin_ops(PR.BFV_PN15QP880, 4, local_rank, max(args.steps // 2, 2), warmup, 8, args.lanes)
 
     if not args.no_extras and world > 1:
         # party-sharded MulRelin over NCCL (strong scaling of ONE op; the headline above is weak scaling over independent batches)

@@ -165,6 +165,13 @@ int mkhe_ckks_mul_relin(mkhe_ctx *ctx, int level, int nb_rescales, int same_oper
                         const mkhe_swk *rlk_b, const mkhe_swk *rlk_d, const mkhe_swk *rlk_v, mkhe_swk u,
                         int nOut, const int *idsOut, const mkhe_poly *out);
 
+/* ---- mkrlwe.Decryptor (the step after the path)
+ * Decrypt(ciphertext, skSet, plaintext)                      mkrlwe/decryptor.go:48-66 (PartialDecrypt :26-43 per party, ReduceLvl)
+ *   ct[0] = component "0", ct[1+t] = component of party t; sk[t] = that party's SecretKey.Value.Q (NTT domain, Montgomery form)
+ *   uploaded as a poly; pt receives the coefficient-domain plaintext, canonical, level+1 limbs.  The ciphertext is not modified
+ *   (the reference works on a CopyNew).  Secret keys only ever reach the device if the caller puts them there. */
+int mkhe_decrypt(mkhe_ctx *ctx, int level, int n, const mkhe_poly *ct, const mkhe_poly *sk, mkhe_poly pt);
+
 /* ---- mkbfv (polys in basis R have 2*nQ limbs: Q limbs then QMul limbs) */
 /* FastBasisExtender.ModUpQtoR(polyQ, polyR)                  mkbfv/basis_extension.go:49-63 */
 int mkhe_bfv_modup_q_to_r(mkhe_ctx *ctx, mkhe_poly polyQ, mkhe_poly polyR);

@@ -330,6 +330,9 @@ class Context:
     def ckks_mul_ptxt(self, level, pt, hin, hout):
         self.check(self.dll.mkhe_ckks_mul_ptxt(self.ptr, C.c_int(level), C.c_uint64(pt), C.c_int(len(hin)), _harr(hin), _harr(hout)))
 
+    def decrypt(self, level, ct, sk, pt):
+        self.check(self.dll.mkhe_decrypt(self.ptr, C.c_int(level), C.c_int(len(sk)), _harr(ct), _harr(sk), C.c_uint64(pt)))
+
     # multi-GPU (party sharding, NCCL)
     def comm_unique_id(self) -> bytes:
         buf = (C.c_uint8 * 128)()

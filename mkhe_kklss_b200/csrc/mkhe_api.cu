@@ -1627,6 +1627,36 @@ int mkhe_ckks_mul_ptxt(mkhe_ctx *ctx, int level, mkhe_poly pt, int n, const mkhe
     return ntt_inv(ctx, qs, n, tn.data(), po.data());
 }
 
+/* Decryptor.Decrypt (mkrlwe/decryptor.go:48-66) = PartialDecrypt (:26-43) for every party, then ReduceLvl:
+ * pt = Reduce(ct["0"] + sum_t InvNTT(NTT(ct[id_t]) (.) sk_t)).  The accumulation order of the reference follows a Go map; every
+ * partial sum is the same residue, and the output is canonical, so the order is immaterial. */
+int mkhe_decrypt(mkhe_ctx *ctx, int level, int n, const mkhe_poly *ct, const mkhe_poly *sk, mkhe_poly pt) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    if (n < 0 || n + 1 > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_INVALID, "Decrypt: bad party count %d", n);
+    std::vector<u64 *> pc, ps, tn;
+    TRY(polys_of(ctx, n + 1, ct, level + 1, pc, "ct", ACC_READ));
+    TRY(polys_of(ctx, n, sk, level + 1, ps, "sk", ACC_READ));
+    POLY(o, pt);
+    if (o->cap_limbs < level + 1) return fail(ctx, MKHE_ERR_INVALID, "Decrypt: plaintext has too few limbs");
+    TRY(poly_pool(ctx, "decrypt_ntt", std::max(n, 1), ctx->nQ, tn));
+    const Slots qs = q_slots(level);
+    LimbArgs a;
+    fill(a, qs, ctx->logN);
+    if (n > 0) {
+        TRY(ntt_fwd(ctx, qs, n, pc.data() + 1, tn.data()));
+        PtrList other;
+        memset(&other, 0, sizeof other);
+        for (int t = 0; t < n; t++) { a.in.p[t] = tn[t]; a.out.p[t] = tn[t]; other.p[t] = ps[t]; }
+        LAUNCH(k_mul_mont, dim3(ctx->N / MKHE_THREADS, level + 1, n), dim3(MKHE_THREADS), 0, a, other, ctx->d_mods);
+        TRY(ntt_inv(ctx, qs, n, tn.data(), tn.data()));
+    }
+    for (int t = 0; t < n; t++) a.in.p[t] = tn[t];
+    LAUNCH(k_decrypt_sum, dim3(ctx->N / MKHE_THREADS, level + 1), dim3(MKHE_THREADS), 0, a, (const u64 *)pc[0], n, o->d, ctx->d_mods);
+    o->nlimbs = level + 1;
+    return MKHE_OK;
+}
+
 // ---- mkbfv ------------------------------------------------------------------------------------------
 namespace {
 int need_bfv(mkhe_ctx *ctx) {

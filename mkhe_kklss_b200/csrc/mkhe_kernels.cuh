@@ -1014,6 +1014,25 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_neg(LimbArgs a, const ModC *mo
     a.out.p[b][off] = q - a.in.p[b][off];
 }
 
+// Decryptor (mkrlwe/decryptor.go:26-66): MulCoeffsMontgomeryLvl of NTT(c_id) by the secret key (NTT domain, Montgomery form), and
+// the final accumulation c_0 + sum_id InvNTT(...) with ReduceLvl (canonical output).  grid = (N/256, nlimbs[, npolys])
+__global__ void __launch_bounds__(MKHE_THREADS) k_mul_mont(LimbArgs a, PtrList other, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const int limb = blockIdx.y, b = blockIdx.z;
+    const ModC m = mods[a.mod_of_limb[limb]];
+    const long off = (long)a.slot_of[limb] * N + (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    a.out.p[b][off] = mred(a.in.p[b][off], other.p[b][off], m.q, m.qinv);
+}
+__global__ void __launch_bounds__(MKHE_THREADS) k_decrypt_sum(LimbArgs a, const u64 *c0, int nparts, u64 *pt, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const int limb = blockIdx.y;
+    const ModC m = mods[a.mod_of_limb[limb]];
+    const long off = (long)a.slot_of[limb] * N + (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    u64 acc = c0[off];                                   // may be non-canonical (q from a rotation): AddLvl = one conditional subtraction
+    for (int t = 0; t < nparts; t++) acc = csub(acc + a.in.p[t][off], m.q);
+    pt[off] = csub(barrett_lazy(acc, m.q, m.mu), m.q);   // ReduceLvl
+}
+
 // BFV tensor products in ring R (mkbfv/keyswitch_hoisted.go:144-181): out = A*B (+ C*D), operands may be lazy (<4q)
 __global__ void __launch_bounds__(MKHE_THREADS) k_mul2(const u64 *A, const u64 *B, const u64 *Cc, const u64 *D, u64 *out,
                                                         LimbArgs a, const ModC *mods) {

@@ -291,3 +291,23 @@ class KeySwitcher:
         ids = ctIn.ids()
         self.ctx.conjugate(level, ctIn.handles(ids), [ckSet.GetConjugationKey(i).h for i in ids],
                            self.Parameters.CRS[-2].h, ctOut.handles(ids))
+
+
+class Decryptor:
+    """mkrlwe.Decryptor (decryptor.go:8-66) on the device: `skSet` maps a party id to its SecretKey.Value.Q uploaded as a Poly
+    (NTT domain, Montgomery form).  Returns the coefficient-domain plaintext poly (rlwe.Plaintext.Value); decoding stays on the
+    host like in the reference (mkckks/decryptor.go)."""
+
+    def __init__(self, params):
+        self.params = params
+        self.ctx = params.ctx
+
+    def Decrypt(self, ciphertext, skSet):
+        ids = ciphertext.ids()
+        for i in ids:
+            if i not in skSet:
+                raise RuntimeError("Cannot Decrypt: there is a missing secretkey")
+        level = ciphertext.Level()
+        pt = Poly(self.ctx, level + 1)
+        self.ctx.decrypt(level, ciphertext.handles(ids), [skSet[i].h for i in ids], pt.h)
+        return pt

@@ -366,6 +366,19 @@ def check_ckks_semantics(w: CKKSWorld):
     err = np.abs(got - np.roll(msum, -2)).max()
     bound = 2.0 ** (-np.log2(lit.scale) + np.log2(n) + 11)
     assert err <= bound, f"Rotate precision {np.log2(err):.1f} > {np.log2(bound):.1f}"
+    # Decrypt on the device (mkrlwe/decryptor.go:48-66): the plaintext poly is the oracle's, bit for bit
+    dsk = {i: mkrlwe.Poly.from_numpy(w.ctx, w.sks[i].Q) for i in w.ids}
+    ddec = mkrlwe.Decryptor(w.dp)
+    for dc in (dres, drot, dct):
+        got_pt = ddec.Decrypt(dc, dsk).numpy()
+        want_pt = dec.decrypt(O.Ciphertext(dc.numpy(), dc.Scale), w.sks)
+        assert_same(got_pt, want_pt, "Decrypt")
+    try:
+        ddec.Decrypt(dct, {w.ids[0]: dsk[w.ids[0]]} if len(w.ids) > 1 else {})
+    except RuntimeError as e:
+        assert "missing secretkey" in str(e)
+    else:
+        raise AssertionError("Decrypt must panic when a secret key is missing")
     # element-wise ops on device outputs, the reference's thresholds (mkckks_test.go:228-318: Add / Sub +11; the product
     # thresholds +12 for the plaintext product and the constant multiples)
     bound = 2.0 ** (-np.log2(lit.scale) + np.log2(n) + 12)
