@@ -99,3 +99,65 @@ class Evaluator:
             [g(i).b1.h for i in ids1], [g(i).b2.h for i in ids1], [g(i).d1.h for i in ids0], [g(i).d2.h for i in ids0],
             [g(i).v.h for i in ids0], self.params.CRS[-1].h, idsO, ctOut.handles(idsO))
         return ctOut
+
+    # -- the rest of the public evaluator (mkbfv/evaluator.go:25-82,152-226): element-wise ops on ring Q and the key switches
+    #    of mkrlwe.KeySwitcher, all at the single (maximum) level BFV works at
+    def newCiphertextBinary(self, op0, op1):
+        return mkrlwe.Ciphertext.new(self.ctx, op0.IDSet().Union(op1.IDSet()), self.params.MaxLevel())
+
+    def _evaluate_new(self, op0, op1, sub):
+        """evaluateInPlace (evaluator.go:31-46) + Sub's NegLvl of the components missing from op0 (:67-75)"""
+        ctOut = self.newCiphertextBinary(op0, op1)
+        level = self.params.MaxLevel()
+        for k in ctOut.Value:
+            in0, in1 = k in op0.Value, k in op1.Value
+            o = ctOut.Value[k].h
+            if in0 and in1:
+                (self.ctx.poly_sub if sub else self.ctx.poly_add)(level, op0.Value[k].h, op1.Value[k].h, o)
+            elif in0:
+                self.ctx.poly_copy_lvl(level, o, op0.Value[k].h)
+            elif sub:
+                self.ctx.poly_neg(level, op1.Value[k].h, o)
+            else:
+                self.ctx.poly_copy_lvl(level, o, op1.Value[k].h)
+        return ctOut
+
+    def AddNew(self, op0, op1):
+        return self._evaluate_new(op0, op1, False)
+
+    def SubNew(self, op0, op1):
+        return self._evaluate_new(op0, op1, True)
+
+    def _copy(self, ct):
+        out = mkrlwe.Ciphertext.new(self.ctx, ct.IDSet(), self.params.MaxLevel())
+        for k in ct.Value:
+            self.ctx.poly_copy(out.Value[k].h, ct.Value[k].h)
+        return out
+
+    def RotateNew(self, ct0, rotidx, rkSet):
+        """evaluator.go:152-196 (power-of-two chaining when rotidx has no CRS entry)"""
+        n2 = self.params.N() // 2
+        rotidx %= n2
+        if rotidx == 0:
+            return self._copy(ct0)
+        ctOut = mkrlwe.Ciphertext.new(self.ctx, ct0.IDSet(), self.params.MaxLevel())
+        if rotidx in self.params.CRS:
+            self.ksw.Rotate(ct0, rotidx, rkSet, ctOut)
+            return ctOut
+        ctTmp = self._copy(ct0)
+        k = 1
+        while rotidx > 0:
+            if rotidx % 2 != 0:
+                self.ksw.Rotate(ctTmp, k, rkSet, ctOut)
+                for key in ctOut.Value:
+                    self.ctx.poly_copy(ctTmp.Value[key].h, ctOut.Value[key].h)
+            rotidx //= 2
+            k *= 2
+        ctTmp.free()
+        return ctOut
+
+    def ConjugateNew(self, ct0, ckSet):
+        """evaluator.go:198-226"""
+        ctOut = mkrlwe.Ciphertext.new(self.ctx, ct0.IDSet(), self.params.MaxLevel())
+        self.ksw.Conjugate(ct0, ckSet, ctOut)
+        return ctOut

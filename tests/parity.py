@@ -491,6 +491,45 @@ def check_bfv_mul_relin(w: BFVWorld, ids0, ids1, same=False):
     return dout
 
 
+def check_bfv_linear_ops(w: BFVWorld):
+    """mkbfv.Evaluator.{AddNew, SubNew, RotateNew, ConjugateNew} (mkbfv/evaluator.go:25-82,152-226): ring-Q element-wise ops and the
+    mkrlwe key switches at the top level; the oracle side is the same arithmetic through its CKKS-agnostic evaluator"""
+    p = w.op
+    for rot in (1, 2):
+        if rot not in p.CRS:
+            p.add_crs(rot)
+            w.dp.SetCRS(rot, p.CRS[rot])
+    if -2 not in w.dp.CRS:
+        w.dp.SetCRS(-2, p.CRS[-2])
+    oev = O.CKKSEvaluator(p, 1.0)
+    ork, drk = {}, mkrlwe.RotationKeySet()
+    ock, dck = {}, mkrlwe.ConjugationKeySet()
+    for i in w.ids:
+        ork[i] = {r: uniform_swk(w.prng, p) for r in (1, 2)}
+        for r, a in ork[i].items():
+            drk.AddRotationKey(i, r, mkrlwe.SwitchingKey(w.ctx, a))
+        ock[i] = uniform_swk(w.prng, p)
+        dck.AddConjugationKey(i, mkrlwe.SwitchingKey(w.ctx, ock[i]))
+    wrap = lambda c: O.Ciphertext(c.value, 1.0)
+
+    def cmp(dct, oct_, what):
+        dv = dct.numpy()
+        assert set(dv) == set(oct_.value), what
+        for k in oct_.value:
+            assert_same(dv[k], oct_.value[k], f"{what}[{k}]")
+
+    for i0, i1 in ((w.ids, w.ids), (w.ids[:1], w.ids[1:] or w.ids), (w.ids[:1], w.ids)):
+        o0, d0 = w.random_ct(i0)
+        o1, d1 = w.random_ct(i1)
+        cmp(w.dev.AddNew(d0, d1), oev.add_new(wrap(o0), wrap(o1)), f"bfv AddNew {i0} {i1}")
+        cmp(w.dev.SubNew(d0, d1), oev.sub_new(wrap(o0), wrap(o1)), f"bfv SubNew {i0} {i1}")
+    o0, d0 = w.random_ct(w.ids)
+    cmp(w.dev.RotateNew(d0, 2, drk), oev.rotate_new(wrap(o0), 2, ork), "bfv RotateNew(2)")
+    cmp(w.dev.RotateNew(d0, 3, drk), oev.rotate_new(wrap(o0), 3, ork), "bfv RotateNew(3, chained)")
+    cmp(w.dev.RotateNew(d0, 0, drk), wrap(o0), "bfv RotateNew(0)")
+    cmp(w.dev.ConjugateNew(d0, dck), oev.conjugate_new(wrap(o0), ock), "bfv ConjugateNew")
+
+
 def check_bfv_semantics(w: BFVWorld):
     """T3: exact plaintext equality after decrypting the DEVICE result (mkbfv_test.go:412)"""
     p = w.op

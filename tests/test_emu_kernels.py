@@ -41,6 +41,7 @@ def test_bfv_kernels_under_emulation(emu):
     parity.check_bfv_conv(w)
     parity.check_bfv_mul_relin(w, [0, 1], [0, 1])
     parity.check_bfv_mul_relin(w, [0], [0, 1])
+    parity.check_bfv_linear_ops(w)
     w.close()
 
 

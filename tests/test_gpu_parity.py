@@ -58,6 +58,7 @@ def test_bfv_parity(logN, k):
     parity.check_bfv_mul_relin(w, w.ids, w.ids, same=True)
     parity.check_bfv_mul_relin(w, w.ids[:1], w.ids[1:])
     parity.check_bfv_mul_relin(w, w.ids[:1], w.ids)
+    parity.check_bfv_linear_ops(w)
     w.close()
 
 
