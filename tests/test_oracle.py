@@ -171,6 +171,32 @@ def test_ckks_semantic_thresholds(lit):
     assert np.log2(err) <= -logscale + logslots + 11
 
 
+@pytest.mark.parametrize("level", ["max", 0])
+def test_external_product_and_decompose_noise(level):
+    """mkrlwe_test.go:456-505 (ExternalProductMaxLevel) and :507-610 (DecomposeMaxLevel / MinLevel) restated: with sg =
+    GenSwitchingKey(sk), ExternalProduct(c, sg) and Decompose(c) . sg followed by ModDown both equal c * s up to noise whose
+    inner sum (log2OfInnerSum, :92-150) stays below 2^(10 + logN)"""
+    lit = PR.CKKS_PN14QP439.at_logn(12)
+    p = O.MKParams(lit.logN, lit.Q, lit.P, 2, seed=0xB2000021, crs_rots=[])
+    kg = O.KeyGenerator(p, seed=5)
+    sk = kg.gen_secret_key(0)
+    sg = kg.gen_switching_key(sk)
+    L = p.max_level() if level == "max" else level
+    c = O.PRNG(77).uniform(p.ringQ, L)
+    ks = O.KeySwitcher(p)
+    rq = p.ringQ
+    cs = rq.intt(rq.mul_mont(rq.ntt(c, L), np.ascontiguousarray(sk.Q[:L + 1]), L), L)          # c * s
+
+    def inner_sum_log2(poly):
+        return sum(abs(v) for v in O.crt_centered(list(lit.Q[:L + 1]), poly)).bit_length()
+
+    ext = ks.external_product(L, c, sg)
+    assert inner_sum_log2(rq.sub(ext, cs, L)) <= 10 + lit.logN
+    # Decompose, the digit-by-digit product accumulated over QP, ModDown: the same value as ExternalProduct, bit for bit
+    ext2 = ks.external_product_hoisted(L, ks.decompose(L, c), sg)
+    assert np.array_equal(ext, ext2)
+
+
 def test_rotation_stores_negated_zero_as_q():
     """the permutation writes q - c unreduced, so c = 0 becomes q_j"""
     lit, p, sks, pks, rlks, rks, cks = _ckks_world(logN=10)
