@@ -318,7 +318,7 @@ class DeviceWorkload:
         return ms
 
 
-def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dist, barrier, allmax, nlanes=2):
+def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dist, barrier, allmax, nlanes=2, p2p=True):
     """BASELINE config 4: ONE MulRelinNew whose per-party key switches are sharded over the ranks (mkhe_ckks_mul_relin_sharded:
     rank g holds the relinearisation keys of its parties only, the partial x, y and the c_0 contributions are summed with
     ncclAllReduce over NVLink and reduced mod q).  Operand ciphertexts are replicated (they are small); every rank issues the
@@ -330,6 +330,15 @@ def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dis
     uid = [ctx.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(world, rank, uid[0])
+
+    def enable_p2p(c):
+        """fused exchange over peer memory (mkhe_p2p_export / _import) instead of the 112 MiB all-reduce of x || y"""
+        hs = [None] * world
+        dist.all_gather_object(hs, c.p2p_export())
+        c.p2p_import(world, rank, hs)
+
+    if p2p:
+        enable_p2p(ctx)
     mods, beta = list(lit.Q) + list(lit.P), len(lit.Q)
     mk = lambda rng: uniform_limbs(rng, mods, (beta,), lit.N)
     params.SetCRS(-1, mk(np.random.default_rng(0xB2000040)))            # the CRS is common to all ranks
@@ -354,6 +363,8 @@ def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dis
         uid = [ln.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ln.comm_init(world, rank, uid[0])
+        if p2p:
+            enable_p2p(ln)
         lanes.append(ln)
     outs = [mkckks.Ciphertext.new(params, ids, level, lit.scale) for _ in lanes]
 
@@ -660,6 +671,8 @@ def main():
                 if args.lanes > 1:
                     extra[f"sharded_mulrelin_k{ks}_one_lane_ops_s"] = sharded_mul_relin(lit, ks, rank, world, local_rank, max(args.steps // 4, 2),
                                                                                         warmup, 4, dist, barrier, allmax, nlanes=1)
+                extra[f"sharded_mulrelin_k{ks}_nccl_allreduce_ops_s"] = sharded_mul_relin(lit, ks, rank, world, local_rank, max(args.steps // 4, 2),
+                                                                                          warmup, 4, dist, barrier, allmax, nlanes=args.lanes, p2p=False)
             except Exception as e:      # a missing NCCL build must not take the headline down with it
                 extra[f"sharded_mulrelin_k{ks}_error"] = str(e)[:200]
 

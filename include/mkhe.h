@@ -204,6 +204,14 @@ int mkhe_bfv_mul_relin(mkhe_ctx *ctx,
 int mkhe_comm_unique_id(uint8_t out[128]);
 int mkhe_comm_init(mkhe_ctx *ctx, int nranks, int rank, const uint8_t unique_id[128]);
 int mkhe_comm_destroy(mkhe_ctx *ctx);
+/* Fused exchange over peer memory (NVLink / NVSwitch) for the sharded MulRelin: after mkhe_comm_init every rank calls
+ * mkhe_p2p_export (allocates its two exchange buffers, returns their CUDA IPC handles: 2 x 64 bytes), the host hands the
+ * concatenation of all ranks' 128 bytes to mkhe_p2p_import on every rank.  From then on the partial x, y of
+ * mkhe_ckks_mul_relin_sharded are written by the multiply-accumulate kernel straight into their owner's memory, summed there and
+ * the sums written straight into every rank's x||y -- no 112 MiB all-reduce; NCCL only provides two tiny barriers per op and the
+ * all-reduce of the c_0 contributions.  One node, one process per GPU, at most 8 ranks. */
+int mkhe_p2p_export(mkhe_ctx *ctx, uint8_t out[128]);
+int mkhe_p2p_import(mkhe_ctx *ctx, int nranks, int rank, const uint8_t *all_handles);
 /* party-sharded MulRelinNew: every rank passes the same (replicated) operand ciphertexts and id lists, but only holds
  * the relinearization keys of the parties in own_ids (other entries of rlk_* may be 0).  Partial x, y and the c_0
  * contributions are summed with ncclAllReduce(uint64, sum) and reduced mod q -- bit-identical to the single-GPU result

@@ -345,6 +345,17 @@ class Context:
         buf = (C.c_uint8 * 128)(*uid)
         self.check(self.dll.mkhe_comm_init(self.ptr, C.c_int(nranks), C.c_int(rank), buf))
 
+    def p2p_export(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self.check(self.dll.mkhe_p2p_export(self.ptr, buf))
+        return bytes(buf)
+
+    def p2p_import(self, nranks, rank, handles: list):
+        """handles[r] = rank r's p2p_export() bytes"""
+        blob = b"".join(handles)
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.check(self.dll.mkhe_p2p_import(self.ptr, C.c_int(nranks), C.c_int(rank), arr))
+
     def ckks_mul_relin_sharded(self, level, nb_rescales, ids0, op0, ids1, op1, own_ids, rlk_b, rlk_d, rlk_v, u, idsOut, out):
         self.check(self.dll.mkhe_ckks_mul_relin_sharded(
             self.ptr, C.c_int(level), C.c_int(nb_rescales),

@@ -92,6 +92,10 @@ struct mkhe_ctx {
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void *nccl = nullptr;
+    // fused exchange of the party-sharded MulRelin over peer memory (mkhe_p2p_export / _import)
+    bool p2p = false;
+    u64 *p2p_stage = nullptr, *p2p_xy = nullptr, *p2p_flag = nullptr;
+    u64 *peer_stage[MKHE_MAX_RANKS] = {nullptr}, *peer_xy[MKHE_MAX_RANKS] = {nullptr};
     int nranks = 1, rank = 0;
     // per-kernel CUDA-event profiling (bench.py's roofline leg)
     bool profiling = false;
@@ -724,6 +728,59 @@ int allreduce_mod(mkhe_ctx *ctx, u64 *buf, size_t count, const Slots &s, int nbu
 #endif
 }
 
+// ---- fused exchange over peer memory ------------------------------------------------------------------
+void fill_p2p(mkhe_ctx *ctx, P2PArgs &p, int which) {
+    memset(&p, 0, sizeof p);
+    p.nranks = ctx->nranks;
+    p.rank = ctx->rank;
+    p.which = which;
+    p.swk_elems = (long)swk_elems(ctx);
+    for (int r = 0; r < ctx->nranks; r++) { p.peer_stage[r] = ctx->peer_stage[r]; p.peer_xy[r] = ctx->peer_xy[r]; }
+}
+// a tiny all-reduce as a barrier in stream order: when it completes on this rank, every rank has finished the work it had
+// enqueued before its own call (kernel completion makes the peer stores visible)
+int p2p_barrier(mkhe_ctx *ctx) {
+#if !defined(MKHE_EMU) && defined(MKHE_WITH_NCCL)
+    if (ncclAllReduce(ctx->p2p_flag, ctx->p2p_flag, 1, ncclUint64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream) != ncclSuccess)
+        return fail(ctx, MKHE_ERR_NCCL, "barrier all-reduce failed");
+    return MKHE_OK;
+#else
+    return fail(ctx, MKHE_ERR_UNSUPPORTED, "built without NCCL");
+#endif
+}
+int mac_parties_scatter(mkhe_ctx *ctx, int level, int n, u64 *const *key, u64 *const *hst, int which) {
+    Slots s = qp_slots(ctx, level);
+    if (n > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_UNSUPPORTED, "more than %d parties", MKHE_MAX_PARTIES_K);
+    MacPartiesArgs a;
+    memset(&a, 0, sizeof a);
+    a.nparties = n;                       // 0 parties: the rank contributes zeros (it still has to write its partial)
+    a.beta = beta_of(ctx, level);
+    a.dmax = ctx->dmax;
+    a.nslots = s.n;
+    a.logN = ctx->logN;
+    for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; }
+    for (int i = 0; i < n; i++) { a.key.p[i] = key[i]; a.hst.p[i] = hst[i]; }
+    P2PArgs p;
+    fill_p2p(ctx, p, which);
+    LAUNCH(k_mac_parties_scatter, dim3(ctx->N / (2 * MKHE_THREADS), s.n, a.beta), dim3(MKHE_THREADS), 0, a, p, ctx->d_mods);
+    return MKHE_OK;
+}
+int reduce_gather(mkhe_ctx *ctx, int level) {
+    Slots s = qp_slots(ctx, level);
+    GatherArgs a;
+    memset(&a, 0, sizeof a);
+    a.beta = beta_of(ctx, level);
+    a.dmax = ctx->dmax;
+    a.nslots = s.n;
+    a.logN = ctx->logN;
+    for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; }
+    P2PArgs p;
+    fill_p2p(ctx, p, 0);
+    const long seg = ctx->N / ctx->nranks;
+    LAUNCH(k_reduce_gather, dim3((unsigned)(seg / (2 * MKHE_THREADS)), s.n, 2 * a.beta), dim3(MKHE_THREADS), 0, a, p, ctx->d_mods);
+    return MKHE_OK;
+}
+
 // MulAndRelinHoisted on raw device pointers (mkrlwe/keyswitch_hoisted.go:44-179).
 // With an active Shard only the owned parties' keys / hoisted forms are touched: the partial x, y and the c_0
 // contributions are summed over ranks (exact: every accumulation of the reference is a modular add, App. A.4);
@@ -750,7 +807,9 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     std::vector<u64 *> d_o = pick(o0, rlk_d), v_o = pick(o0, rlk_v), h0_o = pick(o0, h0), b_o = pick(o1, rlk_b), h1_o = pick(o1, h1);
     const int m0 = (int)o0.size(), m1 = (int)o1.size();
     std::vector<u64 *> xy;
-    TRY(swk_pool(ctx, "xy", 2, xy));
+    const bool p2p = sh.active && ctx->p2p;
+    if (p2p) { xy.push_back(ctx->p2p_xy); xy.push_back(ctx->p2p_xy + swk_elems(ctx)); }
+    else TRY(swk_pool(ctx, "xy", 2, xy));
     u64 *x = xy[0], *y = xy[1];
     std::vector<u64 *> p, hp, tn;
     TRY(poly_pool(ctx, "relin_p", m0, ctx->nQ, p));
@@ -761,11 +820,21 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     if (hoist0) TRY(decompose_impl(ctx, level, n0, op0 + 1, h0, 0));
     if (hoist1) TRY(decompose_impl(ctx, level, n1, op1 + 1, h1, 0));
     // steps 2-3 (:79-117): x = MForm(sum d_id (.) h0_id), y = MForm(sum b_id (.) h1_id)
-    if (m0) TRY(mac_parties(ctx, level, m0, d_o.data(), h0_o.data(), x));
-    else CU(cudaMemsetAsync(x, 0, swk_elems(ctx) * 8, ctx->stream));
-    if (m1) TRY(mac_parties(ctx, level, m1, b_o.data(), h1_o.data(), y));
-    else CU(cudaMemsetAsync(y, 0, swk_elems(ctx) * 8, ctx->stream));
-    if (sh.active) TRY(allreduce_mod(ctx, x, 2 * swk_elems(ctx), qps, 2 * ctx->beta_max, (long)ctx->dmax * N));
+    if (p2p) {
+        // fused: the partial sums are written straight into their owners' memory, summed there and the results written
+        // straight into every rank's x||y (peer stores over NVLink); two stream-ordered barriers instead of a 112 MiB all-reduce
+        TRY(mac_parties_scatter(ctx, level, m0, d_o.data(), h0_o.data(), 0));
+        TRY(mac_parties_scatter(ctx, level, m1, b_o.data(), h1_o.data(), 1));
+        TRY(p2p_barrier(ctx));
+        TRY(reduce_gather(ctx, level));
+        TRY(p2p_barrier(ctx));
+    } else {
+        if (m0) TRY(mac_parties(ctx, level, m0, d_o.data(), h0_o.data(), x));
+        else CU(cudaMemsetAsync(x, 0, swk_elems(ctx) * 8, ctx->stream));
+        if (m1) TRY(mac_parties(ctx, level, m1, b_o.data(), h1_o.data(), y));
+        else CU(cudaMemsetAsync(y, 0, swk_elems(ctx) * 8, ctx->stream));
+        if (sh.active) TRY(allreduce_mod(ctx, x, 2 * swk_elems(ctx), qps, 2 * ctx->beta_max, (long)ctx->dmax * N));
+    }
 
     // step 4 (:119-144): tensor product in the NTT domain, then InvNTT of every output component.
     // With alpha = 1, digit i of a hoisted form is limb i of the poly broadcast to every modulus, so its limb i IS
@@ -1076,6 +1145,13 @@ void mkhe_ctx_destroy(mkhe_ctx *ctx) {
     cudaStreamSynchronize(ctx->h2d);
     cudaStreamSynchronize(ctx->d2h);
     mkhe_comm_destroy(ctx);
+#ifndef MKHE_EMU
+    for (int r = 0; r < MKHE_MAX_RANKS; r++) {
+        if (ctx->peer_stage[r] && ctx->peer_stage[r] != ctx->p2p_stage) cudaIpcCloseMemHandle(ctx->peer_stage[r]);
+        if (ctx->peer_xy[r] && ctx->peer_xy[r] != ctx->p2p_xy) cudaIpcCloseMemHandle(ctx->peer_xy[r]);
+    }
+    if (ctx->p2p_stage) { cudaFree(ctx->p2p_stage); cudaFree(ctx->p2p_xy); cudaFree(ctx->p2p_flag); }
+#endif
     for (auto &kv : ctx->scratch) cudaFree(kv.second.p);
     for (cudaEvent_t e : ctx->lane_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1901,6 +1977,56 @@ int mkhe_comm_destroy(mkhe_ctx *ctx) {
     if (ctx->nccl) { ncclCommDestroy((ncclComm_t)ctx->nccl); ctx->nccl = nullptr; }
 #endif
     return MKHE_OK;
+}
+
+// peer-memory exchange for the sharded MulRelin: every rank exports the IPC handles of its two exchange buffers, the host passes
+// all of them to every rank (any transport: the bench uses torch.distributed), import maps the peers' buffers
+int mkhe_p2p_export(mkhe_ctx *ctx, uint8_t out[128]) {
+    CHECK_CTX();
+#if !defined(MKHE_EMU)
+    if (!out) return MKHE_ERR_INVALID;
+    const size_t bytes = 2 * swk_elems(ctx) * 8;
+    if (!ctx->p2p_stage) {
+        CU(cudaMalloc((void **)&ctx->p2p_stage, bytes));
+        CU(cudaMalloc((void **)&ctx->p2p_xy, bytes));
+        CU(cudaMalloc((void **)&ctx->p2p_flag, 256));
+        CU(cudaMemset(ctx->p2p_stage, 0, bytes));
+        CU(cudaMemset(ctx->p2p_xy, 0, bytes));
+        CU(cudaMemset(ctx->p2p_flag, 0, 256));
+    }
+    cudaIpcMemHandle_t h0, h1;
+    CU(cudaIpcGetMemHandle(&h0, ctx->p2p_stage));
+    CU(cudaIpcGetMemHandle(&h1, ctx->p2p_xy));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out, &h0, 64);
+    memcpy(out + 64, &h1, 64);
+    return MKHE_OK;
+#else
+    (void)out;
+    return fail(ctx, MKHE_ERR_UNSUPPORTED, "no peer memory under emulation");
+#endif
+}
+int mkhe_p2p_import(mkhe_ctx *ctx, int nranks, int rank, const uint8_t *all_handles) {
+    CHECK_CTX();
+#if !defined(MKHE_EMU)
+    if (!all_handles || nranks < 2 || nranks > MKHE_MAX_RANKS || rank < 0 || rank >= nranks) return fail(ctx, MKHE_ERR_INVALID, "bad rank layout");
+    if (!ctx->nccl || ctx->nranks != nranks || ctx->rank != rank) return fail(ctx, MKHE_ERR_NCCL, "mkhe_comm_init with the same layout comes first");
+    if (!ctx->p2p_stage) return fail(ctx, MKHE_ERR_INVALID, "mkhe_p2p_export comes first");
+    if (ctx->N % (nranks * 2 * MKHE_THREADS) != 0) return fail(ctx, MKHE_ERR_UNSUPPORTED, "N too small for %d ranks", nranks);
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) { ctx->peer_stage[r] = ctx->p2p_stage; ctx->peer_xy[r] = ctx->p2p_xy; continue; }
+        cudaIpcMemHandle_t h0, h1;
+        memcpy(&h0, all_handles + (size_t)r * 128, 64);
+        memcpy(&h1, all_handles + (size_t)r * 128 + 64, 64);
+        CU(cudaIpcOpenMemHandle((void **)&ctx->peer_stage[r], h0, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle((void **)&ctx->peer_xy[r], h1, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ctx->p2p = true;
+    return MKHE_OK;
+#else
+    (void)nranks; (void)rank; (void)all_handles;
+    return fail(ctx, MKHE_ERR_UNSUPPORTED, "no peer memory under emulation");
+#endif
 }
 
 // ---- measurement ------------------------------------------------------------------------------------

@@ -703,6 +703,78 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_mac_parties(MacPartiesArgs a, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3'' party-sharded x / y generation fused with the exchange: the multiply-accumulate of k_mac_parties, but every
+//   result goes STRAIGHT into the memory of the rank that owns its position (peer stores over NVLink / NVSwitch; cudaIpc-mapped
+//   buffers) instead of a local buffer that a collective would then move.  A (digit, limb) row of N coefficients is split into
+//   nranks segments of N / nranks; rank r owns segment r of every row.  On the owner, stage[src][which][digit][slot][segment]
+//   receives the partial of rank `src`.  k_reduce_gather then sums the nranks partials of the rank's own segments, reduces mod q
+//   (the partials are canonical residues in Montgomery form: MForm is linear) and stores the result into the x||y buffers of ALL
+//   ranks.  Between the two kernels and after the second one the host enqueues a tiny all-reduce as a stream-ordered barrier.
+//   grid as k_mac_parties.
+// ------------------------------------------------------------------------------------------------
+#define MKHE_MAX_RANKS 8
+struct P2PArgs {
+    u64 *peer_stage[MKHE_MAX_RANKS];     // stage buffer of every rank (index = owner)
+    u64 *peer_xy[MKHE_MAX_RANKS];        // x||y buffer of every rank
+    int nranks, rank;
+    int which;                           // 0 = x, 1 = y
+    long swk_elems;                      // beta_max * dmax * N
+};
+__global__ void __launch_bounds__(MKHE_THREADS) k_mac_parties_scatter(MacPartiesArgs a, P2PArgs p, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const int digit = blockIdx.z, slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
+    const ModC m = mods[mi];
+    const long c = ((long)blockIdx.x * MKHE_THREADS + threadIdx.x) * 2;
+    const long off = ((long)digit * a.dmax + slot) * N + c;
+    u64 hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
+    for (int t = 0; t < a.nparties; t++) {
+        ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(a.key.p[t] + off);
+        ulonglong2 hh = *reinterpret_cast<const ulonglong2 *>(a.hst.p[t] + off);
+        mac128(hi0, lo0, kk.x, hh.x);
+        mac128(hi1, lo1, kk.y, hh.y);
+        if ((t & 7) == 7) {
+            hi0 = csub(barrett_lazy(hi0, m.q, m.mu), m.q);
+            hi1 = csub(barrett_lazy(hi1, m.q, m.mu), m.q);
+        }
+    }
+    hi0 = csub(barrett_lazy(hi0, m.q, m.mu), m.q);
+    hi1 = csub(barrett_lazy(hi1, m.q, m.mu), m.q);
+    const u64 r0 = mred(mont_reduce(hi0, lo0, m.q, m.qinv), m.r2, m.q, m.qinv);
+    const u64 r1 = mred(mont_reduce(hi1, lo1, m.q, m.qinv), m.r2, m.q, m.qinv);
+    const long seg = N / p.nranks;
+    const int owner = (int)(c / seg);
+    const long row = ((long)p.which * (p.swk_elems / N) + (long)digit * a.dmax + slot);     // row index in x||y
+    u64 *dst = p.peer_stage[owner] + ((long)p.rank * 2 * (p.swk_elems / N) + row) * seg + (c - (long)owner * seg);
+    *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(r0, r1);
+}
+// grid = (seg / (256 * 2), nslots, 2 * beta): blockIdx.z = which * beta + digit
+struct GatherArgs {
+    int beta, dmax, nslots;
+    int slots[MKHE_MAX_SLOTS];
+    int mods[MKHE_MAX_SLOTS];
+    int logN;
+};
+__global__ void __launch_bounds__(MKHE_THREADS) k_reduce_gather(GatherArgs a, P2PArgs p, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const int which = blockIdx.z / a.beta, digit = blockIdx.z - which * a.beta;
+    const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
+    const ModC m = mods[mi];
+    const long seg = N / p.nranks;
+    const long cs = ((long)blockIdx.x * MKHE_THREADS + threadIdx.x) * 2;          // within the segment
+    const long rows = p.swk_elems / N;
+    const long row = (long)which * rows + (long)digit * a.dmax + slot;
+    u64 s0 = 0, s1 = 0;
+    for (int src = 0; src < p.nranks; src++) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p.peer_stage[p.rank] + ((long)src * 2 * rows + row) * seg + cs);
+        s0 += v.x;                     // <= 8 canonical residues below 2^60: no overflow
+        s1 += v.y;
+    }
+    const ulonglong2 r = make_ulonglong2(csub(barrett_lazy(s0, m.q, m.mu), m.q), csub(barrett_lazy(s1, m.q, m.mu), m.q));
+    const long off = row * N + (long)p.rank * seg + cs;
+    for (int dst = 0; dst < p.nranks; dst++) *reinterpret_cast<ulonglong2 *>(p.peer_xy[dst] + off) = r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4 / K8  exact RNS basis conversion (modUpExact = reconstructRNS + multSum,
 //   mkrlwe/basis_extension.go:337-357,537-646) and the ModDown combine (:203-229).
 //   One thread per coefficient.  The fp64 estimate of the overflow count v is reproduced operation by

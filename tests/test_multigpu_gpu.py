@@ -25,7 +25,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, k, logN, out_q):
+def _worker(rank, world, port, k, logN, out_q, p2p=False):
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path[:0] = [os.path.dirname(here), here]
@@ -48,6 +48,10 @@ def _worker(rank, world, port, k, logN, out_q):
     uid = [dp.ctx.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     dp.ctx.comm_init(world, rank, uid[0])
+    if p2p:                                         # fused exchange over peer memory instead of the big all-reduce
+        hs = [None] * world
+        dist.all_gather_object(hs, dp.ctx.p2p_export())
+        dp.ctx.p2p_import(world, rank, hs)
     own = sharding.owned_parties(ids, world, rank)
     rlk = mkrlwe.RelinearizationKeySet()
     for i in own:                                   # a rank only ever holds its own parties' keys
@@ -56,6 +60,9 @@ def _worker(rank, world, port, k, logN, out_q):
     c0 = mkckks.Ciphertext.from_numpy(dp.ctx, v0, lit.scale)
     c1 = mkckks.Ciphertext.from_numpy(dp.ctx, v1, lit.scale)
     res = ev.MulRelinNew(c0, c1, rlk, all_ids=ids)
+    if p2p:                                         # back to back: the exchange buffers are reused without host synchronisation
+        for _ in range(3):
+            res = ev.MulRelinNew(c0, c1, rlk, all_ids=ids)
     mine = {kk: res.Value[kk].numpy() for kk in res.valid if kk != "0" or rank == 0}
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
@@ -72,15 +79,15 @@ def _worker(rank, world, port, k, logN, out_q):
 
 
 @pytest.mark.skipif(_ndev() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("k,world", [(4, 2), (3, 2)])
-def test_party_sharded_mul_relin_nccl(k, world):
+@pytest.mark.parametrize("k,world,p2p", [(4, 2, False), (3, 2, False), (4, 2, True), (3, 2, True)])
+def test_party_sharded_mul_relin_nccl(k, world, p2p):
     import torch.multiprocessing as mp
     if _ndev() < world:
         pytest.skip("not enough GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, k, 12, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, k, 12, q, p2p)) for r in range(world)]
     for pr in procs:
         pr.start()
     for pr in procs:
