@@ -867,7 +867,13 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
             ta.out.p[1 + t] = out[1 + t];
         }
         LAUNCH(k_tensor, dim3(N / MKHE_THREADS, level + 1), dim3(MKHE_THREADS), 0, ta, ctx->d_mods);
-        TRY(ntt_inv(ctx, qs, nOut + 1, out, out));
+        if (sh.active) {        // only component "0" and the components of this rank's parties are completed here
+            std::vector<u64 *> mine{out[0]};
+            for (int t = 0; t < nOut; t++) if (sh.owns(idsOut[t])) mine.push_back(out[1 + t]);
+            TRY(ntt_inv(ctx, qs, (int)mine.size(), mine.data(), mine.data()));
+        } else {
+            TRY(ntt_inv(ctx, qs, nOut + 1, out, out));
+        }
         // the tensor term of c_0 is counted once across ranks
         if (sh.active && ctx->rank != 0) CU(cudaMemsetAsync(out[0], 0, (size_t)(level + 1) * N * 8, ctx->stream));
     }
@@ -1526,8 +1532,10 @@ int mkhe_ckks_mul_relin_sharded(mkhe_ctx *ctx, int level, int nb_rescales, int n
     }
     TRY(decompose_impl(ctx, level, (int)in0.size(), in0.data(), pool0.data(), 0));
     TRY(decompose_impl(ctx, level, (int)in1.size(), in1.data(), pool1.data(), 0));
+    // the forms of the owned parties are fresh (made above): the tensor step reads NTT(op_id) from their diagonals; the other
+    // parties' components are not completed on this rank, so nothing else has to be transformed
     TRY(mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
-                               vd.data(), vv.data(), uk->d, nOut, idsOut, po.data(), sh));
+                               vd.data(), vv.data(), uk->d, nOut, idsOut, po.data(), sh, false, false, true, true));
     TRY(rescale_impl(ctx, level, nb_rescales, nOut + 1, po.data(), po.data()));
     for (int t = 0; t <= nOut; t++) reinterpret_cast<Obj *>(out[t])->nlimbs = level + 1 - nb_rescales;
     return MKHE_OK;
