@@ -54,6 +54,7 @@ struct mkhe_ctx {
     int logN = 0, N = 0, nQ = 0, nP = 0, nQMul = 0, gamma = 2, device = 0;
     int S1 = 0, dmax = 0;
     int p2_timing_n = 0;
+    bool debug_sync = false;              // development: host-synchronise after every launch (MKHE_DEBUG_SYNC=<n-th context of the process>)
     int num_sms = 148;                    // persistent kernels size their grids from it
     int alpha = 1, beta_max = 0;          // alpha = #P/gamma limbs per digit, beta_max = ceil(nQ/alpha) digits (mkrlwe/params.go:63-71)
     LiftTable *d_lift = nullptr;          // alpha > 1: [beta_max][alpha-1] tables of the Decomposer
@@ -179,6 +180,7 @@ struct OpScope {
             cudaEventRecord(pb_, ctx->stream);                        \
             ctx->prof.push_back({#kernel, pa_, pb_});                 \
         }                                                             \
+        if (ctx->debug_sync) cudaStreamSynchronize(ctx->stream);      \
         CU(cudaGetLastError());                                       \
     } while (0)
 
@@ -842,7 +844,8 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     // diagonal of h_id instead of being transformed again -- the same kernel produced it from the same input, bit for bit.
     {
         Slots qs = q_slots(level);
-        const bool dg0 = fresh0 && ctx->alpha == 1, dg1 = fresh1 && ctx->alpha == 1;
+        const bool nodiag = getenv("MKHE_DEBUG_NODIAG") != nullptr;
+        const bool dg0 = fresh0 && ctx->alpha == 1 && !nodiag, dg1 = fresh1 && ctx->alpha == 1 && !nodiag;
         std::vector<u64 *> src, dst;
         src.push_back(op0[0]); dst.push_back(tn[0]);
         src.push_back(op1[0]); dst.push_back(tn[n0 + 1]);
@@ -1014,6 +1017,12 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     int ndev = mkhe_device_count();
     if (ndev <= 0 || device < 0 || device >= ndev) return MKHE_ERR_CUDA;   // no GPU: fail loudly, there is no CPU path
     mkhe_ctx *ctx = new mkhe_ctx();
+    {
+        static int created = 0;
+        created++;
+        const char *e = getenv("MKHE_DEBUG_SYNC");
+        if (e && atoi(e) == created) ctx->debug_sync = true;
+    }
     ctx->root = ctx;
     ctx->lanes.push_back(ctx);
     ctx->logN = logN; ctx->N = 1 << logN; ctx->nQ = nQ; ctx->nP = nP; ctx->gamma = gamma; ctx->device = device;
