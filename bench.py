@@ -147,7 +147,7 @@ class ClockSampler:
 class DeviceWorkload:
     """keys + ciphertext pool of one GPU"""
 
-    def __init__(self, lit, k, device, seed, rots=(2,), npairs=4, batch=16, lanes=1):
+    def __init__(self, lit, k, device, seed, rots=(2,), npairs=4, batch=16, lanes=2):
         from mkhe_kklss_b200 import mkckks, mkrlwe
         self.lit, self.k, self.rots, self.batch = lit, k, rots, batch
         self.level = len(lit.Q) - 1
@@ -318,7 +318,7 @@ class DeviceWorkload:
         return ms
 
 
-def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dist, barrier, allmax, nlanes=1, p2p=True):
+def sharded_mul_relin(lit, k, rank, world, local_rank, steps, warmup, batch, dist, barrier, allmax, nlanes=2, p2p=True):
     """BASELINE config 4: ONE MulRelinNew whose per-party key switches are sharded over the ranks (mkhe_ckks_mul_relin_sharded:
     rank g holds the relinearisation keys of its parties only, the partial x, y and the c_0 contributions are summed with
     ncclAllReduce over NVLink and reduced mod q).  Operand ciphertexts are replicated (they are small); every rank issues the
@@ -471,13 +471,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--parties", type=int, default=4)
     ap.add_argument("--batch", type=int, default=16, help="ciphertext pairs (MulRelin ops) per step")
-    ap.add_argument("--lanes", type=int, default=1,
-                    help="lanes (mkhe_ctx_fork) the ops of a step are spread over, per GPU.  Default 1: with two lanes (or two "
-                         "contexts) running MulRelin concurrently on one GPU, tools/stress_lanes.py / stress_two_ctx.py find a few "
-                         "per cent of results wrong (a whole 16 KiB tile stale; cause not found yet, DESIGN.md), so concurrent "
-                         "lanes are NOT part of the measured path")
-    ap.add_argument("--no-extras", action="store_true", help="skip the k=8 / hoisted-Rotate side measurements")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, help="lanes (mkhe_ctx_fork) the ops of a step are spread over, per GPU")
     ap.add_argument("--lib", default=None, help="development: load this build of the library instead of the in-tree one")
     ap.add_argument("--sweep", default=None, help="party-count sweep (BASELINE config 4), e.g. 2,4,8,16,32: prints one JSON line "
                                                   "with MulRelin and hoisted-Rotate ops/s per k instead of the headline run")

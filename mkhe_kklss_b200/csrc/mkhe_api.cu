@@ -54,6 +54,12 @@ struct mkhe_ctx {
     int logN = 0, N = 0, nQ = 0, nP = 0, nQMul = 0, gamma = 2, device = 0;
     int S1 = 0, dmax = 0;
     int p2_timing_n = 0;
+    bool debug_ck = false;                // development: checksum every scratch buffer after every launch (MKHE_DEBUG_CK=<n-th context>)
+    u64 *ck_log = nullptr;
+    u64 *ck_snap = nullptr;
+    size_t ck_snap_bytes = 0;
+    int ck_n = 0;
+    std::vector<std::string> ck_names;
     bool debug_sync = false;              // development: host-synchronise after every launch (MKHE_DEBUG_SYNC=<n-th context of the process>)
     int num_sms = 148;                    // persistent kernels size their grids from it
     int alpha = 1, beta_max = 0;          // alpha = #P/gamma limbs per digit, beta_max = ceil(nQ/alpha) digits (mkrlwe/params.go:63-71)
@@ -122,6 +128,39 @@ int fail(mkhe_ctx *c, int code, const char *fmt, ...) {
     if (c) c->err = buf;
     return code;
 }
+#define MKHE_CK_MAX_LAUNCHES 4096
+#define MKHE_CK_SLOTS 16
+void debug_checksums(mkhe_ctx *ctx, const char *kernel) {
+    if (!ctx->ck_log) {
+        cudaMalloc((void **)&ctx->ck_log, (size_t)MKHE_CK_MAX_LAUNCHES * MKHE_CK_SLOTS * 8);
+        cudaMemsetAsync(ctx->ck_log, 0, (size_t)MKHE_CK_MAX_LAUNCHES * MKHE_CK_SLOTS * 8, ctx->stream);
+    }
+    if (ctx->ck_n >= MKHE_CK_MAX_LAUNCHES) return;
+    const char *only = getenv("MKHE_DEBUG_CK_ONLY");
+    if (only && !strstr(kernel, only)) return;
+    if (const char *snap = getenv("MKHE_DEBUG_SNAP")) {          // keep a copy of one scratch buffer per matching launch
+        auto it = ctx->scratch.find(snap);
+        if (it != ctx->scratch.end() && ctx->ck_n < 64) {
+            if (!ctx->ck_snap) cudaMalloc((void **)&ctx->ck_snap, it->second.bytes * 64);
+            ctx->ck_snap_bytes = it->second.bytes;
+            cudaMemcpyAsync((char *)ctx->ck_snap + (size_t)ctx->ck_n * it->second.bytes, it->second.p, it->second.bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        }
+        ctx->ck_names.push_back(kernel);
+        ctx->ck_n++;
+        return;                                                   // snapshots only: no checksum kernels
+    }
+    int idx = 0;
+    std::string names = kernel;
+    for (auto &kv : ctx->scratch) {
+        if (idx >= MKHE_CK_SLOTS) break;
+        names += " " + kv.first;
+        MKHE_LAUNCH(k_checksum, dim3(296), dim3(MKHE_THREADS), 0, ctx->stream, kv.second.p, kv.second.bytes / 8,
+                    ctx->ck_log + (size_t)ctx->ck_n * MKHE_CK_SLOTS + idx);
+        idx++;
+    }
+    ctx->ck_names.push_back(names);
+    ctx->ck_n++;
+}
 #define CU(call)                                                                                      \
     do {                                                                                              \
         cudaError_t e_ = (call);                                                                      \
@@ -181,6 +220,7 @@ struct OpScope {
             ctx->prof.push_back({#kernel, pa_, pb_});                 \
         }                                                             \
         if (ctx->debug_sync) cudaStreamSynchronize(ctx->stream);      \
+        if (ctx->debug_ck) debug_checksums(ctx, #kernel);             \
         CU(cudaGetLastError());                                       \
     } while (0)
 
@@ -352,6 +392,7 @@ int launch_pass2(mkhe_ctx *ctx, const Slots &s, int np, u64 *const *bufs, int co
     b.inst_stride = inst_stride;
     b.nslots = s.n;
     b.logN = ctx->logN;
+    b.magic = 0x9e3779b97f4a7c15ull;
     const long per_slot = (long)tiles * b.ninst;
     for (int i = 0; i < s.n; i++) {
         b.slots[i] = s.slot[i];
@@ -526,6 +567,7 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
                 MacDigitsArgs a;
                 memset(&a, 0, sizeof a);
                 a.nsets = nsets;
+                a.magic = 0x9e3779b97f4a7c15ull;
                 a.beta = beta_of(ctx, levelQ);
                 a.digit_stride = (long)ctx->dmax * ctx->N;
                 a.nslots = s.n;
@@ -1022,6 +1064,8 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
         created++;
         const char *e = getenv("MKHE_DEBUG_SYNC");
         if (e && atoi(e) == created) ctx->debug_sync = true;
+        e = getenv("MKHE_DEBUG_CK");
+        if (e && atoi(e) == created) ctx->debug_ck = true;
     }
     ctx->root = ctx;
     ctx->lanes.push_back(ctx);
@@ -2101,6 +2145,32 @@ int mkhe_debug_p2_timing(mkhe_ctx *ctx, uint64_t *out, int cap, int *n) {
     return MKHE_OK;
 }
 #endif
+
+int mkhe_debug_snap_read(mkhe_ctx *ctx, int row, uint64_t *out, size_t cap_bytes, size_t *bytes) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->ck_snap || row < 0 || row >= 64 || cap_bytes < ctx->ck_snap_bytes) return fail(ctx, MKHE_ERR_INVALID, "no snapshot");
+    *bytes = ctx->ck_snap_bytes;
+    CU(cudaMemcpy(out, (char *)ctx->ck_snap + (size_t)row * ctx->ck_snap_bytes, ctx->ck_snap_bytes, cudaMemcpyDeviceToHost));
+    return MKHE_OK;
+}
+// development: the checksum log (one row of 16 sums per launch since the last call) and the row labels "kernel scratch-names..."
+int mkhe_debug_ck_fetch(mkhe_ctx *ctx, uint64_t *out, int cap_rows, int *nrows, char *names, size_t names_cap) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    *nrows = std::min(cap_rows, ctx->ck_n);
+    if (*nrows > 0 && ctx->ck_log) CU(cudaMemcpy(out, ctx->ck_log, (size_t)*nrows * MKHE_CK_SLOTS * 8, cudaMemcpyDeviceToHost));
+    std::string all;
+    for (int i = 0; i < *nrows; i++) all += ctx->ck_names[i] + "\n";
+    if (names && names_cap) snprintf(names, names_cap, "%s", all.c_str());
+    if (ctx->ck_log) {
+        CU(cudaMemsetAsync(ctx->ck_log, 0, (size_t)MKHE_CK_MAX_LAUNCHES * MKHE_CK_SLOTS * 8, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->ck_n = 0;
+    ctx->ck_names.clear();
+    return MKHE_OK;
+}
 
 int mkhe_bench_butterfly_peak(mkhe_ctx *ctx, double *butterflies_per_s) {
     CHECK_CTX();

@@ -34,6 +34,7 @@ __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 by
 __device__ __forceinline__ void named_sync(int id, int nthreads) { emu_barrier(id, nthreads); }
 __device__ __forceinline__ void consume16(const u64 *) {}
 __device__ __forceinline__ void consume4(u64, u64, u64, u64) {}
+__device__ __forceinline__ void anchor_side_effect() {}
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 #else
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -71,6 +72,9 @@ __device__ __forceinline__ void consume16(const u64 *v) {
                  : "memory");
 }
 __device__ __forceinline__ void consume4(u64 a, u64 b, u64 c, u64 d) { asm volatile("" ::"l"(a), "l"(b), "l"(c), "l"(d) : "memory"); }
+// an instruction with a side effect (never reordered across a barrier); callers predicate it on values whose producers must
+// have completed before the barrier that follows
+__device__ __forceinline__ void anchor_side_effect() { asm volatile("nanosleep.u32 1;" ::: "memory"); }
 // barrier among `nthreads` threads of the CTA (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *bar) {
@@ -82,6 +86,14 @@ __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 by
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
+#endif
+
+// loads of data that an EARLIER KERNEL of the same stream wrote: through L2 (ld.global.cg), never from this SM's L1
+#ifdef MKHE_EMU
+template <class T> __device__ __forceinline__ T ld_cg(const T *p) { return *p; }
+#else
+__device__ __forceinline__ u64 ld_cg(const u64 *p) { return __ldcg(p); }
+__device__ __forceinline__ ulonglong2 ld_cg(const ulonglong2 *p) { return __ldcg(p); }
 #endif
 
 #define MKHE_MAX_PARTIES_K 66     // entries of a kernel-argument pointer list (64 parties + component "0" + 1)

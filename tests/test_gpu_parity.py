@@ -44,6 +44,48 @@ def test_cnn_inference_flow():
     parity.check_cnn_flow(PR.CNN_PN14QP433)
 
 
+def test_concurrent_lanes_stress():
+    """full-size MulRelinNew and hoisted Rotate calls on two lanes with NO synchronisation in between (the bench's schedule), every
+    result compared with the oracle.  Guards the hazard that only concurrency exposed: with another kernel's CTAs on the SM the
+    shared-memory loads of k_mac_digits could still be in flight when the TMA refill of their stage landed (hazard 1)."""
+    w = parity.CKKSWorld(PR.CKKS_PN15QP880, 2, rots=(2,))
+    ids, level = w.ids, w.op.max_level()
+    o0, d0 = w.random_ct(ids, level)
+    o1, d1 = w.random_ct(ids, level)
+    want = w.oev.mul_relin_new(o0, o1, w.o_rlk)
+    want_rot = w.oev.rotate_hoisted_new(o0, 2, w.oev.hoisted_form(o0), w.o_rk)
+    lanes = [w.ctx, w.ctx.fork()]
+    dh = w.dev.HoistedForm(d0)
+    B = 16
+    from mkhe_kklss_b200 import mkckks
+    outs = [mkckks.Ciphertext.new(w.dp, ids, level, w.lit.scale) for _ in range(B)]
+    rots = [mkckks.Ciphertext.new(w.dp, ids, level, w.lit.scale) for _ in range(B)]
+    g = w.d_rlk.GetRelinearizationKey
+    kb, kd, kv = ([g(i).Value[j].h for i in ids] for j in range(3))
+    rk = [w.d_rk.GetRotationKey(i, 2).h for i in ids]
+    nb, _ = w.dev._nb_rescales(w.lit.scale * w.lit.scale, level, w.lit.scale)
+    bad = []
+    for r in range(10):
+        for i in range(B):
+            a, b = lanes[i % 2], lanes[(i + 1) % 2]
+            a.ckks_mul_relin(level, nb, False, ids, d0.handles(ids), ids, d1.handles(ids), kb, kd, kv, w.dp.CRS[-1].h, ids, outs[i].handles(ids))
+            if r % 2:
+                b.rotate_hoisted(level, 2, d0.handles(ids), [dh[t].h for t in ids], rk, w.dp.CRS[2].h, rots[i].handles(ids))
+            else:
+                b.ckks_mul_relin(level, nb, False, ids, d0.handles(ids), ids, d1.handles(ids), kb, kd, kv, w.dp.CRS[-1].h, ids, rots[i].handles(ids))
+        for ln in lanes:
+            ln.sync()
+        for i in range(B):
+            for key in ["0"] + ids:
+                if not np.array_equal(w.ctx.poly_download(outs[i].Value[key].h, level + 1 - nb), want.value[key]):
+                    bad.append((r, i, "mul", key))
+                ref = want_rot.value[key] if r % 2 else want.value[key]
+                if not np.array_equal(w.ctx.poly_download(rots[i].Value[key].h, ref.shape[0]), ref):
+                    bad.append((r, i, "other lane", key))
+    assert not bad, bad[:8]
+    w.close()
+
+
 def test_ckks_semantics_on_device_outputs():
     w = parity.CKKSWorld(PR.CKKS_PN14QP439.at_logn(12), 2, real_keys=True)
     parity.check_ckks_semantics(w)

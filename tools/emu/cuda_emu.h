@@ -56,6 +56,7 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline unsigned long long __double2ull_rz(double x) { return (unsigned long long)x; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }      // fibers are cooperative
 
 // ---- runtime API subset -------------------------------------------------------------------------

@@ -13,7 +13,7 @@ if os.environ.get("MKHE_LIB"):
     _lib._default = _lib.Library(os.path.abspath(os.environ["MKHE_LIB"]))
 victim = sys.argv[1]
 rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-noise = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+noise = sys.argv[3] if len(sys.argv) > 3 else "mul"          # 0 / mul / decompose / extprod / ntt / copy
 B = 16
 w = parity.CKKSWorld(PR.CKKS_PN15QP880, 2, rots=(2,))
 ids, level = w.ids, w.op.max_level()
@@ -26,6 +26,8 @@ g = w.d_rlk.GetRelinearizationKey
 kb, kd, kv = ([g(i).Value[j].h for i in ids] for j in range(3))
 nb, _ = w.dev._nb_rescales(w.lit.scale * w.lit.scale, level, w.lit.scale)
 nout = mkckks.Ciphertext.new(w.dp, ids, level, w.lit.scale)
+nswk, nswk2, npoly = mkrlwe.SwitchingKey(w.ctx), mkrlwe.SwitchingKey(w.ctx), mkrlwe.Poly(w.ctx, level + 1)
+w.ctx.decompose(level, d1.Value["0"].h, nswk2.h)
 a = o0.value["0"]
 pa = d0.Value["0"]
 ks = w.oev.ksw
@@ -83,10 +85,22 @@ else:
 bad = 0
 for r in range(rounds):
     for i in range(B):
-        if noise:
+        if noise in ("1", "mul"):
             for p in nout.Value.values():
                 p.set_nlimbs(level + 1)
             lanes[1].ckks_mul_relin(level, nb, False, ids, d0.handles(ids), ids, d1.handles(ids), kb, kd, kv, w.dp.CRS[-1].h, ids, nout.handles(ids))
+        elif noise == "decompose":
+            for _ in range(6):
+                lanes[1].decompose(level, d1.Value["0"].h, nswk.h)
+        elif noise == "extprod":
+            for _ in range(12):
+                lanes[1].external_product_hoisted(level, nswk2.h, g(1).Value[1].h, npoly.h)
+        elif noise == "ntt":
+            for _ in range(40):
+                lanes[1].ntt(level, d1.Value["0"].h, npoly.h)
+        elif noise == "copy":
+            for _ in range(40):
+                lanes[1].poly_copy(npoly.h, d1.Value["0"].h)
         run(i)
         run(i)          # twice into the same output: more victim work per noise op
     for ln in lanes:
