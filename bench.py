@@ -472,6 +472,8 @@ def main():
     ap.add_argument("--parties", type=int, default=4)
     ap.add_argument("--batch", type=int, default=16, help="ciphertext pairs (MulRelin ops) per step")
     ap.add_argument("--lanes", type=int, default=2, help="lanes (mkhe_ctx_fork) the ops of a step are spread over, per GPU")
+    ap.add_argument("--no-extras", action="store_true", help="skip the k=8 / hoisted-Rotate / other-config side measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lib", default=None, help="development: load this build of the library instead of the in-tree one")
     ap.add_argument("--sweep", default=None, help="party-count sweep (BASELINE config 4), e.g. 2,4,8,16,32: prints one JSON line "
                                                   "with MulRelin and hoisted-Rotate ops/s per k instead of the headline run")
