@@ -38,7 +38,10 @@ struct Obj {
     bool xfer_pending = false;      // the context's stream has not been ordered after it yet
     // forked contexts (lanes): the last op of every lane that touched the object, so that a use on another lane is ordered
     // after it (read-after-write, write-after-read, write-after-write).  Unused while the root has no forks.
-    struct Use { cudaEvent_t ev = nullptr; bool valid = false, wrote = false; };
+    // ev: the lane's last op that touched the object (a slot of the lane's event ring: a recycled slot only makes a waiter wait
+    // longer); wev: the lane's last op that WROTE it (an event of its own, so later reads by the same lane do not move it --
+    // otherwise every reader on another lane would wait for the writer lane's most recent op, e.g. on keys uploaded once)
+    struct Use { cudaEvent_t ev = nullptr, wev = nullptr, wev_own = nullptr; bool valid = false, wrote = false; };
     Use use[MKHE_MAX_LANES];
 };
 enum AccessMode { ACC_WRITE = 0, ACC_READ = 1 };       // the default is the conservative one
@@ -186,7 +189,18 @@ struct OpScope {
             }
             for (auto &t : c->touched) {
                 Obj::Use &u = t.o->use[c->lane];
-                u.wrote = (u.valid && u.wrote) || t.write;
+                if (t.write) {
+                    if (c->override_ev) {
+                        u.wev = nullptr;                    // an asynchronous upload: its completion is the object's xfer event
+                    } else {
+                        if (!u.wev_own) cudaEventCreateWithFlags(&u.wev_own, cudaEventDisableTiming);
+                        cudaEventRecord(u.wev_own, c->stream);
+                        u.wev = u.wev_own;
+                    }
+                    u.wrote = true;
+                } else if (!u.valid) {
+                    u.wrote = false;
+                }
                 u.valid = true;
                 u.ev = ev;
             }
@@ -237,7 +251,8 @@ Obj *as_obj(mkhe_ctx *ctx, uint64_t h, int kind, int mode = ACC_WRITE) {
         for (int l = 0; l < MKHE_MAX_LANES; l++) {
             if (l == ctx->lane) continue;
             Obj::Use &u = o->use[l];
-            if (u.valid && (u.wrote || write)) cudaStreamWaitEvent(ctx->stream, u.ev, 0);
+            if (u.valid && write) cudaStreamWaitEvent(ctx->stream, u.ev, 0);                      // after every earlier use
+            else if (u.valid && u.wrote && u.wev) cudaStreamWaitEvent(ctx->stream, u.wev, 0);    // after the last write only
             if (write) u.valid = false;             // ordered before this op; later users wait for this lane instead
         }
         ctx->touched.push_back({o, write});
@@ -1215,11 +1230,19 @@ void mkhe_ctx_destroy(mkhe_ctx *ctx) {
     for (cudaEvent_t e : ctx->lane_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->root == ctx) {
-        for (Obj *o : ctx->objs) { if (o->xfer) cudaEventDestroy(o->xfer); cudaFree(o->d); delete o; }
+        for (Obj *o : ctx->objs) {
+            if (o->xfer) cudaEventDestroy(o->xfer);
+            for (auto &u : o->use) if (u.wev_own) cudaEventDestroy(u.wev_own);
+            cudaFree(o->d);
+            delete o;
+        }
         cudaFree(ctx->d_mods); cudaFree(ctx->d_twf); cudaFree(ctx->d_twi); cudaFree(ctx->d_twf_tiled); cudaFree(ctx->d_twi_tiled);
         cudaFree(ctx->d_conv_PtoQ); cudaFree(ctx->d_conv_QtoQMul); cudaFree(ctx->d_conv_QMultoQ); cudaFree(ctx->d_lift);
     } else {
-        for (Obj *o : ctx->root->objs) o->use[ctx->lane] = Obj::Use();       // the lane's work has completed (synchronised above)
+        for (Obj *o : ctx->root->objs) {                                      // the lane's work has completed (synchronised above)
+            if (o->use[ctx->lane].wev_own) cudaEventDestroy(o->use[ctx->lane].wev_own);
+            o->use[ctx->lane] = Obj::Use();
+        }
         ctx->root->lanes[ctx->lane] = nullptr;
         while (!ctx->root->lanes.empty() && !ctx->root->lanes.back()) ctx->root->lanes.pop_back();
     }
@@ -1274,6 +1297,7 @@ int mkhe_poly_free(mkhe_ctx *ctx, mkhe_poly h) {
     POLY(o, h);
     TRY(sync_all_users(ctx, o));
     if (o->xfer) cudaEventDestroy(o->xfer);
+    for (auto &u : o->use) if (u.wev_own) cudaEventDestroy(u.wev_own);
     CU(cudaFree(o->d));
     ctx->root->objs.erase(o);
     ctx->touched.clear();
@@ -1376,6 +1400,7 @@ int mkhe_swk_free(mkhe_ctx *ctx, mkhe_swk h) {
     SWK(o, h);
     TRY(sync_all_users(ctx, o));
     if (o->xfer) cudaEventDestroy(o->xfer);
+    for (auto &u : o->use) if (u.wev_own) cudaEventDestroy(u.wev_own);
     CU(cudaFree(o->d));
     ctx->root->objs.erase(o);
     ctx->touched.clear();
