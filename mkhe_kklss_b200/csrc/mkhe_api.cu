@@ -383,7 +383,6 @@ int dispatch_s1(mkhe_ctx *ctx, F &&f) {
     return fail(ctx, MKHE_ERR_UNSUPPORTED, "logN = %d unsupported (12..16)", ctx->logN);
 }
 
-const size_t SMEM_TILE = MKHE_XBUF * 8;                      // the padded exchange buffer
 const size_t SMEM_PASS2 = MKHE_P2_SMEM;                      // twiddles + per group: exchange and landing buffers
 const int COLGROUPS = MKHE_TILE / MKHE_NTT_THREADS;              // CTAs per limb in the column passes
 
