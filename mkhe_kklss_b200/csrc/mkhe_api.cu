@@ -397,7 +397,7 @@ int pick_chunks(int count, long ctas_per_chunk) {
 #ifndef MKHE_P2_BIGW
 #define MKHE_P2_BIGW 19          // cost of a tile of a 59/60-bit modulus in sixteenths of a normal one (the sweeps)
 #endif
-int launch_pass2(mkhe_ctx *ctx, const Slots &s, int np, u64 *const *bufs, int count, long inst_stride) {
+int launch_pass2(mkhe_ctx *ctx, const Slots &s, int np, u64 *const *bufs, int count, long inst_stride, bool lazy_out = false) {
     const int tiles = ctx->N / MKHE_TILE;
     Pass2Args b;
     memset(&b, 0, sizeof b);
@@ -407,6 +407,7 @@ int launch_pass2(mkhe_ctx *ctx, const Slots &s, int np, u64 *const *bufs, int co
     b.nslots = s.n;
     b.logN = ctx->logN;
     b.magic = 0x9e3779b97f4a7c15ull;
+    b.lazy_out = lazy_out ? 1 : 0;
     const long per_slot = (long)tiles * b.ninst;
     for (int i = 0; i < s.n; i++) {
         b.slots[i] = s.slot[i];
@@ -475,7 +476,8 @@ int ntt_inv(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
 }
 
 // Decompose: digits in_limb0 .. in_limb0+beta-1 of each input poly -> swk-shaped outputs (NTT domain)
-int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *const *out, int in_limb0) {
+// lazy: the NTT outputs of the broadcast digits stay un-reduced (< 2^64, congruent) -- only for forms that never leave the op
+int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *const *out, int in_limb0, bool lazy = false) {
     const int alpha = ctx->alpha, beta = beta_of(ctx, levelQ);
     if (alpha > 1 && in_limb0 != 0) return fail(ctx, MKHE_ERR_UNSUPPORTED, "DecomposeBFV relies on alpha = 1 (mkbfv/keyswitch.go:64-67)");
     // digits [0, nlift) hold more than one limb and take the exact lift; a last digit of a single limb is a broadcast
@@ -524,7 +526,7 @@ int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *c
             }));
             std::vector<u64 *> bufs(np);
             for (int i = 0; i < np; i++) bufs[i] = out[p0 + i] + nlift * digit_elems;
-            TRY(launch_pass2(ctx, s, np, bufs.data(), nd, digit_elems));
+            TRY(launch_pass2(ctx, s, np, bufs.data(), nd, digit_elems, lazy));
         }
     }
     return MKHE_OK;
@@ -875,8 +877,12 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     TRY(poly_pool(ctx, "tensor_ntt", n0 + n1 + 2, ctx->nQ, tn));
     if (nOut + 1 > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_UNSUPPORTED, "too many parties");
 
-    if (hoist0) TRY(decompose_impl(ctx, level, n0, op0 + 1, h0, 0));
-    if (hoist1) TRY(decompose_impl(ctx, level, n1, op1 + 1, h1, 0));
+    // Forms made and consumed inside this op skip the canonical reduction of the NTT outputs: their consumers are the 128-bit
+    // multiply-accumulates (<= 14 terms of < 2^60 * 2^64 fit) and the tensor product's Montgomery multiply, all of which reduce
+    // properly, so every value that leaves the op is the same canonical residue.
+    const bool lazy = ctx->alpha == 1 && beta_of(ctx, level) <= 14;
+    if (hoist0) TRY(decompose_impl(ctx, level, n0, op0 + 1, h0, 0, lazy));
+    if (hoist1) TRY(decompose_impl(ctx, level, n1, op1 + 1, h1, 0, lazy));
     // steps 2-3 (:79-117): x = MForm(sum d_id (.) h0_id), y = MForm(sum b_id (.) h1_id)
     if (p2p) {
         // fused: the partial sums are written straight into their owners' memory, summed there and the results written
@@ -945,7 +951,7 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     }
     // step 6 (:167-178): Decompose(p_id) ; c_id += u [.] p_id ; c_0 += v_id [.] p_id   (the two products of a party share p_id)
     if (m0 > 0) {
-        TRY(decompose_impl(ctx, level, m0, p.data(), hp.data(), 0));
+        TRY(decompose_impl(ctx, level, m0, p.data(), hp.data(), 0, lazy));
         std::vector<Prod> pr;
         for (int t = 0; t < m0; t++) {
             pr.push_back(Prod{{u, nullptr}, {hp[t], nullptr}, out[1 + find_id(nOut, idsOut, ids0[o0[t]])], true});
@@ -1607,8 +1613,9 @@ int mkhe_ckks_mul_relin_sharded(mkhe_ctx *ctx, int level, int nb_rescales, int n
         vb[t] = b->d; vh1[t] = pool1[i];
         in1.push_back(p1[1 + t]);
     }
-    TRY(decompose_impl(ctx, level, (int)in0.size(), in0.data(), pool0.data(), 0));
-    TRY(decompose_impl(ctx, level, (int)in1.size(), in1.data(), pool1.data(), 0));
+    const bool lazy = ctx->alpha == 1 && beta_of(ctx, level) <= 14;       // forms that never leave the op (see mul_relin_hoisted_impl)
+    TRY(decompose_impl(ctx, level, (int)in0.size(), in0.data(), pool0.data(), 0, lazy));
+    TRY(decompose_impl(ctx, level, (int)in1.size(), in1.data(), pool1.data(), 0, lazy));
     // the forms of the owned parties are fresh (made above): the tensor step reads NTT(op_id) from their diagonals; the other
     // parties' components are not completed on this rank, so nothing else has to be transformed
     TRY(mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),

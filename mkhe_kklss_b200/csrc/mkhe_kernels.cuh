@@ -369,6 +369,7 @@ struct Pass2Args {
     int wslot[MKHE_MAX_SLOTS];       // cost of one tile of that slot (16 = a modulus below 2^57; the 59/60-bit ones sweep and cost more)
     long wstart[MKHE_MAX_SLOTS + 1]; // cumulative cost before slot s; wstart[nslots] = total
     u64 magic;                       // an unlikely 64-bit value (anchor in the kernel); equality only costs a nanosleep
+    int lazy_out;                    // store the un-reduced outputs (below 2^64, congruent): for forms that only feed the 128-bit MACs
     int logN;
 #ifdef MKHE_P2_TIMING
     u64 *timing;                     // development builds: per CTA {start ns, end ns, SM id, tiles}
@@ -502,9 +503,14 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
             u64 *o = cur_ptr + tid * 16;
             cur = mail[grp].off;
             cur_ptr = mail[grp].ptr;
+            if (a.lazy_out) {
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                st_global_v4(o + 4 * k, canon(v[4 * k], m), canon(v[4 * k + 1], m), canon(v[4 * k + 2], m), canon(v[4 * k + 3], m));
+                for (int k = 0; k < 4; k++) st_global_v4(o + 4 * k, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    st_global_v4(o + 4 * k, canon(v[4 * k], m), canon(v[4 * k + 1], m), canon(v[4 * k + 2], m), canon(v[4 * k + 3], m));
+            }
         }
     }
 #ifdef MKHE_P2_TIMING
