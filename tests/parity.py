@@ -244,6 +244,29 @@ def check_lanes(w: CKKSWorld, rounds=3, level=None):
                 other.ctx.poly_upload(poly.h, o2.value[kk])
             drot2 = other.RotateNew(d0, rot, w.d_rk)
             pend.append((o0, o1, o2, dout, drot, dsq, drot2))
+    # asynchronous transfers across lanes: lane 0 uploads from pinned memory without waiting, lane 1 consumes at once (it has to
+    # wait for the COPY, not for the call), then lane 0 overwrites the operand while lane 1's download of the result is in flight
+    o3, _ = w.random_ct(ids, level)
+    fresh = mkckks.Ciphertext.new(w.dp, ids, level, w.lit.scale)
+    pins = {}
+    for kk, poly in fresh.Value.items():
+        pins[kk] = ev[0].ctx.host_alloc(o3.value[kk].shape)
+        pins[kk][...] = o3.value[kk]
+        ev[0].ctx.poly_upload_async(poly.h, pins[kk])
+    drot3 = ev[1].RotateNew(fresh, rot, w.d_rk)
+    back = {kk: ev[1].ctx.host_alloc(o3.value[kk].shape) for kk in drot3.Value}
+    for kk, poly in drot3.Value.items():
+        ev[1].ctx.poly_download_async(poly.h, back[kk])
+    o4, _ = w.random_ct(ids, level)
+    for kk, poly in fresh.Value.items():
+        ev[0].ctx.poly_upload(poly.h, o4.value[kk])                      # write-after-read across lanes
+    drot4 = ev[0].RotateNew(fresh, rot, w.d_rk)
+    for e in ev:
+        e.ctx.sync()
+    want3 = w.oev.rotate_new(o3, rot, w.o_rk)
+    for kk in want3.value:
+        assert_same(back[kk], want3.value[kk], f"lanes: asynchronous upload on one lane, use + asynchronous download on the other [{kk}]")
+    w.compare_ct(drot4, w.oev.rotate_new(o4, rot, w.o_rk), "lanes: overwrite after the other lane's read")
     for n, (o0, o1, o2, dout, drot, dsq, drot2) in enumerate(pend):
         oout = w.oev.mul_relin_new(o0, o1, w.o_rlk)
         w.compare_ct(dout, oout, f"lanes[{n}] MulRelinNew")
