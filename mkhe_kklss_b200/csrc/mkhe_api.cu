@@ -608,7 +608,8 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
                     j += G;
                 }
                 if (ng == 0) continue;
-                const dim3 grid(ctx->N / (2 * MKHE_THREADS), s.n, ng);
+                a.ngroups = ng;
+                const dim3 grid(ctx->N / (2 * MKHE_THREADS) * ng, s.n);
                 switch (G) {
                     case 4: LAUNCH(k_mac_digits<4>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(4), a, ctx->d_mods); break;
                     case 3: LAUNCH(k_mac_digits<3>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(3), a, ctx->d_mods); break;
