@@ -463,6 +463,22 @@ def cpu_oracle_run(lit, k, steps, warmup, threads, seed=0xB2000002):
     return steps / dt, cores, dt / steps
 
 
+def oracle_result(lit, k, seed=0xB2000002, pair=0, threads=0):
+    """the checker: MulRelinNew of ciphertext pair `pair` of the timed workload (same seeds as DeviceWorkload) on the oracle"""
+    from oracle import oracle as O
+    O.set_threads(threads or (os.cpu_count() or 1))
+    p = O.MKParams(lit.logN, lit.Q, lit.P, 2, seed=seed, crs_rots=[])
+    hk = host_keys(lit, k, seed)
+    p.CRS[-1] = hk["u"]
+    rl = {i: O.RelinKey(i, *hk["rlk"][i]) for i in range(k)}
+    ev = O.CKKSEvaluator(p, lit.scale)
+    rng = np.random.default_rng(seed + 99)
+    level = len(lit.Q) - 1
+    for _ in range(pair + 1):
+        a, b = host_ct(lit, k, level, rng), host_ct(lit, k, level, rng)
+    return ev.mul_relin_new(O.Ciphertext(a, lit.scale), O.Ciphertext(b, lit.scale), rl).value
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -576,6 +592,19 @@ def main():
     ms_e2e = allmax(wl.timed_wall(e2e_fn, args.steps, warmup, barrier))
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
+    # outputs of the TIMED workload kept for the parity check below (compared with the oracle on the same seeds): the
+    # device-resident result of pair 0 (op 0 runs on lane 0) and the end-to-end path's host landing buffer of pair 0
+    # (op n lands in buffer (n % lanes, (n // lanes) % 2); with 4 pairs and 2 lanes buffer (0, 0) always holds pair 0)
+    parity_got = None
+    if rank == 0 and not args.no_cpu_baseline:
+        wl.sync()
+        wl.mul_relin_op(0, lane=0)
+        wl.sync()
+        nl = wl.level + 1 - wl.nb
+        parity_got = {"device": {kk: wl.ctx.poly_download(p_.h, nl) for kk, p_ in wl.outs[0].Value.items()}}
+        if (2 * len(wl.lanes)) % len(wl.pairs) == 0:
+            parity_got["e2e"] = {kk: np.array(v) for kk, v in wl.res_host[0][0].items()}
+
     # per-kernel profile pass (events around every launch; separate from the timed region above)
     psteps = 8                      # MulRelin ops in the profiled pass
     wl.ctx.profile_begin()
@@ -619,7 +648,12 @@ def main():
         per_launch_bytes = model["kernel_bytes"].get(dom, 0) / max(d["launches_per_step"], 1e-9)
         per_launch_s = d["ms_per_step"] * 1e-3 / max(d["launches_per_step"], 1e-9)
         ach = per_launch_bytes / per_launch_s / 1e9 if per_launch_s else 0.0
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+        int_frac, hbm_frac = d.get("int_frac") or 0.0, ach / hbm_peak
+        int_bound = int_frac > hbm_frac           # the roofline is the larger of the two fractions
+        roofline = {"kernel": dom, "bound": "int" if int_bound else "hbm",
+                    "achieved": d.get("butterflies_per_s") if int_bound else ach, "peak": bfly_peak if int_bound else hbm_peak,
+                    "unit": "butterflies/s" if int_bound else "GB/s", "frac": max(int_frac, hbm_frac),
+                    "hbm": {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac},
                     "traffic": (traffic.get(dom) or {}).get("dram_bytes_per_launch"),
                     "traffic_source": (traffic.get(dom) or {}).get("source"),
                     # the ncu capture is ONE launch (the hoisting of 4 polys); its own algorithmic bytes, for a like-for-like ratio
@@ -683,6 +717,17 @@ def main():
                "sample": f"3 full MulRelinNew calls after 1 warm-up, same workload ({sec:.2f} s each), single thread like the Go reference; "
                          "oracle/ C restatement (the Go reference cannot be built here)"}
 
+    parity_check = None
+    if parity_got is not None:
+        # the checker (oracle/) on the seeds of the timed workload; every limb of every component must be identical
+        want = oracle_result(lit, k, seed=0xB2000002 + rank, pair=0)
+        parity_check = {"config": config["workload"], "oracle": "oracle/ C restatement (checker only)", "compared": {}}
+        for leg, got in parity_got.items():
+            eq = set(map(str, got)) == set(map(str, want)) and all(np.array_equal(got[kk], want[kk]) for kk in want)
+            parity_check["compared"][leg] = bool(eq)
+        parity_check["equal"] = all(parity_check["compared"].values())
+        parity_check["words_compared"] = int(sum(v.size for v in want.values()) * len(parity_got))
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms / args.steps, "ms_per_op": ms / args.steps / B, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -691,7 +736,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io[0], "d2h_bytes_per_step": bytes_io[1],
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches_timed,
-                "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "extra": extra}
+                "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity_check, "kernels": kernels, "extra": extra}
         print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

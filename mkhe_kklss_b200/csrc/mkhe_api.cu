@@ -63,6 +63,8 @@ struct mkhe_ctx {
     size_t ck_snap_bytes = 0;
     int ck_n = 0;
     std::vector<std::string> ck_names;
+    bool l2_hints = true;                 // L2 eviction priorities on the bulk copies of k_mac_intt (MKHE_DEBUG_NO_L2_HINTS switches them off: A/B runs)
+    bool debug_nodiag = false;            // development: transform every tensor operand instead of reading the hoisted diagonal (MKHE_DEBUG_NODIAG, read once)
     bool debug_sync = false;              // development: host-synchronise after every launch (MKHE_DEBUG_SYNC=<n-th context of the process>)
     int num_sms = 148;                    // persistent kernels size their grids from it
     int alpha = 1, beta_max = 0;          // alpha = #P/gamma limbs per digit, beta_max = ceil(nQ/alpha) digits (mkrlwe/params.go:63-71)
@@ -538,16 +540,17 @@ int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *c
 struct Prod {
     u64 *key[2], *hst[2];
     u64 *dst;
-    bool add;
+    bool add;                 // start from dst's current contents (ringQ.AddLvl) instead of zero
+    const u64 *src = nullptr; // start from this poly instead (overrides add); e.g. RotateHoisted's copy of ctIn["0"]
 };
 
-int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &prods) {
+int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &prods, u64 galEl = 0) {
     const int nb = (int)prods.size();
     if (nb == 0) return MKHE_OK;
     const int tiles = ctx->N / MKHE_TILE;
     const Slots s = qp_slots(ctx, levelQ);
-    const int vslot = ctx->dmax;                              // spare limb of every accumulator: the overflow estimate v
-    const size_t qp = (size_t)(ctx->dmax + 1) * ctx->N;
+    const int vslot = ctx->dmax;                              // nP spare limbs of every accumulator: the terms of the overflow estimate v
+    const size_t qp = (size_t)(ctx->dmax + ctx->nP) * ctx->N;
     for (int b0 = 0; b0 < nb; b0 += MKHE_MD_PRODUCTS) {
         const int n = std::min(MKHE_MD_PRODUCTS, nb - b0);
         // targets of this chunk; a target must not straddle chunks (its products are summed by one CTA)
@@ -576,63 +579,63 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
         std::vector<u64 *> bufs(n);
         for (int i = 0; i < n; i++) bufs[i] = accqp + (size_t)i * qp;
 
-        // ---- multiply-accumulate over the digits; neighbours sharing one operand form a group
-        int i = 0;
-        while (i < n) {
-            for (int G = MKHE_MAC_G; G >= 1; G--) {
-                MacDigitsArgs a;
+        // ---- multiply-accumulate over the digits fused with the inverse pass A (k_mac_intt); neighbours sharing one operand
+        //      form a group of two, the rest run as groups of one
+        std::vector<std::pair<int, int>> groups[3];          // groups[G]: (first product, shared side: 1 = key, 0 = hoisted form)
+        for (int i = 0; i < n;) {
+            bool sk = i + 1 < n, sh = i + 1 < n;
+            for (int t = 0; t < nsets && i + 1 < n; t++) {
+                sk = sk && prods[b0 + i + 1].key[t] == prods[b0 + i].key[t];
+                sh = sh && prods[b0 + i + 1].hst[t] == prods[b0 + i].hst[t];
+            }
+            if (sk || sh) { groups[2].push_back({i, sk ? 1 : 0}); i += 2; }
+            else { groups[1].push_back({i, 1}); i += 1; }
+        }
+        for (int G = 2; G >= 1; G--)
+            for (size_t g0 = 0; g0 < groups[G].size(); g0 += MKHE_MI_GROUPS) {
+                const int ng = (int)std::min<size_t>(MKHE_MI_GROUPS, groups[G].size() - g0);
+                MacInttArgs a;
                 memset(&a, 0, sizeof a);
                 a.nsets = nsets;
-                a.magic = 0x9e3779b97f4a7c15ull;
                 a.beta = beta_of(ctx, levelQ);
+                a.ngroups = ng;
                 a.digit_stride = (long)ctx->dmax * ctx->N;
                 a.nslots = s.n;
+                a.galEl = galEl;
                 a.logN = ctx->logN;
                 for (int k = 0; k < s.n; k++) { a.slots[k] = s.slot[k]; a.mods[k] = s.mod[k]; }
-                int ng = 0, j = i;
-                while (j + G <= n && ng < MKHE_MAC_GROUPS) {
+                for (int gi = 0; gi < ng; gi++) {
+                    const int j = groups[G][g0 + gi].first;
+                    const bool sk = groups[G][g0 + gi].second != 0;
                     const Prod &p0 = prods[b0 + j];
-                    bool sk = true, sh = true;
-                    for (int g = 1; g < G; g++)
-                        for (int t = 0; t < nsets; t++) {
-                            sk = sk && prods[b0 + j + g].key[t] == p0.key[t];
-                            sh = sh && prods[b0 + j + g].hst[t] == p0.hst[t];
-                        }
-                    if (!sk && !sh) break;
                     for (int t = 0; t < nsets; t++) {
-                        a.shared[t][ng] = sk ? p0.key[t] : p0.hst[t];
-                        for (int g = 0; g < G; g++) a.priv[t][ng * MKHE_MAC_G + g] = sk ? prods[b0 + j + g].hst[t] : prods[b0 + j + g].key[t];
+                        a.shared[t][gi] = sk ? p0.key[t] : p0.hst[t];
+                        for (int g = 0; g < G; g++) a.priv[t][gi * 2 + g] = sk ? prods[b0 + j + g].hst[t] : prods[b0 + j + g].key[t];
                     }
-                    for (int g = 0; g < G; g++) a.out[ng * MKHE_MAC_G + g] = bufs[j + g];
-                    ng++;
-                    j += G;
+                    for (int g = 0; g < G; g++) a.out[gi * 2 + g] = bufs[j + g];
                 }
-                if (ng == 0) continue;
-                a.ngroups = ng;
-                const dim3 grid(ctx->N / (2 * MKHE_THREADS) * ng, s.n);
-                switch (G) {
-                    case 4: LAUNCH(k_mac_digits<4>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(4), a, ctx->d_mods); break;
-                    case 3: LAUNCH(k_mac_digits<3>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(3), a, ctx->d_mods); break;
-                    case 2: LAUNCH(k_mac_digits<2>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(2), a, ctx->d_mods); break;
-                    default: LAUNCH(k_mac_digits<1>, grid, dim3(MKHE_THREADS), MKHE_MAC_SMEM(1), a, ctx->d_mods); break;
-                }
-                i = j;
-                break;
+                // an operand that several groups of this launch stream (u of every party, a rotation's a, x / y) is worth keeping
+                // in L2; everything else is read exactly once
+                a.l2_hints = ctx->l2_hints ? 1 : 0;
+                for (int gi = 0; gi < ng; gi++)
+                    for (int o = 0; o <= G; o++) {
+                        const u64 *ptr = o == 0 ? a.shared[0][gi] : a.priv[0][gi * 2 + o - 1];
+                        int cnt = 0;
+                        for (int gj = 0; gj < ng; gj++) {
+                            cnt += a.shared[0][gj] == ptr;
+                            for (int g = 0; g < G; g++) cnt += a.priv[0][gj * 2 + g] == ptr;
+                        }
+                        if (cnt > 1) {
+                            if (o == 0) a.shared_multi |= 1u << gi;
+                            else a.priv_multi |= (u64)1 << (2 * gi + o - 1);
+                        }
+                    }
+                const long nunits = (long)s.n * tiles * ng;
+                const dim3 grid((unsigned)std::min<long>(ctx->num_sms, nunits));
+                if (G == 2) LAUNCH(k_mac_intt<2>, grid, dim3(MKHE_MI_THREADS(2)), MKHE_MI_SMEM(2), a, ctx->d_mods, ctx->d_twi_tiled);
+                else LAUNCH(k_mac_intt<1>, grid, dim3(MKHE_MI_THREADS(1)), MKHE_MI_SMEM(1), a, ctx->d_mods, ctx->d_twi_tiled);
             }
-        }
-        // ---- inverse NTT pass A on every QP accumulator
-        for (int k0 = 0; k0 < n; k0 += MKHE_MAX_PARTIES_K) {
-            const int nk = std::min(MKHE_MAX_PARTIES_K, n - k0);
-            InvAArgs a;
-            memset(&a, 0, sizeof a);
-            a.nslots = s.n;
-            a.logN = ctx->logN;
-            a.nbatch = nk;
-            for (int k = 0; k < s.n; k++) { a.slots[k] = s.slot[k]; a.mods[k] = s.mod[k]; }
-            for (int k = 0; k < nk; k++) { a.in.p[k] = bufs[k0 + k]; a.out.p[k] = bufs[k0 + k]; }
-            LAUNCH(k_intt_passA, dim3(tiles, s.n, (nk + MKHE_PA_GROUPS - 1) / MKHE_PA_GROUPS), dim3(MKHE_PA_THREADS), MKHE_PA_SMEM, a, ctx->d_mods, ctx->d_twi_tiled);
-        }
-        // ---- pass B fused with ModDown and the accumulation
+        // ---- pass B fused with ModDown, the accumulation and (rotations) the automorphism
         ModDownPArgs pa;
         memset(&pa, 0, sizeof pa);
         pa.np_limbs = ctx->nP;
@@ -642,7 +645,7 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
         for (int k = 0; k < n; k++) pa.acc[k] = bufs[k];
         TRY(dispatch_s1(ctx, [&](auto S) -> int {
             auto k_moddown_P_ = k_moddown_P<decltype(S)::value>;
-            LAUNCH(k_moddown_P_, dim3(COLGROUPS, n), dim3(MKHE_NTT_THREADS), 0, pa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi);
+            LAUNCH(k_moddown_P_, dim3(COLGROUPS, n, ctx->nP), dim3(MKHE_NTT_THREADS), 0, pa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi);
             return MKHE_OK;
         }));
         for (size_t t0 = 0; t0 < tg.size(); t0 += MKHE_MD_TARGETS) {
@@ -652,11 +655,19 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
             qa.np_limbs = ctx->nP;
             qa.p_slot0 = ctx->nQ;
             qa.vslot = vslot;
+            qa.galEl = galEl;
+            if (galEl) {                 // galEl^-1 mod 2N (2-adic Newton iteration: every step doubles the number of correct bits)
+                const u64 mask = ((u64)2 << ctx->logN) - 1;
+                u64 inv = 1;
+                for (int it = 0; it < 6; it++) inv = (inv * (2 - galEl * inv)) & mask;
+                qa.galInv = inv;
+            }
             qa.logN = ctx->logN;
             int cnt = 0;
             for (int t = 0; t < ntg; t++) {
+                const Prod &p0 = prods[b0 + members[t0 + t][0]];
                 qa.dst[t] = tg[t0 + t];
-                qa.has_acc[t] = prods[b0 + members[t0 + t][0]].add ? 1 : 0;
+                qa.src[t] = p0.src ? p0.src : (p0.add ? tg[t0 + t] : nullptr);
                 qa.first[t] = cnt;
                 for (int m : members[t0 + t]) qa.acc[cnt++] = bufs[m];
             }
@@ -664,11 +675,12 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
             TRY(dispatch_s1(ctx, [&](auto S) -> int {
                 constexpr int s1 = decltype(S)::value;
                 const dim3 grid(COLGROUPS, levelQ + 1, ntg);
+                const size_t rowsm = galEl ? ((size_t)8 << s1) * MKHE_NTT_THREADS : 0;      // the row permutation of a rotation
                 switch (ctx->nP) {
-                    case 1: { auto k_moddown_Q_ = k_moddown_Q<s1, 1>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
-                    case 2: { auto k_moddown_Q_ = k_moddown_Q<s1, 2>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
-                    case 3: { auto k_moddown_Q_ = k_moddown_Q<s1, 3>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
-                    case 4: { auto k_moddown_Q_ = k_moddown_Q<s1, 4>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), 0, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 1: { auto k_moddown_Q_ = k_moddown_Q<s1, 1>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 2: { auto k_moddown_Q_ = k_moddown_Q<s1, 2>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 3: { auto k_moddown_Q_ = k_moddown_Q<s1, 3>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 4: { auto k_moddown_Q_ = k_moddown_Q<s1, 4>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
                     default: return fail(ctx, MKHE_ERR_UNSUPPORTED, "key switch with %d special primes (1..4 supported)", ctx->nP);
                 }
                 return MKHE_OK;
@@ -907,7 +919,7 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
     // diagonal of h_id instead of being transformed again -- the same kernel produced it from the same input, bit for bit.
     {
         Slots qs = q_slots(level);
-        const bool nodiag = getenv("MKHE_DEBUG_NODIAG") != nullptr;
+        const bool nodiag = ctx->debug_nodiag;
         const bool dg0 = fresh0 && ctx->alpha == 1 && !nodiag, dg1 = fresh1 && ctx->alpha == 1 && !nodiag;
         std::vector<u64 *> src, dst;
         src.push_back(op0[0]); dst.push_back(tn[0]);
@@ -1008,16 +1020,30 @@ u64 galois_for_rotation(int logN, int k) {
 int rotate_hoisted_impl(mkhe_ctx *ctx, int level, int rotidx, int n, u64 *const *ct_in, u64 *const *hoisted,
                         u64 *const *rk, u64 *a, u64 *const *out) {
     while (rotidx < 0) rotidx += ctx->N / 2;
+    const u64 galEl = galois_for_rotation(ctx->logN, rotidx);
+    bool alias = false;                   // the permuted store scatters over the whole output: it must not be an input
+    for (int t = 0; t <= n; t++)
+        for (int r = 0; r <= n; r++) alias = alias || out[t] == ct_in[r];
+    std::vector<Prod> pr;
+    if (!alias) {
+        // ctOut["0"] = ctIn["0"] + sum_id rk_id [.] h_id, ctOut[id] = a [.] h_id, each stored through the automorphism by the
+        // ModDown kernel itself (no copy of ctIn["0"], no separate permutation pass)
+        for (int t = 0; t < n; t++) {     // the two products of a party share its hoisted form
+            pr.push_back(Prod{{a, nullptr}, {hoisted[t], nullptr}, out[1 + t], false});
+            pr.push_back(Prod{{rk[t], nullptr}, {hoisted[t], nullptr}, out[0], false, ct_in[0]});
+        }
+        if (n == 0) return automorph_impl(ctx, level, galEl, 1, ct_in, out);
+        return ext_products(ctx, level, 1, pr, galEl);
+    }
     std::vector<u64 *> tmp;
     TRY(poly_pool(ctx, "rot_tmp", n + 1, ctx->nQ, tmp));
     CU(cudaMemcpyAsync(tmp[0], ct_in[0], (size_t)(level + 1) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    std::vector<Prod> pr;
-    for (int t = 0; t < n; t++) {         // the two products of a party share its hoisted form
+    for (int t = 0; t < n; t++) {
         pr.push_back(Prod{{a, nullptr}, {hoisted[t], nullptr}, tmp[1 + t], false});
         pr.push_back(Prod{{rk[t], nullptr}, {hoisted[t], nullptr}, tmp[0], true});
     }
     TRY(ext_products(ctx, level, 1, pr));
-    return automorph_impl(ctx, level, galois_for_rotation(ctx->logN, rotidx), n + 1, tmp.data(), out);
+    return automorph_impl(ctx, level, galEl, n + 1, tmp.data(), out);
 }
 
 }  // namespace
@@ -1087,6 +1113,8 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
         if (e && atoi(e) == created) ctx->debug_sync = true;
         e = getenv("MKHE_DEBUG_CK");
         if (e && atoi(e) == created) ctx->debug_ck = true;
+        ctx->debug_nodiag = getenv("MKHE_DEBUG_NODIAG") != nullptr;
+        ctx->l2_hints = getenv("MKHE_DEBUG_NO_L2_HINTS") == nullptr;
     }
     ctx->root = ctx;
     ctx->lanes.push_back(ctx);
@@ -1113,10 +1141,8 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
 #ifndef MKHE_EMU
     cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PASS2);
     cudaFuncSetAttribute(k_intt_passA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_PA_SMEM);
-    cudaFuncSetAttribute(k_mac_digits<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(1));
-    cudaFuncSetAttribute(k_mac_digits<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(2));
-    cudaFuncSetAttribute(k_mac_digits<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(3));
-    cudaFuncSetAttribute(k_mac_digits<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MAC_SMEM(4));
+    cudaFuncSetAttribute(k_mac_intt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MI_SMEM(1));
+    cudaFuncSetAttribute(k_mac_intt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MI_SMEM(2));
 #endif
     std::vector<int> src, dst;
     for (int j = 0; j < nP; j++) src.push_back(nQ + j);
@@ -1129,6 +1155,14 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     return MKHE_OK;
 }
 
+static void mkhe_ctx_destroy_lane_streams(mkhe_ctx *f) {
+    if (f->stream) cudaStreamDestroy(f->stream);
+    if (f->h2d) cudaStreamDestroy(f->h2d);
+    if (f->d2h) cudaStreamDestroy(f->d2h);
+    if (f->ev_compute) cudaEventDestroy(f->ev_compute);
+    if (f->ev0) cudaEventDestroy(f->ev0);
+    if (f->ev1) cudaEventDestroy(f->ev1);
+}
 // a lane: shares the root's moduli, tables, keys and ciphertext objects (handles are valid on every lane), owns its stream,
 // copy streams and scratch pools.  Ops on different lanes run concurrently on the device; uses of one object on different lanes
 // are ordered automatically (events).  A context and its forks are driven from one host thread at a time.
@@ -1148,6 +1182,8 @@ int mkhe_ctx_fork(mkhe_ctx *parent, mkhe_ctx **out) {
     f->beta_max = root->beta_max; f->d_lift = root->d_lift; f->T = root->T; f->mod = root->mod; f->tabs = root->tabs;
     f->d_mods = root->d_mods; f->d_twf = root->d_twf; f->d_twi = root->d_twi; f->d_twf_tiled = root->d_twf_tiled; f->d_twi_tiled = root->d_twi_tiled;
     f->tables_dirty = false;
+    f->debug_nodiag = root->debug_nodiag;
+    f->l2_hints = root->l2_hints;
     f->d_conv_PtoQ = root->d_conv_PtoQ; f->d_conv_QtoQMul = root->d_conv_QtoQMul; f->d_conv_QMultoQ = root->d_conv_QMultoQ;
     f->h_mformQMul = root->h_mformQMul;
     f->root = root;
@@ -1158,6 +1194,17 @@ int mkhe_ctx_fork(mkhe_ctx *parent, mkhe_ctx **out) {
     cudaEventCreate(&f->ev_compute);
     cudaEventCreate(&f->ev0);
     cudaEventCreate(&f->ev1);
+    // Work queued on the live lanes BEFORE this fork left no per-object use records when the root was alone (the bookkeeping is
+    // skipped with a single lane): the new lane's stream starts after everything enqueued so far on every live lane, so its
+    // first use of any existing object (pending outputs, the memsets of fresh allocations) is ordered after it.
+    for (mkhe_ctx *l : root->lanes) {
+        if (!l) continue;
+        if (cudaEventRecord(l->ev_compute, l->stream) != cudaSuccess || cudaStreamWaitEvent(f->stream, l->ev_compute, 0) != cudaSuccess) {
+            mkhe_ctx_destroy_lane_streams(f);
+            delete f;
+            return fail(parent, MKHE_ERR_CUDA, "fork: ordering the new lane after the live lanes failed");
+        }
+    }
     if ((int)root->lanes.size() <= lane) root->lanes.resize(lane + 1, nullptr);
     root->lanes[lane] = f;
     *out = f;
@@ -1414,7 +1461,8 @@ int mkhe_swk_free(mkhe_ctx *ctx, mkhe_swk h) {
     return MKHE_OK;
 }
 static int swk_limb_off(mkhe_ctx *ctx, int digit, int is_p, int limb, size_t *off) {
-    if (digit < 0 || digit >= ctx->nQ) return fail(ctx, MKHE_ERR_INVALID, "digit %d out of range", digit);
+    // a switching key holds beta_max = ceil(nQ / alpha) digits (keys.go:245-256), not nQ
+    if (digit < 0 || digit >= ctx->beta_max) return fail(ctx, MKHE_ERR_INVALID, "digit %d out of range [0,%d)", digit, ctx->beta_max);
     if (limb < 0 || limb >= (is_p ? ctx->nP : ctx->nQ)) return fail(ctx, MKHE_ERR_INVALID, "limb %d out of range", limb);
     *off = ((size_t)digit * ctx->dmax + (is_p ? ctx->nQ : 0) + limb) * ctx->N;
     return MKHE_OK;
@@ -1423,6 +1471,7 @@ int mkhe_swk_upload_limb(mkhe_ctx *ctx, mkhe_swk h, int digit, int is_p, int lim
     CHECK_CTX();
     SWK(o, h);
     size_t off;
+    if (!src) return fail(ctx, MKHE_ERR_INVALID, "null source buffer");
     TRY(swk_limb_off(ctx, digit, is_p, limb, &off));
     CU(cudaMemcpyAsync(o->d + off, src, (size_t)ctx->N * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1432,6 +1481,7 @@ int mkhe_swk_download_limb(mkhe_ctx *ctx, mkhe_swk h, int digit, int is_p, int l
     CHECK_CTX();
     SWK_R(o, h);
     size_t off;
+    if (!dst) return fail(ctx, MKHE_ERR_INVALID, "null destination buffer");
     TRY(swk_limb_off(ctx, digit, is_p, limb, &off));
     CU(cudaMemcpyAsync(dst, o->d + off, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1440,6 +1490,7 @@ int mkhe_swk_download_limb(mkhe_ctx *ctx, mkhe_swk h, int digit, int is_p, int l
 int mkhe_swk_upload(mkhe_ctx *ctx, mkhe_swk h, const uint64_t *src) {
     CHECK_CTX();
     SWK(o, h);
+    if (!src) return fail(ctx, MKHE_ERR_INVALID, "null source buffer");
     CU(cudaMemcpyAsync(o->d, src, swk_elems(ctx) * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return MKHE_OK;
@@ -1447,6 +1498,7 @@ int mkhe_swk_upload(mkhe_ctx *ctx, mkhe_swk h, const uint64_t *src) {
 int mkhe_swk_download(mkhe_ctx *ctx, mkhe_swk h, uint64_t *dst) {
     CHECK_CTX();
     SWK_R(o, h);
+    if (!dst) return fail(ctx, MKHE_ERR_INVALID, "null destination buffer");
     CU(cudaMemcpyAsync(dst, o->d, swk_elems(ctx) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return MKHE_OK;
@@ -1458,6 +1510,9 @@ int mkhe_ntt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out) {
     POLY_R(i, in);
     POLY(o, out);
     if (level < 0 || level >= i->cap_limbs || level >= o->cap_limbs) return fail(ctx, MKHE_ERR_INVALID, "level %d out of range", level);
+    // level >= nQ selects the BFV ring R = Q u QMul (2 nQ limbs): both polys must hold all of them
+    if (level >= ctx->nQ && (ctx->nQMul == 0 || i->cap_limbs < 2 * ctx->nQ || o->cap_limbs < 2 * ctx->nQ))
+        return fail(ctx, MKHE_ERR_INVALID, "level %d: a transform over R = Q u QMul needs BFV parameters and polys of %d limbs", level, 2 * ctx->nQ);
     Slots s = (level >= ctx->nQ) ? r_slots(ctx) : q_slots(level);
     return ntt_fwd(ctx, s, 1, &i->d, &o->d);
 }
@@ -1466,6 +1521,9 @@ int mkhe_intt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out) {
     POLY_R(i, in);
     POLY(o, out);
     if (level < 0 || level >= i->cap_limbs || level >= o->cap_limbs) return fail(ctx, MKHE_ERR_INVALID, "level %d out of range", level);
+    // level >= nQ selects the BFV ring R = Q u QMul (2 nQ limbs): both polys must hold all of them
+    if (level >= ctx->nQ && (ctx->nQMul == 0 || i->cap_limbs < 2 * ctx->nQ || o->cap_limbs < 2 * ctx->nQ))
+        return fail(ctx, MKHE_ERR_INVALID, "level %d: a transform over R = Q u QMul needs BFV parameters and polys of %d limbs", level, 2 * ctx->nQ);
     Slots s = (level >= ctx->nQ) ? r_slots(ctx) : q_slots(level);
     return ntt_inv(ctx, s, 1, &i->d, &o->d);
 }

@@ -27,11 +27,16 @@ __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ void prefetch_l2(const void *) {}
 // TMA bulk copies complete at issue under emulation; the mbarrier keeps its transaction count and phase, so a waiter
 // really waits for the thread that issues the copy
-__device__ __forceinline__ void mbar_init(u64 *bar, int) { emu_mbar_init(bar); }
+__device__ __forceinline__ void mbar_init(u64 *bar, int count) { emu_mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_arrive(u64 *bar) { emu_mbar_arrive(bar); }
+__device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) { emu_mbar_expect_tx(bar, bytes); }
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { emu_mbar_wait(bar, parity); }
 __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *bar) { memcpy(smem, gmem, bytes); emu_mbar_complete_tx(bar, bytes); }
 __device__ __forceinline__ void named_sync(int id, int nthreads) { emu_barrier(id, nthreads); }
+__device__ __forceinline__ u64 l2_policy_evict_first() { return 0; }
+__device__ __forceinline__ u64 l2_policy_evict_last() { return 0; }
+__device__ __forceinline__ void tma_load_1d_hint(void *smem, const void *gmem, u32 bytes, u64 *bar, u64) { memcpy(smem, gmem, bytes); emu_mbar_complete_tx(bar, bytes); }
 __device__ __forceinline__ void consume16(const u64 *) {}
 __device__ __forceinline__ void consume4(u64, u64, u64, u64) {}
 __device__ __forceinline__ void anchor_side_effect() {}
@@ -52,6 +57,14 @@ __device__ __forceinline__ void mbar_init(u64 *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 }
+// consumer -> producer: one arrival on an "empty" barrier.  The default .release semantics order the thread's earlier
+// shared-memory reads of the stage before the arrival, so a producer that has observed the completed phase (try_wait,
+// .acquire) may let the TMA engine overwrite the stage.
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// generic-proxy writes (st.global / st.shared) before, async-proxy (TMA) reads of the same bytes after
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile(
@@ -81,6 +94,16 @@ __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      (unsigned)__cvta_generic_to_shared(smem)),
                  "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+// L2 eviction priorities for the bulk copies: a stream that is read exactly once (keys, hoisted forms) should not push out what
+// other CTAs are about to read again (an operand common to several product groups, the twiddle tables)
+__device__ __forceinline__ u64 l2_policy_evict_first() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u64 l2_policy_evict_last() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void tma_load_1d_hint(void *smem, const void *gmem, u32 bytes, u64 *bar, u64 policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
@@ -145,6 +168,13 @@ __device__ __forceinline__ void mac128(u64 &hi, u64 &lo, u64 a, u64 b) {
     hi += ph + (lo < pl ? 1ull : 0ull);
 }
 
+
+// acc += a*b on a 128-bit accumulator; the compiler's __int128 lowering chains IMAD.WIDE with carries (about 12 instructions
+// per product, against 19 for mul.lo + mul.hi + a compare-and-select carry)
+typedef unsigned __int128 u128;
+__device__ __forceinline__ void mac128w(u128 &acc, u64 a, u64 b) { acc += (u128)a * b; }
+__device__ __forceinline__ u64 hi64(u128 x) { return (u64)(x >> 64); }
+__device__ __forceinline__ u64 lo64(u128 x) { return (u64)x; }
 
 // ------------------------------------------------------------------------------------------------
 // 32-bit building blocks.  Measured on B200 (tools/ubench, profiles/r01b_ubench_raw.txt): IMAD.WIDE.U32 and

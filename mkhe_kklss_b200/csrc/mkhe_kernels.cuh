@@ -524,95 +524,174 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3  digit multiply-accumulate, streaming:  O_g = sum_{set} sum_{i<beta} S[set][i] (.) P_g[set][i]
-//   (MulCoeffsMontgomery[AndAdd]Lvl loops of mkrlwe/keyswitch_hoisted.go:24-32; two sets for
-//   mkbfv/keyswitch_hoisted.go:20-30).  A group = one shared swk-shaped operand S (x, y, a hoisted form ...)
-//   against G private ones, so the shared stream is read once for G products.  Raw 128-bit accumulation
-//   (<= 256 terms of < 2^120), one Montgomery reduction at the end: the same canonical value as the reference's
-//   reduce-every-term loop.  Output: limb `slot` of out[g] in NTT order, canonical.
-//   grid = (N/512 * ngroups, nslots), 2 adjacent coefficients per thread; operands staged by TMA bulk copies.
+// K3+K2  digit multiply-accumulate FUSED with the inverse pass A:  acc_g = sum_{set} sum_{i<beta} S[set][i] (.) P_g[set][i]
+//   (MulCoeffsMontgomery[AndAdd]Lvl loops of mkrlwe/keyswitch_hoisted.go:24-32; two sets for mkbfv/keyswitch_hoisted.go:20-30),
+//   one Montgomery reduction, then the first 11 Gentleman-Sande stages of InvNTT[Lazy]Lvl (:34-35) on the accumulator tile while
+//   it is still on chip -- the integer work of the transform hides under a kernel that is bound by the key / hoisted-form stream.
+//
+//   Persistent, ONE CTA per SM, warp specialised:
+//     * G consumer groups of 128 threads: group g owns product g of the unit (shared operand S against its private operand P_g).
+//     * one producer warp (one elected lane) that only issues TMA bulk copies.
+//   A unit = (group of G products, limb slot, tile of 2048 coefficients).  Units are dealt round robin over the CTAs with the
+//   product group varying fastest, so the CTAs that stream a common operand (the CRS entry u of every party's products, a
+//   rotation's a, x or y of MulRelin) touch the same tile of it at the same time and it comes from DRAM once.
+//   Stages of the ring: (G+1) boxes of 16 KiB = the 2048-coefficient tile of S and of every P_g for one term (set, digit).
+//   Synchronisation is a full/empty mbarrier pair per stage:
+//     producer: wait empty[st] (phase parity) -> mbarrier.arrive.expect_tx full[st] -> cp.async.bulk x (G+1)
+//     consumer: wait full[st] -> ld.shared of the stage + MACs -> mbarrier.arrive empty[st] (release: after its last read)
+//   The 2047 inverse twiddles of the unit's (modulus, tile) travel the same way (tw_full / tw_empty), requested after the unit's
+//   last term so that the producer never waits for pass A of the previous unit while it could prefetch.
+//   Output: pass-A values (< 4q) of limb `slot` of out[g], as k_intt_passA leaves them for the ModDown kernels.
 // ------------------------------------------------------------------------------------------------
-#define MKHE_MAC_GROUPS 16
-#define MKHE_MAC_G 4
-struct MacDigitsArgs {
-    const u64 *shared[2][MKHE_MAC_GROUPS];
-    const u64 *priv[2][MKHE_MAC_GROUPS * MKHE_MAC_G];
-    u64 *out[MKHE_MAC_GROUPS * MKHE_MAC_G];
+#define MKHE_MI_GROUPS 32                                       // product groups per launch
+#define MKHE_MI_BOX (MKHE_TILE * 8)                              // bytes of one operand tile
+#define MKHE_MI_STAGES(G) ((G) == 1 ? 4 : 3)
+#define MKHE_MI_THREADS(G) (2 * (G) * MKHE_NTT_THREADS + 32)
+#define MKHE_MI_NBARS(G) (2 * MKHE_MI_STAGES(G) + 2 + 2 * (G))
+#define MKHE_MI_SMEM(G) (MKHE_TILE * 16 + MKHE_MI_STAGES(G) * ((G) + 1) * MKHE_MI_BOX + (G) * MKHE_XBUF * 8 + 8 * MKHE_MI_NBARS(G))
+struct MacInttArgs {
+    const u64 *shared[2][MKHE_MI_GROUPS];
+    const u64 *priv[2][MKHE_MI_GROUPS * 2];
+    u64 *out[MKHE_MI_GROUPS * 2];
     int nsets, beta, ngroups;
-    u64 magic;               // an unlikely 64-bit value (see the anchor in the kernel); equality only costs a nanosleep
     long digit_stride;       // dmax * N
     int nslots;
     int slots[MKHE_MAX_SLOTS];
     int mods[MKHE_MAX_SLOTS];
+    u64 galEl;               // != 0 (RotateHoisted): the columns of every tile are stored permuted, x -> x * galEl mod 2048 (see k_moddown_Q)
+    unsigned shared_multi;   // bit grp: the group's shared operand is also streamed by another group of the launch
+    u64 priv_multi;          // bit 2 grp + g: the same for the group's private operand g
+    int l2_hints;            // use the two masks for L2 eviction priorities (evict_last for common operands, evict_first for the rest)
     int logN;
 };
-#define MKHE_MAC_STAGES 4
-#define MKHE_MAC_TILE (2 * MKHE_THREADS)                       // coefficients per CTA: one 4 KiB TMA box per operand and digit
-#define MKHE_MAC_SMEM(G) (MKHE_MAC_STAGES * ((G) + 1) * MKHE_MAC_TILE * 8 + MKHE_MAC_STAGES * 8)
 template <int G>
-__global__ void __launch_bounds__(MKHE_THREADS) k_mac_digits(MacDigitsArgs a, const ModC *mods) {
+__global__ void __launch_bounds__(MKHE_MI_THREADS(G), 1) k_mac_intt(MacInttArgs a, const ModC *mods, const ulonglong2 *tiled_inv) {
     MKHE_SMEM(smraw);
-    constexpr int BOX = MKHE_MAC_TILE * 8;                     // bytes per operand and stage
-    u64 *bars = reinterpret_cast<u64 *>(smraw + MKHE_MAC_STAGES * (G + 1) * BOX);
+    constexpr int NS = MKHE_MI_STAGES(G), BOX = MKHE_MI_BOX, STAGE = (G + 1) * BOX, NG = G * MKHE_NTT_THREADS;
+    ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw);                                   // 32 KiB inverse twiddles of the unit
+    unsigned char *ring = smraw + MKHE_TILE * 16;
+    unsigned char *xb = ring + NS * STAGE;
+    u64 *full = reinterpret_cast<u64 *>(xb + G * MKHE_XBUF * 8), *empty = full + NS, *tw_full = empty + NS, *tw_empty = tw_full + 1;
+    u64 *ho_full = tw_empty + 1, *ho_empty = ho_full + G;        // hand-over of a product's accumulator tile: MAC group -> transform group
     const long N = 1L << a.logN;
-    // the group index varies fastest over the grid: groups that stream the same private operand (the CRS entry u of every
-    // party's products, a rotation's `a`) touch the same 4 KiB of it at about the same time, so it comes from DRAM once
-    // (measured before: 702 MB per launch for 4 parties instead of the 528 MB that are compulsory)
-    const int tid = threadIdx.x, grp = blockIdx.x % a.ngroups, slot = a.slots[blockIdx.y];
-    const ModC m = mods[a.mods[blockIdx.y]];
-    const long off = (long)slot * N + (long)(blockIdx.x / a.ngroups) * MKHE_MAC_TILE;
+    const int ntiles = (int)(N / MKHE_TILE);
     const int nterms = a.nsets * a.beta;
-    // the operand tiles of term (set, digit) arrive by TMA in a ring of MKHE_MAC_STAGES stages
-    auto issue = [&](int term) {
-        const int st = term % MKHE_MAC_STAGES, t = term / a.beta, i = term - t * a.beta;
-        const long d = (long)i * a.digit_stride + off;
-        unsigned char *dst = smraw + st * (G + 1) * BOX;
-        mbar_expect_tx(&bars[st], (G + 1) * BOX);
-        tma_load_1d(dst, a.shared[t][grp] + d, BOX, &bars[st]);
-#pragma unroll
-        for (int g = 0; g < G; g++) tma_load_1d(dst + (1 + g) * BOX, a.priv[t][grp * MKHE_MAC_G + g] + d, BOX, &bars[st]);
-    };
-    if (tid == 0) {
-        for (int st = 0; st < MKHE_MAC_STAGES; st++) mbar_init(&bars[st], 1);
+    const int nunits = a.nslots * ntiles * a.ngroups;
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < NS; st++) { mbar_init(&full[st], 1); mbar_init(&empty[st], NG); }
+        mbar_init(tw_full, 1);
+        mbar_init(tw_empty, NG);
+        for (int g = 0; g < G; g++) { mbar_init(&ho_full[g], MKHE_NTT_THREADS); mbar_init(&ho_empty[g], MKHE_NTT_THREADS); }
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int t = 0; t < MKHE_MAC_STAGES && t < nterms; t++) issue(t);
-    }
-    u64 hi[G][2], lo[G][2];
+    const int tid = threadIdx.x & (MKHE_NTT_THREADS - 1);
+    if (threadIdx.x >= 2 * NG) {
+        // ---- producer warp: one lane issues every copy of the CTA
+        if (threadIdx.x != 2 * NG) return;
+        const u64 pol_once = l2_policy_evict_first(), pol_again = l2_policy_evict_last();
+        unsigned T = 0, nu = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x, nu++) {
+            const int grp = u % a.ngroups, r = u / a.ngroups, tile = r % ntiles, sidx = r / ntiles;
+            const long off = (long)a.slots[sidx] * N + (long)tile * MKHE_TILE;
+            const u64 pol_s = (a.shared_multi >> grp) & 1 ? pol_again : pol_once;
+            u64 pol_p[G];
 #pragma unroll
-    for (int g = 0; g < G; g++) hi[g][0] = hi[g][1] = lo[g][0] = lo[g][1] = 0;
-    for (int term = 0; term < nterms; term++) {
-        const int st = term % MKHE_MAC_STAGES;
-        mbar_wait(&bars[st], (term / MKHE_MAC_STAGES) & 1);
-        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(smraw + st * (G + 1) * BOX) + tid;
-        const ulonglong2 s = src[0];
-        ulonglong2 p[G];
+            for (int g = 0; g < G; g++) pol_p[g] = (a.priv_multi >> (2 * grp + g)) & 1 ? pol_again : pol_once;
+            for (int term = 0; term < nterms; term++, T++) {
+                const int st = T % NS, t = term / a.beta, i = term - t * a.beta;
+                mbar_wait(&empty[st], ((T / NS) & 1) ^ 1);                  // passes at once for the first NS fills
+                const long d = (long)i * a.digit_stride + off;
+                unsigned char *dst = ring + st * STAGE;
+                mbar_expect_tx(&full[st], STAGE);
+                if (a.l2_hints) {
+                    tma_load_1d_hint(dst, a.shared[t][grp] + d, BOX, &full[st], pol_s);
 #pragma unroll
-        for (int g = 0; g < G; g++) p[g] = src[(1 + g) * MKHE_THREADS];
+                    for (int g = 0; g < G; g++) tma_load_1d_hint(dst + (1 + g) * BOX, a.priv[t][grp * 2 + g] + d, BOX, &full[st], pol_p[g]);
+                } else {
+                    tma_load_1d(dst, a.shared[t][grp] + d, BOX, &full[st]);
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            mac128(hi[g][0], lo[g][0], s.x, p[g].x);
-            mac128(hi[g][1], lo[g][1], s.y, p[g].y);
+                    for (int g = 0; g < G; g++) tma_load_1d(dst + (1 + g) * BOX, a.priv[t][grp * 2 + g] + d, BOX, &full[st]);
+                }
+            }
+            // the unit's twiddles are needed only after its last term; the previous unit's pass A (the last reader of the
+            // twiddle buffer) ran beside this unit's terms and is long over, so this wait does not block
+            mbar_wait(tw_empty, (nu & 1) ^ 1);
+            mbar_expect_tx(tw_full, MKHE_TILE * 16);
+            tma_load_1d(stw, tiled_inv + ((long)a.mods[sidx] * ntiles + tile) * MKHE_TILE, MKHE_TILE * 16, tw_full);
         }
-        // the accumulators depend on every value read from stage st: anchoring them before the barrier guarantees the
-        // shared-memory loads have completed before thread 0 lets the TMA (async proxy) overwrite the stage
-#pragma unroll
-        for (int g = 0; g < G; g++) consume4(hi[g][0], lo[g][0], hi[g][1], lo[g][1]);
-        {   // a side effect predicated on the accumulators: the shared-memory loads behind them HAVE returned before the barrier
-            u64 chk = 0;
-#pragma unroll
-            for (int g = 0; g < G; g++) chk ^= lo[g][0] + hi[g][1] + (lo[g][1] ^ hi[g][0]);
-            if (chk == a.magic) anchor_side_effect();
-        }
-        __syncthreads();                                   // every thread has read stage st
-        if (tid == 0 && term + MKHE_MAC_STAGES < nterms) issue(term + MKHE_MAC_STAGES);
+        return;
     }
+    if (threadIdx.x < NG) {
+        // ---- multiply-accumulate groups: group g accumulates product g of every unit and hands the reduced tile over
+        const int g = threadIdx.x / MKHE_NTT_THREADS;
+        u64 *xbuf = reinterpret_cast<u64 *>(xb) + g * MKHE_XBUF;
+        unsigned T = 0, nu = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x, nu++) {
+            const int sidx = (u / a.ngroups) / ntiles;
+            const ModC m = mods[a.mods[sidx]];
+            u128 acc[16];
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-        const u64 h0 = csub(barrett_lazy(hi[g][0], m.q, m.mu), m.q), h1 = csub(barrett_lazy(hi[g][1], m.q, m.mu), m.q);
-        *reinterpret_cast<ulonglong2 *>(a.out[grp * MKHE_MAC_G + g] + off + 2 * tid) =
-            make_ulonglong2(mont_reduce(h0, lo[g][0], m.q, m.qinv), mont_reduce(h1, lo[g][1], m.q, m.qinv));
+            for (int k = 0; k < 16; k++) acc[k] = 0;
+            for (int term = 0; term < nterms; term++, T++) {
+                const int st = T % NS;
+                mbar_wait(&full[st], (T / NS) & 1);
+                const ulonglong2 *sS = reinterpret_cast<const ulonglong2 *>(ring + st * STAGE) + tid;
+                const ulonglong2 *sP = sS + (1 + g) * (MKHE_TILE / 2);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {                    // coefficients 2 (128 j + tid) and + 1: conflict-free 16-byte reads
+                    const ulonglong2 sv = sS[j * MKHE_NTT_THREADS], pv = sP[j * MKHE_NTT_THREADS];
+                    mac128w(acc[2 * j], sv.x, pv.x);
+                    mac128w(acc[2 * j + 1], sv.y, pv.y);
+                }
+                mbar_arrive(&empty[st]);                         // after this thread's last read of the stage
+            }
+            // one reduction per coefficient (the same canonical value as the reference's reduce-every-term loop), stored where the
+            // transform's layout C expects it (thread t holds elements 16 t + k; exchange map 2 of the tile rounds)
+            mbar_wait(&ho_empty[g], (nu & 1) ^ 1);               // the transform group has left the exchange buffer (previous unit)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = 2 * (j * MKHE_NTT_THREADS + tid);
+                u64 *dstp = xbuf + idx + (idx >> 4);
+                dstp[0] = mont_reduce(csub(barrett_lazy(hi64(acc[2 * j]), m.q, m.mu), m.q), lo64(acc[2 * j]), m.q, m.qinv);
+                dstp[1] = mont_reduce(csub(barrett_lazy(hi64(acc[2 * j + 1]), m.q, m.mu), m.q), lo64(acc[2 * j + 1]), m.q, m.qinv);
+            }
+            mbar_arrive(&ho_full[g]);
+        }
+        return;
+    }
+    // ---- transform groups: inverse pass A of product g's tile, beside the multiply-accumulates of the next unit
+    {
+        const int g = (threadIdx.x - NG) / MKHE_NTT_THREADS;
+        u64 *xbuf = reinterpret_cast<u64 *>(xb) + g * MKHE_XBUF;
+        const XAddr x(xbuf, tid);
+        const TwShared tw(stw, tid);
+        unsigned nu = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x, nu++) {
+            const int grp = u % a.ngroups, r = u / a.ngroups, tile = r % ntiles, sidx = r / ntiles;
+            const ModC m = mods[a.mods[sidx]];
+            u64 v[16];
+            mbar_wait(&ho_full[g], nu & 1);
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = x.c2[k];
+            mbar_wait(tw_full, nu & 1);
+            tile_inv(v, x, tw, nttc(m), 1 + g);
+            mbar_arrive(tw_empty);                               // after this thread's last twiddle read
+            if (a.galEl) {
+                // Rotation: X -> X^galEl sends coefficient i = x + 2048 row to (x galEl mod 2048) + 2048 row' (+ a sign): columns go
+                // to columns.  The column part of the permutation is applied here, on chip, so that the ModDown kernel reads AND
+                // writes whole columns contiguously; pass B does not care (every column uses the same twiddles).
+                named_sync(1 + g, MKHE_NTT_THREADS);             // every thread has read its pass-A values from the buffer
+#pragma unroll
+                for (int k = 0; k < 16; k++) xbuf[((u64)(k * 128 + tid) * a.galEl) & (MKHE_TILE - 1)] = v[k];
+                named_sync(1 + g, MKHE_NTT_THREADS);
+#pragma unroll
+                for (int k = 0; k < 16; k++) v[k] = xbuf[k * 128 + tid];
+            }
+            mbar_arrive(&ho_empty[g]);                           // ... and its last access to the exchange buffer
+            u64 *o = a.out[grp * 2 + g] + (long)a.slots[sidx] * N + (long)tile * MKHE_TILE;
+#pragma unroll
+            for (int k = 0; k < 16; k++) o[k * 128 + tid] = v[k];
+        }
     }
 }
 
@@ -703,19 +782,19 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_mac_parties(MacPartiesArgs a, 
     const int digit = blockIdx.z, slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
     const ModC m = mods[mi];
     const long off = ((long)digit * a.dmax + slot) * N + ((long)blockIdx.x * MKHE_THREADS + threadIdx.x) * 2;
-    u64 hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
+    u128 a0 = 0, a1 = 0;
     for (int t = 0; t < a.nparties; t++) {
         ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(a.key.p[t] + off);
         ulonglong2 hh = *reinterpret_cast<const ulonglong2 *>(a.hst.p[t] + off);
-        mac128(hi0, lo0, kk.x, hh.x);
-        mac128(hi1, lo1, kk.y, hh.y);
-        if ((t & 7) == 7) {
-            hi0 = csub(barrett_lazy(hi0, m.q, m.mu), m.q);
-            hi1 = csub(barrett_lazy(hi1, m.q, m.mu), m.q);
+        mac128w(a0, kk.x, hh.x);
+        mac128w(a1, kk.y, hh.y);
+        if ((t & 7) == 7) {                    // keep the high words below q: 8 more products of < 2^124 fit
+            a0 = ((u128)csub(barrett_lazy(hi64(a0), m.q, m.mu), m.q) << 64) | lo64(a0);
+            a1 = ((u128)csub(barrett_lazy(hi64(a1), m.q, m.mu), m.q) << 64) | lo64(a1);
         }
     }
-    hi0 = csub(barrett_lazy(hi0, m.q, m.mu), m.q);
-    hi1 = csub(barrett_lazy(hi1, m.q, m.mu), m.q);
+    const u64 hi0 = csub(barrett_lazy(hi64(a0), m.q, m.mu), m.q), lo0 = lo64(a0);
+    const u64 hi1 = csub(barrett_lazy(hi64(a1), m.q, m.mu), m.q), lo1 = lo64(a1);
     u64 r0 = mred(mont_reduce(hi0, lo0, m.q, m.qinv), m.r2, m.q, m.qinv);
     u64 r1 = mred(mont_reduce(hi1, lo1, m.q, m.qinv), m.r2, m.q, m.qinv);
     *reinterpret_cast<ulonglong2 *>(a.out + off) = make_ulonglong2(r0, r1);
@@ -745,19 +824,19 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_mac_parties_scatter(MacParties
     const ModC m = mods[mi];
     const long c = ((long)blockIdx.x * MKHE_THREADS + threadIdx.x) * 2;
     const long off = ((long)digit * a.dmax + slot) * N + c;
-    u64 hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
+    u128 a0 = 0, a1 = 0;
     for (int t = 0; t < a.nparties; t++) {
         ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(a.key.p[t] + off);
         ulonglong2 hh = *reinterpret_cast<const ulonglong2 *>(a.hst.p[t] + off);
-        mac128(hi0, lo0, kk.x, hh.x);
-        mac128(hi1, lo1, kk.y, hh.y);
-        if ((t & 7) == 7) {
-            hi0 = csub(barrett_lazy(hi0, m.q, m.mu), m.q);
-            hi1 = csub(barrett_lazy(hi1, m.q, m.mu), m.q);
+        mac128w(a0, kk.x, hh.x);
+        mac128w(a1, kk.y, hh.y);
+        if ((t & 7) == 7) {                    // keep the high words below q: 8 more products of < 2^124 fit
+            a0 = ((u128)csub(barrett_lazy(hi64(a0), m.q, m.mu), m.q) << 64) | lo64(a0);
+            a1 = ((u128)csub(barrett_lazy(hi64(a1), m.q, m.mu), m.q) << 64) | lo64(a1);
         }
     }
-    hi0 = csub(barrett_lazy(hi0, m.q, m.mu), m.q);
-    hi1 = csub(barrett_lazy(hi1, m.q, m.mu), m.q);
+    const u64 hi0 = csub(barrett_lazy(hi64(a0), m.q, m.mu), m.q), lo0 = lo64(a0);
+    const u64 hi1 = csub(barrett_lazy(hi64(a1), m.q, m.mu), m.q), lo1 = lo64(a1);
     const u64 r0 = mred(mont_reduce(hi0, lo0, m.q, m.qinv), m.r2, m.q, m.qinv);
     const u64 r1 = mred(mont_reduce(hi1, lo1, m.q, m.qinv), m.r2, m.q, m.qinv);
     const long seg = N / p.nranks;
@@ -856,15 +935,16 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_conv(ConvArgs a, const ConvTab
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2+K4  tail of the key switch: InvNTT pass B fused with ModDownQPtoQ and the accumulation into the target
-//   (mkrlwe/keyswitch_hoisted.go:34-39, basis_extension.go:192-232 with the P -> Q lift of :337-357,537-646).
-//   Works on the per-product QP accumulators after pass A; slot `vslot` of each accumulator is spare.
-//   k_moddown_P : per product, P limbs only: pass B, then y_i = x_i * (P/p_i)^-1 mod p_i in place of limb nQ+i and the
-//                 fp64 overflow estimate v (same operation order as reconstructRNS) into slot `vslot`.
-//                 grid = (16, nproducts)
-//   k_moddown_Q : per target poly and Q limb j: for every product of the target: pass B of limb j, lift of the P part
-//                 (multSum, lazy value reproduced), (lift - x) * -P^-1, exact adds into the target.
-//                 grid = (16, level+1, ntargets)
+// K2+K4  tail of the key switch: InvNTT pass B fused with ModDownQPtoQ, the accumulation into the target and (for rotations)
+//   the automorphism  (mkrlwe/keyswitch_hoisted.go:34-39,217-245, basis_extension.go:192-232 with the P -> Q lift of
+//   :337-357,537-646).  Works on the per-product QP accumulators after pass A; every accumulator has nP spare limb slots.
+//   k_moddown_P : per product and P limb i: pass B, then y_i = x_i * (P/p_i)^-1 mod p_i in place of limb nQ+i, and the term
+//                 fl(fl(y_i) / fl(p_i)) of the fp64 overflow estimate into spare slot i (reconstructRNS adds exactly these
+//                 terms, in limb order, RN).  grid = (16, nproducts, nP)
+//   k_moddown_Q : per target poly and Q limb j: for every product of the target: pass B of limb j, v = trunc(sum of the terms),
+//                 lift of the P part (multSum, lazy value reproduced), (lift - x) * -P^-1, exact adds onto `src` (the target's
+//                 current contents, another poly, or zero); the result is stored through X -> X^galEl with the reference's
+//                 unreduced negation when galEl != 0.  grid = (16, level+1, ntargets)
 // ------------------------------------------------------------------------------------------------
 #define MKHE_MD_TARGETS 66
 #define MKHE_MD_PRODUCTS 132
@@ -878,43 +958,37 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_P(ModDownPArgs a, 
     constexpr int E = 1 << S1;
     const ConvTable &tab = *tabp;
     const long N = 1L << a.logN;
-    const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x;
+    const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x, i = blockIdx.z;
     u64 *base = a.acc[blockIdx.y] + col;
-    double vi[E];
+    const int mi = tab.src_mod[i];
+    const ModC m = mods[mi];
+    u64 *p = base + (long)(a.p_slot0 + i) * N;
+    u64 v[E];
 #pragma unroll
-    for (int k = 0; k < E; k++) vi[k] = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < a.np_limbs; i++) {
-        const int mi = tab.src_mod[i];
-        const ModC m = mods[mi];
-        u64 *p = base + (long)(a.p_slot0 + i) * N;
-        u64 v[E];
+    for (int k = 0; k < E; k++) v[k] = ld_cg(p + (long)k * MKHE_TILE);
+    cols_inv<S1>(v, twi + (long)mi * N, nttc(m), m);
+    const u64 f = tab.qoverqiinvqi[i];
+    u64 *vp = base + (long)(a.vslot + i) * N;
 #pragma unroll
-        for (int k = 0; k < E; k++) v[k] = ld_cg(p + (long)k * MKHE_TILE);
-        cols_inv<S1>(v, twi + (long)mi * N, nttc(m), m);
-        const u64 f = tab.qoverqiinvqi[i];
-#pragma unroll
-        for (int k = 0; k < E; k++) {
-            const u64 y = mred(v[k], f, m.q, m.qinv);
-            vi[k] = __dadd_rn(vi[k], __ddiv_rn(__ull2double_rn(y), m.qd));
-            p[(long)k * MKHE_TILE] = y;
-        }
+    for (int k = 0; k < E; k++) {
+        const u64 y = mred(v[k], f, m.q, m.qinv);
+        p[(long)k * MKHE_TILE] = y;
+        vp[(long)k * MKHE_TILE] = (u64)__double_as_longlong(__ddiv_rn(__ull2double_rn(y), m.qd));
     }
-    u64 *vp = base + (long)a.vslot * N;
-#pragma unroll
-    for (int k = 0; k < E; k++) vp[(long)k * MKHE_TILE] = __double2ull_rz(vi[k]);
 }
 
 struct ModDownQArgs {
     u64 *dst[MKHE_MD_TARGETS];
-    int has_acc[MKHE_MD_TARGETS];          // start from the target's current contents (AddLvl) or from zero
+    const u64 *src[MKHE_MD_TARGETS];       // the sum starts from this poly (AddLvl onto the target or onto another poly); nullptr = zero
     int first[MKHE_MD_TARGETS + 1];        // products of target t: acc[first[t]] .. acc[first[t+1]-1]
     const u64 *acc[MKHE_MD_PRODUCTS];
     int np_limbs, p_slot0, vslot;
+    u64 galEl, galInv;                     // != 0 (RotateHoisted): the result goes through X -> X^galEl; the accumulators arrive with
+                                           // their columns already permuted (k_mac_intt); galInv = galEl^-1 mod 2N
     int logN;
 };
 template <int S1, int NP>
-__global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_Q(ModDownQArgs a, const ConvTable *tabp, const ModC *mods, const ulonglong2 *twi) {
+__global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown_Q(ModDownQArgs a, const ConvTable *tabp, const ModC *mods, const ulonglong2 *twi) {
     constexpr int E = 1 << S1, HB = E < 8 ? E : 8;
     const ConvTable &tab = *tabp;
     const long N = 1L << a.logN;
@@ -927,11 +1001,14 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_Q(ModDownQArgs a, 
 #pragma unroll
     for (int i = 0; i <= NP; i++) vq[i] = tab.vtimesqmodp[j][i];
     const u64 md = tab.moddown[j];
-    u64 *dst = a.dst[t] + (long)j * N + col;
+    // with an automorphism this thread works on stored column `col` = original column xo of the products (pass B treats every
+    // column alike); the polynomial the sum starts from is not permuted and is read at the original positions
+    const int xo = a.galEl ? (int)(((u64)col * a.galInv) & (MKHE_TILE - 1)) : col;
     u64 r[E];
-    if (a.has_acc[t]) {
+    if (a.src[t]) {
+        const u64 *sp = a.src[t] + (long)j * N + xo;
 #pragma unroll
-        for (int k = 0; k < E; k++) r[k] = ld_cg(dst + (long)k * MKHE_TILE);
+        for (int k = 0; k < E; k++) r[k] = ld_cg(sp + (long)k * MKHE_TILE);
     } else {
 #pragma unroll
         for (int k = 0; k < E; k++) r[k] = 0;
@@ -948,9 +1025,13 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_Q(ModDownQArgs a, 
             u64 y[NP][HB], ov[HB];
 #pragma unroll
             for (int k = 0; k < HB; k++) {
+                double vi = 0.0;                  // reconstructRNS: vi += fl(y_i)/fl(p_i), limb order, RN; then truncation
 #pragma unroll
-                for (int i = 0; i < NP; i++) y[i][k] = ld_cg(src + (long)(a.p_slot0 + i) * N + (long)(h + k) * MKHE_TILE);
-                ov[k] = ld_cg(src + (long)a.vslot * N + (long)(h + k) * MKHE_TILE);
+                for (int i = 0; i < NP; i++) {
+                    y[i][k] = ld_cg(src + (long)(a.p_slot0 + i) * N + (long)(h + k) * MKHE_TILE);
+                    vi = __dadd_rn(vi, __longlong_as_double((long long)ld_cg(src + (long)(a.vslot + i) * N + (long)(h + k) * MKHE_TILE)));
+                }
+                ov[k] = __double2ull_rz(vi);
             }
 #pragma unroll
             for (int k = 0; k < HB; k++) {
@@ -967,8 +1048,25 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_Q(ModDownQArgs a, 
             }
         }
     }
+    u64 *dst = a.dst[t] + (long)j * N;
+    if (a.galEl == 0) {
 #pragma unroll
-    for (int k = 0; k < E; k++) dst[(long)k * MKHE_TILE] = r[k];
+        for (int k = 0; k < E; k++) dst[col + (long)k * MKHE_TILE] = r[k];
+    } else {
+        // keyswitch_hoisted.go:217-245: out[(i*galEl) & (N-1)] = ((i*galEl) >> logN) & 1 ? q - c : c   (c = 0 is stored as q).
+        // i = xo + 2048 k lands in column (xo galEl mod 2048) = col, row ((i galEl) >> 11) mod E: the rows of the column are permuted
+        // through shared memory so that every store of the warp is contiguous.
+        MKHE_SMEM(smraw);                          // E * 128 * 8 bytes of dynamic shared memory (launches with galEl != 0 only)
+        u64 (*rowbuf)[MKHE_NTT_THREADS] = reinterpret_cast<u64 (*)[MKHE_NTT_THREADS]>(smraw);
+#pragma unroll
+        for (int k = 0; k < E; k++) {
+            const u64 raw = (u64)(xo + k * MKHE_TILE) * a.galEl;
+            rowbuf[(raw >> 11) & (E - 1)][threadIdx.x] = ((raw >> a.logN) & 1) ? m.q - r[k] : r[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < E; k++) dst[col + (long)k * MKHE_TILE] = rowbuf[k][threadIdx.x];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -118,6 +118,15 @@ class Evaluator:
     def MulRelinNew(self, op0, op1, rlkSet):
         """evaluator.go:416-443: hoist (once when op0 is op1), MulAndRelinHoisted, Rescale -- ONE device call
         (mkhe_ckks_mul_relin); this is what the reference benchmark times (mkckks_benchmark_test.go:78-82)."""
+        if self.params.Alpha() > 1 and op0 is not op1 and op0.Level() != op1.Level():
+            # The reference decomposes every operand at ITS OWN level (evaluator.go:431-437).  With alpha > 1 the last digit
+            # used at the output level then comes from a full alpha-limb group of the higher operand, not from the partial
+            # group a decomposition at the output level would lift: hoist explicitly, per operand (alpha = 1: identical).
+            h0, h1 = self.HoistedForm(op0), self.HoistedForm(op1)
+            out = self.MulRelinHoistedNew(op0, op1, h0, h1, rlkSet)
+            for h in list(h0.values()) + list(h1.values()):
+                h.free()
+            return out
         ctOut = self.newCiphertextBinary(op0, op1)
         level = ctOut.Level()
         scale = op0.ScalingFactor() * op1.ScalingFactor()

@@ -277,6 +277,64 @@ def check_lanes(w: CKKSWorld, rounds=3, level=None):
     ev[1].ctx.close()
 
 
+def check_mixed_levels(w: CKKSWorld):
+    """alpha > 1 with operands at DIFFERENT levels: the reference hoists each operand at its own level
+    (mkckks/evaluator.go:431-437), so the last digit in use is lifted from a different limb group than a decomposition at
+    the output level would take"""
+    L = w.op.max_level()
+    for l0, l1 in ((L, L - 1), (L - 2, L), (L, L - 3)):
+        o0, d0 = w.random_ct(w.ids, l0)
+        o1, d1 = w.random_ct(w.ids, l1)
+        oout = w.oev.mul_relin_new(o0, o1, w.o_rlk)
+        dout = w.dev.MulRelinNew(d0, d1, w.d_rlk)
+        assert dout.Level() == oout.level() and dout.Scale == oout.scale
+        w.compare_ct(dout, oout, f"MulRelinNew at levels ({l0}, {l1}), alpha = {w.dp.Alpha()}")
+
+
+def check_abi_negative(w: CKKSWorld):
+    """a switching key holds beta_max = ceil(nQ / alpha) digits: the per-limb upload / download must reject digit >= beta_max
+    (alpha > 1 sets have beta_max < nQ) and null host pointers instead of touching memory past the allocation; a transform
+    over R = Q u QMul needs BFV parameters"""
+    import ctypes as C
+    ctx, dll = w.ctx, w.ctx.dll
+    alpha, nQ = w.dp.Alpha(), len(w.lit.Q)
+    beta_max = (nQ + alpha - 1) // alpha
+    assert alpha > 1 and beta_max < nQ
+    sk = mkrlwe.SwitchingKey(ctx)
+    buf = np.zeros(w.lit.N, dtype=np.uint64)
+    ptr = buf.ctypes.data_as(C.POINTER(C.c_uint64))
+    h = C.c_uint64(sk.h)
+    assert dll.mkhe_swk_upload_limb(ctx.ptr, h, C.c_int(beta_max - 1), C.c_int(0), C.c_int(0), ptr) == 0
+    for digit in (beta_max, nQ - 1, nQ, -1):
+        assert dll.mkhe_swk_upload_limb(ctx.ptr, h, C.c_int(digit), C.c_int(0), C.c_int(0), ptr) != 0, digit
+        assert dll.mkhe_swk_download_limb(ctx.ptr, h, C.c_int(digit), C.c_int(0), C.c_int(0), ptr) != 0, digit
+    assert dll.mkhe_swk_upload_limb(ctx.ptr, h, C.c_int(0), C.c_int(0), C.c_int(0), None) != 0
+    assert dll.mkhe_swk_download_limb(ctx.ptr, h, C.c_int(0), C.c_int(0), C.c_int(0), None) != 0
+    pq = mkrlwe.Poly(ctx, nQ + 1)
+    assert dll.mkhe_ntt(ctx.ptr, C.c_int(nQ), C.c_uint64(pq.h), C.c_uint64(pq.h)) != 0
+
+
+def check_fork_after_queued_work(w: CKKSWorld, rounds=4):
+    """a lane forked AFTER work was queued on the root is ordered behind that work: the product of an asynchronous MulRelinNew
+    on the root is consumed at once by the new lane (no synchronisation in between)"""
+    L = w.op.max_level()
+    rot = sorted(r for r in w.op.CRS if r > 0)[0]
+    pend = []
+    for r in range(rounds):
+        o0, d0 = w.random_ct(w.ids, L)
+        o1, d1 = w.random_ct(w.ids, L)
+        dout = w.dev.MulRelinNew(d0, d1, w.d_rlk)        # queued on the root, still running
+        ev2 = w.dev.ShallowCopy() if r < 3 else pend[0][4]   # fork now (at most 4 lanes per root)
+        drot = ev2.RotateNew(dout, rot, w.d_rk)          # first use of the pending output on the new lane
+        pend.append((o0, o1, dout, drot, ev2))
+    for o0, o1, dout, drot, ev2 in pend:
+        oout = w.oev.mul_relin_new(o0, o1, w.o_rlk)
+        w.compare_ct(dout, oout, "MulRelinNew before the fork")
+        w.compare_ct(drot, w.oev.rotate_new(oout, rot, w.o_rk), "RotateNew on a lane forked after the product was queued")
+    for *_, ev2 in pend[:3]:
+        ev2.ctx.close()
+
+
 def check_elementwise(w: CKKSWorld):
     """the evaluator ops either side of the key switches: AddNew / SubNew over different id sets, levels
     and scales (scale alignment through MultByConst), MultByConst with integer / fractional / negative / complex constants,

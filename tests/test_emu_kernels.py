@@ -58,6 +58,16 @@ def test_wide_digits_under_emulation(emu, lit):
     w.close()
 
 
+def test_mixed_levels_and_abi_checks_under_emulation(emu):
+    w = parity.CKKSWorld(PR.PN16QP1761_Q7.at_logn(12), 2, lib=emu)
+    parity.check_mixed_levels(w)
+    parity.check_abi_negative(w)
+    w.close()
+    w = parity.CKKSWorld(PR.CKKS_PN14QP439.at_logn(12), 2, lib=emu, rots=(1,))
+    parity.check_fork_after_queued_work(w, rounds=2)
+    w.close()
+
+
 def test_pn16qp1761_full_limb_count_under_emulation(emu):
     """34 + 4 limbs, 17 two-limb digits"""
     w = parity.CKKSWorld(PR.PN16QP1761.at_logn(12), 2, lib=emu, rots=(1,))

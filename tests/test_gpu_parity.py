@@ -146,6 +146,27 @@ def test_full_size_properties():
     w.close()
 
 
+@pytest.mark.parametrize("k", [4, 8])
+def test_benchmarked_ckks_config_against_oracle(k):
+    """BASELINE config 2 exactly as bench.py times it (mkckks_benchmark_test.go:55-84): PN15QP880, logN = 15, level 13, k = 4 and
+    k = 8 parties, op0 != op1 with all k ids -- MulRelinNew, the square, HoistedForm + RotateHoistedNew (rot 2) and RotateNew,
+    every limb of every component against the oracle (OpenMP over limbs: about a second per op)."""
+    w = parity.CKKSWorld(PR.CKKS_PN15QP880, k, rots=(2,))
+    parity.check_mul_relin_new(w, w.ids, w.ids)
+    parity.check_mul_relin_new(w, w.ids, w.ids, same=True)
+    parity.check_rotate(w, w.ids, 2)
+    w.close()
+
+
+def test_benchmarked_bfv_config_against_oracle():
+    """BASELINE config 3 (mkbfv_bench_test.go:39-64): mkbfv MulRelinNew at PN15QP880, logN = 15, k = 4, against the oracle;
+    op0 != op1 and the square (ct, ct) the reference benchmark times"""
+    w = parity.BFVWorld(PR.BFV_PN15QP880, 4)
+    parity.check_bfv_mul_relin(w, w.ids, w.ids)
+    parity.check_bfv_mul_relin(w, w.ids, w.ids, same=True)
+    w.close()
+
+
 def test_full_size_one_party_against_oracle():
     """one full-size (logN = 15, 14 limbs) MulRelinNew with k = 1 against the oracle (a few seconds of CPU)"""
     w = parity.CKKSWorld(PR.CKKS_PN15QP880, 1, rots=(1,))
@@ -288,6 +309,24 @@ def test_wide_digits(lit, logN):
     parity.check_decompose(w, level=4)
     parity.check_mul_relin_new(w, w.ids, w.ids, level=5)
     parity.check_rotate(w, w.ids, 1, level=4)
+    w.close()
+
+
+def test_wide_digits_mixed_levels():
+    w = parity.CKKSWorld(PR.PN16QP1761_Q7.at_logn(12), 2)
+    parity.check_mixed_levels(w)
+    w.close()
+
+
+def test_abi_rejects_out_of_range_key_digits():
+    w = parity.CKKSWorld(PR.PN16QP1761_Q7.at_logn(12), 1, rots=())
+    parity.check_abi_negative(w)
+    w.close()
+
+
+def test_fork_after_queued_work():
+    w = parity.CKKSWorld(PR.CKKS_PN15QP880.at_logn(14), 2, rots=(1,))
+    parity.check_fork_after_queued_work(w)
     w.close()
 
 

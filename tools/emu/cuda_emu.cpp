@@ -56,15 +56,31 @@ void emu_syncwarp() {
     const int warp = w->current / 32, lanes = w->nthreads - warp * 32 < 32 ? w->nthreads - warp * 32 : 32;
     emu_barrier(16 + warp, lanes);
 }
-// mbarrier with transaction count: low 32 bits = bytes still expected, high 32 bits = completed phases
-void emu_mbar_init(unsigned long long *bar) { *bar = 0; }
-void emu_mbar_expect_tx(unsigned long long *bar, unsigned bytes) { *bar += bytes; }
+// mbarrier: pending arrivals + outstanding transaction bytes of the current phase; the phase completes when both reach zero and
+// the arrival count is re-armed (PTX mbarrier semantics).  Word layout (the kernels only see an opaque 64-bit slot):
+//   bits 0..23 tx bytes, 24..35 pending arrivals, 36..47 arrival count of a phase, 48..63 completed phases
+namespace {
+inline void mbar_check(unsigned long long *bar) {
+    const unsigned long long tx = *bar & 0xffffffull, pend = (*bar >> 24) & 0xfffull, cnt = (*bar >> 36) & 0xfffull;
+    if (tx == 0 && pend == 0) *bar = (cnt << 24) | (cnt << 36) | ((((*bar >> 48) + 1) & 0xffffull) << 48);
+}
+}  // namespace
+void emu_mbar_init(unsigned long long *bar, int count) { *bar = ((unsigned long long)count << 24) | ((unsigned long long)count << 36); }
+void emu_mbar_arrive(unsigned long long *bar) {
+    *bar -= 1ull << 24;
+    mbar_check(bar);
+}
+void emu_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {       // mbarrier.arrive.expect_tx: one arrival + bytes to come
+    *bar += bytes;
+    *bar -= 1ull << 24;
+    mbar_check(bar);
+}
 void emu_mbar_complete_tx(unsigned long long *bar, unsigned bytes) {
     *bar -= bytes;
-    if ((unsigned)(*bar & 0xffffffffull) == 0) *bar += 1ull << 32;
+    mbar_check(bar);
 }
 void emu_mbar_wait(unsigned long long *bar, unsigned parity) {
-    while ((((unsigned)(*bar >> 32)) & 1u) == parity) emu_yield();
+    while ((((unsigned)(*bar >> 48)) & 1u) == parity) emu_yield();
 }
 
 double emu_now_ms() {

@@ -33,7 +33,8 @@ extern thread_local unsigned char *emu_smem;           // dynamic shared memory 
 void emu_syncthreads();
 void emu_syncwarp();
 void emu_barrier(int id, int nthreads);
-void emu_mbar_init(unsigned long long *bar);
+void emu_mbar_init(unsigned long long *bar, int count);
+void emu_mbar_arrive(unsigned long long *bar);
 void emu_mbar_expect_tx(unsigned long long *bar, unsigned bytes);
 void emu_mbar_complete_tx(unsigned long long *bar, unsigned bytes);
 void emu_mbar_wait(unsigned long long *bar, unsigned parity);
@@ -44,6 +45,7 @@ void emu_mbar_wait(unsigned long long *bar, unsigned parity);
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __constant__
 #define __syncthreads() emu_syncthreads()
 #define EMU_SHARED_DECL(type, name) type *name = reinterpret_cast<type *>(emu_smem)
@@ -55,6 +57,8 @@ static inline double __ull2double_rn(unsigned long long x) { return (double)x; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline unsigned long long __double2ull_rz(double x) { return (unsigned long long)x; }
+static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
+static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }      // fibers are cooperative

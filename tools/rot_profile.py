@@ -4,6 +4,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mkhe_kklss_b200 import params as PR
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+if len(sys.argv) > 2:                      # another build of the library (A/B runs)
+    from mkhe_kklss_b200 import _lib
+    _lib._default = _lib.Library(os.path.abspath(sys.argv[2]))
 sys.argv = sys.argv[:1]
 from bench import DeviceWorkload
 wl = DeviceWorkload(PR.CKKS_PN15QP880, k, 0, seed=3, batch=8, lanes=1)
