@@ -63,6 +63,7 @@ struct mkhe_ctx {
     size_t ck_snap_bytes = 0;
     int ck_n = 0;
     std::vector<std::string> ck_names;
+    int hoist_digits = 0;                 // development: digits per hoisting launch pair (MKHE_DEBUG_HOIST_DIGITS, read once; 0 = all)
     bool l2_hints = true;                 // L2 eviction priorities on the bulk copies of k_mac_intt (MKHE_DEBUG_NO_L2_HINTS switches them off: A/B runs)
     bool debug_nodiag = false;            // development: transform every tensor operand instead of reading the hoisted diagonal (MKHE_DEBUG_NODIAG, read once)
     bool debug_sync = false;              // development: host-synchronise after every launch (MKHE_DEBUG_SYNC=<n-th context of the process>)
@@ -408,7 +409,6 @@ int launch_pass2(mkhe_ctx *ctx, const Slots &s, int np, u64 *const *bufs, int co
     b.inst_stride = inst_stride;
     b.nslots = s.n;
     b.logN = ctx->logN;
-    b.magic = 0x9e3779b97f4a7c15ull;
     b.lazy_out = lazy_out ? 1 : 0;
     const long per_slot = (long)tiles * b.ninst;
     for (int i = 0; i < s.n; i++) {
@@ -509,26 +509,31 @@ int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *c
             TRY(ntt_fwd(ctx, s, (int)ent.size(), ent.data(), ent.data()));
         }
         if (nlift < beta) {
-            const int nd = beta - nlift;
-            BcastArgs a;
-            memset(&a, 0, sizeof a);
-            a.in_limb0 = in_limb0;
-            a.in_limb_stride = alpha;
-            a.digit0 = nlift;
-            a.dmax = ctx->dmax;
-            a.nslots = s.n;
-            a.slot_groups = std::min(s.n, pick_chunks(s.n, (long)COLGROUPS * nd * np));
-            a.logN = ctx->logN;
-            for (int i = 0; i < s.n; i++) a.slots[i] = s.slot[i];
-            for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
-            TRY(dispatch_s1(ctx, [&](auto S) -> int {
-                auto k_bcast_ntt_pass1_ = k_bcast_ntt_pass1<decltype(S)::value>;
-                LAUNCH(k_bcast_ntt_pass1_, dim3(COLGROUPS * a.slot_groups, nd, np), dim3(MKHE_NTT_THREADS), 0, a, ctx->d_mods, ctx->d_twf);
-                return MKHE_OK;
-            }));
-            std::vector<u64 *> bufs(np);
-            for (int i = 0; i < np; i++) bufs[i] = out[p0 + i] + nlift * digit_elems;
-            TRY(launch_pass2(ctx, s, np, bufs.data(), nd, digit_elems, lazy));
+            // development knob (MKHE_DEBUG_HOIST_DIGITS=n): hoist n digits per launch pair, so that pass 1's output (n * D limbs per
+            // poly) is still L2 resident when pass 2 reads it back -- the measured alternative to a single-pass transform
+            const int chunk = ctx->hoist_digits > 0 ? ctx->hoist_digits : beta - nlift;
+            for (int d0 = nlift; d0 < beta; d0 += chunk) {
+                const int nd = std::min(chunk, beta - d0);
+                BcastArgs a;
+                memset(&a, 0, sizeof a);
+                a.in_limb0 = in_limb0;
+                a.in_limb_stride = alpha;
+                a.digit0 = d0;
+                a.dmax = ctx->dmax;
+                a.nslots = s.n;
+                a.slot_groups = std::min(s.n, pick_chunks(s.n, (long)COLGROUPS * nd * np));
+                a.logN = ctx->logN;
+                for (int i = 0; i < s.n; i++) a.slots[i] = s.slot[i];
+                for (int i = 0; i < np; i++) { a.in.p[i] = in[p0 + i]; a.out.p[i] = out[p0 + i]; }
+                TRY(dispatch_s1(ctx, [&](auto S) -> int {
+                    auto k_bcast_ntt_pass1_ = k_bcast_ntt_pass1<decltype(S)::value>;
+                    LAUNCH(k_bcast_ntt_pass1_, dim3(COLGROUPS * a.slot_groups, nd, np), dim3(MKHE_NTT_THREADS), 0, a, ctx->d_mods, ctx->d_twf);
+                    return MKHE_OK;
+                }));
+                std::vector<u64 *> bufs(np);
+                for (int i = 0; i < np; i++) bufs[i] = out[p0 + i] + d0 * digit_elems;
+                TRY(launch_pass2(ctx, s, np, bufs.data(), nd, digit_elems, lazy));
+            }
         }
     }
     return MKHE_OK;
@@ -663,9 +668,12 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
                 qa.galInv = inv;
             }
             qa.logN = ctx->logN;
-            int cnt = 0;
+            int cnt = 0, max_split = 1;
             for (int t = 0; t < ntg; t++) {
                 const Prod &p0 = prods[b0 + members[t0 + t][0]];
+                const size_t np = members[t0 + t].size();
+                qa.split[t] = np >= 4 ? 4 : (np >= 2 ? 2 : 1);
+                max_split = std::max(max_split, qa.split[t]);
                 qa.dst[t] = tg[t0 + t];
                 qa.src[t] = p0.src ? p0.src : (p0.add ? tg[t0 + t] : nullptr);
                 qa.first[t] = cnt;
@@ -674,8 +682,8 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
             qa.first[ntg] = cnt;
             TRY(dispatch_s1(ctx, [&](auto S) -> int {
                 constexpr int s1 = decltype(S)::value;
-                const dim3 grid(COLGROUPS, levelQ + 1, ntg);
-                const size_t rowsm = galEl ? ((size_t)8 << s1) * MKHE_NTT_THREADS : 0;      // the row permutation of a rotation
+                const dim3 grid(COLGROUPS * max_split, levelQ + 1, ntg);
+                const size_t rowsm = MKHE_MDQ_SMEM(s1);      // partial sums of split targets, the row permutation of a rotation
                 switch (ctx->nP) {
                     case 1: { auto k_moddown_Q_ = k_moddown_Q<s1, 1>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
                     case 2: { auto k_moddown_Q_ = k_moddown_Q<s1, 2>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
@@ -1115,6 +1123,7 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
         if (e && atoi(e) == created) ctx->debug_ck = true;
         ctx->debug_nodiag = getenv("MKHE_DEBUG_NODIAG") != nullptr;
         ctx->l2_hints = getenv("MKHE_DEBUG_NO_L2_HINTS") == nullptr;
+        if (const char *hd = getenv("MKHE_DEBUG_HOIST_DIGITS")) ctx->hoist_digits = atoi(hd);
     }
     ctx->root = ctx;
     ctx->lanes.push_back(ctx);
@@ -1184,6 +1193,7 @@ int mkhe_ctx_fork(mkhe_ctx *parent, mkhe_ctx **out) {
     f->tables_dirty = false;
     f->debug_nodiag = root->debug_nodiag;
     f->l2_hints = root->l2_hints;
+    f->hoist_digits = root->hoist_digits;
     f->d_conv_PtoQ = root->d_conv_PtoQ; f->d_conv_QtoQMul = root->d_conv_QtoQMul; f->d_conv_QMultoQ = root->d_conv_QMultoQ;
     f->h_mformQMul = root->h_mformQMul;
     f->root = root;

@@ -37,9 +37,6 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) { emu_barrier(i
 __device__ __forceinline__ u64 l2_policy_evict_first() { return 0; }
 __device__ __forceinline__ u64 l2_policy_evict_last() { return 0; }
 __device__ __forceinline__ void tma_load_1d_hint(void *smem, const void *gmem, u32 bytes, u64 *bar, u64) { memcpy(smem, gmem, bytes); emu_mbar_complete_tx(bar, bytes); }
-__device__ __forceinline__ void consume16(const u64 *) {}
-__device__ __forceinline__ void consume4(u64, u64, u64, u64) {}
-__device__ __forceinline__ void anchor_side_effect() {}
 __device__ __forceinline__ void st_global_v4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 #else
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -77,17 +74,6 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(a), "r"(parity) : "memory");
 }
-// scheduling anchor: the 16 values must be in registers here (volatile asm statements keep their order, so whatever
-// produced them -- in particular the shared-memory loads behind them -- has completed before a following barrier)
-__device__ __forceinline__ void consume16(const u64 *v) {
-    asm volatile("" ::"l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]), "l"(v[4]), "l"(v[5]), "l"(v[6]), "l"(v[7]), "l"(v[8]), "l"(v[9]),
-                 "l"(v[10]), "l"(v[11]), "l"(v[12]), "l"(v[13]), "l"(v[14]), "l"(v[15])
-                 : "memory");
-}
-__device__ __forceinline__ void consume4(u64 a, u64 b, u64 c, u64 d) { asm volatile("" ::"l"(a), "l"(b), "l"(c), "l"(d) : "memory"); }
-// an instruction with a side effect (never reordered across a barrier); callers predicate it on values whose producers must
-// have completed before the barrier that follows
-__device__ __forceinline__ void anchor_side_effect() { asm volatile("nanosleep.u32 1;" ::: "memory"); }
 // barrier among `nthreads` threads of the CTA (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *bar) {

@@ -368,7 +368,6 @@ struct Pass2Args {
     int mods[MKHE_MAX_SLOTS];        // modulus index of that slot
     int wslot[MKHE_MAX_SLOTS];       // cost of one tile of that slot (16 = a modulus below 2^57; the 59/60-bit ones sweep and cost more)
     long wstart[MKHE_MAX_SLOTS + 1]; // cumulative cost before slot s; wstart[nslots] = total
-    u64 magic;                       // an unlikely 64-bit value (anchor in the kernel); equality only costs a nanosleep
     int lazy_out;                    // store the un-reduced outputs (below 2^64, congruent): for forms that only feed the 128-bit MACs
     int logN;
 #ifdef MKHE_P2_TIMING
@@ -380,7 +379,8 @@ struct Pass2Args {
 #endif
 #define MKHE_P2_THREADS (MKHE_P2_GROUPS * MKHE_NTT_THREADS)
 #define MKHE_P2_GROUP_BYTES (MKHE_XBUF * 8 + MKHE_TILE * 8)
-#define MKHE_P2_SMEM (MKHE_TILE * 16 + MKHE_P2_GROUPS * MKHE_P2_GROUP_BYTES + 8 * (1 + MKHE_P2_GROUPS) + 16 + 16 * MKHE_P2_GROUPS)
+#define MKHE_P2_NBARS (2 * (1 + MKHE_P2_GROUPS))          // tw_full, in_full[groups], tw_empty, in_empty[groups]
+#define MKHE_P2_SMEM (MKHE_TILE * 16 + MKHE_P2_GROUPS * MKHE_P2_GROUP_BYTES + 8 * MKHE_P2_NBARS + 16 + 16 * MKHE_P2_GROUPS)
 
 // the work of a launch is the list of tiles (slot, tile, instance), instance fastest; CTA c of G owns the stretch whose cumulative
 // cost lies in [c, c+1) * total / G.  The boundary is the first list index whose cumulative cost reaches the target.
@@ -400,6 +400,10 @@ struct P2Mail { int off, pad; u64 *ptr; };       // a group's next tile, publish
 //   groups take tiles from a shared counter (a group that the warp schedulers favour simply transforms more tiles).  The tiles
 //   of one (slot, tile) pair are consecutive: the pair's 2047 twiddles arrive once by TMA; a group's next 16 KiB input tile is
 //   prefetched by TMA into its landing buffer while the current one is transformed.
+//   Both TMA targets are recycled through a full / empty mbarrier pair: the readers arrive on the "empty" barrier after their last
+//   shared-memory read of the buffer (release), the issuing thread waits for that phase (acquire) before it re-arms the "full"
+//   barrier and issues the next cp.async.bulk -- a CTA barrier alone does not order reads that are merely issued before an
+//   async-proxy write.
 #ifdef MKHE_P2_MAXNREG
 __global__ void __maxnreg__(MKHE_P2_MAXNREG) k_ntt_pass2(
 #else
@@ -412,9 +416,10 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
     u64 *xbuf = reinterpret_cast<u64 *>(smraw + MKHE_TILE * 16 + grp * MKHE_P2_GROUP_BYTES);           // 17 KiB exchange
     u64 *inbuf = xbuf + MKHE_XBUF;                                                                    // 16 KiB landing
     unsigned char *tail = smraw + MKHE_TILE * 16 + MKHE_P2_GROUPS * MKHE_P2_GROUP_BYTES;
-    u64 *bars = reinterpret_cast<u64 *>(tail);
-    int *ctr = reinterpret_cast<int *>(tail + 8 * (1 + MKHE_P2_GROUPS));
-    P2Mail *mail = reinterpret_cast<P2Mail *>(tail + 8 * (1 + MKHE_P2_GROUPS) + 16);
+    u64 *bars = reinterpret_cast<u64 *>(tail);                    // [0] twiddles full, [1 + g] input tile of group g full
+    u64 *tw_empty = bars + 1 + MKHE_P2_GROUPS, *in_empty = tw_empty + 1;
+    int *ctr = reinterpret_cast<int *>(tail + 8 * MKHE_P2_NBARS);
+    P2Mail *mail = reinterpret_cast<P2Mail *>(tail + 8 * MKHE_P2_NBARS + 16);
     const long N = 1L << a.logN;
     const int ntiles = (int)(N / MKHE_TILE);
     const int per_slot = ntiles * a.ninst;          // the tile list has at most 40 * 32 * 64 * 40 entries: 32-bit indices (no 64-bit divisions)
@@ -431,6 +436,8 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
     };
     if (threadIdx.x == 0) {
         for (int b = 0; b <= MKHE_P2_GROUPS; b++) mbar_init(&bars[b], 1);
+        mbar_init(tw_empty, MKHE_P2_THREADS);
+        for (int b = 0; b < MKHE_P2_GROUPS; b++) mbar_init(&in_empty[b], MKHE_NTT_THREADS);
         *ctr = MKHE_P2_GROUPS;                      // group g starts with tile g of the stretch
     }
 #ifdef MKHE_P2_TIMING
@@ -454,7 +461,7 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
     const TwShared tw(stw, tid);
     const XAddr x(xbuf, tid);
     u32 tw_phase = 0, in_phase = 0;
-    bool first = true;
+    u32 npairs = 0;                                 // (slot, tile) pairs this CTA has finished
     for (int seg = w_begin; seg < w_end;) {         // CTA-uniform walk over the (slot, tile) pairs of the stretch
         const int sidx = seg / per_slot;
         const int tile = (seg - sidx * per_slot) / a.ninst;
@@ -465,10 +472,9 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
         const ModC m = mods[mi];
         const NttC c = nttc(m);
         const bool big = m.big != 0;
-        // every group has left the previous pair (its twiddles are about to be overwritten)
-        if (!first) __syncthreads();
-        first = false;
         if (threadIdx.x == 0) {
+            // every thread of the CTA has read the previous pair's twiddles for the last time (they are about to be overwritten)
+            if (npairs) mbar_wait(tw_empty, (npairs - 1) & 1);
             mbar_expect_tx(&bars[0], MKHE_TILE * 16);
             tma_load_1d(stw, tiled + ((long)mi * ntiles + tile) * MKHE_TILE, MKHE_TILE * 16, &bars[0]);
         }
@@ -476,29 +482,26 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
         tw_phase ^= 1;
         while (cur < seg_end) {
             mbar_wait(&bars[1 + grp], in_phase);
-            in_phase ^= 1;
             u64 v[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = inbuf[k * 128 + tid];
+            mbar_arrive(&in_empty[grp]);                    // this thread's last read of the landing buffer
             tile_fwd_A(v, tw, c, big);
-            consume16(v);
-            if (v[0] == a.magic) anchor_side_effect();      // every output of round A depends on all 16 loaded values: a side effect
-                                                            // predicated on one of them cannot be scheduled before the loads returned
-            // Round A has CONSUMED the values read from the landing buffer, so those shared-memory loads have completed: a
-            // barrier alone does not order still-queued generic-proxy loads before the TMA (async-proxy) write that refills
-            // the buffer.  The same barrier tells that everybody has left the previous tile's exchange buffer and mail slot.
+            // everybody of the group has left the previous tile's exchange buffer and mail slot
             named_sync(1 + grp, MKHE_NTT_THREADS);
             if (tid == 0) {
                 const int nxt = atomicAdd(ctr, 1);
                 u64 *np = nullptr;
                 if (nxt < nwork) {                  // the next tile may belong to the next pair: its data does not depend on twiddles
                     np = tile_ptr(w_begin + nxt);
+                    mbar_wait(&in_empty[grp], in_phase);    // all 128 readers have arrived: the buffer may be overwritten
                     mbar_expect_tx(&bars[1 + grp], MKHE_TILE * 8);
                     tma_load_1d(inbuf, np, MKHE_TILE * 8, &bars[1 + grp]);
                 }
                 mail[grp].off = nxt;
                 mail[grp].ptr = np;
             }
+            in_phase ^= 1;
             tile_fwd_BC(v, x, tw, c, big, 1 + grp);         // its barrier publishes the mail slot
             u64 *o = cur_ptr + tid * 16;
             cur = mail[grp].off;
@@ -512,6 +515,8 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
                     st_global_v4(o + 4 * k, canon(v[4 * k], m), canon(v[4 * k + 1], m), canon(v[4 * k + 2], m), canon(v[4 * k + 3], m));
             }
         }
+        mbar_arrive(tw_empty);                              // this thread is done with the pair's twiddles
+        npairs++;
     }
 #ifdef MKHE_P2_TIMING
     __syncthreads();
@@ -887,6 +892,11 @@ struct ConvTable {            // device-resident constants of one (source basis 
     u64 qoverqimodp[MKHE_CONV_MAX][MKHE_CONV_MAX];   // [j][i] Q/q_i mod p_j, Montgomery
     u64 vtimesqmodp[MKHE_CONV_MAX][MKHE_CONV_MAX + 1];   // [j][v] (-v*Q) mod p_j
     u64 moddown[MKHE_CONV_MAX];             // [j] p_j - MForm(prod src^-1 mod p_j)   (ModDown only)
+    // the key switch's ModDownQPtoQ in closed form (n1 <= 4 special primes): with S = prod src,
+    //   MRed(lift + 2 p_j - x, moddown[j]) = (x - lift) S^-1 = x S^-1 - sum_i y_i src_i^-1 + v   (mod p_j),
+    // because lift = sum_i y_i (S / src_i) - v S.  Shoup pairs of S^-1 and of -(src_i^-1) mod p_j:
+    u64 md_sinv[MKHE_CONV_MAX][2];
+    u64 md_nsrcinv[MKHE_CONV_MAX][MKHE_LIFT_MAX_SRC][2];
 };
 enum { CONV_MODUP = 0, CONV_MODDOWN = 1 };
 struct ConvArgs {
@@ -981,31 +991,44 @@ struct ModDownQArgs {
     u64 *dst[MKHE_MD_TARGETS];
     const u64 *src[MKHE_MD_TARGETS];       // the sum starts from this poly (AddLvl onto the target or onto another poly); nullptr = zero
     int first[MKHE_MD_TARGETS + 1];        // products of target t: acc[first[t]] .. acc[first[t+1]-1]
+    int split[MKHE_MD_TARGETS];            // 1, 2 or 4: the products of target t are dealt over `split` thread lanes of a CTA
     const u64 *acc[MKHE_MD_PRODUCTS];
     int np_limbs, p_slot0, vslot;
     u64 galEl, galInv;                     // != 0 (RotateHoisted): the result goes through X -> X^galEl; the accumulators arrive with
                                            // their columns already permuted (k_mac_intt); galInv = galEl^-1 mod 2N
     int logN;
 };
+#define MKHE_MDQ_SMEM(S1) (((size_t)8 << (S1)) * MKHE_NTT_THREADS)
+// grid = (16 * max split, level+1, ntargets).  A target with several products (c_0 of a rotation or of the relinearisation: one
+// product per party) would otherwise be one long serial chain per thread while the single-product targets finish early: its
+// products are dealt over `split` lanes of the CTA (thread = (lane, column), 128 / split columns per CTA), every lane sums its
+// share and the partial sums meet in shared memory (exact modular adds, any order).
 template <int S1, int NP>
 __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown_Q(ModDownQArgs a, const ConvTable *tabp, const ModC *mods, const ulonglong2 *twi) {
     constexpr int E = 1 << S1, HB = E < 8 ? E : 8;
+    MKHE_SMEM(smraw);                          // E * 128 * 8 bytes
+    u64 (*rowbuf)[MKHE_NTT_THREADS] = reinterpret_cast<u64 (*)[MKHE_NTT_THREADS]>(smraw);
     const ConvTable &tab = *tabp;
     const long N = 1L << a.logN;
-    const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x, j = blockIdx.y, t = blockIdx.z;
+    const int j = blockIdx.y, t = blockIdx.z;
+    const int PP = a.split[t], cols_per = MKHE_NTT_THREADS / PP;
+    if ((int)blockIdx.x >= (MKHE_TILE / MKHE_NTT_THREADS) * PP) return;
+    const int lane = threadIdx.x / cols_per, cin = threadIdx.x - lane * cols_per;
+    const int col = blockIdx.x * cols_per + cin;
     const ModC m = mods[tab.dst_mod[j]];          // == modulus j
     const NttC c = nttc(m);
-    u64 cji[NP], vq[NP + 1];
+    // ModDownQPtoQ in closed form (see ConvTable): d = x P^-1 - sum_i y_i p_i^-1 + v mod q_j, three lazy Shoup products and one
+    // canonical reduction instead of multSum's 128-bit accumulation, its Montgomery fold and a full MRed -- the same canonical
+    // residue the reference stores (basis_extension.go:203-229)
+    u64 sinv[2], nsi[NP][2];
+    sinv[0] = tab.md_sinv[j][0]; sinv[1] = tab.md_sinv[j][1];
 #pragma unroll
-    for (int i = 0; i < NP; i++) cji[i] = tab.qoverqimodp[j][i];
-#pragma unroll
-    for (int i = 0; i <= NP; i++) vq[i] = tab.vtimesqmodp[j][i];
-    const u64 md = tab.moddown[j];
+    for (int i = 0; i < NP; i++) { nsi[i][0] = tab.md_nsrcinv[j][i][0]; nsi[i][1] = tab.md_nsrcinv[j][i][1]; }
     // with an automorphism this thread works on stored column `col` = original column xo of the products (pass B treats every
     // column alike); the polynomial the sum starts from is not permuted and is read at the original positions
     const int xo = a.galEl ? (int)(((u64)col * a.galInv) & (MKHE_TILE - 1)) : col;
     u64 r[E];
-    if (a.src[t]) {
+    if (a.src[t] && lane == 0) {
         const u64 *sp = a.src[t] + (long)j * N + xo;
 #pragma unroll
         for (int k = 0; k < E; k++) r[k] = ld_cg(sp + (long)k * MKHE_TILE);
@@ -1014,7 +1037,7 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
         for (int k = 0; k < E; k++) r[k] = 0;
     }
 #pragma unroll 1
-    for (int s = a.first[t]; s < a.first[t + 1]; s++) {
+    for (int s = a.first[t] + lane; s < a.first[t + 1]; s += PP) {
         const u64 *src = a.acc[s] + col;
         u64 v[E];
 #pragma unroll
@@ -1035,37 +1058,53 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
             }
 #pragma unroll
             for (int k = 0; k < HB; k++) {
-                u64 rlo = 0, rhi = 0;
+                u64 d = shoup4(v[h + k], sinv[0], sinv[1], c.nq) + ov[k];        // each product below 4q: the sum stays below 2^64
 #pragma unroll
-                for (int i = 0; i < NP; i++) mac128(rhi, rlo, y[i][k], cji[i]);
-                u64 vt = vq[0];
-#pragma unroll
-                for (int i = 1; i <= NP; i++) vt = ov[k] == (u64)i ? vq[i] : vt;
-                const u64 hhi = mulhi(rlo * m.qinv, m.q);
-                const u64 lift = rhi - hhi + m.q + vt;                    // lazy, exactly multSum's value
-                const u64 d = mred(lift + 2 * m.q - v[h + k], md, m.q, m.qinv);
-                r[h + k] = csub(r[h + k] + d, m.q);
+                for (int i = 0; i < NP; i++) {
+                    d += shoup4(y[i][k], nsi[i][0], nsi[i][1], c.nq);
+                    if (NP > 2 && i == 1) d = canon(d, m);      // at most three lazy products (12q < 2^64) between reductions
+                }
+                r[h + k] = csub(r[h + k] + canon(d, m), m.q);
             }
+        }
+    }
+    if (PP > 1) {                              // the lanes' partial sums meet in lane 0 (CTA-uniform branch)
+#pragma unroll 1
+        for (int l = 1; l < PP; l++) {
+            if (lane == l) {
+#pragma unroll
+                for (int k = 0; k < E; k++) rowbuf[k][cin] = r[k];
+            }
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < E; k++) r[k] = csub(r[k] + rowbuf[k][cin], m.q);     // r[k] may be a non-canonical start value (q): one subtraction, like AddLvl
+            }
+            __syncthreads();
         }
     }
     u64 *dst = a.dst[t] + (long)j * N;
     if (a.galEl == 0) {
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < E; k++) dst[col + (long)k * MKHE_TILE] = r[k];
+            for (int k = 0; k < E; k++) dst[col + (long)k * MKHE_TILE] = r[k];
+        }
     } else {
         // keyswitch_hoisted.go:217-245: out[(i*galEl) & (N-1)] = ((i*galEl) >> logN) & 1 ? q - c : c   (c = 0 is stored as q).
         // i = xo + 2048 k lands in column (xo galEl mod 2048) = col, row ((i galEl) >> 11) mod E: the rows of the column are permuted
         // through shared memory so that every store of the warp is contiguous.
-        MKHE_SMEM(smraw);                          // E * 128 * 8 bytes of dynamic shared memory (launches with galEl != 0 only)
-        u64 (*rowbuf)[MKHE_NTT_THREADS] = reinterpret_cast<u64 (*)[MKHE_NTT_THREADS]>(smraw);
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < E; k++) {
-            const u64 raw = (u64)(xo + k * MKHE_TILE) * a.galEl;
-            rowbuf[(raw >> 11) & (E - 1)][threadIdx.x] = ((raw >> a.logN) & 1) ? m.q - r[k] : r[k];
+            for (int k = 0; k < E; k++) {
+                const u64 raw = (u64)(xo + k * MKHE_TILE) * a.galEl;
+                rowbuf[(raw >> 11) & (E - 1)][cin] = ((raw >> a.logN) & 1) ? m.q - r[k] : r[k];
+            }
         }
         __syncthreads();
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < E; k++) dst[col + (long)k * MKHE_TILE] = rowbuf[k][threadIdx.x];
+            for (int k = 0; k < E; k++) dst[col + (long)k * MKHE_TILE] = rowbuf[k][cin];
+        }
     }
 }
 

@@ -163,6 +163,15 @@ inline void gen_conv_table(ConvTable &c, const std::vector<u64> &mod, const std:
         u64 inv = 1;
         for (int i = 0; i < c.n1; i++) inv = h_mulmod(inv, h_invmod(mod[src[i]] % pj, pj), pj);
         c.moddown[j] = pj - h_mform(inv, pj);
+        if (c.n1 <= MKHE_LIFT_MAX_SRC) {          // closed form of the key switch's ModDown (k_moddown_Q)
+            c.md_sinv[j][0] = inv;
+            c.md_sinv[j][1] = h_shoup(inv, pj);
+            for (int i = 0; i < c.n1; i++) {
+                const u64 ni = pj - h_invmod(mod[src[i]] % pj, pj);
+                c.md_nsrcinv[j][i][0] = ni;
+                c.md_nsrcinv[j][i][1] = h_shoup(ni, pj);
+            }
+        }
     }
 }
 
