@@ -212,6 +212,29 @@ int mkhe_comm_destroy(mkhe_ctx *ctx);
  * all-reduce of the c_0 contributions.  One node, one process per GPU, at most 8 ranks. */
 int mkhe_p2p_export(mkhe_ctx *ctx, uint8_t out[128]);
 int mkhe_p2p_import(mkhe_ctx *ctx, int nranks, int rank, const uint8_t *all_handles);
+/* ---- multi-GPU: limb-sharded MulRelinNew.  A team = the contexts ("ranks") that execute ONE op together: rank r
+ * owns the limb slots s with s mod nranks == r of every key, hoisted form and accumulator (mkrlwe/keyswitch_hoisted.go:44-179 is
+ * limb-local apart from ModDown's P limbs, the re-decomposed p_id and the final Rescale).  The three exchanges are peer stores from
+ * the epilogues of the kernels that produce the data (NVLink / NVSwitch), ordered by an in-kernel flag barrier; no collective
+ * library is involved.  Every rank passes the same (replicated) operands and key handles and ends with the whole result,
+ * bit-identical to mkhe_ckks_mul_relin.
+ *   ranks in different processes: mkhe_team_export on every rank (allocates the rank's team memory for ciphertexts of up to
+ *     max_parties parties and returns its 64-byte CUDA IPC handle); the host hands the concatenation of all handles (rank order)
+ *     to mkhe_team_import on every rank.
+ *   ranks inside one process (several GPUs, or several contexts on one GPU as in the tests): mkhe_team_join_local with the
+ *     contexts of all ranks, called once per rank.
+ * Every lane (mkhe_ctx_fork) that issues limb-sharded ops joins a team of its own.  mkhe_team_status reports a barrier that gave
+ * up waiting for a rank (5 s): the op's results are then undefined. */
+int mkhe_team_export(mkhe_ctx *ctx, int max_parties, uint8_t out[64]);
+int mkhe_team_import(mkhe_ctx *ctx, int nranks, int rank, const uint8_t *all_handles);
+int mkhe_team_join_local(mkhe_ctx *ctx, int max_parties, int nranks, int rank, mkhe_ctx *const *members);
+int mkhe_team_status(mkhe_ctx *ctx, int *timed_out);
+int mkhe_team_flags(mkhe_ctx *ctx, uint64_t out[17]);   /* diagnostics: flag / status words of this rank + barriers issued */
+int mkhe_ckks_mul_relin_limbs(mkhe_ctx *ctx, int level, int nb_rescales,
+                              int n0, const int *ids0, const mkhe_poly *op0,
+                              int n1, const int *ids1, const mkhe_poly *op1,
+                              const mkhe_swk *rlk_b, const mkhe_swk *rlk_d, const mkhe_swk *rlk_v, mkhe_swk u,
+                              int nOut, const int *idsOut, const mkhe_poly *out);
 /* party-sharded MulRelinNew: every rank passes the same (replicated) operand ciphertexts and id lists, but only holds
  * the relinearization keys of the parties in own_ids (other entries of rlk_* may be 0).  Partial x, y and the c_0
  * contributions are summed with ncclAllReduce(uint64, sum) and reduced mod q -- bit-identical to the single-GPU result

@@ -365,6 +365,42 @@ class Context:
             _harr(rlk_b), _harr(rlk_d), _harr(rlk_v), C.c_uint64(u),
             C.c_int(len(idsOut)), _intarr(idsOut), _harr(out)))
 
+    # limb-sharded ops: the team of ranks
+    def team_export(self, max_parties) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self.check(self.dll.mkhe_team_export(self.ptr, C.c_int(max_parties), buf))
+        return bytes(buf)
+
+    def team_import(self, nranks, rank, handles: list):
+        """handles[r] = rank r's team_export() bytes"""
+        assert len(handles) == nranks and all(len(h) == 64 for h in handles)
+        blob = b"".join(handles)
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.check(self.dll.mkhe_team_import(self.ptr, C.c_int(nranks), C.c_int(rank), arr))
+
+    def team_join_local(self, max_parties, rank, members: list):
+        """ranks inside one process: members[r] = the Context of rank r (members[rank] is self)"""
+        arr = (C.c_void_p * len(members))(*[m.ptr for m in members])
+        self.check(self.dll.mkhe_team_join_local(self.ptr, C.c_int(max_parties), C.c_int(len(members)), C.c_int(rank), arr))
+
+    def team_timed_out(self) -> bool:
+        v = C.c_int(0)
+        self.check(self.dll.mkhe_team_status(self.ptr, C.byref(v)))
+        return bool(v.value)
+
+    def team_flags(self):
+        buf = (C.c_uint64 * 17)()
+        self.check(self.dll.mkhe_team_flags(self.ptr, buf))
+        return list(buf)
+
+    def ckks_mul_relin_limbs(self, level, nb_rescales, ids0, op0, ids1, op1, rlk_b, rlk_d, rlk_v, u, idsOut, out):
+        self.check(self.dll.mkhe_ckks_mul_relin_limbs(
+            self.ptr, C.c_int(level), C.c_int(nb_rescales),
+            C.c_int(len(ids0)), _intarr(ids0), _harr(op0),
+            C.c_int(len(ids1)), _intarr(ids1), _harr(op1),
+            _harr(rlk_b), _harr(rlk_d), _harr(rlk_v), C.c_uint64(u),
+            C.c_int(len(idsOut)), _intarr(idsOut), _harr(out)))
+
     # BFV
     def bfv_modup_q_to_r(self, hq, hr):
         self.check(self.dll.mkhe_bfv_modup_q_to_r(self.ptr, C.c_uint64(hq), C.c_uint64(hr)))

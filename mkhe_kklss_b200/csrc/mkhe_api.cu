@@ -17,6 +17,7 @@
 #include <vector>
 
 #ifndef MKHE_EMU
+#include <cuda.h>            // types of the stream memory operations only: the entry point is fetched at run time (no libcuda link)
 #ifdef MKHE_WITH_NCCL
 #include <nccl.h>
 #endif
@@ -110,6 +111,18 @@ struct mkhe_ctx {
     u64 *p2p_stage = nullptr, *p2p_xy = nullptr, *p2p_flag = nullptr;
     u64 *peer_stage[MKHE_MAX_RANKS] = {nullptr}, *peer_xy[MKHE_MAX_RANKS] = {nullptr};
     int nranks = 1, rank = 0;
+    // limb-sharded ops: the team memory of this rank / lane and the ranks' mappings of it
+    struct Team {
+        int n = 0, rank = 0, maxk = 0;
+        u64 *mem = nullptr;                 // this rank's block (cudaMalloc)
+        size_t elems = 0;
+        u64 *peer[MKHE_MAX_RANKS] = {nullptr};
+        bool ipc[MKHE_MAX_RANKS] = {false}; // peer[r] came from cudaIpcOpenMemHandle
+        u64 epoch = 0;                      // barriers passed so far (the same on every rank: all ranks issue the same ops)
+        size_t off_pp = 0, off_p = 0, off_g = 0;
+        u64 timeout_ns = 5000000000ull;
+        bool spin = false;                  // development: the spinning-kernel barrier instead of the stream memory wait
+    } team;
     // per-kernel CUDA-event profiling (bench.py's roofline leg)
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -292,6 +305,42 @@ int get_scratch(mkhe_ctx *ctx, const std::string &name, size_t bytes, u64 **out)
     }
     *out = s.p;
     return MKHE_OK;
+}
+
+// CUDA loads a kernel lazily at its first launch, and that load may have to wait until the device is idle.  An op of a team must
+// never hit one: a rank's in-kernel barrier can be spinning on the device at that moment, waiting for work the blocked host thread
+// has not enqueued yet.  So every kernel this context can launch is loaded when the context is made.
+template <class K> void preload(K kernel) {
+#ifndef MKHE_EMU
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kernel);
+#else
+    (void)kernel;
+#endif
+}
+template <int S1> void preload_s1(int nP) {
+    preload(k_bcast_ntt_pass1<S1>); preload(k_ntt_pass1<S1>); preload(k_intt_passB<S1>); preload(k_moddown_P<S1>);
+    switch (nP) {
+        case 1: preload(k_moddown_Q<S1, 1>); break;
+        case 2: preload(k_moddown_Q<S1, 2>); break;
+        case 3: preload(k_moddown_Q<S1, 3>); break;
+        default: preload(k_moddown_Q<S1, 4>); break;
+    }
+}
+void preload_kernels(const mkhe_ctx *ctx) {
+    switch (ctx->S1) {
+        case 1: preload_s1<1>(ctx->nP); break;
+        case 2: preload_s1<2>(ctx->nP); break;
+        case 3: preload_s1<3>(ctx->nP); break;
+        case 4: preload_s1<4>(ctx->nP); break;
+        default: preload_s1<5>(ctx->nP); break;
+    }
+    preload(k_tile_twiddles); preload(k_decomp_lift); preload(k_ntt_pass2); preload(k_mac_intt<1>); preload(k_mac_intt<2>);
+    preload(k_intt_passA); preload(k_mac_parties); preload(k_mac_parties_scatter); preload(k_reduce_gather);
+    preload(k_conv<CONV_MODUP>); preload(k_conv<CONV_MODDOWN>); preload(k_tensor); preload(k_addsub<true>); preload(k_addsub<false>);
+    preload(k_reduce); preload(k_rescale); preload(k_automorph); preload(k_scale); preload(k_mul_const); preload(k_neg);
+    preload(k_mul_mont); preload(k_decrypt_sum); preload(k_mul2); preload(k_checksum); preload(k_bfly_peak);
+    preload(k_team_barrier); preload(k_team_signal); preload(k_team_gather);
 }
 
 int upload_tables(mkhe_ctx *ctx) {
@@ -479,13 +528,15 @@ int ntt_inv(mkhe_ctx *ctx, const Slots &s, int npolys, u64 *const *in, u64 *cons
 
 // Decompose: digits in_limb0 .. in_limb0+beta-1 of each input poly -> swk-shaped outputs (NTT domain)
 // lazy: the NTT outputs of the broadcast digits stay un-reduced (< 2^64, congruent) -- only for forms that never leave the op
-int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *const *out, int in_limb0, bool lazy = false) {
+int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *const *out, int in_limb0, bool lazy = false,
+                   const Slots *only = nullptr) {
     const int alpha = ctx->alpha, beta = beta_of(ctx, levelQ);
     if (alpha > 1 && in_limb0 != 0) return fail(ctx, MKHE_ERR_UNSUPPORTED, "DecomposeBFV relies on alpha = 1 (mkbfv/keyswitch.go:64-67)");
     // digits [0, nlift) hold more than one limb and take the exact lift; a last digit of a single limb is a broadcast
     const int nsrc_last = levelQ + 1 - alpha * (beta - 1);
     const int nlift = alpha == 1 ? 0 : (nsrc_last == 1 ? beta - 1 : beta);
-    Slots s = qp_slots(ctx, levelQ);
+    Slots s = only ? *only : qp_slots(ctx, levelQ);          // limb sharding: the target limbs this rank owns
+    if (s.n == 0) return MKHE_OK;
     const long digit_elems = (long)ctx->dmax * ctx->N;
     for (int p0 = 0; p0 < npolys; p0 += MKHE_MAX_PARTIES_K) {
         int np = std::min(MKHE_MAX_PARTIES_K, npolys - p0);
@@ -542,18 +593,85 @@ int decompose_impl(mkhe_ctx *ctx, int levelQ, int npolys, u64 *const *in, u64 *c
 // One external product of a batch:  dst (+)= ModDown(INTT(sum_{set} sum_i key[set][i] (.) hst[set][i]))
 //   (ExternalProductHoisted, mkrlwe/keyswitch_hoisted.go:10-40).  Products that name the same dst are summed
 //   into it (exact modular adds, any order); `add` = start from dst's current contents (ringQ.AddLvl) instead of zero.
+// ---- limb sharding: which limb slots a rank owns, the team's barrier ---------------------------------------------------
+int owner_of_slot(const mkhe_ctx *ctx, int slot) { return slot % ctx->team.n; }       // stable over levels: keys can be stored sharded
+Slots own_slots(const mkhe_ctx *ctx, const Slots &all) {
+    Slots s;
+    for (int i = 0; i < all.n; i++)
+        if (owner_of_slot(ctx, all.slot[i]) == ctx->team.rank) { s.slot[s.n] = all.slot[i]; s.mod[s.n++] = all.mod[i]; }
+    return s;
+}
+void fill_team(const mkhe_ctx *ctx, TeamArgs &t) {
+    memset(&t, 0, sizeof t);
+    t.nranks = ctx->team.n;
+    t.rank = ctx->team.rank;
+    for (int r = 0; r < ctx->team.n; r++) t.peer[r] = ctx->team.peer[r];
+}
+#ifndef MKHE_EMU
+typedef CUresult (*wait_value64_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+wait_value64_fn stream_wait_value64() {
+    static wait_value64_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+            fn = (wait_value64_fn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+#endif
+// every rank's earlier work on this lane (its peer stores included) is complete before any rank's later work starts.
+// Signal kernel + stream memory wait; the spinning kernel k_team_barrier is the fallback where stream memory operations are
+// not available (and MKHE_DEBUG_SPIN_BARRIER forces it).
+int team_barrier(mkhe_ctx *ctx) {
+    TeamArgs t;
+    fill_team(ctx, t);
+    ctx->team.epoch++;
+    if (ctx->team.n <= 1) return MKHE_OK;
+#ifndef MKHE_EMU
+    wait_value64_fn wait = ctx->team.spin ? nullptr : stream_wait_value64();
+    if (wait) {
+        LAUNCH(k_team_signal, dim3(1), dim3(32), 0, t);
+        // CU_STREAM_WAIT_VALUE_FLUSH (flush of outstanding remote writes) exists only where the platform can do it; without it the
+        // ordering still holds: the peers' data stores precede their release-add at system scope, the kernels behind the wait start
+        // with an invalidated L1 and read through L2, the point of coherence for writes that arrive over NVLink
+        static bool can_flush = true;
+        const CUdeviceptr addr = (CUdeviceptr)(ctx->team.mem + MKHE_TEAM_COUNTER);
+        const cuuint64_t target = (cuuint64_t)(ctx->team.epoch * (u64)(ctx->team.n - 1));
+        CUresult r = CUDA_ERROR_NOT_SUPPORTED;
+        if (can_flush) r = wait((CUstream)ctx->stream, addr, target, CU_STREAM_WAIT_VALUE_GEQ | CU_STREAM_WAIT_VALUE_FLUSH);
+        if (r == CUDA_ERROR_NOT_SUPPORTED) {
+            can_flush = false;
+            r = wait((CUstream)ctx->stream, addr, target, CU_STREAM_WAIT_VALUE_GEQ);
+        }
+        if (r == CUDA_SUCCESS) return MKHE_OK;
+        return fail(ctx, MKHE_ERR_CUDA, "cuStreamWaitValue64 failed (%d)", (int)r);
+    }
+#endif
+    LAUNCH(k_team_barrier, dim3(1), dim3(32), 0, t, ctx->team.epoch, ctx->team.timeout_ns);
+    return MKHE_OK;
+}
+
 struct Prod {
     u64 *key[2], *hst[2];
     u64 *dst;
     bool add;                 // start from dst's current contents (ringQ.AddLvl) instead of zero
     const u64 *src = nullptr; // start from this poly instead (overrides add); e.g. RotateHoisted's copy of ctIn["0"]
+    long team_off = -1;       // limb-sharded ops: >= 0 = the result has to be complete on every rank: stored into every rank's team
+                              // memory at this element offset (dst = this rank's image of that place)
 };
 
-int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &prods, u64 galEl = 0) {
+// `team`: limb-sharded execution -- only the limb slots this rank owns are computed; the P parts travel to every rank from the
+// epilogue of k_moddown_P, followed by a barrier
+int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &prods, u64 galEl = 0, bool team = false) {
     const int nb = (int)prods.size();
     if (nb == 0) return MKHE_OK;
     const int tiles = ctx->N / MKHE_TILE;
-    const Slots s = qp_slots(ctx, levelQ);
+    const Slots s = team ? own_slots(ctx, qp_slots(ctx, levelQ)) : qp_slots(ctx, levelQ);
+    if (team && nb > 2 * ctx->team.maxk) return fail(ctx, MKHE_ERR_INVALID, "team memory sized for %d parties", ctx->team.maxk);
     const int vslot = ctx->dmax;                              // nP spare limbs of every accumulator: the terms of the overflow estimate v
     const size_t qp = (size_t)(ctx->dmax + ctx->nP) * ctx->N;
     for (int b0 = 0; b0 < nb; b0 += MKHE_MD_PRODUCTS) {
@@ -596,7 +714,7 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
             if (sk || sh) { groups[2].push_back({i, sk ? 1 : 0}); i += 2; }
             else { groups[1].push_back({i, 1}); i += 1; }
         }
-        for (int G = 2; G >= 1; G--)
+        for (int G = 2; G >= 1 && s.n > 0; G--)
             for (size_t g0 = 0; g0 < groups[G].size(); g0 += MKHE_MI_GROUPS) {
                 const int ng = (int)std::min<size_t>(MKHE_MI_GROUPS, groups[G].size() - g0);
                 MacInttArgs a;
@@ -647,19 +765,26 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
         pa.p_slot0 = ctx->nQ;
         pa.vslot = vslot;
         pa.logN = ctx->logN;
-        for (int k = 0; k < n; k++) pa.acc[k] = bufs[k];
-        TRY(dispatch_s1(ctx, [&](auto S) -> int {
-            auto k_moddown_P_ = k_moddown_P<decltype(S)::value>;
-            LAUNCH(k_moddown_P_, dim3(COLGROUPS, n, ctx->nP), dim3(MKHE_NTT_THREADS), 0, pa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi);
-            return MKHE_OK;
-        }));
+        const size_t pp_elems = (size_t)2 * ctx->nP * ctx->N;        // P part of one product in the team memory
+        for (int i = 0; i < ctx->nP; i++)
+            if (!team || owner_of_slot(ctx, ctx->nQ + i) == ctx->team.rank) pa.plist[pa.nplist++] = i;
+        if (team) fill_team(ctx, pa.team);
+        for (int k = 0; k < n; k++) { pa.acc[k] = bufs[k]; pa.pp_off[k] = (long)(ctx->team.off_pp + (size_t)k * pp_elems); }
+        if (pa.nplist > 0)
+            TRY(dispatch_s1(ctx, [&](auto S) -> int {
+                auto k_moddown_P_ = k_moddown_P<decltype(S)::value>;
+                LAUNCH(k_moddown_P_, dim3(COLGROUPS, n, pa.nplist), dim3(MKHE_NTT_THREADS), 0, pa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi);
+                return MKHE_OK;
+            }));
+        if (team) TRY(team_barrier(ctx));                     // every rank has every product's P part
         for (size_t t0 = 0; t0 < tg.size(); t0 += MKHE_MD_TARGETS) {
             const int ntg = (int)std::min<size_t>(MKHE_MD_TARGETS, tg.size() - t0);
             ModDownQArgs qa;
             memset(&qa, 0, sizeof qa);
             qa.np_limbs = ctx->nP;
-            qa.p_slot0 = ctx->nQ;
-            qa.vslot = vslot;
+            for (int j = 0; j <= levelQ; j++)
+                if (!team || owner_of_slot(ctx, j) == ctx->team.rank) qa.qlist[qa.nqlist++] = j;
+            if (team) fill_team(ctx, qa.team);
             qa.galEl = galEl;
             if (galEl) {                 // galEl^-1 mod 2N (2-adic Newton iteration: every step doubles the number of correct bits)
                 const u64 mask = ((u64)2 << ctx->logN) - 1;
@@ -676,13 +801,18 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
                 max_split = std::max(max_split, qa.split[t]);
                 qa.dst[t] = tg[t0 + t];
                 qa.src[t] = p0.src ? p0.src : (p0.add ? tg[t0 + t] : nullptr);
+                qa.dst_team_off[t] = team ? p0.team_off : -1;
                 qa.first[t] = cnt;
-                for (int m : members[t0 + t]) qa.acc[cnt++] = bufs[m];
+                for (int m : members[t0 + t]) {
+                    qa.pp[cnt] = team ? ctx->team.mem + ctx->team.off_pp + (size_t)m * pp_elems : bufs[m] + (size_t)ctx->nQ * ctx->N;
+                    qa.acc[cnt++] = bufs[m];
+                }
             }
             qa.first[ntg] = cnt;
+            if (qa.nqlist == 0) continue;
             TRY(dispatch_s1(ctx, [&](auto S) -> int {
                 constexpr int s1 = decltype(S)::value;
-                const dim3 grid(COLGROUPS * max_split, levelQ + 1, ntg);
+                const dim3 grid(COLGROUPS * max_split, qa.nqlist, ntg);
                 const size_t rowsm = MKHE_MDQ_SMEM(s1);      // partial sums of split targets, the row permutation of a rotation
                 switch (ctx->nP) {
                     case 1: { auto k_moddown_Q_ = k_moddown_Q<s1, 1>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
@@ -711,8 +841,9 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nb, int nsets, u64 *const *key0,
 }
 
 // x_i = MForm(sum_t MRed(key_t[i], hst_t[i]))   (keyswitch_hoisted.go:79-117)
-int mac_parties(mkhe_ctx *ctx, int level, int n, u64 *const *key, u64 *const *hst, u64 *out) {
-    Slots s = qp_slots(ctx, level);
+int mac_parties(mkhe_ctx *ctx, int level, int n, u64 *const *key, u64 *const *hst, u64 *out, const Slots *only = nullptr) {
+    Slots s = only ? *only : qp_slots(ctx, level);
+    if (s.n == 0) return MKHE_OK;
     if (n > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_UNSUPPORTED, "more than %d parties", MKHE_MAX_PARTIES_K);
     MacPartiesArgs a;
     memset(&a, 0, sizeof a);
@@ -848,7 +979,7 @@ int mac_parties_scatter(mkhe_ctx *ctx, int level, int n, u64 *const *key, u64 *c
 }
 int reduce_gather(mkhe_ctx *ctx, int level) {
     Slots s = qp_slots(ctx, level);
-    GatherArgs a;
+    ReduceGatherArgs a;
     memset(&a, 0, sizeof a);
     a.beta = beta_of(ctx, level);
     a.dmax = ctx->dmax;
@@ -944,7 +1075,7 @@ int mul_relin_hoisted_impl(mkhe_ctx *ctx, int level, int n0, const int *ids0, u6
         ta.nout = nOut;
         ta.nlimbs = level + 1;
         ta.logN = ctx->logN;
-        for (int i = 0; i <= level; i++) ta.mod_of_limb[i] = i;
+        for (int i = 0; i <= level; i++) ta.limbs[i] = i;
         ta.out.p[0] = out[0];
         for (int t = 0; t < nOut; t++) {
             int i0 = find_id(n0, ids0, idsOut[t]), i1 = find_id(n1, ids1, idsOut[t]);
@@ -1003,6 +1134,105 @@ int rescale_impl(mkhe_ctx *ctx, int level, int nb, int npolys, u64 *const *in, u
             for (int i = 0; i < np; i++) { a.in.p[i] = (r == 0) ? in[p0 + i] : out[p0 + i]; a.out.p[i] = out[p0 + i]; }
             LAUNCH(k_rescale, dim3(ctx->N / MKHE_THREADS, np), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
         }
+    }
+    return MKHE_OK;
+}
+
+// Limb-sharded MulRelinNew (mkckks/evaluator.go:416-443 + mkrlwe/keyswitch_hoisted.go:44-179 + Rescale :359-398).
+// Every rank holds the (replicated) operand ciphertexts and computes the limb slots it owns of every hoisted form, of x, y, of
+// the tensor product and of every key-switch accumulator: steps 1-6 of MulAndRelinHoisted are limb-local except
+//   (i)  ModDown needs the P limbs of every product on every rank     -> k_moddown_P stores them into every rank's team memory,
+//   (ii) Decompose(p_id) needs all limbs of p_id on every rank        -> k_moddown_Q stores its limbs of p_id into every rank's,
+//   (iii) Rescale needs the last limb, the caller needs a whole result -> k_team_gather stores the rank's limbs into every rank's,
+// each followed by one in-kernel flag barrier (k_team_barrier): four barriers per op, no collective library on the data path.
+// Bit-identical to the single-GPU op: every value is computed by the same kernels from the same inputs, only elsewhere.
+int mul_relin_limbs_impl(mkhe_ctx *ctx, int level, int nb_rescales, int n0, const int *ids0, u64 *const *op0, int n1, const int *ids1,
+                         u64 *const *op1, u64 *const *rlk_b, u64 *const *rlk_d, u64 *const *rlk_v, u64 *u, int nOut,
+                         const int *idsOut, u64 *const *out) {
+    mkhe_ctx::Team &tm = ctx->team;
+    const int N = ctx->N;
+    if (ctx->alpha != 1) return fail(ctx, MKHE_ERR_UNSUPPORTED, "limb-sharded MulRelin relies on alpha = 1 (the tensor step reads the hoisted diagonal)");
+    if (std::max(n0, n1) > tm.maxk || nOut > tm.maxk) return fail(ctx, MKHE_ERR_INVALID, "team memory sized for %d parties", tm.maxk);
+    const Slots qp_own = own_slots(ctx, qp_slots(ctx, level)), q_own = own_slots(ctx, q_slots(level));
+    std::vector<u64 *> h0, h1, xy, hp, tn;
+    TRY(swk_pool(ctx, "hoistpool0", n0, h0));
+    TRY(swk_pool(ctx, "hoistpool1", n1, h1));
+    TRY(swk_pool(ctx, "xy", 2, xy));
+    TRY(swk_pool(ctx, "relin_hp", n0, hp));
+    TRY(poly_pool(ctx, "tensor_ntt", 2, ctx->nQ, tn));
+    const bool lazy = beta_of(ctx, level) <= 14;          // forms that never leave the op (see mul_relin_hoisted_impl)
+    // hoisting and x, y: the owned target limbs of every digit (the digit limbs themselves come from the replicated operands)
+    TRY(decompose_impl(ctx, level, n0, op0 + 1, h0.data(), 0, lazy, &qp_own));
+    TRY(decompose_impl(ctx, level, n1, op1 + 1, h1.data(), 0, lazy, &qp_own));
+    if (n0) TRY(mac_parties(ctx, level, n0, rlk_d, h0.data(), xy[0], &qp_own));
+    if (n1) TRY(mac_parties(ctx, level, n1, rlk_b, h1.data(), xy[1], &qp_own));
+    // tensor product on the owned Q limbs (NTT(op_id limb i) = limb i of digit i of the fresh form)
+    if (q_own.n > 0) {
+        u64 *src[2] = {op0[0], op1[0]}, *dst[2] = {tn[0], tn[1]};
+        TRY(ntt_fwd(ctx, q_own, 2, src, dst));
+        TensorArgs ta;
+        memset(&ta, 0, sizeof ta);
+        ta.A0 = tn[0];
+        ta.B0 = tn[1];
+        ta.strideA = ta.strideB = (long)(ctx->dmax + 1) * N;
+        ta.nout = nOut;
+        ta.nlimbs = q_own.n;
+        ta.logN = ctx->logN;
+        for (int i = 0; i < q_own.n; i++) ta.limbs[i] = q_own.slot[i];
+        ta.out.p[0] = out[0];
+        for (int t = 0; t < nOut; t++) {
+            const int i0 = find_id(n0, ids0, idsOut[t]), i1 = find_id(n1, ids1, idsOut[t]);
+            ta.A.p[t] = i0 >= 0 ? h0[i0] : nullptr;
+            ta.B.p[t] = i1 >= 0 ? h1[i1] : nullptr;
+            ta.out.p[1 + t] = out[1 + t];
+        }
+        LAUNCH(k_tensor, dim3(N / MKHE_THREADS, q_own.n), dim3(MKHE_THREADS), 0, ta, ctx->d_mods);
+        TRY(ntt_inv(ctx, q_own, nOut + 1, out, out));
+    }
+    // c_id += x [.] h1_id and p_id = y [.] h0_id; the limbs of p_id go to every rank
+    const size_t poly_elems = (size_t)ctx->nQ * N;
+    std::vector<u64 *> p(n0);
+    for (int t = 0; t < n0; t++) p[t] = tm.mem + tm.off_p + (size_t)t * poly_elems;
+    {
+        std::vector<Prod> pr;
+        for (int t = 0; t < n1; t++) pr.push_back(Prod{{xy[0], nullptr}, {h1[t], nullptr}, out[1 + find_id(nOut, idsOut, ids1[t])], true});
+        for (int t = 0; t < n0; t++) {
+            Prod q{{xy[1], nullptr}, {h0[t], nullptr}, p[t], false};
+            q.team_off = (long)(tm.off_p + (size_t)t * poly_elems);
+            pr.push_back(q);
+        }
+        TRY(ext_products(ctx, level, 1, pr, 0, true));
+        TRY(team_barrier(ctx));                            // every p_id is complete on every rank
+    }
+    if (n0 > 0) {
+        TRY(decompose_impl(ctx, level, n0, p.data(), hp.data(), 0, lazy, &qp_own));
+        std::vector<Prod> pr;
+        for (int t = 0; t < n0; t++) {
+            pr.push_back(Prod{{u, nullptr}, {hp[t], nullptr}, out[1 + find_id(nOut, idsOut, ids0[t])], true});
+            pr.push_back(Prod{{rlk_v[t], nullptr}, {hp[t], nullptr}, out[0], true});
+        }
+        TRY(ext_products(ctx, level, 1, pr, 0, true));
+    }
+    // the rank's limbs of the result go to every rank, Rescale runs on the gathered copy into the caller's polys
+    std::vector<u64 *> g(nOut + 1);
+    for (int t = 0; t <= nOut; t++) g[t] = tm.mem + tm.off_g + (size_t)t * poly_elems;
+    if (q_own.n > 0) {
+        GatherArgs ga;
+        memset(&ga, 0, sizeof ga);
+        ga.nslots = q_own.n;
+        ga.logN = ctx->logN;
+        for (int i = 0; i < q_own.n; i++) ga.slots[i] = q_own.slot[i];
+        for (int t = 0; t <= nOut; t++) { ga.src.p[t] = out[t]; ga.dst_off[t] = (long)(tm.off_g + (size_t)t * poly_elems); }
+        TeamArgs ta;
+        fill_team(ctx, ta);
+        LAUNCH(k_team_gather, dim3(N / (2 * MKHE_THREADS), q_own.n, nOut + 1), dim3(MKHE_THREADS), 0, ga, ta);
+    }
+    TRY(team_barrier(ctx));
+    if (nb_rescales > 0) {
+        TRY(rescale_impl(ctx, level, 1, nOut + 1, g.data(), out));
+        if (nb_rescales > 1) TRY(rescale_impl(ctx, level - 1, nb_rescales - 1, nOut + 1, out, out));
+    } else {
+        for (int t = 0; t <= nOut; t++) CU(cudaMemcpyAsync(out[t], g[t], (size_t)(level + 1) * N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     return MKHE_OK;
 }
@@ -1153,6 +1383,7 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     cudaFuncSetAttribute(k_mac_intt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MI_SMEM(1));
     cudaFuncSetAttribute(k_mac_intt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MI_SMEM(2));
 #endif
+    preload_kernels(ctx);
     std::vector<int> src, dst;
     for (int j = 0; j < nP; j++) src.push_back(nQ + j);
     for (int j = 0; j < nQ; j++) dst.push_back(j);
@@ -1289,6 +1520,11 @@ void mkhe_ctx_destroy(mkhe_ctx *ctx) {
     }
     if (ctx->p2p_stage) { cudaFree(ctx->p2p_stage); cudaFree(ctx->p2p_xy); cudaFree(ctx->p2p_flag); }
 #endif
+#ifndef MKHE_EMU
+    for (int r = 0; r < MKHE_MAX_RANKS; r++)
+        if (ctx->team.ipc[r] && ctx->team.peer[r]) cudaIpcCloseMemHandle(ctx->team.peer[r]);
+#endif
+    if (ctx->team.mem) cudaFree(ctx->team.mem);
     for (auto &kv : ctx->scratch) cudaFree(kv.second.p);
     for (cudaEvent_t e : ctx->lane_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -2188,6 +2424,132 @@ int mkhe_p2p_import(mkhe_ctx *ctx, int nranks, int rank, const uint8_t *all_hand
     (void)nranks; (void)rank; (void)all_handles;
     return fail(ctx, MKHE_ERR_UNSUPPORTED, "no peer memory under emulation");
 #endif
+}
+
+// ---- limb-sharded ops: the team of ranks ---------------------------------------------------------------
+namespace {
+int team_alloc(mkhe_ctx *ctx, int max_parties) {
+    mkhe_ctx::Team &tm = ctx->team;
+    if (tm.mem && tm.maxk >= max_parties) return MKHE_OK;
+    if (tm.mem) return fail(ctx, MKHE_ERR_INVALID, "team memory already exported for %d parties", tm.maxk);
+    if (max_parties < 1 || max_parties > MKHE_MAX_PARTIES) return fail(ctx, MKHE_ERR_INVALID, "max_parties out of range");
+    const size_t N = ctx->N;
+    tm.off_pp = MKHE_TEAM_FLAGS;
+    tm.off_p = tm.off_pp + (size_t)2 * max_parties * 2 * ctx->nP * N;
+    tm.off_g = tm.off_p + (size_t)max_parties * ctx->nQ * N;
+    tm.elems = tm.off_g + (size_t)(max_parties + 1) * ctx->nQ * N;
+    if (cudaMalloc((void **)&tm.mem, tm.elems * 8) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMalloc(%zu) failed for the team memory", tm.elems * 8);
+    CU(cudaMemsetAsync(tm.mem, 0, tm.elems * 8, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    tm.maxk = max_parties;
+    tm.spin = getenv("MKHE_DEBUG_SPIN_BARRIER") != nullptr;
+    return MKHE_OK;
+}
+}  // namespace
+
+int mkhe_team_export(mkhe_ctx *ctx, int max_parties, uint8_t out[64]) {
+    CHECK_CTX();
+#if !defined(MKHE_EMU)
+    if (!out) return MKHE_ERR_INVALID;
+    TRY(team_alloc(ctx, max_parties));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->team.mem));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out, &h, 64);
+    return MKHE_OK;
+#else
+    (void)max_parties; (void)out;
+    return fail(ctx, MKHE_ERR_UNSUPPORTED, "no inter-process memory under emulation");
+#endif
+}
+int mkhe_team_import(mkhe_ctx *ctx, int nranks, int rank, const uint8_t *all_handles) {
+    CHECK_CTX();
+#if !defined(MKHE_EMU)
+    mkhe_ctx::Team &tm = ctx->team;
+    if (!all_handles || nranks < 1 || nranks > MKHE_MAX_RANKS || rank < 0 || rank >= nranks) return fail(ctx, MKHE_ERR_INVALID, "bad rank layout");
+    if (!tm.mem) return fail(ctx, MKHE_ERR_INVALID, "mkhe_team_export comes first");
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) { tm.peer[r] = tm.mem; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + (size_t)r * 64, 64);
+        CU(cudaIpcOpenMemHandle((void **)&tm.peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+        tm.ipc[r] = true;
+    }
+    tm.n = nranks;
+    tm.rank = rank;
+    return MKHE_OK;
+#else
+    (void)nranks; (void)rank; (void)all_handles;
+    return fail(ctx, MKHE_ERR_UNSUPPORTED, "no inter-process memory under emulation");
+#endif
+}
+int mkhe_team_join_local(mkhe_ctx *ctx, int max_parties, int nranks, int rank, mkhe_ctx *const *members) {
+    CHECK_CTX();
+    mkhe_ctx::Team &tm = ctx->team;
+    if (!members || nranks < 1 || nranks > MKHE_MAX_RANKS || rank < 0 || rank >= nranks || members[rank] != ctx)
+        return fail(ctx, MKHE_ERR_INVALID, "bad rank layout");
+    TRY(team_alloc(ctx, max_parties));
+    for (int r = 0; r < nranks; r++) {
+        mkhe_ctx *m = members[r];
+        if (!m || m->logN != ctx->logN || m->nQ != ctx->nQ || m->nP != ctx->nP) return fail(ctx, MKHE_ERR_INVALID, "team members must share the parameters");
+        if (m != ctx) {
+            if (cudaSetDevice(m->device) != cudaSuccess) return fail(ctx, MKHE_ERR_CUDA, "cudaSetDevice failed");
+            int rc = team_alloc(m, max_parties);
+            cudaSetDevice(ctx->device);
+            if (rc != MKHE_OK) return fail(ctx, rc, "team memory of member %d: %s", r, m->err.c_str());
+#ifndef MKHE_EMU
+            if (m->device != ctx->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(m->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, MKHE_ERR_CUDA, "no peer access from device %d to %d", ctx->device, m->device);
+                cudaGetLastError();
+            }
+#endif
+        }
+        tm.peer[r] = m->team.mem;
+    }
+    tm.n = nranks;
+    tm.rank = rank;
+    return MKHE_OK;
+}
+int mkhe_team_status(mkhe_ctx *ctx, int *timed_out) {
+    CHECK_CTX();
+    if (!timed_out) return MKHE_ERR_INVALID;
+    *timed_out = 0;
+    if (!ctx->team.mem) return MKHE_OK;
+    u64 w = 0;
+    CU(cudaMemcpyAsync(&w, ctx->team.mem + MKHE_MAX_RANKS, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *timed_out = w != 0;
+    return MKHE_OK;
+}
+// diagnostics: the 16 flag / status words at the base of this rank's team memory and the number of barriers it has issued
+int mkhe_team_flags(mkhe_ctx *ctx, uint64_t out[17]) {
+    CHECK_CTX();
+    if (!out || !ctx->team.mem) return MKHE_ERR_INVALID;
+    CU(cudaMemcpy(out, ctx->team.mem, 16 * 8, cudaMemcpyDeviceToHost));
+    out[16] = ctx->team.epoch;
+    return MKHE_OK;
+}
+int mkhe_ckks_mul_relin_limbs(mkhe_ctx *ctx, int level, int nb_rescales, int n0, const int *ids0, const mkhe_poly *op0, int n1,
+                              const int *ids1, const mkhe_poly *op1, const mkhe_swk *rlk_b, const mkhe_swk *rlk_d,
+                              const mkhe_swk *rlk_v, mkhe_swk u, int nOut, const int *idsOut, const mkhe_poly *out) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    TRY(check_ids(ctx, n0, ids0, n1, ids1, nOut, idsOut));
+    if (ctx->team.n < 1) return fail(ctx, MKHE_ERR_INVALID, "mkhe_team_import / mkhe_team_join_local has not been called");
+    if (nb_rescales < 0 || nb_rescales > level) return fail(ctx, MKHE_ERR_INVALID, "cannot Rescale: nb_rescales = %d at level %d", nb_rescales, level);
+    std::vector<u64 *> p0, p1, po, vb, vd, vv;
+    TRY(polys_of(ctx, n0 + 1, op0, level + 1, p0, "op0", ACC_READ));
+    TRY(polys_of(ctx, n1 + 1, op1, level + 1, p1, "op1", ACC_READ));
+    TRY(polys_of(ctx, nOut + 1, out, level + 1, po, "out"));
+    TRY(swks_of(ctx, n1, rlk_b, vb, "rlk_b", ACC_READ));
+    TRY(swks_of(ctx, n0, rlk_d, vd, "rlk_d", ACC_READ));
+    TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v", ACC_READ));
+    SWK_R(uk, u);
+    TRY(mul_relin_limbs_impl(ctx, level, nb_rescales, n0, ids0, p0.data(), n1, ids1, p1.data(), vb.data(), vd.data(), vv.data(), uk->d,
+                             nOut, idsOut, po.data()));
+    for (int t = 0; t <= nOut; t++) reinterpret_cast<Obj *>(out[t])->nlimbs = level + 1 - nb_rescales;
+    return MKHE_OK;
 }
 
 // ---- measurement ------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@
 #define MKHE_TILE 2048
 #define MKHE_NTT_THREADS 128     // NTT kernels: 16 elements per thread
 #define MKHE_THREADS 256         // element-wise kernels
+#define MKHE_MAX_RANKS 8          // ranks of a multi-GPU team
 #define MKHE_MAX_SLOTS 40        // limb slots per launch list (nQ + nP <= 40: PN16QP1761 has 34 + 4)
 
 // exchange buffer: the three register layouts of a tile (see tile_fwd) meet in one padded buffer with two
@@ -815,7 +816,6 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_mac_parties(MacPartiesArgs a, 
 //   ranks.  Between the two kernels and after the second one the host enqueues a tiny all-reduce as a stream-ordered barrier.
 //   grid as k_mac_parties.
 // ------------------------------------------------------------------------------------------------
-#define MKHE_MAX_RANKS 8
 struct P2PArgs {
     u64 *peer_stage[MKHE_MAX_RANKS];     // stage buffer of every rank (index = owner)
     u64 *peer_xy[MKHE_MAX_RANKS];        // x||y buffer of every rank
@@ -851,13 +851,13 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_mac_parties_scatter(MacParties
     *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(r0, r1);
 }
 // grid = (seg / (256 * 2), nslots, 2 * beta): blockIdx.z = which * beta + digit
-struct GatherArgs {
+struct ReduceGatherArgs {
     int beta, dmax, nslots;
     int slots[MKHE_MAX_SLOTS];
     int mods[MKHE_MAX_SLOTS];
     int logN;
 };
-__global__ void __launch_bounds__(MKHE_THREADS) k_reduce_gather(GatherArgs a, P2PArgs p, const ModC *mods) {
+__global__ void __launch_bounds__(MKHE_THREADS) k_reduce_gather(ReduceGatherArgs a, P2PArgs p, const ModC *mods) {
     const long N = 1L << a.logN;
     const int which = blockIdx.z / a.beta, digit = blockIdx.z - which * a.beta;
     const int slot = a.slots[blockIdx.y], mi = a.mods[blockIdx.y];
@@ -945,6 +945,83 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_conv(ConvArgs a, const ConvTab
 }
 
 // ------------------------------------------------------------------------------------------------
+// Team of ranks (limb-sharded ops): every rank owns a set of limb slots of every key, hoisted form and accumulator.
+//   Each rank has one block of "team memory" that all ranks map (CUDA IPC across processes, plain pointers inside one process):
+//     u64 [0, 8)  arrival flags of the barrier (flag r = last epoch rank r has reached)      [8] status word (1 = barrier timed out)
+//     then the exchange areas (element offsets from the base are the same on every rank): P parts of the key-switch accumulators,
+//     the polys that have to be complete on every rank before they are decomposed again, the gathered result.
+//   Producers write their limbs straight into EVERY rank's copy (peer stores over NVLink / NVSwitch) from the epilogue of the
+//   kernel that computes them; k_team_barrier then orders the consumers behind all producers.
+// ------------------------------------------------------------------------------------------------
+#define MKHE_TEAM_FLAGS 16                 // u64 words reserved at the base of the team memory
+struct TeamArgs {
+    u64 *peer[MKHE_MAX_RANKS];             // base of rank r's team memory as mapped by this rank
+    int nranks, rank;
+};
+#ifdef MKHE_EMU
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) { *p = v; }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) { return *p; }
+__device__ __forceinline__ u64 global_timer_ns() { return 0; }
+__device__ __forceinline__ void fence_system() {}
+#else
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) { u64 v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ u64 global_timer_ns() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void fence_system() { __threadfence_system(); }
+#endif
+// Barrier among the ranks, in stream order: everything this rank enqueued before it (peer stores included) is complete and
+// visible before its flag is raised on the peers; the kernel returns when every rank has raised its flag here.  One warp; lane r
+// talks to rank r.  A rank that never arrives (a crashed peer) ends the wait after `timeout_ns` with the status word set instead
+// of hanging the device.
+__global__ void __launch_bounds__(32) k_team_barrier(TeamArgs t, u64 epoch, u64 timeout_ns) {
+    const int lane = threadIdx.x;
+    fence_system();
+    if (lane < t.nranks) st_release_sys(t.peer[lane] + t.rank, epoch);
+    if (lane < t.nranks) {
+        const u64 *mine = t.peer[t.rank] + lane;
+        const u64 t0 = global_timer_ns();
+        while (ld_acquire_sys(mine) < epoch) {
+#ifdef MKHE_EMU
+            break;                         // the emulator runs one rank at a time: only single-rank teams get here
+#else
+            if (global_timer_ns() - t0 > timeout_ns) { t.peer[t.rank][MKHE_MAX_RANKS] = 1; break; }
+            __nanosleep(64);
+#endif
+        }
+    }
+    fence_system();
+}
+// The barrier as it is normally issued: this kernel only SIGNALS (one system-scope release-add on every peer's arrival counter, after
+// a system fence that orders the rank's earlier peer stores), the wait is a stream memory operation on the rank's own counter
+// (cuStreamWaitValue64, >= epoch * (nranks - 1), with a flush of outstanding remote writes) -- no thread spins on an SM, so the
+// barrier does not depend on kernels of different streams being co-resident.  Word MKHE_TEAM_COUNTER of the team memory.
+#define MKHE_TEAM_COUNTER 9
+#ifdef MKHE_EMU
+__device__ __forceinline__ void red_release_sys_add(u64 *p, u64 v) { *p += v; }
+#else
+__device__ __forceinline__ void red_release_sys_add(u64 *p, u64 v) { asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+#endif
+__global__ void __launch_bounds__(32) k_team_signal(TeamArgs t) {
+    const int lane = threadIdx.x;
+    fence_system();
+    if (lane < t.nranks && lane != t.rank) red_release_sys_add(t.peer[lane] + MKHE_TEAM_COUNTER, 1);
+}
+// result gather: limb `slot` of every listed poly goes to the same place of every rank's gather area.  grid = (N/512, nslots, npolys)
+struct GatherArgs {
+    PtrList src;             // per poly (local)
+    long dst_off[MKHE_MAX_PARTIES_K];      // per poly: element offset of its image in the team memory
+    int nslots;
+    int slots[MKHE_MAX_SLOTS];
+    int logN;
+};
+__global__ void __launch_bounds__(MKHE_THREADS) k_team_gather(GatherArgs a, TeamArgs t) {
+    const long N = 1L << a.logN;
+    const long off = (long)a.slots[blockIdx.y] * N + ((long)blockIdx.x * MKHE_THREADS + threadIdx.x) * 2;
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(a.src.p[blockIdx.z] + off);
+    for (int r = 0; r < t.nranks; r++) *reinterpret_cast<ulonglong2 *>(t.peer[r] + a.dst_off[blockIdx.z] + off) = v;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2+K4  tail of the key switch: InvNTT pass B fused with ModDownQPtoQ, the accumulation into the target and (for rotations)
 //   the automorphism  (mkrlwe/keyswitch_hoisted.go:34-39,217-245, basis_extension.go:192-232 with the P -> Q lift of
 //   :337-357,537-646).  Works on the per-product QP accumulators after pass A; every accumulator has nP spare limb slots.
@@ -961,6 +1038,9 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_conv(ConvArgs a, const ConvTab
 struct ModDownPArgs {
     u64 *acc[MKHE_MD_PRODUCTS];
     int np_limbs, p_slot0, vslot;
+    int nplist, plist[4];                  // the P limbs this launch handles (blockIdx.z indexes the list): all of them, or a rank's share
+    long pp_off[MKHE_MD_PRODUCTS];         // team mode: element offset of the product's P part (y_0.., then the fp64 terms) in the team memory
+    TeamArgs team;                         // nranks = 0: single GPU, results stay in the accumulator's own P and spare slots
     int logN;
 };
 template <int S1>
@@ -968,7 +1048,7 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_P(ModDownPArgs a, 
     constexpr int E = 1 << S1;
     const ConvTable &tab = *tabp;
     const long N = 1L << a.logN;
-    const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x, i = blockIdx.z;
+    const int col = blockIdx.x * MKHE_NTT_THREADS + threadIdx.x, i = a.plist[blockIdx.z];
     u64 *base = a.acc[blockIdx.y] + col;
     const int mi = tab.src_mod[i];
     const ModC m = mods[mi];
@@ -978,12 +1058,27 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_P(ModDownPArgs a, 
     for (int k = 0; k < E; k++) v[k] = ld_cg(p + (long)k * MKHE_TILE);
     cols_inv<S1>(v, twi + (long)mi * N, nttc(m), m);
     const u64 f = tab.qoverqiinvqi[i];
-    u64 *vp = base + (long)(a.vslot + i) * N;
+    if (a.team.nranks == 0) {
+        u64 *vp = base + (long)(a.vslot + i) * N;
 #pragma unroll
-    for (int k = 0; k < E; k++) {
-        const u64 y = mred(v[k], f, m.q, m.qinv);
-        p[(long)k * MKHE_TILE] = y;
-        vp[(long)k * MKHE_TILE] = (u64)__double_as_longlong(__ddiv_rn(__ull2double_rn(y), m.qd));
+        for (int k = 0; k < E; k++) {
+            const u64 y = mred(v[k], f, m.q, m.qinv);
+            p[(long)k * MKHE_TILE] = y;
+            vp[(long)k * MKHE_TILE] = (u64)__double_as_longlong(__ddiv_rn(__ull2double_rn(y), m.qd));
+        }
+    } else {
+        // limb sharding: this rank owns P limb i; every rank's ModDown of its Q limbs needs it -> peer stores into every rank's
+        // copy of the product's P part (the all-gather of SURVEY 8e (2), fused into the kernel that produces the data)
+        const long o = a.pp_off[blockIdx.y] + col;
+#pragma unroll
+        for (int k = 0; k < E; k++) {
+            const u64 y = mred(v[k], f, m.q, m.qinv);
+            const u64 d = (u64)__double_as_longlong(__ddiv_rn(__ull2double_rn(y), m.qd));
+            for (int r = 0; r < a.team.nranks; r++) {
+                a.team.peer[r][o + (long)i * N + (long)k * MKHE_TILE] = y;
+                a.team.peer[r][o + (long)(a.np_limbs + i) * N + (long)k * MKHE_TILE] = d;
+            }
+        }
     }
 }
 
@@ -993,7 +1088,13 @@ struct ModDownQArgs {
     int first[MKHE_MD_TARGETS + 1];        // products of target t: acc[first[t]] .. acc[first[t+1]-1]
     int split[MKHE_MD_TARGETS];            // 1, 2 or 4: the products of target t are dealt over `split` thread lanes of a CTA
     const u64 *acc[MKHE_MD_PRODUCTS];
-    int np_limbs, p_slot0, vslot;
+    const u64 *pp[MKHE_MD_PRODUCTS];       // P part of product s: y_i at pp + i N, fp64 term i at pp + (nP + i) N (the accumulator's own P and
+                                           // spare slots, or the rank's copy in the team memory)
+    int nqlist, qlist[MKHE_MAX_SLOTS];     // the Q limbs this launch handles (blockIdx.y indexes the list)
+    long dst_team_off[MKHE_MD_TARGETS];    // >= 0: the target has to be complete on every rank (it is decomposed again): stored into
+                                           // every rank's team memory at this element offset instead of dst
+    TeamArgs team;
+    int np_limbs;
     u64 galEl, galInv;                     // != 0 (RotateHoisted): the result goes through X -> X^galEl; the accumulators arrive with
                                            // their columns already permuted (k_mac_intt); galInv = galEl^-1 mod 2N
     int logN;
@@ -1010,7 +1111,7 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
     u64 (*rowbuf)[MKHE_NTT_THREADS] = reinterpret_cast<u64 (*)[MKHE_NTT_THREADS]>(smraw);
     const ConvTable &tab = *tabp;
     const long N = 1L << a.logN;
-    const int j = blockIdx.y, t = blockIdx.z;
+    const int j = a.qlist[blockIdx.y], t = blockIdx.z;
     const int PP = a.split[t], cols_per = MKHE_NTT_THREADS / PP;
     if ((int)blockIdx.x >= (MKHE_TILE / MKHE_NTT_THREADS) * PP) return;
     const int lane = threadIdx.x / cols_per, cin = threadIdx.x - lane * cols_per;
@@ -1039,6 +1140,7 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
 #pragma unroll 1
     for (int s = a.first[t] + lane; s < a.first[t + 1]; s += PP) {
         const u64 *src = a.acc[s] + col;
+        const u64 *pps = a.pp[s] + col;
         u64 v[E];
 #pragma unroll
         for (int k = 0; k < E; k++) v[k] = ld_cg(src + (long)j * N + (long)k * MKHE_TILE);
@@ -1051,8 +1153,8 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
                 double vi = 0.0;                  // reconstructRNS: vi += fl(y_i)/fl(p_i), limb order, RN; then truncation
 #pragma unroll
                 for (int i = 0; i < NP; i++) {
-                    y[i][k] = ld_cg(src + (long)(a.p_slot0 + i) * N + (long)(h + k) * MKHE_TILE);
-                    vi = __dadd_rn(vi, __longlong_as_double((long long)ld_cg(src + (long)(a.vslot + i) * N + (long)(h + k) * MKHE_TILE)));
+                    y[i][k] = ld_cg(pps + (long)i * N + (long)(h + k) * MKHE_TILE);
+                    vi = __dadd_rn(vi, __longlong_as_double((long long)ld_cg(pps + (long)(a.np_limbs + i) * N + (long)(h + k) * MKHE_TILE)));
                 }
                 ov[k] = __double2ull_rz(vi);
             }
@@ -1084,7 +1186,15 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
         }
     }
     u64 *dst = a.dst[t] + (long)j * N;
-    if (a.galEl == 0) {
+    if (a.dst_team_off[t] >= 0) {              // limb sharding: limb j of this poly goes to every rank (peer stores)
+        if (lane == 0) {
+            const long o = a.dst_team_off[t] + (long)j * N + col;
+            for (int rk = 0; rk < a.team.nranks; rk++) {
+#pragma unroll
+                for (int k = 0; k < E; k++) a.team.peer[rk][o + (long)k * MKHE_TILE] = r[k];
+            }
+        }
+    } else if (a.galEl == 0) {
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < E; k++) dst[col + (long)k * MKHE_TILE] = r[k];
@@ -1122,13 +1232,13 @@ struct TensorArgs {
     PtrList out;                  // [0] = component "0", [1+t]
     int nout;                     // parties in the output
     int nlimbs;
-    int mod_of_limb[MKHE_MAX_SLOTS];
+    int limbs[MKHE_MAX_SLOTS];    // the Q limbs of this launch (all of them up to the level, or a rank's share); limb == modulus index
     int logN;
 };
 __global__ void __launch_bounds__(MKHE_THREADS) k_tensor(TensorArgs a, const ModC *mods) {
     const long N = 1L << a.logN;
-    const int limb = blockIdx.y;
-    const ModC m = mods[a.mod_of_limb[limb]];
+    const int limb = a.limbs[blockIdx.y];
+    const ModC m = mods[limb];
     const long x = (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
     const long off = (long)limb * N + x;
     const long offA = (long)limb * a.strideA + x, offB = (long)limb * a.strideB + x;

@@ -143,6 +143,28 @@ class Evaluator:
         ctOut.Scale = newScale
         return ctOut
 
+    def MulRelinLimbSharded(self, op0, op1, rlkSet, ctOut=None):
+        """MulRelinNew executed by a team of ranks (mkhe_ckks_mul_relin_limbs): this rank computes the limb slots it owns, the
+        exchanges are peer stores fused into the producing kernels; every rank passes the same operands and gets the whole
+        result.  The context must have joined a team (Context.team_import / team_join_local).  ctOut: a ciphertext made by
+        newCiphertextBinary(op0, op1) beforehand (nothing is allocated during the call then), or None."""
+        if ctOut is None:
+            ctOut = self.newCiphertextBinary(op0, op1)
+        level = min(op0.Level(), op1.Level())
+        scale = op0.ScalingFactor() * op1.ScalingFactor()
+        nb, newScale = (0, scale)
+        if scale != 0 and level != 0 and self.params.Scale() > 0:
+            nb, newScale = self._nb_rescales(scale, level, self.params.Scale())
+        ids0, ids1, idsO = op0.ids(), op1.ids(), ctOut.ids()
+        self.ctx.ckks_mul_relin_limbs(
+            level, nb, ids0, op0.handles(ids0), ids1, op1.handles(ids1),
+            [rlkSet.GetRelinearizationKey(i).Value[0].h for i in ids1],
+            [rlkSet.GetRelinearizationKey(i).Value[1].h for i in ids0],
+            [rlkSet.GetRelinearizationKey(i).Value[2].h for i in ids0],
+            self.params.CRS[-1].h, idsO, ctOut.handles(idsO))
+        ctOut.Scale = newScale
+        return ctOut
+
     def _normalize(self, rotidx):
         n2 = self.params.N() // 2
         while rotidx >= n2:

@@ -335,6 +335,70 @@ def check_fork_after_queued_work(w: CKKSWorld, rounds=4):
         ev2.ctx.close()
 
 
+def check_limb_sharded(lit, nparties, nranks, lib=None, level=None, rounds=2, ids0=None, ids1=None, seed=0xB2000061):
+    """limb-sharded MulRelinNew (mkhe_ckks_mul_relin_limbs) on `nranks` ranks living in ONE process on ONE device (every rank is a
+    context of its own; mkhe_team_join_local): every rank's result is the oracle's whole result, bit for bit.  The ops of all
+    ranks are enqueued without any host synchronisation, op after op: the in-kernel barriers are the only ordering."""
+    op = O.MKParams(lit.logN, lit.Q, lit.P, lit.gamma, seed=seed, crs_rots=[])
+    prng = O.PRNG(seed ^ 0x7EA3)
+    oev = O.CKKSEvaluator(op, lit.scale)
+    ids = list(range(nparties))
+    ids0 = ids if ids0 is None else ids0
+    ids1 = ids if ids1 is None else ids1
+    o_rlk = {i: O.RelinKey(i, uniform_swk(prng, op), uniform_swk(prng, op), uniform_swk(prng, op)) for i in ids}
+    level = op.max_level() if level is None else level
+    ranks = []
+    for r in range(nranks):
+        dp = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, lib=lib, gamma=lit.gamma)
+        dp.SetCRS(-1, op.CRS[-1])
+        rl = mkrlwe.RelinearizationKeySet()
+        for i in ids:
+            rl.AddRelinearizationKey(mkrlwe.RelinearizationKey(dp.ctx, i, o_rlk[i].b, o_rlk[i].d, o_rlk[i].v))
+        ranks.append((dp, rl))
+    ctxs = [dp.ctx for dp, _ in ranks]
+    for r, c in enumerate(ctxs):
+        c.team_join_local(nparties, r, ctxs)
+    # Everything that allocates happens BEFORE the first sharded op: a device memory allocation is an implicit synchronisation point
+    # between the streams of one process (CUDA programming guide, "Implicit Synchronization"), and with all ranks in one process a
+    # spinning barrier of one rank would then sit in front of the other ranks' kernels.  (Ranks in processes of their own, one per
+    # GPU, do not share a device.)  The warm-up op sizes every scratch pool of the context.
+    want, ops = [], []
+    evs = [mkckks.Evaluator(dp) for dp, _ in ranks]
+    for n in range(rounds):
+        val0 = {"0": uniform_poly(prng, op.ringQ, level), **{i: uniform_poly(prng, op.ringQ, level) for i in ids0}}
+        val1 = {"0": uniform_poly(prng, op.ringQ, level), **{i: uniform_poly(prng, op.ringQ, level) for i in ids1}}
+        o0, o1 = O.Ciphertext({k: v.copy() for k, v in val0.items()}, lit.scale), O.Ciphertext({k: v.copy() for k, v in val1.items()}, lit.scale)
+        want.append(oev.mul_relin_new(o0, o1, o_rlk))
+        row = []
+        for (dp, rl), ev in zip(ranks, evs):
+            d0 = mkckks.Ciphertext.from_numpy(dp.ctx, val0, lit.scale)
+            d1 = mkckks.Ciphertext.from_numpy(dp.ctx, val1, lit.scale)
+            row.append((d0, d1, ev.newCiphertextBinary(d0, d1)))
+        ops.append(row)
+    for (dp, rl), ev, (d0, d1, _) in zip(ranks, evs, ops[0]):
+        ev.MulRelinNew(d0, d1, rl).free()                          # warm-up on one rank alone (not sharded)
+        dp.ctx.sync()
+    outs = []
+    for row in ops:
+        res = []
+        for (dp, rl), ev, (d0, d1, dout) in zip(ranks, evs, row):   # enqueue on every rank, op after op, no synchronisation
+            res.append(ev.MulRelinLimbSharded(d0, d1, rl, dout))
+        outs.append(res)
+    for c in ctxs:
+        c.sync()
+    for c in ctxs:
+        assert not c.team_timed_out(), f"a team barrier timed out; flags per rank: {[x.team_flags() for x in ctxs]}"
+    for n, row in enumerate(outs):
+        for r, dout in enumerate(row):
+            assert dout.Level() == want[n].level() and dout.Scale == want[n].scale
+            dv = dout.numpy()
+            assert set(dv) == set(want[n].value)
+            for k in want[n].value:
+                assert_same(dv[k], want[n].value[k], f"limb-sharded MulRelinNew, {nranks} ranks, op {n}, rank {r} [{k}]")
+    for c in ctxs:
+        c.close()
+
+
 def check_elementwise(w: CKKSWorld):
     """the evaluator ops either side of the key switches: AddNew / SubNew over different id sets, levels
     and scales (scale alignment through MultByConst), MultByConst with integer / fractional / negative / complex constants,

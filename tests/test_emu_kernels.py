@@ -68,6 +68,13 @@ def test_mixed_levels_and_abi_checks_under_emulation(emu):
     w.close()
 
 
+def test_limb_sharded_single_rank_under_emulation(emu):
+    """the limb-sharded op with a team of ONE rank (the emulator runs one rank at a time): team memory indirection of the P parts,
+    the broadcast of p_id, the gather + Rescale path -- against the oracle"""
+    parity.check_limb_sharded(PR.CKKS_PN14QP439.at_logn(12), 2, 1, lib=emu)
+    parity.check_limb_sharded(PR.CKKS_PN15QP880.at_logn(12), 3, 1, lib=emu, level=5, ids0=[0, 1], ids1=[1, 2])
+
+
 def test_pn16qp1761_full_limb_count_under_emulation(emu):
     """34 + 4 limbs, 17 two-limb digits"""
     w = parity.CKKSWorld(PR.PN16QP1761.at_logn(12), 2, lib=emu, rots=(1,))

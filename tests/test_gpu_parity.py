@@ -167,6 +167,24 @@ def test_benchmarked_bfv_config_against_oracle():
     w.close()
 
 
+@pytest.mark.parametrize("lit,logN,k,nranks", [(PR.CKKS_PN14QP439, 12, 2, 2), (PR.CKKS_PN15QP880, 12, 3, 4), (PR.CKKS_PN15QP880, 13, 4, 8),
+                                               (PR.CNN_PN14QP433, 14, 2, 3), (PR.CKKS_PN15QP880, 15, 4, 2)],
+                         ids=lambda x: getattr(x, "name", str(x)))
+def test_limb_sharded_mul_relin(lit, logN, k, nranks):
+    """MulRelinNew executed by a team of ranks, each computing the limb slots it owns (peer-store exchanges fused into
+    k_moddown_P / k_moddown_Q / k_team_gather, in-kernel flag barriers).  The ranks of these cases are contexts on ONE device, so
+    the driver's single-GPU test run covers the whole protocol; every rank's result against the oracle.  The last case is the
+    benchmarked size."""
+    parity.check_limb_sharded(lit.at_logn(logN), k, nranks, rounds=3 if logN < 15 else 2)
+
+
+def test_limb_sharded_id_sets_and_levels():
+    lit = PR.CKKS_PN15QP880.at_logn(12)
+    parity.check_limb_sharded(lit, 3, 4, level=5, ids0=[0, 1], ids1=[1, 2])      # overlapping id sets below the top level
+    parity.check_limb_sharded(lit, 3, 8, level=2, ids0=[0], ids1=[1, 2])         # more ranks than limbs: some ranks own nothing
+    parity.check_limb_sharded(lit, 2, 2, level=1)                                # the lowest level a product can be rescaled from
+
+
 def test_full_size_one_party_against_oracle():
     """one full-size (logN = 15, 14 limbs) MulRelinNew with k = 1 against the oracle (a few seconds of CPU)"""
     w = parity.CKKSWorld(PR.CKKS_PN15QP880, 1, rots=(1,))
