@@ -47,14 +47,34 @@ def uniform_limbs(rng, moduli, shape_prefix, N):
     return out
 
 
-def host_keys(lit, k, seed, rots=()):
+def iter_host_keys(lit, k, seed, rots=()):
+    """uniform key material in a fixed order, one switching key at a time (k = 32 is 5.4 GiB: nothing is kept on the host)"""
     rng = np.random.default_rng(seed)
     mods = list(lit.Q) + list(lit.P)
     beta = len(lit.Q)
     mk = lambda: uniform_limbs(rng, mods, (beta,), lit.N)
-    keys = {"u": mk(), "rlk": [(mk(), mk(), mk()) for _ in range(k)]}
-    keys["a"] = {r: mk() for r in rots}
-    keys["rk"] = [{r: mk() for r in rots} for _ in range(k)]
+    yield ("u", None, None, mk())
+    for i in range(k):
+        for j in range(3):
+            yield ("rlk", i, j, mk())
+    for r in rots:
+        yield ("a", r, None, mk())
+    for i in range(k):
+        for r in rots:
+            yield ("rk", i, r, mk())
+
+
+def host_keys(lit, k, seed, rots=()):
+    keys = {"rlk": [[None] * 3 for _ in range(k)], "a": {}, "rk": [{} for _ in range(k)]}
+    for kind, i, j, arr in iter_host_keys(lit, k, seed, rots):
+        if kind == "u":
+            keys["u"] = arr
+        elif kind == "rlk":
+            keys["rlk"][i][j] = arr
+        elif kind == "a":
+            keys["a"][i] = arr
+        else:
+            keys["rk"][i][j] = arr
     return keys
 
 
@@ -76,11 +96,12 @@ def algorithmic_model(k, ell, nP, N):
         "k_ntt_pass2": 2 * (3 * k * beta * D + 2 * ell) * limb,
         "k_ntt_pass1": 2 * 2 * ell * limb,
         "k_mac_parties": (4 * k * beta * D + 2 * beta * D) * limb,
-        "k_mac_digits": (4 * k * beta * D + 3 * beta * D + 4 * k * D) * limb,
-        "k_intt_passA": 2 * ((k + 1) * ell + 4 * k * D) * limb,
+        # digit multiply-accumulate fused with the inverse pass A: keys + hoisted forms + x, y, u once, 4k QP accumulators out
+        "k_mac_intt": (4 * k * beta * D + 3 * beta * D + 4 * k * D) * limb,
+        "k_intt_passA": 2 * (k + 1) * ell * limb,                      # tensor outputs only
         "k_intt_passB": 2 * (k + 1) * ell * limb,
-        "k_moddown_P": 4 * k * (2 * nP + 1) * limb,
-        "k_moddown_Q": (4 * k * (ell + nP + 1) + (2 * k + 1) * ell + (3 * k + 1) * ell) * limb,
+        "k_moddown_P": 4 * k * 3 * nP * limb,
+        "k_moddown_Q": (4 * k * (ell + 2 * nP) + (2 * k + 1) * ell + (3 * k + 1) * ell) * limb,
         "k_tensor": (3 * k + 3) * ell * limb,
         "k_rescale": (k + 1) * (2 * ell - 1) * limb,
     }
@@ -89,7 +110,8 @@ def algorithmic_model(k, ell, nP, N):
         "k_bcast_ntt_pass1": 3 * k * beta * D * (N // 2) * s1,
         "k_ntt_pass2": (3 * k * beta * D + 2 * ell) * (N // 2) * 11,
         "k_ntt_pass1": 2 * ell * (N // 2) * s1,
-        "k_intt_passA": ((k + 1) * ell + 4 * k * D) * (N // 2) * 11,
+        "k_mac_intt": 4 * k * D * (N // 2) * 11,
+        "k_intt_passA": (k + 1) * ell * (N // 2) * 11,
         "k_intt_passB": (k + 1) * ell * (N // 2) * s1,
         "k_moddown_P": 4 * k * nP * (N // 2) * s1,
         "k_moddown_Q": 4 * k * ell * (N // 2) * s1,
@@ -147,25 +169,32 @@ class ClockSampler:
 class DeviceWorkload:
     """keys + ciphertext pool of one GPU"""
 
-    def __init__(self, lit, k, device, seed, rots=(2,), npairs=4, batch=16, lanes=2):
+    def __init__(self, lit, k, device, seed, rots=(2,), npairs=4, batch=16, lanes=2, team=None):
+        """team = (world, rank, dist): the ops are limb-sharded over the ranks (mkhe_ckks_mul_relin_limbs); every rank builds the
+        SAME keys and ciphertexts (same seed) and every lane joins a team of its own"""
         from mkhe_kklss_b200 import mkckks, mkrlwe
-        self.lit, self.k, self.rots, self.batch = lit, k, rots, batch
+        self.lit, self.k, self.rots, self.batch, self.team = lit, k, rots, batch, team
         self.level = len(lit.Q) - 1
         self.params = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, device=device)
         self.ctx = self.params.ctx
         self.ev = mkckks.Evaluator(self.params)
-        hk = host_keys(lit, k, seed, rots)
-        self.hk = hk
-        self.params.SetCRS(-1, hk["u"])
-        for r in rots:
-            self.params.SetCRS(r, hk["a"][r])
         self.rlk = mkrlwe.RelinearizationKeySet()
         self.rk = mkrlwe.RotationKeySet()
-        for i in range(k):
-            b, d, v = hk["rlk"][i]
-            self.rlk.AddRelinearizationKey(mkrlwe.RelinearizationKey(self.ctx, i, b, d, v))
-            for r in rots:
-                self.rk.AddRotationKey(i, r, mkrlwe.SwitchingKey(self.ctx, hk["rk"][i][r]))
+        part = {}
+        for kind, i, j, arr in iter_host_keys(lit, k, seed, rots):      # uploaded one by one
+            if kind == "u":
+                self.params.SetCRS(-1, arr)
+            elif kind == "a":
+                self.params.SetCRS(i, arr)
+            elif kind == "rk":
+                self.rk.AddRotationKey(i, j, mkrlwe.SwitchingKey(self.ctx, arr))
+            else:
+                part[j] = mkrlwe.SwitchingKey(self.ctx, arr)
+                if j == 2:
+                    rl = mkrlwe.RelinearizationKey.__new__(mkrlwe.RelinearizationKey)
+                    rl.ID, rl.Value = i, [part[0], part[1], part[2]]
+                    self.rlk.AddRelinearizationKey(rl)
+                    part = {}
         rng = np.random.default_rng(seed + 99)
         self.host_pairs = [(host_ct(lit, k, self.level, rng), host_ct(lit, k, self.level, rng)) for _ in range(npairs)]
         self.pairs = [(mkckks.Ciphertext.from_numpy(self.ctx, a, lit.scale), mkckks.Ciphertext.from_numpy(self.ctx, b, lit.scale))
@@ -174,6 +203,12 @@ class DeviceWorkload:
         # lanes: forks of the context (mkhe_ctx_fork) -- same keys and ciphertext handles, own stream and scratch pools; op n
         # runs on lane n % lanes, so the bandwidth-bound stages of one op overlap the integer-bound ones of its neighbour
         self.lanes = [self.ctx] + [self.ctx.fork() for _ in range(lanes - 1)]
+        if team:
+            world, rank, dist = team
+            for ln in self.lanes:                       # CUDA IPC handles of every rank's team memory, lane by lane
+                hs = [None] * world
+                dist.all_gather_object(hs, ln.team_export(k))
+                ln.team_import(world, rank, hs)
         self.outs = [mkckks.Ciphertext.new(self.params, self.ids, self.level, lit.scale) for _ in self.lanes]
         self.out = self.outs[0]
         self.nb, self.new_scale = self.ev._nb_rescales(lit.scale * lit.scale, self.level, lit.scale)
@@ -183,11 +218,23 @@ class DeviceWorkload:
         self.kv = [g(i).Value[2].h for i in self.ids]
         self.ctx.sync()
 
-    def mul_relin_op(self, i, lane=None):
+    def _issue(self, ln, a, b, out, sharded=None):
+        """one MulRelinNew on lane ln: limb-sharded over the team when there is one"""
+        if (self.team is not None) if sharded is None else sharded:
+            self.lanes[ln].ckks_mul_relin_limbs(self.level, self.nb, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
+                                                self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, out.handles(self.ids))
+        else:
+            self.lanes[ln].ckks_mul_relin(self.level, self.nb, False, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
+                                          self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, out.handles(self.ids))
+
+    def mul_relin_op(self, i, lane=None, sharded=None):
         a, b = self.pairs[i % len(self.pairs)]
         ln = i % len(self.lanes) if lane is None else lane
-        self.lanes[ln].ckks_mul_relin(self.level, self.nb, False, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
-                                      self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, self.outs[ln].handles(self.ids))
+        self._issue(ln, a, b, self.outs[ln], sharded)
+
+    def result(self, lane=0):
+        nl = self.level + 1 - self.nb
+        return {kk: self.ctx.poly_download(p_.h, nl) for kk, p_ in self.outs[lane].Value.items()}
 
     def mul_relin_step(self, i):
         for j in range(self.batch):
@@ -266,9 +313,17 @@ class DeviceWorkload:
         nbytes = 0
         for ct, hp in ((a, pa), (b, pb)):
             for kk, poly in ct.Value.items():
-                lane.poly_upload_async(poly.h, hp[kk])
-                nbytes += hp[kk].nbytes
+                if self.team:           # this rank's share of the ciphertext: the limbs it owns (the all-gather over NVLink follows)
+                    for limb in self.own_limbs(self.level + 1):
+                        lane.poly_upload_limb_async(poly.h, limb, hp[kk][limb])
+                        nbytes += hp[kk][limb].nbytes
+                else:
+                    lane.poly_upload_async(poly.h, hp[kk])
+                    nbytes += hp[kk].nbytes
         return nbytes
+
+    def own_limbs(self, nlimbs):
+        return [j for j in range(nlimbs) if self.ctx.team_owns_limb(j)]
 
     def e2e_step(self, i):
         """`batch` times through the C ABI with HOST buffers: upload both operand ciphertexts, MulRelinNew, download the
@@ -291,12 +346,18 @@ class DeviceWorkload:
             a, b = self.pairs[n % len(self.pairs)]
             par = (n // L) % 2
             out = self.e2e_outs[ln][par]
-            lane.ckks_mul_relin(self.level, self.nb, False, self.ids, a.handles(self.ids), self.ids, b.handles(self.ids),
-                                self.kb, self.kd, self.kv, self.params.CRS[-1].h, self.ids, out.handles(self.ids))
+            if self.team:               # every rank uploaded 1 / N of both operands: make them whole on every rank
+                lane.team_allgather(self.level, a.handles(self.ids) + b.handles(self.ids))
+            self._issue(ln, a, b, out)
             for kk, poly in out.Value.items():
                 dst = self.res_host[ln][par][kk]
-                lane.poly_download_async(poly.h, dst)
-                d2h += dst.nbytes
+                if self.team:           # ... and reads back its share of the result
+                    for limb in self.own_limbs(dst.shape[0]):
+                        lane.poly_download_limb_async(poly.h, limb, dst[limb])
+                        d2h += dst[limb].nbytes
+                else:
+                    lane.poly_download_async(poly.h, dst)
+                    d2h += dst.nbytes
             self.e2e_n += 1
         return h2d, d2h
 
@@ -485,7 +546,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--parties", type=int, default=4)
+    ap.add_argument("--parties", type=int, default=8, help="parties of the headline workload (BASELINE config 2: n = 4 and n = 8)")
     ap.add_argument("--batch", type=int, default=16, help="ciphertext pairs (MulRelin ops) per step")
     ap.add_argument("--lanes", type=int, default=2, help="lanes (mkhe_ctx_fork) the ops of a step are spread over, per GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the k=8 / hoisted-Rotate / other-config side measurements")
@@ -508,6 +569,8 @@ def main():
                           f"k={k} parties, op0 != op1",
               "params": lit.name, "logN": lit.logN, "parties": k, "level": ell - 1, "ops_per_step": args.batch,
               "lanes_per_gpu": args.lanes,
+              "parallelism": "one GPU" if world == 1 else f"every op limb-sharded over the {world} GPUs (rank r owns the limb slots s with s mod {world} == r; "
+                                                         "peer-store exchanges over NVLink, in-stream barriers; total work fixed)",
               "l2_policy": "inputs larger than L2: every step streams the relinearisation keys "
                            f"({(3 * k + 1) * ell * (ell + nP) * 8 * N / 2**20:.0f} MiB) and cycles 4 ciphertext pairs"}
 
@@ -549,9 +612,10 @@ def main():
     # ---------------- GPU arm ----------------------------------------------------------------------
     dist = None
     if world > 1:
-        # keep stdout to the one JSON line: whatever NCCL has to say (its version banner included) goes to a file
-        os.environ["NCCL_DEBUG"] = os.environ.get("MKHE_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mkhe_nccl.%h.%p.log")
+        # keep stdout to the one JSON line: NCCL's communicator lines (init only: "comm ... rank r nranks N") go to stderr
+        os.environ["NCCL_DEBUG"] = os.environ.get("MKHE_NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
@@ -573,14 +637,18 @@ def main():
         return float(t.item())
 
     B = args.batch
-    wl = DeviceWorkload(lit, k, local_rank, seed=0xB2000002 + rank, batch=B, lanes=args.lanes)
+    # N > 1: ONE stream of ops, every op limb-sharded over the N GPUs (strong scaling: the total work is that of N = 1); every
+    # rank holds the same keys and operand ciphertexts (same seed) and ends every op with the whole result
+    team = (world, rank, dist) if world > 1 else None
+    SEED = 0xB2000002
+    wl = DeviceWorkload(lit, k, local_rank, seed=SEED, batch=B, lanes=args.lanes, team=team)
     clocks = ClockSampler(local_rank)
     clocks.start()
     ms = wl.timed(wl.mul_relin_step, args.steps, warmup, barrier)
     launches_timed = wl.last_launches
     clk = clocks.stop()
     ms = allmax(ms)
-    value = world * B * args.steps / (ms * 1e-3)
+    value = B * args.steps / (ms * 1e-3)
 
     # end to end through host buffers
     wl.prepare_e2e()
@@ -590,20 +658,33 @@ def main():
         bytes_io[0], bytes_io[1] = wl.e2e_step(i)
 
     ms_e2e = allmax(wl.timed_wall(e2e_fn, args.steps, warmup, barrier))
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    e2e_value = B * args.steps / (ms_e2e * 1e-3)
 
     # outputs of the TIMED workload kept for the parity check below (compared with the oracle on the same seeds): the
     # device-resident result of pair 0 (op 0 runs on lane 0) and the end-to-end path's host landing buffer of pair 0
     # (op n lands in buffer (n % lanes, (n // lanes) % 2); with 4 pairs and 2 lanes buffer (0, 0) always holds pair 0)
-    parity_got = None
+    parity_got, sharded_parity = None, None
+    e2e_limbs = wl.own_limbs(wl.level + 1 - wl.nb) if team else None
+    wl.sync()
+    wl.mul_relin_op(0, lane=0)
+    wl.sync()
+    res_dev = wl.result(0)
     if rank == 0 and not args.no_cpu_baseline:
-        wl.sync()
-        wl.mul_relin_op(0, lane=0)
-        wl.sync()
-        nl = wl.level + 1 - wl.nb
-        parity_got = {"device": {kk: wl.ctx.poly_download(p_.h, nl) for kk, p_ in wl.outs[0].Value.items()}}
+        parity_got = {"device": res_dev}
         if (2 * len(wl.lanes)) % len(wl.pairs) == 0:
             parity_got["e2e"] = {kk: np.array(v) for kk, v in wl.res_host[0][0].items()}
+    if team:
+        # the limb-sharded result of every rank against the single-GPU op (mkhe_ckks_mul_relin) of the same rank on the same operands
+        wl.mul_relin_op(0, lane=0, sharded=False)
+        wl.sync()
+        res_one = wl.result(0)
+        eq = all(np.array_equal(res_dev[kk], res_one[kk]) for kk in res_one)
+        import torch
+        t = torch.tensor([1 if eq else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        sharded_parity = {"n_ranks": world, "equal_on_every_rank": bool(int(t.item())), "timed_out": bool(wl.ctx.team_timed_out()),
+                          "against": "mkhe_ckks_mul_relin (one GPU) on the same keys and ciphertexts, every rank compares its own whole result",
+                          "words_compared_per_rank": int(sum(v.size for v in res_one.values()))}
 
     # per-kernel profile pass (events around every launch; separate from the timed region above)
     psteps = 8                      # MulRelin ops in the profiled pass
@@ -612,6 +693,9 @@ def main():
         wl.mul_relin_op(i, lane=0)         # one lane only: the per-kernel times are those of kernels running alone
     prof = wl.ctx.profile_end()
     model = algorithmic_model(k, ell, nP, N)
+    if world > 1:                   # a rank computes its share of the limb slots: per-rank algorithmic work = 1 / N of the op's
+        model["kernel_bytes"] = {kk: v / world for kk, v in model["kernel_bytes"].items()}
+        model["kernel_butterflies"] = {kk: v / world for kk, v in model["kernel_butterflies"].items()}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -677,12 +761,13 @@ def main():
         extra[f"rotate_hoisted_k{k}_ops_s"] = B * args.steps / (ms_rot * 1e-3)
         wl.ctx.close()
         del wl
-        wl8 = DeviceWorkload(lit, 8, local_rank, seed=0xB2000008, batch=B, lanes=args.lanes)
+        ko = 4 if k != 4 else 8        # the other party count of BASELINE config 2
+        wl8 = DeviceWorkload(lit, ko, local_rank, seed=0xB2000008, batch=B, lanes=args.lanes)
         ms8 = wl8.timed(wl8.mul_relin_step, args.steps, warmup)
-        extra["mulrelin_k8_ops_s"] = B * args.steps / (ms8 * 1e-3)
+        extra[f"mulrelin_k{ko}_ops_s"] = B * args.steps / (ms8 * 1e-3)
         wl8.prepare_rotate()
         ms_rot8 = wl8.timed(wl8.rotate_step, args.steps, warmup)
-        extra["rotate_hoisted_k8_ops_s"] = B * args.steps / (ms_rot8 * 1e-3)
+        extra[f"rotate_hoisted_k{ko}_ops_s"] = B * args.steps / (ms_rot8 * 1e-3)
         wl8.ctx.close()
         del wl8
         # the other BASELINE configs as side measurements: config 1 (PN14QP439, k = 2, the reference's CPU-runnable case) and
@@ -695,24 +780,41 @@ def main():
         extra["bfv_mulrelin_PN15QP880_k4_ops_s"] = bfv_mul_relin_ops(PR.BFV_PN15QP880, 4, local_rank, max(args.steps // 2, 2), warmup, 8, args.lanes)
 
     if not args.no_extras and world > 1:
-        # party-sharded MulRelin over NCCL (strong scaling of ONE op; the headline above is weak scaling over independent batches)
-        for ks in sorted({8, max(world, 2) * 2}):
-            if ks < world:
+        wl.ctx.close()
+        del wl
+        # other party counts, limb-sharded the same way (BASELINE config 4); k = 32 only on 4+ GPUs (5.4 GiB of keys per rank)
+        for ks in [4, 16] + ([32] if world >= 4 else []):
+            if ks == k:
                 continue
             try:
-                extra[f"sharded_mulrelin_k{ks}_ops_s"] = sharded_mul_relin(lit, ks, rank, world, local_rank, max(args.steps // 4, 2), warmup,
-                                                                           4, dist, barrier, allmax, nlanes=args.lanes)
-                if args.lanes > 1:
-                    extra[f"sharded_mulrelin_k{ks}_one_lane_ops_s"] = sharded_mul_relin(lit, ks, rank, world, local_rank, max(args.steps // 4, 2),
-                                                                                        warmup, 4, dist, barrier, allmax, nlanes=1)
-                extra[f"sharded_mulrelin_k{ks}_nccl_allreduce_ops_s"] = sharded_mul_relin(lit, ks, rank, world, local_rank, max(args.steps // 4, 2),
-                                                                                          warmup, 4, dist, barrier, allmax, nlanes=args.lanes, p2p=False)
-            except Exception as e:      # a missing NCCL build must not take the headline down with it
-                extra[f"sharded_mulrelin_k{ks}_error"] = str(e)[:200]
+                w2 = DeviceWorkload(lit, ks, local_rank, seed=0xB2000100 + ks, batch=4, lanes=args.lanes, team=team, npairs=2, rots=())
+                st = max(args.steps // 4, 2)
+                ms2 = allmax(w2.timed(w2.mul_relin_step, st, warmup, barrier))
+                extra[f"limb_sharded_mulrelin_k{ks}_ops_s"] = w2.batch * st / (ms2 * 1e-3)
+                w2.ctx.close()
+                del w2
+            except Exception as e:
+                extra[f"limb_sharded_mulrelin_k{ks}_error"] = str(e)[:200]
+        # for comparison: independent replicas, one stream of ops per GPU, no exchange (weak scaling; round 1's multi-GPU headline)
+        try:
+            w3 = DeviceWorkload(lit, 4, local_rank, seed=0xB2000300 + rank, batch=B, lanes=args.lanes, npairs=2, rots=())
+            ms3 = allmax(w3.timed(w3.mul_relin_step, max(args.steps // 2, 2), warmup, barrier))
+            extra["replicas_weak_mulrelin_k4_ops_s"] = world * B * max(args.steps // 2, 2) / (ms3 * 1e-3)
+            w3.ctx.close()
+            del w3
+        except Exception as e:
+            extra["replicas_weak_error"] = str(e)[:200]
+        # ... and round 1's party sharding (fused peer-memory exchange of the partial x || y, NCCL for barriers) at the headline k
+        if k >= world:
+            try:
+                extra[f"party_sharded_mulrelin_k{k}_ops_s"] = sharded_mul_relin(lit, k, rank, world, local_rank, max(args.steps // 4, 2), warmup,
+                                                                               4, dist, barrier, allmax, nlanes=args.lanes)
+            except Exception as e:
+                extra["party_sharded_error"] = str(e)[:200]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ops, cores, sec = cpu_oracle_run(lit, k, 3, 1, 1)
+        ops, cores, sec = cpu_oracle_run(lit, k, 3, 1, 1, seed=SEED)
         cpu = {"value": ops, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"3 full MulRelinNew calls after 1 warm-up, same workload ({sec:.2f} s each), single thread like the Go reference; "
                          "oracle/ C restatement (the Go reference cannot be built here)"}
@@ -720,23 +822,29 @@ def main():
     parity_check = None
     if parity_got is not None:
         # the checker (oracle/) on the seeds of the timed workload; every limb of every component must be identical
-        want = oracle_result(lit, k, seed=0xB2000002 + rank, pair=0)
+        want = oracle_result(lit, k, seed=SEED, pair=0)
         parity_check = {"config": config["workload"], "oracle": "oracle/ C restatement (checker only)", "compared": {}}
         for leg, got in parity_got.items():
-            eq = set(map(str, got)) == set(map(str, want)) and all(np.array_equal(got[kk], want[kk]) for kk in want)
+            eq = set(map(str, got)) == set(map(str, want))
+            for kk in want:
+                if leg == "e2e" and team:        # the rank read back the limbs it owns
+                    eq = eq and all(np.array_equal(got[kk][j], want[kk][j]) for j in e2e_limbs)
+                else:
+                    eq = eq and np.array_equal(got[kk], want[kk])
             parity_check["compared"][leg] = bool(eq)
         parity_check["equal"] = all(parity_check["compared"].values())
         parity_check["words_compared"] = int(sum(v.size for v in want.values()) * len(parity_got))
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-                "ms_per_step": ms / args.steps, "ms_per_op": ms / args.steps / B, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "ms_per_op": ms / args.steps / B, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": config,
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io[0], "d2h_bytes_per_step": bytes_io[1],
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches_timed,
-                "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity_check, "kernels": kernels, "extra": extra}
+                "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity_check, "sharded_parity": sharded_parity,
+                "kernels": kernels, "extra": extra}
         print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

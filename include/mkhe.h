@@ -82,6 +82,9 @@ int mkhe_poly_upload_limb(mkhe_ctx *ctx, mkhe_poly p, int limb, const uint64_t *
 int mkhe_poly_download_limb(mkhe_ctx *ctx, mkhe_poly p, int limb, uint64_t *dst);
 int mkhe_poly_upload(mkhe_ctx *ctx, mkhe_poly p, const uint64_t *src, int nlimbs);        /* contiguous [nlimbs][N] */
 int mkhe_poly_download(mkhe_ctx *ctx, mkhe_poly p, uint64_t *dst, int nlimbs);
+/* one limb, asynchronous, on the copy streams (same ordering rules as mkhe_poly_upload_async / _download_async) */
+int mkhe_poly_upload_limb_async(mkhe_ctx *ctx, mkhe_poly h, int limb, const uint64_t *src);
+int mkhe_poly_download_limb_async(mkhe_ctx *ctx, mkhe_poly h, int limb, uint64_t *dst);
 int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dst, mkhe_poly src);                          /* ring.Poly.Copy */
 int mkhe_poly_copy_lvl(mkhe_ctx *ctx, int level, mkhe_poly dst, mkhe_poly src);           /* ring.CopyValuesLvl (mkckks/evaluator.go:297-301): limbs 0..level, views unchanged */
 /* Asynchronous transfers for pipelines that keep the device busy while ciphertexts stream over PCIe (the Go shim's lazy
@@ -229,6 +232,11 @@ int mkhe_team_export(mkhe_ctx *ctx, int max_parties, uint8_t out[64]);
 int mkhe_team_import(mkhe_ctx *ctx, int nranks, int rank, const uint8_t *all_handles);
 int mkhe_team_join_local(mkhe_ctx *ctx, int max_parties, int nranks, int rank, mkhe_ctx *const *members);
 int mkhe_team_status(mkhe_ctx *ctx, int *timed_out);
+/* every rank holds valid data in the limbs it owns (limb mod nranks == rank, mkhe_team_owns_limb) of each listed poly -- e.g.
+ * uploaded there, 1 / nranks of the ciphertext per rank over PCIe; afterwards (in stream order) limbs 0..level of every poly are
+ * valid on every rank: the rank's limbs go to every rank's staging area by peer stores, barrier, local copy. */
+int mkhe_team_allgather(mkhe_ctx *ctx, int level, int npolys, const mkhe_poly *polys);
+int mkhe_team_owns_limb(mkhe_ctx *ctx, int limb);
 int mkhe_team_flags(mkhe_ctx *ctx, uint64_t out[17]);   /* diagnostics: flag / status words of this rank + barriers issued */
 int mkhe_ckks_mul_relin_limbs(mkhe_ctx *ctx, int level, int nb_rescales,
                               int n0, const int *ids0, const mkhe_poly *op0,

@@ -388,6 +388,20 @@ class Context:
         self.check(self.dll.mkhe_team_status(self.ptr, C.byref(v)))
         return bool(v.value)
 
+    def team_allgather(self, level, polys):
+        self.check(self.dll.mkhe_team_allgather(self.ptr, C.c_int(level), C.c_int(len(polys)), _harr(polys)))
+
+    def team_owns_limb(self, limb) -> bool:
+        return bool(self.dll.mkhe_team_owns_limb(self.ptr, C.c_int(limb)))
+
+    def poly_upload_limb_async(self, h, limb, arr: np.ndarray):
+        assert arr.dtype == np.uint64 and arr.flags.c_contiguous and arr.size == self.N
+        self.check(self.dll.mkhe_poly_upload_limb_async(self.ptr, C.c_uint64(h), C.c_int(limb), arr.ctypes.data_as(u64p)))
+
+    def poly_download_limb_async(self, h, limb, arr: np.ndarray):
+        assert arr.dtype == np.uint64 and arr.flags.c_contiguous and arr.size == self.N
+        self.check(self.dll.mkhe_poly_download_limb_async(self.ptr, C.c_uint64(h), C.c_int(limb), arr.ctypes.data_as(u64p)))
+
     def team_flags(self):
         buf = (C.c_uint64 * 17)()
         self.check(self.dll.mkhe_team_flags(self.ptr, buf))

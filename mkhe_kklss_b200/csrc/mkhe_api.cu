@@ -119,7 +119,8 @@ struct mkhe_ctx {
         u64 *peer[MKHE_MAX_RANKS] = {nullptr};
         bool ipc[MKHE_MAX_RANKS] = {false}; // peer[r] came from cudaIpcOpenMemHandle
         u64 epoch = 0;                      // barriers passed so far (the same on every rank: all ranks issue the same ops)
-        size_t off_pp = 0, off_p = 0, off_g = 0;
+        size_t off_pp = 0, off_p = 0, off_g = 0, off_in = 0;   // + two staging areas of 2 (maxk + 1) polys for mkhe_team_allgather
+        unsigned in_parity = 0;
         u64 timeout_ns = 5000000000ull;
         bool spin = false;                  // development: the spinning-kernel barrier instead of the stream memory wait
     } team;
@@ -340,7 +341,7 @@ void preload_kernels(const mkhe_ctx *ctx) {
     preload(k_conv<CONV_MODUP>); preload(k_conv<CONV_MODDOWN>); preload(k_tensor); preload(k_addsub<true>); preload(k_addsub<false>);
     preload(k_reduce); preload(k_rescale); preload(k_automorph); preload(k_scale); preload(k_mul_const); preload(k_neg);
     preload(k_mul_mont); preload(k_decrypt_sum); preload(k_mul2); preload(k_checksum); preload(k_bfly_peak);
-    preload(k_team_barrier); preload(k_team_signal); preload(k_team_gather);
+    preload(k_team_barrier); preload(k_team_signal); preload(k_team_gather); preload(k_copy_limbs);
 }
 
 int upload_tables(mkhe_ctx *ctx) {
@@ -797,7 +798,7 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
             for (int t = 0; t < ntg; t++) {
                 const Prod &p0 = prods[b0 + members[t0 + t][0]];
                 const size_t np = members[t0 + t].size();
-                qa.split[t] = np >= 4 ? 4 : (np >= 2 ? 2 : 1);
+                qa.split[t] = np >= 8 ? 8 : (np >= 4 ? 4 : (np >= 2 ? 2 : 1));
                 max_split = std::max(max_split, qa.split[t]);
                 qa.dst[t] = tg[t0 + t];
                 qa.src[t] = p0.src ? p0.src : (p0.add ? tg[t0 + t] : nullptr);
@@ -1204,28 +1205,40 @@ int mul_relin_limbs_impl(mkhe_ctx *ctx, int level, int nb_rescales, int n0, cons
         TRY(ext_products(ctx, level, 1, pr, 0, true));
         TRY(team_barrier(ctx));                            // every p_id is complete on every rank
     }
+    // the rank's limbs of the result go to every rank's gather area: straight from the epilogue of the last ModDown for the
+    // components it completes (component "0" and the parties of op0), by k_team_gather for the others
+    std::vector<u64 *> g(nOut + 1);
+    std::vector<bool> gathered(nOut + 1, false);
+    for (int t = 0; t <= nOut; t++) g[t] = tm.mem + tm.off_g + (size_t)t * poly_elems;
     if (n0 > 0) {
         TRY(decompose_impl(ctx, level, n0, p.data(), hp.data(), 0, lazy, &qp_own));
         std::vector<Prod> pr;
         for (int t = 0; t < n0; t++) {
-            pr.push_back(Prod{{u, nullptr}, {hp[t], nullptr}, out[1 + find_id(nOut, idsOut, ids0[t])], true});
-            pr.push_back(Prod{{rlk_v[t], nullptr}, {hp[t], nullptr}, out[0], true});
+            const int c = 1 + find_id(nOut, idsOut, ids0[t]);
+            Prod a{{u, nullptr}, {hp[t], nullptr}, out[c], true};
+            a.team_off = (long)(tm.off_g + (size_t)c * poly_elems);
+            Prod b{{rlk_v[t], nullptr}, {hp[t], nullptr}, out[0], true};
+            b.team_off = (long)tm.off_g;
+            pr.push_back(a);
+            pr.push_back(b);
+            gathered[c] = gathered[0] = true;
         }
         TRY(ext_products(ctx, level, 1, pr, 0, true));
     }
-    // the rank's limbs of the result go to every rank, Rescale runs on the gathered copy into the caller's polys
-    std::vector<u64 *> g(nOut + 1);
-    for (int t = 0; t <= nOut; t++) g[t] = tm.mem + tm.off_g + (size_t)t * poly_elems;
     if (q_own.n > 0) {
         GatherArgs ga;
         memset(&ga, 0, sizeof ga);
         ga.nslots = q_own.n;
         ga.logN = ctx->logN;
         for (int i = 0; i < q_own.n; i++) ga.slots[i] = q_own.slot[i];
-        for (int t = 0; t <= nOut; t++) { ga.src.p[t] = out[t]; ga.dst_off[t] = (long)(tm.off_g + (size_t)t * poly_elems); }
-        TeamArgs ta;
-        fill_team(ctx, ta);
-        LAUNCH(k_team_gather, dim3(N / (2 * MKHE_THREADS), q_own.n, nOut + 1), dim3(MKHE_THREADS), 0, ga, ta);
+        int ng = 0;
+        for (int t = 0; t <= nOut; t++)
+            if (!gathered[t]) { ga.src.p[ng] = out[t]; ga.dst_off[ng++] = (long)(tm.off_g + (size_t)t * poly_elems); }
+        if (ng > 0) {
+            TeamArgs ta;
+            fill_team(ctx, ta);
+            LAUNCH(k_team_gather, dim3(N / (2 * MKHE_THREADS), q_own.n, ng), dim3(MKHE_THREADS), 0, ga, ta);
+        }
     }
     TRY(team_barrier(ctx));
     if (nb_rescales > 0) {
@@ -1659,6 +1672,18 @@ int mkhe_poly_download_async(mkhe_ctx *ctx, mkhe_poly h, uint64_t *dst, int nlim
     POLY_R(o, h);
     if (nlimbs < 1 || nlimbs > o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
     return async_transfer(ctx, o, ctx->d2h, [&] { return cudaMemcpyAsync(dst, o->d, (size_t)nlimbs * ctx->N * 8, cudaMemcpyDeviceToHost, ctx->d2h); });
+}
+int mkhe_poly_upload_limb_async(mkhe_ctx *ctx, mkhe_poly h, int limb, const uint64_t *src) {
+    CHECK_CTX();
+    POLY(o, h);
+    if (limb < 0 || limb >= o->cap_limbs || !src) return fail(ctx, MKHE_ERR_INVALID, "limb %d out of range", limb);
+    return async_transfer(ctx, o, ctx->h2d, [&] { return cudaMemcpyAsync(o->d + (size_t)limb * ctx->N, src, (size_t)ctx->N * 8, cudaMemcpyHostToDevice, ctx->h2d); });
+}
+int mkhe_poly_download_limb_async(mkhe_ctx *ctx, mkhe_poly h, int limb, uint64_t *dst) {
+    CHECK_CTX();
+    POLY_R(o, h);
+    if (limb < 0 || limb >= o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "limb %d out of range", limb);
+    return async_transfer(ctx, o, ctx->d2h, [&] { return cudaMemcpyAsync(dst, o->d + (size_t)limb * ctx->N, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->d2h); });
 }
 int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dsth, mkhe_poly srch) {
     CHECK_CTX();
@@ -2437,7 +2462,8 @@ int team_alloc(mkhe_ctx *ctx, int max_parties) {
     tm.off_pp = MKHE_TEAM_FLAGS;
     tm.off_p = tm.off_pp + (size_t)2 * max_parties * 2 * ctx->nP * N;
     tm.off_g = tm.off_p + (size_t)max_parties * ctx->nQ * N;
-    tm.elems = tm.off_g + (size_t)(max_parties + 1) * ctx->nQ * N;
+    tm.off_in = tm.off_g + (size_t)(max_parties + 1) * ctx->nQ * N;
+    tm.elems = tm.off_in + (size_t)2 * 2 * (max_parties + 1) * ctx->nQ * N;
     if (cudaMalloc((void **)&tm.mem, tm.elems * 8) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMalloc(%zu) failed for the team memory", tm.elems * 8);
     CU(cudaMemsetAsync(tm.mem, 0, tm.elems * 8, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -2521,6 +2547,44 @@ int mkhe_team_status(mkhe_ctx *ctx, int *timed_out) {
     CU(cudaStreamSynchronize(ctx->stream));
     *timed_out = w != 0;
     return MKHE_OK;
+}
+int mkhe_team_allgather(mkhe_ctx *ctx, int level, int npolys, const mkhe_poly *polys) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    mkhe_ctx::Team &tm = ctx->team;
+    if (tm.n < 1) return fail(ctx, MKHE_ERR_INVALID, "mkhe_team_import / mkhe_team_join_local has not been called");
+    if (npolys < 1 || npolys > 2 * (tm.maxk + 1) || npolys > MKHE_MAX_PARTIES_K) return fail(ctx, MKHE_ERR_INVALID, "allgather of %d polys (team memory sized for %d)", npolys, 2 * (tm.maxk + 1));
+    std::vector<u64 *> pp;
+    TRY(polys_of(ctx, npolys, polys, level + 1, pp, "polys"));
+    if (tm.n == 1) return MKHE_OK;
+    const Slots own = own_slots(ctx, q_slots(level));
+    const size_t poly_elems = (size_t)ctx->nQ * ctx->N;
+    const size_t base = tm.off_in + (size_t)(tm.in_parity++ & 1) * 2 * (tm.maxk + 1) * poly_elems;     // two areas, alternating
+    GatherArgs ga;
+    memset(&ga, 0, sizeof ga);
+    ga.logN = ctx->logN;
+    for (int i = 0; i < npolys; i++) { ga.src.p[i] = pp[i]; ga.dst_off[i] = (long)(base + (size_t)i * poly_elems); }
+    if (own.n > 0) {
+        ga.nslots = own.n;
+        for (int i = 0; i < own.n; i++) ga.slots[i] = own.slot[i];
+        TeamArgs ta;
+        fill_team(ctx, ta);
+        LAUNCH(k_team_gather, dim3(ctx->N / (2 * MKHE_THREADS), own.n, npolys), dim3(MKHE_THREADS), 0, ga, ta);
+    }
+    TRY(team_barrier(ctx));
+    // the other ranks' limbs: from this rank's staging area into the polys
+    PtrList dst;
+    memset(&dst, 0, sizeof dst);
+    ga.nslots = 0;
+    for (int j = 0; j <= level; j++)
+        if (owner_of_slot(ctx, j) != tm.rank) ga.slots[ga.nslots++] = j;
+    for (int i = 0; i < npolys; i++) { ga.src.p[i] = tm.mem + base + (size_t)i * poly_elems; dst.p[i] = pp[i]; }
+    if (ga.nslots > 0) LAUNCH(k_copy_limbs, dim3(ctx->N / (2 * MKHE_THREADS), ga.nslots, npolys), dim3(MKHE_THREADS), 0, ga, dst);
+    return MKHE_OK;
+}
+int mkhe_team_owns_limb(mkhe_ctx *ctx, int limb) {
+    if (!ctx || ctx->team.n < 1) return 1;
+    return owner_of_slot(ctx, limb) == ctx->team.rank ? 1 : 0;
 }
 // diagnostics: the 16 flag / status words at the base of this rank's team memory and the number of barriers it has issued
 int mkhe_team_flags(mkhe_ctx *ctx, uint64_t out[17]) {

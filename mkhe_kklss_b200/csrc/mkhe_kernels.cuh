@@ -969,6 +969,19 @@ __device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) { u64 v; asm volatil
 __device__ __forceinline__ u64 global_timer_ns() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void fence_system() { __threadfence_system(); }
 #endif
+struct GatherArgs {
+    PtrList src;             // per poly (local)
+    long dst_off[MKHE_MAX_PARTIES_K];      // per poly: element offset of its image in the team memory
+    int nslots;
+    int slots[MKHE_MAX_SLOTS];
+    int logN;
+};
+// limbs `slots` of src[b] -> dst[b] on this device (the second half of mkhe_team_allgather).  grid = (N/512, nslots, npolys)
+__global__ void __launch_bounds__(MKHE_THREADS) k_copy_limbs(GatherArgs a, PtrList dst) {
+    const long N = 1L << a.logN;
+    const long off = (long)a.slots[blockIdx.y] * N + ((long)blockIdx.x * MKHE_THREADS + threadIdx.x) * 2;
+    *reinterpret_cast<ulonglong2 *>(dst.p[blockIdx.z] + off) = *reinterpret_cast<const ulonglong2 *>(a.src.p[blockIdx.z] + off);
+}
 // Barrier among the ranks, in stream order: everything this rank enqueued before it (peer stores included) is complete and
 // visible before its flag is raised on the peers; the kernel returns when every rank has raised its flag here.  One warp; lane r
 // talks to rank r.  A rank that never arrives (a crashed peer) ends the wait after `timeout_ns` with the status word set instead
@@ -1007,13 +1020,6 @@ __global__ void __launch_bounds__(32) k_team_signal(TeamArgs t) {
     if (lane < t.nranks && lane != t.rank) red_release_sys_add(t.peer[lane] + MKHE_TEAM_COUNTER, 1);
 }
 // result gather: limb `slot` of every listed poly goes to the same place of every rank's gather area.  grid = (N/512, nslots, npolys)
-struct GatherArgs {
-    PtrList src;             // per poly (local)
-    long dst_off[MKHE_MAX_PARTIES_K];      // per poly: element offset of its image in the team memory
-    int nslots;
-    int slots[MKHE_MAX_SLOTS];
-    int logN;
-};
 __global__ void __launch_bounds__(MKHE_THREADS) k_team_gather(GatherArgs a, TeamArgs t) {
     const long N = 1L << a.logN;
     const long off = (long)a.slots[blockIdx.y] * N + ((long)blockIdx.x * MKHE_THREADS + threadIdx.x) * 2;
@@ -1086,7 +1092,7 @@ struct ModDownQArgs {
     u64 *dst[MKHE_MD_TARGETS];
     const u64 *src[MKHE_MD_TARGETS];       // the sum starts from this poly (AddLvl onto the target or onto another poly); nullptr = zero
     int first[MKHE_MD_TARGETS + 1];        // products of target t: acc[first[t]] .. acc[first[t+1]-1]
-    int split[MKHE_MD_TARGETS];            // 1, 2 or 4: the products of target t are dealt over `split` thread lanes of a CTA
+    int split[MKHE_MD_TARGETS];            // 1, 2, 4 or 8: the products of target t are dealt over `split` thread lanes of a CTA
     const u64 *acc[MKHE_MD_PRODUCTS];
     const u64 *pp[MKHE_MD_PRODUCTS];       // P part of product s: y_i at pp + i N, fp64 term i at pp + (nP + i) N (the accumulator's own P and
                                            // spare slots, or the rank's copy in the team memory)
@@ -1171,19 +1177,19 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
         }
     }
     if (PP > 1) {                              // the lanes' partial sums meet in lane 0 (CTA-uniform branch)
-#pragma unroll 1
-        for (int l = 1; l < PP; l++) {
-            if (lane == l) {
+        if (lane > 0) {
 #pragma unroll
-                for (int k = 0; k < E; k++) rowbuf[k][cin] = r[k];
-            }
-            __syncthreads();
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < E; k++) r[k] = csub(r[k] + rowbuf[k][cin], m.q);     // r[k] may be a non-canonical start value (q): one subtraction, like AddLvl
-            }
-            __syncthreads();
+            for (int k = 0; k < E; k++) rowbuf[k][threadIdx.x] = r[k];
         }
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll 1
+            for (int l = 1; l < PP; l++) {
+#pragma unroll
+                for (int k = 0; k < E; k++) r[k] = csub(r[k] + rowbuf[k][l * cols_per + cin], m.q);   // r[k] may be a non-canonical start value (q): one subtraction, like AddLvl
+            }
+        }
+        __syncthreads();
     }
     u64 *dst = a.dst[t] + (long)j * N;
     if (a.dst_team_off[t] >= 0) {              // limb sharding: limb j of this poly goes to every rank (peer stores)

@@ -399,6 +399,40 @@ def check_limb_sharded(lit, nparties, nranks, lib=None, level=None, rounds=2, id
         c.close()
 
 
+def check_team_allgather(lit, nranks, npolys=3, lib=None, level=None, rounds=3):
+    """mkhe_team_allgather: every rank uploads only the limbs it owns (limb mod nranks == rank), afterwards every rank holds
+    every limb -- ranks = contexts on one device, several gathers back to back (the two staging areas alternate)"""
+    op = O.MKParams(lit.logN, lit.Q, lit.P, lit.gamma, seed=0xB2000071, crs_rots=[])
+    prng = O.PRNG(0xA11)
+    level = op.max_level() if level is None else level
+    dps = [mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, lib=lib, gamma=lit.gamma) for _ in range(nranks)]
+    ctxs = [dp.ctx for dp in dps]
+    for r, c in enumerate(ctxs):
+        c.team_join_local(max(npolys, 2), r, ctxs)
+    data = [[uniform_poly(prng, op.ringQ, level) for _ in range(npolys)] for _ in range(rounds)]
+    polys = [[[mkrlwe.Poly(c, level + 1) for _ in range(npolys)] for c in ctxs] for _ in range(rounds)]
+    for n in range(rounds):
+        for r, c in enumerate(ctxs):
+            for i in range(npolys):
+                junk = np.full((level + 1, lit.N), 0xDEAD0000 + r, dtype=np.uint64)
+                c.poly_upload(polys[n][r][i].h, junk)
+                for j in range(level + 1):
+                    assert c.team_owns_limb(j) == (j % nranks == r)
+                    if c.team_owns_limb(j):
+                        c.poly_upload_limb(polys[n][r][i].h, j, data[n][i][j])
+    for n in range(rounds):
+        for r, c in enumerate(ctxs):                    # enqueued rank after rank, no synchronisation
+            c.team_allgather(level, [p.h for p in polys[n][r]])
+    for c in ctxs:
+        c.sync()
+    for n in range(rounds):
+        for r, c in enumerate(ctxs):
+            for i in range(npolys):
+                assert_same(c.poly_download(polys[n][r][i].h, level + 1), data[n][i], f"allgather round {n} rank {r} poly {i}")
+    for c in ctxs:
+        c.close()
+
+
 def check_elementwise(w: CKKSWorld):
     """the evaluator ops either side of the key switches: AddNew / SubNew over different id sets, levels
     and scales (scale alignment through MultByConst), MultByConst with integer / fractional / negative / complex constants,

@@ -73,6 +73,7 @@ def test_limb_sharded_single_rank_under_emulation(emu):
     the broadcast of p_id, the gather + Rescale path -- against the oracle"""
     parity.check_limb_sharded(PR.CKKS_PN14QP439.at_logn(12), 2, 1, lib=emu)
     parity.check_limb_sharded(PR.CKKS_PN15QP880.at_logn(12), 3, 1, lib=emu, level=5, ids0=[0, 1], ids1=[1, 2])
+    parity.check_team_allgather(PR.CKKS_PN14QP439.at_logn(12), 1, lib=emu)
 
 
 def test_pn16qp1761_full_limb_count_under_emulation(emu):

@@ -178,6 +178,11 @@ def test_limb_sharded_mul_relin(lit, logN, k, nranks):
     parity.check_limb_sharded(lit.at_logn(logN), k, nranks, rounds=3 if logN < 15 else 2)
 
 
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_team_allgather(nranks):
+    parity.check_team_allgather(PR.CKKS_PN15QP880.at_logn(12), nranks)
+
+
 def test_limb_sharded_id_sets_and_levels():
     lit = PR.CKKS_PN15QP880.at_logn(12)
     parity.check_limb_sharded(lit, 3, 4, level=5, ids0=[0, 1], ids1=[1, 2])      # overlapping id sets below the top level
