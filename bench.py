@@ -174,6 +174,7 @@ class DeviceWorkload:
         SAME keys and ciphertexts (same seed) and every lane joins a team of its own"""
         from mkhe_kklss_b200 import mkckks, mkrlwe
         self.lit, self.k, self.rots, self.batch, self.team = lit, k, rots, batch, team
+        self._own = {}
         self.level = len(lit.Q) - 1
         self.params = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, device=device)
         self.ctx = self.params.ctx
@@ -314,16 +315,17 @@ class DeviceWorkload:
         for ct, hp in ((a, pa), (b, pb)):
             for kk, poly in ct.Value.items():
                 if self.team:           # this rank's share of the ciphertext: the limbs it owns (the all-gather over NVLink follows)
-                    for limb in self.own_limbs(self.level + 1):
-                        lane.poly_upload_limb_async(poly.h, limb, hp[kk][limb])
-                        nbytes += hp[kk][limb].nbytes
+                    lane.poly_upload_owned_async(poly.h, hp[kk])
+                    nbytes += len(self.own_limbs(self.level + 1)) * hp[kk][0].nbytes
                 else:
                     lane.poly_upload_async(poly.h, hp[kk])
                     nbytes += hp[kk].nbytes
         return nbytes
 
     def own_limbs(self, nlimbs):
-        return [j for j in range(nlimbs) if self.ctx.team_owns_limb(j)]
+        if nlimbs not in self._own:
+            self._own[nlimbs] = [j for j in range(nlimbs) if self.ctx.team_owns_limb(j)]
+        return self._own[nlimbs]
 
     def e2e_step(self, i):
         """`batch` times through the C ABI with HOST buffers: upload both operand ciphertexts, MulRelinNew, download the
@@ -352,9 +354,8 @@ class DeviceWorkload:
             for kk, poly in out.Value.items():
                 dst = self.res_host[ln][par][kk]
                 if self.team:           # ... and reads back its share of the result
-                    for limb in self.own_limbs(dst.shape[0]):
-                        lane.poly_download_limb_async(poly.h, limb, dst[limb])
-                        d2h += dst[limb].nbytes
+                    lane.poly_download_owned_async(poly.h, dst)
+                    d2h += len(self.own_limbs(dst.shape[0])) * dst[0].nbytes
                 else:
                     lane.poly_download_async(poly.h, dst)
                     d2h += dst.nbytes
@@ -548,7 +549,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--parties", type=int, default=8, help="parties of the headline workload (BASELINE config 2: n = 4 and n = 8)")
     ap.add_argument("--batch", type=int, default=16, help="ciphertext pairs (MulRelin ops) per step")
-    ap.add_argument("--lanes", type=int, default=2, help="lanes (mkhe_ctx_fork) the ops of a step are spread over, per GPU")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes (mkhe_ctx_fork) the ops of a step are spread over, per GPU (default: 2 on "
+                                                         "one GPU, 3 when the ops are sharded over 4+ GPUs: a third op in flight hides the barriers)")
     ap.add_argument("--no-extras", action="store_true", help="skip the k=8 / hoisted-Rotate / other-config side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lib", default=None, help="development: load this build of the library instead of the in-tree one")
@@ -562,6 +564,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.lanes <= 0:
+        args.lanes = 3 if world >= 4 else 2
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     lit, k = PR.CKKS_PN15QP880, args.parties
     ell, nP, N = len(lit.Q), len(lit.P), lit.N

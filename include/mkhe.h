@@ -85,6 +85,10 @@ int mkhe_poly_download(mkhe_ctx *ctx, mkhe_poly p, uint64_t *dst, int nlimbs);
 /* one limb, asynchronous, on the copy streams (same ordering rules as mkhe_poly_upload_async / _download_async) */
 int mkhe_poly_upload_limb_async(mkhe_ctx *ctx, mkhe_poly h, int limb, const uint64_t *src);
 int mkhe_poly_download_limb_async(mkhe_ctx *ctx, mkhe_poly h, int limb, uint64_t *dst);
+/* the limbs of [0, nlimbs) this rank of a team owns (all of them without a team), between a host buffer in whole-poly layout and the
+ * poly: one strided DMA.  With mkhe_team_allgather this is the multi-GPU upload path: 1 / nranks of a ciphertext per rank over PCIe. */
+int mkhe_poly_upload_owned_async(mkhe_ctx *ctx, mkhe_poly h, const uint64_t *src, int nlimbs);
+int mkhe_poly_download_owned_async(mkhe_ctx *ctx, mkhe_poly h, uint64_t *dst, int nlimbs);
 int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dst, mkhe_poly src);                          /* ring.Poly.Copy */
 int mkhe_poly_copy_lvl(mkhe_ctx *ctx, int level, mkhe_poly dst, mkhe_poly src);           /* ring.CopyValuesLvl (mkckks/evaluator.go:297-301): limbs 0..level, views unchanged */
 /* Asynchronous transfers for pipelines that keep the device busy while ciphertexts stream over PCIe (the Go shim's lazy

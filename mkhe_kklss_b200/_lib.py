@@ -402,6 +402,14 @@ class Context:
         assert arr.dtype == np.uint64 and arr.flags.c_contiguous and arr.size == self.N
         self.check(self.dll.mkhe_poly_download_limb_async(self.ptr, C.c_uint64(h), C.c_int(limb), arr.ctypes.data_as(u64p)))
 
+    def poly_upload_owned_async(self, h, arr: np.ndarray):
+        assert arr.dtype == np.uint64 and arr.flags.c_contiguous and arr.ndim == 2 and arr.shape[1] == self.N
+        self.check(self.dll.mkhe_poly_upload_owned_async(self.ptr, C.c_uint64(h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
+
+    def poly_download_owned_async(self, h, arr: np.ndarray):
+        assert arr.dtype == np.uint64 and arr.flags.c_contiguous and arr.ndim == 2 and arr.shape[1] == self.N
+        self.check(self.dll.mkhe_poly_download_owned_async(self.ptr, C.c_uint64(h), arr.ctypes.data_as(u64p), C.c_int(arr.shape[0])))
+
     def team_flags(self):
         buf = (C.c_uint64 * 17)()
         self.check(self.dll.mkhe_team_flags(self.ptr, buf))

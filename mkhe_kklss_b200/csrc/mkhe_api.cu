@@ -322,10 +322,10 @@ template <class K> void preload(K kernel) {
 template <int S1> void preload_s1(int nP) {
     preload(k_bcast_ntt_pass1<S1>); preload(k_ntt_pass1<S1>); preload(k_intt_passB<S1>); preload(k_moddown_P<S1>);
     switch (nP) {
-        case 1: preload(k_moddown_Q<S1, 1>); break;
-        case 2: preload(k_moddown_Q<S1, 2>); break;
-        case 3: preload(k_moddown_Q<S1, 3>); break;
-        default: preload(k_moddown_Q<S1, 4>); break;
+        case 1: preload(k_moddown_Q<S1, 1, false>); preload(k_moddown_Q<S1, 1, true>); break;
+        case 2: preload(k_moddown_Q<S1, 2, false>); preload(k_moddown_Q<S1, 2, true>); break;
+        case 3: preload(k_moddown_Q<S1, 3, false>); preload(k_moddown_Q<S1, 3, true>); break;
+        default: preload(k_moddown_Q<S1, 4, false>); preload(k_moddown_Q<S1, 4, true>); break;
     }
 }
 void preload_kernels(const mkhe_ctx *ctx) {
@@ -816,10 +816,10 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
                 const dim3 grid(COLGROUPS * max_split, qa.nqlist, ntg);
                 const size_t rowsm = MKHE_MDQ_SMEM(s1);      // partial sums of split targets, the row permutation of a rotation
                 switch (ctx->nP) {
-                    case 1: { auto k_moddown_Q_ = k_moddown_Q<s1, 1>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
-                    case 2: { auto k_moddown_Q_ = k_moddown_Q<s1, 2>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
-                    case 3: { auto k_moddown_Q_ = k_moddown_Q<s1, 3>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
-                    case 4: { auto k_moddown_Q_ = k_moddown_Q<s1, 4>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 1: { auto k_moddown_Q_ = team ? k_moddown_Q<s1, 1, true> : k_moddown_Q<s1, 1, false>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 2: { auto k_moddown_Q_ = team ? k_moddown_Q<s1, 2, true> : k_moddown_Q<s1, 2, false>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 3: { auto k_moddown_Q_ = team ? k_moddown_Q<s1, 3, true> : k_moddown_Q<s1, 3, false>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+                    case 4: { auto k_moddown_Q_ = team ? k_moddown_Q<s1, 4, true> : k_moddown_Q<s1, 4, false>; LAUNCH(k_moddown_Q_, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
                     default: return fail(ctx, MKHE_ERR_UNSUPPORTED, "key switch with %d special primes (1..4 supported)", ctx->nP);
                 }
                 return MKHE_OK;
@@ -1684,6 +1684,30 @@ int mkhe_poly_download_limb_async(mkhe_ctx *ctx, mkhe_poly h, int limb, uint64_t
     POLY_R(o, h);
     if (limb < 0 || limb >= o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "limb %d out of range", limb);
     return async_transfer(ctx, o, ctx->d2h, [&] { return cudaMemcpyAsync(dst, o->d + (size_t)limb * ctx->N, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->d2h); });
+}
+// the limbs of [0, nlimbs) this rank owns (limb mod nranks == rank; all of them without a team), between a host buffer in whole-poly
+// layout and the poly: ONE strided DMA per call
+int mkhe_poly_upload_owned_async(mkhe_ctx *ctx, mkhe_poly h, const uint64_t *src, int nlimbs) {
+    CHECK_CTX();
+    POLY(o, h);
+    if (nlimbs < 1 || nlimbs > o->cap_limbs || !src) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
+    const int n = std::max(ctx->team.n, 1), first = ctx->team.n > 1 ? ctx->team.rank : 0;
+    if (first >= nlimbs) return MKHE_OK;
+    const size_t cnt = (size_t)(nlimbs - first + n - 1) / n, row = (size_t)ctx->N * 8;
+    return async_transfer(ctx, o, ctx->h2d, [&] {
+        return cudaMemcpy2DAsync(o->d + (size_t)first * ctx->N, row * n, src + (size_t)first * ctx->N, row * n, row, cnt, cudaMemcpyHostToDevice, ctx->h2d);
+    });
+}
+int mkhe_poly_download_owned_async(mkhe_ctx *ctx, mkhe_poly h, uint64_t *dst, int nlimbs) {
+    CHECK_CTX();
+    POLY_R(o, h);
+    if (nlimbs < 1 || nlimbs > o->cap_limbs || !dst) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
+    const int n = std::max(ctx->team.n, 1), first = ctx->team.n > 1 ? ctx->team.rank : 0;
+    if (first >= nlimbs) return MKHE_OK;
+    const size_t cnt = (size_t)(nlimbs - first + n - 1) / n, row = (size_t)ctx->N * 8;
+    return async_transfer(ctx, o, ctx->d2h, [&] {
+        return cudaMemcpy2DAsync(dst + (size_t)first * ctx->N, row * n, o->d + (size_t)first * ctx->N, row * n, row, cnt, cudaMemcpyDeviceToHost, ctx->d2h);
+    });
 }
 int mkhe_poly_copy(mkhe_ctx *ctx, mkhe_poly dsth, mkhe_poly srch) {
     CHECK_CTX();

@@ -1078,12 +1078,10 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_P(ModDownPArgs a, 
         const long o = a.pp_off[blockIdx.y] + col;
 #pragma unroll
         for (int k = 0; k < E; k++) {
+            // only y travels (half the bytes of the exchange that loads the P owners' links most); the receivers redo the fp64
+            // division, operation for operation
             const u64 y = mred(v[k], f, m.q, m.qinv);
-            const u64 d = (u64)__double_as_longlong(__ddiv_rn(__ull2double_rn(y), m.qd));
-            for (int r = 0; r < a.team.nranks; r++) {
-                a.team.peer[r][o + (long)i * N + (long)k * MKHE_TILE] = y;
-                a.team.peer[r][o + (long)(a.np_limbs + i) * N + (long)k * MKHE_TILE] = d;
-            }
+            for (int r = 0; r < a.team.nranks; r++) a.team.peer[r][o + (long)i * N + (long)k * MKHE_TILE] = y;
         }
     }
 }
@@ -1110,7 +1108,7 @@ struct ModDownQArgs {
 // product per party) would otherwise be one long serial chain per thread while the single-product targets finish early: its
 // products are dealt over `split` lanes of the CTA (thread = (lane, column), 128 / split columns per CTA), every lane sums its
 // share and the partial sums meet in shared memory (exact modular adds, any order).
-template <int S1, int NP>
+template <int S1, int NP, bool TEAM>
 __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown_Q(ModDownQArgs a, const ConvTable *tabp, const ModC *mods, const ulonglong2 *twi) {
     constexpr int E = 1 << S1, HB = E < 8 ? E : 8;
     MKHE_SMEM(smraw);                          // E * 128 * 8 bytes
@@ -1128,6 +1126,9 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
     // canonical reduction instead of multSum's 128-bit accumulation, its Montgomery fold and a full MRed -- the same canonical
     // residue the reference stores (basis_extension.go:203-229)
     u64 sinv[2], nsi[NP][2];
+    double pqd[NP];                            // fl(p_i): limb-sharded runs recompute the fp64 terms from y_i (only y_i is exchanged)
+#pragma unroll
+    for (int i = 0; i < NP; i++) pqd[i] = mods[tab.src_mod[i]].qd;
     sinv[0] = tab.md_sinv[j][0]; sinv[1] = tab.md_sinv[j][1];
 #pragma unroll
     for (int i = 0; i < NP; i++) { nsi[i][0] = tab.md_nsrcinv[j][i][0]; nsi[i][1] = tab.md_nsrcinv[j][i][1]; }
@@ -1160,7 +1161,9 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
 #pragma unroll
                 for (int i = 0; i < NP; i++) {
                     y[i][k] = ld_cg(pps + (long)i * N + (long)(h + k) * MKHE_TILE);
-                    vi = __dadd_rn(vi, __longlong_as_double((long long)ld_cg(pps + (long)(a.np_limbs + i) * N + (long)(h + k) * MKHE_TILE)));
+                    const double term = TEAM ? __ddiv_rn(__ull2double_rn(y[i][k]), pqd[i])
+                                             : __longlong_as_double((long long)ld_cg(pps + (long)(a.np_limbs + i) * N + (long)(h + k) * MKHE_TILE));
+                    vi = __dadd_rn(vi, term);
                 }
                 ov[k] = __double2ull_rz(vi);
             }
@@ -1192,7 +1195,7 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown
         __syncthreads();
     }
     u64 *dst = a.dst[t] + (long)j * N;
-    if (a.dst_team_off[t] >= 0) {              // limb sharding: limb j of this poly goes to every rank (peer stores)
+    if (TEAM && a.dst_team_off[t] >= 0) {      // limb sharding: limb j of this poly goes to every rank (peer stores)
         if (lane == 0) {
             const long o = a.dst_team_off[t] + (long)j * N + col;
             for (int rk = 0; rk < a.team.nranks; rk++) {
