@@ -17,6 +17,7 @@
 #include <vector>
 
 #ifndef MKHE_EMU
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX: one range per C-ABI call (nsys / ncu timelines show the ops)
 #include <cuda.h>            // types of the stream memory operations only: the entry point is fetched at run time (no libcuda link)
 #ifdef MKHE_WITH_NCCL
 #include <nccl.h>
@@ -193,8 +194,17 @@ void debug_checksums(mkhe_ctx *ctx, const char *kernel) {
 // objects it touched (only when the root has forks)
 struct OpScope {
     mkhe_ctx *c;
-    explicit OpScope(mkhe_ctx *ctx) : c(ctx) {}
+    explicit OpScope(mkhe_ctx *ctx, const char *name) : c(ctx) {
+#ifndef MKHE_EMU
+        nvtxRangePushA(name);
+#else
+        (void)name;
+#endif
+    }
     ~OpScope() {
+#ifndef MKHE_EMU
+        nvtxRangePop();
+#endif
         if (c->touched.empty()) { c->override_ev = nullptr; return; }
         if (c->multi()) {
             cudaEvent_t ev = c->override_ev;
@@ -230,7 +240,7 @@ struct OpScope {
     if (!ctx) return MKHE_ERR_INVALID;                                                                          \
     if (ctx->sticky) return ctx->sticky;                                                                        \
     if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MKHE_ERR_CUDA, "cudaSetDevice failed");      \
-    OpScope op_scope_(ctx)
+    OpScope op_scope_(ctx, __func__)
 #define TRY(expr)                  \
     do {                           \
         int rc_ = (expr);          \
@@ -1300,17 +1310,23 @@ int rotate_hoisted_impl(mkhe_ctx *ctx, int level, int rotidx, int n, u64 *const 
 }  // namespace
 
 namespace {
-// before an object is freed: every lane that may still use it has drained
-int sync_all_users(mkhe_ctx *ctx, Obj *o) {
+// Objects live in the device's stream-ordered memory pool (cudaMallocAsync): allocating and freeing never synchronise the device
+// (the reference allocates a fresh ciphertext per evaluator call, mkckks/evaluator.go:306-316, and leaves it to the GC; a cudaMalloc /
+// cudaFree pair per poly would stall every lane).  An object is released on the freeing lane's stream, after the last use on
+// every other lane and after its last asynchronous transfer.
+int free_object_ordered(mkhe_ctx *ctx, Obj *o) {
     for (mkhe_ctx *l : ctx->root->lanes) {
-        if (!l) continue;
-        if (l != ctx && !o->use[l->lane].valid && !o->xfer) continue;
-        CU(cudaStreamSynchronize(l->stream));
-        if (o->xfer) {
-            CU(cudaStreamSynchronize(l->h2d));
-            CU(cudaStreamSynchronize(l->d2h));
-        }
+        if (!l || l == ctx) continue;
+        const Obj::Use &u = o->use[l->lane];
+        if (u.valid && u.ev) CU(cudaStreamWaitEvent(ctx->stream, u.ev, 0));
     }
+    if (o->xfer) CU(cudaStreamWaitEvent(ctx->stream, o->xfer, 0));
+    CU(cudaFreeAsync(o->d, ctx->stream));
+    if (o->xfer) cudaEventDestroy(o->xfer);
+    for (auto &u : o->use) if (u.wev_own) cudaEventDestroy(u.wev_own);
+    ctx->root->objs.erase(o);
+    ctx->touched.clear();
+    delete o;
     return MKHE_OK;
 }
 // order copy stream `cs` after everything enqueued on the context's stream so far, run `copy` on it, and make the next
@@ -1391,6 +1407,14 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
 #ifndef MKHE_EMU
+    {   // keep freed blocks in the device's pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PASS2);
     cudaFuncSetAttribute(k_intt_passA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_PA_SMEM);
     cudaFuncSetAttribute(k_mac_intt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MKHE_MI_SMEM(1));
@@ -1595,7 +1619,7 @@ int mkhe_poly_alloc(mkhe_ctx *ctx, int nlimbs, mkhe_poly *out) {
     if (!out || nlimbs < 1 || nlimbs > 64) return fail(ctx, MKHE_ERR_INVALID, "bad limb count %d", nlimbs);
     void *p = nullptr;
     size_t bytes = (size_t)nlimbs * ctx->N * 8;
-    if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+    if (cudaMallocAsync(&p, bytes, ctx->stream) != cudaSuccess) { cudaGetLastError(); return fail(ctx, MKHE_ERR_NOMEM, "cudaMallocAsync(%zu) failed", bytes); }
     CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
     Obj *o = new Obj();
     o->kind = OBJ_POLY; o->d = (u64 *)p; o->cap_limbs = nlimbs; o->nlimbs = nlimbs;
@@ -1607,14 +1631,7 @@ int mkhe_poly_alloc(mkhe_ctx *ctx, int nlimbs, mkhe_poly *out) {
 int mkhe_poly_free(mkhe_ctx *ctx, mkhe_poly h) {
     CHECK_CTX();
     POLY(o, h);
-    TRY(sync_all_users(ctx, o));
-    if (o->xfer) cudaEventDestroy(o->xfer);
-    for (auto &u : o->use) if (u.wev_own) cudaEventDestroy(u.wev_own);
-    CU(cudaFree(o->d));
-    ctx->root->objs.erase(o);
-    ctx->touched.clear();
-    delete o;
-    return MKHE_OK;
+    return free_object_ordered(ctx, o);
 }
 int mkhe_poly_set_nlimbs(mkhe_ctx *ctx, mkhe_poly h, int nlimbs) {
     CHECK_CTX();
@@ -1734,7 +1751,7 @@ int mkhe_swk_alloc(mkhe_ctx *ctx, mkhe_swk *out) {
     if (!out) return MKHE_ERR_INVALID;
     void *p = nullptr;
     size_t bytes = swk_elems(ctx) * 8;
-    if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(ctx, MKHE_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+    if (cudaMallocAsync(&p, bytes, ctx->stream) != cudaSuccess) { cudaGetLastError(); return fail(ctx, MKHE_ERR_NOMEM, "cudaMallocAsync(%zu) failed", bytes); }
     CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
     Obj *o = new Obj();
     o->kind = OBJ_SWK; o->d = (u64 *)p; o->cap_limbs = 0; o->nlimbs = 0;
@@ -1746,14 +1763,7 @@ int mkhe_swk_alloc(mkhe_ctx *ctx, mkhe_swk *out) {
 int mkhe_swk_free(mkhe_ctx *ctx, mkhe_swk h) {
     CHECK_CTX();
     SWK(o, h);
-    TRY(sync_all_users(ctx, o));
-    if (o->xfer) cudaEventDestroy(o->xfer);
-    for (auto &u : o->use) if (u.wev_own) cudaEventDestroy(u.wev_own);
-    CU(cudaFree(o->d));
-    ctx->root->objs.erase(o);
-    ctx->touched.clear();
-    delete o;
-    return MKHE_OK;
+    return free_object_ordered(ctx, o);
 }
 static int swk_limb_off(mkhe_ctx *ctx, int digit, int is_p, int limb, size_t *off) {
     // a switching key holds beta_max = ceil(nQ / alpha) digits (keys.go:245-256), not nQ

@@ -67,6 +67,15 @@ class Poly:
             self.ctx.poly_free(self.h)
             self.h = 0
 
+    def __del__(self):
+        # what runtime.SetFinalizer does on the Go side: a dropped poly returns its block to the device pool
+        # (stream-ordered: no synchronisation).  A context that is already closed has released everything itself.
+        try:
+            if self.h and getattr(self.ctx, "ptr", None):
+                self.free()
+        except Exception:
+            pass
+
 
 class SwitchingKey:
     """mkrlwe.SwitchingKey{Value []rlwe.PolyQP} (keys.go:23-25) on the device; also the value type of a
@@ -85,6 +94,13 @@ class SwitchingKey:
         if self.h:
             self.ctx.swk_free(self.h)
             self.h = 0
+
+    def __del__(self):
+        try:
+            if self.h and getattr(self.ctx, "ptr", None):
+                self.free()
+        except Exception:
+            pass
 
 
 class Ciphertext:

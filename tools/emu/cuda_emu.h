@@ -79,6 +79,8 @@ enum { cudaDevAttrMultiProcessorCount = 16 };
 static inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 6; return 0; }    // a small "device": persistent grids stay cheap to emulate
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
+static inline cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return 0; }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return 0; }
