@@ -219,6 +219,30 @@ int mkhe_comm_destroy(mkhe_ctx *ctx);
  * all-reduce of the c_0 contributions.  One node, one process per GPU, at most 8 ranks. */
 int mkhe_p2p_export(mkhe_ctx *ctx, uint8_t out[128]);
 int mkhe_p2p_import(mkhe_ctx *ctx, int nranks, int rank, const uint8_t *all_handles);
+/* ---- key generation and encryption on the device.  Randomness = the counter-based samplers of
+ * mkhe_prng.h ("mkhe-ctr-1"): every sampled polynomial is one stream of (seed, stream); a call documents how many streams it
+ * takes from `stream` on, in the order mkrlwe.KeyGenerator draws them.  Secret and public keys are polys of nQ + nP limbs
+ * (rlwe.PolyQP flattened: Q limbs, then P limbs), NTT domain; secret keys in Montgomery form like the reference's.
+ * Nothing crosses PCIe: at k = 32, logN = 15 that is 5.4 GiB of keys made where they are used. */
+int mkhe_sample_crs(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_swk out);           /* mkrlwe/params.go:47-58,77-99 (AddCRS): uniform then MForm, beta_max * (nQ + nP) streams (digit-major, Q limbs then P limbs) */
+int mkhe_keygen_secret(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, double pzero, mkhe_poly sk);   /* GenSecretKeyWithDistrib keygen.go:44-76 (GenSecretKey: pzero = 0.5): 1 stream */
+int mkhe_keygen_public(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_swk crs_a,
+                       mkhe_poly pk0, mkhe_poly pk1);                                          /* GenPublicKey keygen.go:88-109: 1 stream */
+int mkhe_keygen_switching_key(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_swk out);   /* GenSwitchingKey keygen.go:269-327 (g s + e): beta streams */
+int mkhe_keygen_relin(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_poly r, mkhe_swk crs_a, mkhe_swk crs_u,
+                      mkhe_swk b, mkhe_swk d, mkhe_swk v);                                     /* GenRelinearizationKey keygen.go:137-187: 3 beta streams (b | d | v) */
+int mkhe_keygen_rotation(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, int rotidx, mkhe_poly sk, mkhe_swk crs_rot,
+                         mkhe_swk rk);                                                         /* GenRotationKey keygen.go:190-229: beta streams */
+int mkhe_keygen_conjugation(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_swk crs_cj,
+                            mkhe_swk ck);                                                      /* GenConjugationKey keygen.go:240-266: beta streams */
+/* mkbfv.KeyGenerator.GenRelinearizationKey with GenBFVSwitchingKey (mkbfv/keygen.go:24-162): (b1, d1, v) | (b2, d2); crs_a1 = CRS[0],
+ * crs_a2 = CRS[-3], crs_u = CRS[-1].  5 beta streams: b1[i] = stream + 2i, b2[i] = stream + 2i + 1, then d1 | d2 | v. */
+int mkhe_keygen_bfv_relin(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_poly r, mkhe_swk crs_a1, mkhe_swk crs_a2,
+                          mkhe_swk crs_u, mkhe_swk b1, mkhe_swk b2, mkhe_swk d1, mkhe_swk d2, mkhe_swk v);
+/* Encryptor.Encrypt, coefficient-domain ciphertext (mkrlwe/encryptor.go:55-118); pt = 0: an encryption of zero; 3 streams (w, e0, e1) */
+int mkhe_encrypt(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, int level, mkhe_poly pt, mkhe_poly pk0, mkhe_poly pk1,
+                 mkhe_poly c0, mkhe_poly c1);
+
 /* ---- multi-GPU: limb-sharded MulRelinNew.  A team = the contexts ("ranks") that execute ONE op together: rank r
  * owns the limb slots s with s mod nranks == r of every key, hoisted form and accumulator (mkrlwe/keyswitch_hoisted.go:44-179 is
  * limb-local apart from ModDown's P limbs, the re-decomposed p_id and the final Rescale).  The three exchanges are peer stores from

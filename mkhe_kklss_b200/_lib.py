@@ -333,6 +333,41 @@ class Context:
     def decrypt(self, level, ct, sk, pt):
         self.check(self.dll.mkhe_decrypt(self.ptr, C.c_int(level), C.c_int(len(sk)), _harr(ct), _harr(sk), C.c_uint64(pt)))
 
+    # key generation and encryption on the device ("mkhe-ctr-1" streams, include/mkhe_prng.h)
+    def sample_crs(self, seed, stream, hswk):
+        self.check(self.dll.mkhe_sample_crs(self.ptr, C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(hswk)))
+
+    def keygen_secret(self, seed, stream, pzero, hsk):
+        self.check(self.dll.mkhe_keygen_secret(self.ptr, C.c_uint64(seed), C.c_uint64(stream), C.c_double(pzero), C.c_uint64(hsk)))
+
+    def keygen_public(self, seed, stream, hsk, crs_a, pk0, pk1):
+        self.check(self.dll.mkhe_keygen_public(self.ptr, C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(hsk), C.c_uint64(crs_a),
+                                               C.c_uint64(pk0), C.c_uint64(pk1)))
+
+    def keygen_switching_key(self, seed, stream, hsk, out):
+        self.check(self.dll.mkhe_keygen_switching_key(self.ptr, C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(hsk), C.c_uint64(out)))
+
+    def keygen_relin(self, seed, stream, hsk, hr, crs_a, crs_u, b, d, v):
+        self.check(self.dll.mkhe_keygen_relin(self.ptr, C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(hsk), C.c_uint64(hr),
+                                              C.c_uint64(crs_a), C.c_uint64(crs_u), C.c_uint64(b), C.c_uint64(d), C.c_uint64(v)))
+
+    def keygen_rotation(self, seed, stream, rotidx, hsk, crs_rot, rk):
+        self.check(self.dll.mkhe_keygen_rotation(self.ptr, C.c_uint64(seed), C.c_uint64(stream), C.c_int(rotidx), C.c_uint64(hsk),
+                                                 C.c_uint64(crs_rot), C.c_uint64(rk)))
+
+    def keygen_conjugation(self, seed, stream, hsk, crs_cj, ck):
+        self.check(self.dll.mkhe_keygen_conjugation(self.ptr, C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(hsk), C.c_uint64(crs_cj),
+                                                    C.c_uint64(ck)))
+
+    def keygen_bfv_relin(self, seed, stream, hsk, hr, crs_a1, crs_a2, crs_u, b1, b2, d1, d2, v):
+        self.check(self.dll.mkhe_keygen_bfv_relin(self.ptr, C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(hsk), C.c_uint64(hr),
+                                                  C.c_uint64(crs_a1), C.c_uint64(crs_a2), C.c_uint64(crs_u), C.c_uint64(b1),
+                                                  C.c_uint64(b2), C.c_uint64(d1), C.c_uint64(d2), C.c_uint64(v)))
+
+    def encrypt(self, seed, stream, level, pt, pk0, pk1, c0, c1):
+        self.check(self.dll.mkhe_encrypt(self.ptr, C.c_uint64(seed), C.c_uint64(stream), C.c_int(level), C.c_uint64(pt or 0),
+                                         C.c_uint64(pk0), C.c_uint64(pk1), C.c_uint64(c0), C.c_uint64(c1)))
+
     # multi-GPU (party sharding, NCCL)
     def comm_unique_id(self) -> bytes:
         buf = (C.c_uint8 * 128)()

@@ -351,6 +351,7 @@ void preload_kernels(const mkhe_ctx *ctx) {
     preload(k_conv<CONV_MODUP>); preload(k_conv<CONV_MODDOWN>); preload(k_tensor); preload(k_addsub<true>); preload(k_addsub<false>);
     preload(k_reduce); preload(k_rescale); preload(k_automorph); preload(k_scale); preload(k_mul_const); preload(k_neg);
     preload(k_mul_mont); preload(k_decrypt_sum); preload(k_mul2); preload(k_checksum); preload(k_bfly_peak);
+    preload(k_sample); preload(k_key_fma); preload(k_permute_ntt);
     preload(k_team_barrier); preload(k_team_signal); preload(k_team_gather); preload(k_copy_limbs);
 }
 
@@ -2483,6 +2484,244 @@ int mkhe_p2p_import(mkhe_ctx *ctx, int nranks, int rank, const uint8_t *all_hand
     (void)nranks; (void)rank; (void)all_handles;
     return fail(ctx, MKHE_ERR_UNSUPPORTED, "no peer memory under emulation");
 #endif
+}
+
+// ---- key generation and encryption on the device ---------------------------------------------------
+namespace {
+// `ninst` small polynomials (kind = ternary / gaussian), instance i from stream stream0 + i, lifted to the limb slots `s`
+// (coefficient domain) at out + i * inst_stride
+int sample_small(mkhe_ctx *ctx, int kind, uint64_t seed, uint64_t stream0, uint64_t thr53, int ninst, u64 *out, long inst_stride,
+                 const Slots &s, const u64 *add_to = nullptr, const u64 *add_pt = nullptr) {
+    SampleArgs a;
+    memset(&a, 0, sizeof a);
+    a.out = out; a.inst_stride = inst_stride; a.seed = seed; a.stream0 = stream0; a.stream_stride = 1; a.kind = kind; a.thr53 = thr53;
+    a.add_to = add_to; a.add_pt = add_pt;
+    a.nslots = s.n; a.logN = ctx->logN;
+    for (int i = 0; i < s.n; i++) a.slots[i] = s.slot[i];
+    LAUNCH(k_sample, dim3(ctx->N / MKHE_THREADS, ninst), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    return MKHE_OK;
+}
+// NTT(e_i) for `ninst` gaussian errors over Q u P (GenGaussianError, keygen.go:123-133), swk-shaped
+int gaussian_errors_ntt(mkhe_ctx *ctx, uint64_t seed, uint64_t stream0, int ninst, u64 *buf) {
+    const Slots qp = qp_slots(ctx, ctx->nQ - 1);
+    const long digit_elems = (long)ctx->dmax * ctx->N;
+    TRY(sample_small(ctx, SAMPLE_GAUSS, seed, stream0, 0, ninst, buf, digit_elems, qp));
+    std::vector<u64 *> ent(ninst);
+    for (int i = 0; i < ninst; i++) ent[i] = buf + (long)i * digit_elems;
+    return ntt_fwd(ctx, qp, ninst, ent.data(), ent.data());
+}
+int key_fma(mkhe_ctx *ctx, int ndigits, const u64 *e, const u64 *a, const u64 *s_mul, const u64 *s_gad, u64 *out, int mform_e, int mul_mode,
+            int neg, const u64 *gad = nullptr) {
+    const Slots qp = qp_slots(ctx, ctx->nQ - 1);
+    KeyFmaArgs k;
+    memset(&k, 0, sizeof k);
+    k.e = e; k.a = a; k.s_mul = s_mul; k.s_gad = s_gad; k.out = out; k.gad = gad;
+    k.mform_e = mform_e; k.mul_mode = mul_mode; k.neg = neg;
+    k.alpha = ctx->alpha; k.nQ = ctx->nQ; k.dmax = ctx->dmax;
+    for (int j = 0; j < ctx->nQ; j++) {
+        u64 pm = 1;
+        for (int i = 0; i < ctx->nP; i++) pm = h_mulmod(pm, ctx->mod[ctx->nQ + i] % ctx->mod[j], ctx->mod[j]);
+        k.pmont[j] = h_mform(pm, ctx->mod[j]);
+    }
+    k.nslots = qp.n; k.logN = ctx->logN;
+    for (int i = 0; i < qp.n; i++) k.slots[i] = qp.slot[i];
+    LAUNCH(k_key_fma, dim3(ctx->N / MKHE_THREADS, qp.n, ndigits), dim3(MKHE_THREADS), 0, k, ctx->d_mods);
+    return MKHE_OK;
+}
+int need_qp_poly(mkhe_ctx *ctx, Obj *o, const char *what) {
+    if (o->cap_limbs < ctx->dmax) return fail(ctx, MKHE_ERR_INVALID, "%s needs a poly of nQ + nP = %d limbs (rlwe.PolyQP)", what, ctx->dmax);
+    return MKHE_OK;
+}
+}  // namespace
+
+int mkhe_sample_crs(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_swk out) {
+    CHECK_CTX();
+    SWK(o, out);
+    SampleArgs a;
+    memset(&a, 0, sizeof a);
+    const Slots qp = qp_slots(ctx, ctx->nQ - 1);
+    a.out = o->d; a.inst_stride = (long)ctx->dmax * ctx->N; a.seed = seed; a.stream0 = stream; a.stream_stride = ctx->dmax; a.kind = SAMPLE_UNIFORM;
+    a.mform = 1;                                                     // params.go:54-56: uniform, then MFormLvl
+    a.nslots = qp.n; a.logN = ctx->logN;
+    for (int i = 0; i < qp.n; i++) a.slots[i] = qp.slot[i];
+    LAUNCH(k_sample, dim3(ctx->N / MKHE_THREADS, ctx->beta_max), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    return MKHE_OK;
+}
+int mkhe_keygen_secret(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, double pzero, mkhe_poly sk) {
+    CHECK_CTX();
+    POLY(s, sk);
+    TRY(need_qp_poly(ctx, s, "a secret key"));
+    if (!(pzero >= 0.0 && pzero <= 1.0)) return fail(ctx, MKHE_ERR_INVALID, "P(0) = %g out of range", pzero);
+    const Slots qp = qp_slots(ctx, ctx->nQ - 1);
+    // genSecretKeyFromSampler (keygen.go:44-55): ternary -> every limb of Q u P -> NTT -> MForm
+    TRY(sample_small(ctx, SAMPLE_TERNARY, seed, stream, (uint64_t)(pzero * 9007199254740992.0), 1, s->d, 0, qp));
+    TRY(ntt_fwd(ctx, qp, 1, &s->d, &s->d));
+    ScaleArgs a;
+    memset(&a, 0, sizeof a);
+    a.nlimbs = ctx->dmax; a.logN = ctx->logN;
+    for (int i = 0; i < ctx->dmax; i++) { a.mod_of_limb[i] = i; a.cmont[i] = ctx->tabs[i].c.r2; }
+    a.in.p[0] = s->d; a.out.p[0] = s->d;
+    LAUNCH(k_scale, dim3(ctx->N / MKHE_THREADS, ctx->dmax, 1), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+    s->nlimbs = ctx->dmax;
+    return MKHE_OK;
+}
+int mkhe_keygen_public(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_swk crs_a, mkhe_poly pk0, mkhe_poly pk1) {
+    CHECK_CTX();
+    POLY_R(s, sk); SWK_R(a, crs_a); POLY(p0, pk0); POLY(p1, pk1);
+    TRY(need_qp_poly(ctx, s, "a secret key")); TRY(need_qp_poly(ctx, p0, "a public key")); TRY(need_qp_poly(ctx, p1, "a public key"));
+    // GenPublicKey (keygen.go:88-109): pk1 = CRS[0][0], pk0 = NTT(e) - MRed(sk, pk1)
+    u64 *e;
+    TRY(get_scratch(ctx, "kg_e", swk_elems(ctx) * 8, &e));
+    TRY(gaussian_errors_ntt(ctx, seed, stream, 1, e));
+    CU(cudaMemcpyAsync(p1->d, a->d, (size_t)ctx->dmax * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    TRY(key_fma(ctx, 1, e, a->d, s->d, nullptr, p0->d, 0, 1, 0));
+    p0->nlimbs = p1->nlimbs = ctx->dmax;
+    return MKHE_OK;
+}
+int mkhe_keygen_switching_key(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_swk out) {
+    CHECK_CTX();
+    POLY_R(s, sk); SWK(o, out);
+    TRY(need_qp_poly(ctx, s, "a secret key"));
+    u64 *e;
+    TRY(get_scratch(ctx, "kg_e", swk_elems(ctx) * 8, &e));
+    TRY(gaussian_errors_ntt(ctx, seed, stream, ctx->beta_max, e));
+    return key_fma(ctx, ctx->beta_max, e, nullptr, nullptr, s->d, o->d, 1, 0, 0);
+}
+int mkhe_keygen_relin(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_poly r, mkhe_swk crs_a, mkhe_swk crs_u,
+                      mkhe_swk b, mkhe_swk d, mkhe_swk v) {
+    CHECK_CTX();
+    POLY_R(s, sk); POLY_R(rr, r); SWK_R(a, crs_a); SWK_R(u, crs_u); SWK(kb, b); SWK(kd, d); SWK(kv, v);
+    TRY(need_qp_poly(ctx, s, "a secret key")); TRY(need_qp_poly(ctx, rr, "a secret key"));
+    const int beta = ctx->beta_max;
+    u64 *e;
+    TRY(get_scratch(ctx, "kg_e", swk_elems(ctx) * 8, &e));
+    // GenRelinearizationKey (keygen.go:137-187):  b = -s a + e,  d = -r a + s g + e,  v = -s u - r g + e, streams b | d | v
+    TRY(gaussian_errors_ntt(ctx, seed, stream, beta, e));
+    TRY(key_fma(ctx, beta, e, a->d, s->d, nullptr, kb->d, 1, 1, 0));
+    TRY(gaussian_errors_ntt(ctx, seed, stream + beta, beta, e));
+    TRY(key_fma(ctx, beta, e, a->d, rr->d, s->d, kd->d, 1, 1, 0));
+    TRY(gaussian_errors_ntt(ctx, seed, stream + 2 * (uint64_t)beta, beta, e));
+    return key_fma(ctx, beta, e, u->d, s->d, rr->d, kv->d, 1, 2, 1);
+}
+namespace {
+int permute_sk(mkhe_ctx *ctx, const u64 *in, u64 galEl, u64 **out) {
+    TRY(get_scratch(ctx, "kg_sk", (size_t)ctx->dmax * ctx->N * 8, out));
+    LAUNCH(k_permute_ntt, dim3(ctx->N / MKHE_THREADS, ctx->dmax), dim3(MKHE_THREADS), 0, in, *out, galEl, ctx->dmax, ctx->logN);
+    return MKHE_OK;
+}
+}  // namespace
+int mkhe_keygen_rotation(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, int rotidx, mkhe_poly sk, mkhe_swk crs_rot, mkhe_swk rk) {
+    CHECK_CTX();
+    POLY_R(s, sk); SWK_R(a, crs_rot); SWK(o, rk);
+    TRY(need_qp_poly(ctx, s, "a secret key"));
+    while (rotidx < 0) rotidx += ctx->N / 2;
+    // GenRotationKey (keygen.go:190-229): rk = -sigma^-1(s) a_rot + s g + e
+    const u64 mask = ((u64)2 << ctx->logN) - 1, gal = galois_for_rotation(ctx->logN, rotidx);
+    u64 inv = 1;
+    for (int it = 0; it < 6; it++) inv = (inv * (2 - gal * inv)) & mask;
+    u64 *skOut, *e;
+    TRY(permute_sk(ctx, s->d, inv, &skOut));
+    TRY(get_scratch(ctx, "kg_e", swk_elems(ctx) * 8, &e));
+    TRY(gaussian_errors_ntt(ctx, seed, stream, ctx->beta_max, e));
+    return key_fma(ctx, ctx->beta_max, e, a->d, skOut, s->d, o->d, 1, 1, 0);
+}
+int mkhe_keygen_conjugation(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_swk crs_cj, mkhe_swk ck) {
+    CHECK_CTX();
+    POLY_R(s, sk); SWK_R(a, crs_cj); SWK(o, ck);
+    TRY(need_qp_poly(ctx, s, "a secret key"));
+    // GenConjugationKey (keygen.go:232-266): cj = -s a_cj + sigma_c(s) g + e
+    u64 *skOut, *e;
+    TRY(permute_sk(ctx, s->d, ((u64)2 << ctx->logN) - 1, &skOut));
+    TRY(get_scratch(ctx, "kg_e", swk_elems(ctx) * 8, &e));
+    TRY(gaussian_errors_ntt(ctx, seed, stream, ctx->beta_max, e));
+    return key_fma(ctx, ctx->beta_max, e, a->d, s->d, skOut, o->d, 1, 1, 0);
+}
+/* mkbfv.KeyGenerator.GenRelinearizationKey (mkbfv/keygen.go:24-88) with GenBFVSwitchingKey (:91-162): the gadget of digit i is
+ *   swk1: G_i = floor(R/q_i * t * [(R/q_i)^-1]_{q_i} * P / QMul) = (Q/q_i) t T_i P                      (R = Q QMul; exact)
+ *   swk2: G_i = floor(R/q'_i * t * [(R/q'_i)^-1]_{q'_i} * P / QMul) = floor(Q t T_i P / q'_i)            (q'_i = QMul_i)
+ * reduced here modulo every limb of Q u P without big integers: the first is a product of residues; for the second X = Q t T_i P is
+ * 0 modulo every limb of Q u P, so floor(X / q') = (X - X mod q') / q' = -(X mod q') (q')^-1 there.
+ * Streams: b1[i] = stream + 2i, b2[i] = stream + 2i + 1 (the reference interleaves them), then d1 | d2 | v, beta each. */
+int mkhe_keygen_bfv_relin(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, mkhe_poly sk, mkhe_poly r, mkhe_swk crs_a1, mkhe_swk crs_a2,
+                          mkhe_swk crs_u, mkhe_swk b1, mkhe_swk b2, mkhe_swk d1, mkhe_swk d2, mkhe_swk v) {
+    CHECK_CTX();
+    if (!ctx->nQMul) return fail(ctx, MKHE_ERR_INVALID, "BFV parameters not set (mkhe_ctx_set_bfv)");
+    if (ctx->alpha != 1) return fail(ctx, MKHE_ERR_UNSUPPORTED, "mkbfv key generation needs alpha = 1 (mkbfv/keyswitch.go:64-67)");
+    POLY_R(s, sk); POLY_R(rr, r); SWK_R(a1, crs_a1); SWK_R(a2, crs_a2); SWK_R(u, crs_u);
+    SWK(kb1, b1); SWK(kb2, b2); SWK(kd1, d1); SWK(kd2, d2); SWK(kv, v);
+    TRY(need_qp_poly(ctx, s, "a secret key")); TRY(need_qp_poly(ctx, rr, "a secret key"));
+    const int beta = ctx->beta_max, nQ = ctx->nQ, nP = ctx->nP, D = ctx->dmax;
+    const u64 *Q = ctx->mod.data(), *P = Q + nQ, *QM = Q + nQ + nP;
+    // gadget tables [2][beta][D], Montgomery form
+    std::vector<u64> gad((size_t)2 * beta * D);
+    auto prod_mod = [&](const u64 *f, int n, int skip, u64 m) { u64 x = 1; for (int l = 0; l < n; l++) if (l != skip) x = h_mulmod(x, f[l] % m, m); return x; };
+    for (int i = 0; i < beta; i++) {
+        const u64 qi = Q[i], qmi = QM[i];
+        const u64 T1 = h_invmod(h_mulmod(prod_mod(Q, nQ, i, qi), prod_mod(QM, nQ, -1, qi), qi), qi);           // [(R/q_i)^-1]_{q_i}
+        const u64 T2 = h_invmod(h_mulmod(prod_mod(Q, nQ, -1, qmi), prod_mod(QM, nQ, i, qmi), qmi), qmi);       // [(R/q'_i)^-1]_{q'_i}
+        const u64 Xq = h_mulmod(h_mulmod(prod_mod(Q, nQ, -1, qmi), ctx->T % qmi, qmi), h_mulmod(T2, prod_mod(P, nP, -1, qmi), qmi), qmi);   // X mod q'_i
+        for (int j = 0; j < D; j++) {
+            const u64 m = ctx->mod[j];
+            u64 g1 = h_mulmod(h_mulmod(prod_mod(Q, nQ, i, m), ctx->T % m, m), h_mulmod(T1 % m, prod_mod(P, nP, -1, m), m), m);
+            u64 g2 = h_mulmod((m - Xq % m) % m, h_invmod(qmi % m, m), m);
+            gad[((size_t)0 * beta + i) * D + j] = h_mform(g1, m);
+            gad[((size_t)1 * beta + i) * D + j] = h_mform(g2, m);
+        }
+    }
+    u64 *d_gad, *e;
+    TRY(get_scratch(ctx, "kg_gad", gad.size() * 8, &d_gad));
+    CU(cudaMemcpyAsync(d_gad, gad.data(), gad.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));                          // `gad` is pageable host memory of this frame
+    TRY(get_scratch(ctx, "kg_e", swk_elems(ctx) * 8, &e));
+    const long digit_elems = (long)D * ctx->N;
+    // b1[i] = -s a1[i] + e (stream + 2i), b2[i] = -s a2[i] + e (stream + 2i + 1)
+    {
+        const Slots qp = qp_slots(ctx, nQ - 1);
+        for (int which = 0; which < 2; which++) {
+            SampleArgs a;
+            memset(&a, 0, sizeof a);
+            a.out = e; a.inst_stride = digit_elems; a.seed = seed; a.stream0 = stream + which; a.stream_stride = 2; a.kind = SAMPLE_GAUSS;
+            a.nslots = qp.n; a.logN = ctx->logN;
+            for (int i = 0; i < qp.n; i++) a.slots[i] = qp.slot[i];
+            LAUNCH(k_sample, dim3(ctx->N / MKHE_THREADS, beta), dim3(MKHE_THREADS), 0, a, ctx->d_mods);
+            std::vector<u64 *> ent(beta);
+            for (int i = 0; i < beta; i++) ent[i] = e + (long)i * digit_elems;
+            TRY(ntt_fwd(ctx, qp, beta, ent.data(), ent.data()));
+            TRY(key_fma(ctx, beta, e, which ? a2->d : a1->d, s->d, nullptr, which ? kb2->d : kb1->d, 1, 1, 0));
+        }
+    }
+    // d_k = -r a_k + s G^(k) + e
+    TRY(gaussian_errors_ntt(ctx, seed, stream + 2 * (uint64_t)beta, beta, e));
+    TRY(key_fma(ctx, beta, e, a1->d, rr->d, s->d, kd1->d, 1, 1, 0, d_gad));
+    TRY(gaussian_errors_ntt(ctx, seed, stream + 3 * (uint64_t)beta, beta, e));
+    TRY(key_fma(ctx, beta, e, a2->d, rr->d, s->d, kd2->d, 1, 1, 0, d_gad + (size_t)beta * D));
+    // v = -s u - r g + e with the plain gadget (GenSwitchingKey)
+    TRY(gaussian_errors_ntt(ctx, seed, stream + 4 * (uint64_t)beta, beta, e));
+    return key_fma(ctx, beta, e, u->d, s->d, rr->d, kv->d, 1, 2, 1);
+}
+/* Encryptor.Encrypt, the coefficient-domain branch the CKKS / BFV flows take (mkrlwe/encryptor.go:55-118):
+ *   c0 = InvNTT(MForm(NTT(w)) (.) pk0) + e0 + pt,  c1 = InvNTT(MForm(NTT(w)) (.) pk1) + e1;  w ternary (stream), e0 (stream + 1), e1 (stream + 2) */
+int mkhe_encrypt(mkhe_ctx *ctx, uint64_t seed, uint64_t stream, int level, mkhe_poly pt, mkhe_poly pk0, mkhe_poly pk1, mkhe_poly c0,
+                 mkhe_poly c1) {
+    CHECK_CTX();
+    TRY(check_level(ctx, level));
+    POLY_R(p0, pk0); POLY_R(p1, pk1); POLY(o0, c0); POLY(o1, c1);
+    Obj *ptx = nullptr;
+    if (pt) { ptx = as_obj(ctx, pt, OBJ_POLY, ACC_READ); if (!ptx || ptx->cap_limbs < level + 1) return fail(ctx, MKHE_ERR_INVALID, "Encrypt: bad plaintext"); }
+    if (p0->cap_limbs < level + 1 || p1->cap_limbs < level + 1 || o0->cap_limbs < level + 1 || o1->cap_limbs < level + 1) return fail(ctx, MKHE_ERR_INVALID, "Encrypt: too few limbs");
+    const Slots qs = q_slots(level);
+    std::vector<u64 *> w;
+    TRY(poly_pool(ctx, "enc_w", 1, ctx->nQ, w));
+    TRY(sample_small(ctx, SAMPLE_TERNARY, seed, stream, (uint64_t)1 << 52, 1, w[0], 0, qs));
+    TRY(ntt_fwd(ctx, qs, 1, w.data(), w.data()));
+    TRY(mul2(ctx, qs, w[0], p0->d, nullptr, nullptr, o0->d));          // MForm(w) (.) pk0
+    TRY(mul2(ctx, qs, w[0], p1->d, nullptr, nullptr, o1->d));
+    u64 *outs[2] = {o0->d, o1->d};
+    TRY(ntt_inv(ctx, qs, 2, outs, outs));
+    TRY(sample_small(ctx, SAMPLE_GAUSS, seed, stream + 1, 0, 1, o0->d, 0, qs, o0->d, ptx ? ptx->d : nullptr));
+    TRY(sample_small(ctx, SAMPLE_GAUSS, seed, stream + 2, 0, 1, o1->d, 0, qs, o1->d, nullptr));
+    o0->nlimbs = o1->nlimbs = level + 1;
+    return MKHE_OK;
 }
 
 // ---- limb-sharded ops: the team of ranks ---------------------------------------------------------------

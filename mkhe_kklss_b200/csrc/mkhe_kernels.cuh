@@ -16,6 +16,7 @@
 // is used as uploaded.  Butterfly arithmetic: mkhe_arith.cuh.
 #pragma once
 #include "mkhe_arith.cuh"
+#include "../../include/mkhe_prng.h"
 
 #define MKHE_TILE 2048
 #define MKHE_NTT_THREADS 128     // NTT kernels: 16 elements per thread
@@ -1390,6 +1391,104 @@ __global__ void __launch_bounds__(MKHE_THREADS) k_mul2(const u64 *A, const u64 *
     u64 r = mred(mred(A[off], m.r2, m.q, m.qinv), B[off], m.q, m.qinv);
     if (Cc) r = csub(r + mred(mred(Cc[off], m.r2, m.q, m.qinv), D[off], m.q, m.qinv), m.q);
     out[off] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Key generation and encryption on the device (mkrlwe/keygen.go:44-327, encryptor.go:55-118).
+// Randomness: the counter-based samplers of include/mkhe_prng.h -- one thread per coefficient, any order, the CPU oracle draws
+// the same values.
+// ------------------------------------------------------------------------------------------------
+enum { SAMPLE_TERNARY = 0, SAMPLE_GAUSS = 1, SAMPLE_UNIFORM = 2 };
+struct SampleArgs {
+    u64 *out;                // instance i at out + i * inst_stride, limb slot s at + s * N
+    long inst_stride;
+    u64 seed, stream0;       // small samplers: instance i = stream0 + i * stream_stride; uniform: (instance i, slot s) = stream0 + i * stream_stride + s
+    long stream_stride;
+    int kind;
+    int mform;               // uniform: store MForm(x) (the CRS: params.go:54-56)
+    u64 thr53;               // ternary: floor(P(0) * 2^53)
+    const u64 *add_to;       // optional (encryption: ReadAndAddLvl): out = CRed(add_to + sample) on the same layout
+    const u64 *add_pt;       // optional second addend (the plaintext)
+    int nslots;
+    int slots[MKHE_MAX_SLOTS];
+    int logN;
+};
+// grid = (N/256, ninstances).  Small samplers: one draw per coefficient, written to every listed limb as ring.Sampler.Read +
+// ExtendBasisSmallNormAndCenter do (v >= 0 ? v : q + v).
+__global__ void __launch_bounds__(MKHE_THREADS) k_sample(SampleArgs a, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const u64 j = (u64)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    const int inst = blockIdx.y;
+    u64 *o = a.out + (long)inst * a.inst_stride + j;
+    if (a.kind == SAMPLE_UNIFORM) {
+        for (int s = 0; s < a.nslots; s++) {
+            const int slot = a.slots[s];
+            const ModC m = mods[slot];
+            const u64 x = mkhe_sample_uniform(a.seed, a.stream0 + (u64)inst * (u64)a.stream_stride + (u64)slot, j, m.q);
+            o[(long)slot * N] = a.mform ? mred(x, m.r2, m.q, m.qinv) : x;
+        }
+        return;
+    }
+    const int v = a.kind == SAMPLE_TERNARY ? mkhe_sample_ternary(a.seed, a.stream0 + (u64)inst * (u64)a.stream_stride, j, a.thr53)
+                                           : mkhe_sample_gaussian(a.seed, a.stream0 + (u64)inst * (u64)a.stream_stride, j);
+    for (int s = 0; s < a.nslots; s++) {
+        const int slot = a.slots[s];
+        const u64 q = mods[slot].q;
+        u64 x = v >= 0 ? (u64)v : q - (u64)(-v);
+        const long off = (long)inst * a.inst_stride + (long)slot * N + (long)j;
+        if (a.add_to) x = csub(a.add_to[off] + x, q);
+        if (a.add_pt) x = csub(x + a.add_pt[off], q);
+        o[(long)slot * N] = x;
+    }
+}
+// one digit of a key:  out = [neg] ( [MForm] e  [+ G_digit s_gad]  [-/+ MRed(a, s_mul)] )
+//   (GenSwitchingKey keygen.go:269-327, the relinearisation key's b / d / v :161-186, rotation / conjugation keys :212-264,
+//   the public key :98-108; mkbfv's GenBFVSwitchingKey mkbfv/keygen.go:91-162).  The gadget constant G_digit mod q_slot is P on
+//   the digit's own limbs and 0 elsewhere (pmont), or comes from a table (`gad`, BFV).  grid = (N/256, nslots, ndigits)
+struct KeyFmaArgs {
+    const u64 *e;            // [digit][dmax][N]: NTT(e_i), not in Montgomery form
+    const u64 *a;            // [digit][dmax][N]: CRS operand (NTT, Montgomery) or nullptr
+    const u64 *s_mul;        // [dmax][N]: the secret multiplied with a (NTT, Montgomery)
+    const u64 *s_gad;        // [dmax][N]: the secret of the gadget term (NTT, Montgomery) or nullptr
+    const u64 *gad;          // [digit][dmax]: MForm(G_digit mod q_slot), or nullptr = the P-on-own-limbs gadget of GenSwitchingKey
+    u64 *out;
+    int mform_e;             // e -> MForm(e) first (everything but the public key)
+    int mul_mode;            // 0 none, 1: -= MRed(a, s_mul) (MulCoeffsMontgomeryAndSub), 2: += (..AndAdd)
+    int neg;                 // NegLvl at the end: q - x, unreduced like lattigo
+    int alpha, nQ, dmax;
+    u64 pmont[MKHE_MAX_SLOTS];   // MForm(P mod q_j), Q limbs (MulScalarBigintLvl by P, keygen.go:289)
+    int nslots;
+    int slots[MKHE_MAX_SLOTS];
+    int logN;
+};
+__global__ void __launch_bounds__(MKHE_THREADS) k_key_fma(KeyFmaArgs a, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const int slot = a.slots[blockIdx.y], digit = blockIdx.z;
+    const ModC m = mods[slot];
+    const long j = (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    const long off = ((long)digit * a.dmax + slot) * N + j;
+    u64 x = a.e[off];
+    if (a.mform_e) x = mred(x, m.r2, m.q, m.qinv);
+    if (a.s_gad) {
+        if (a.gad) x = csub(x + mred(a.s_gad[(long)slot * N + j], a.gad[digit * a.dmax + slot], m.q, m.qinv), m.q);
+        else if (slot < a.nQ && slot / a.alpha == digit) x = csub(x + mred(a.s_gad[(long)slot * N + j], a.pmont[slot], m.q, m.qinv), m.q);
+    }
+    if (a.mul_mode) {
+        const u64 t = mred(a.a[off], a.s_mul[(long)slot * N + j], m.q, m.qinv);
+        x = a.mul_mode == 1 ? csub(x + m.q - t, m.q) : csub(x + t, m.q);
+    }
+    if (a.neg) x = m.q - x;
+    a.out[off] = x;
+}
+// ring.PermuteNTTWithIndexLvl with ring.PermuteNTTIndex(galEl, N) (keygen.go:212-214,243-245): out[i] = in[index(i)].  grid = (N/256, nlimbs)
+__global__ void __launch_bounds__(MKHE_THREADS) k_permute_ntt(const u64 *in, u64 *out, u64 galEl, int nlimbs, int logN) {
+    const long N = 1L << logN;
+    const u64 i = (u64)blockIdx.x * MKHE_THREADS + threadIdx.x, mask = ((u64)N << 1) - 1;
+    auto brev = [&](u64 x) { u64 r = 0; for (int b = 0; b < logN; b++) r |= ((x >> b) & 1) << (logN - 1 - b); return r; };
+    const u64 t1 = 2 * brev(i) + 1, t2 = (((galEl * t1) & mask) - 1) >> 1;
+    const u64 idx = brev(t2);
+    const int limb = blockIdx.y;
+    out[(long)limb * N + (long)i] = in[(long)limb * N + (long)idx];
 }
 
 // development: checksum of a buffer (race hunting: identical ops must produce identical intermediate buffers)

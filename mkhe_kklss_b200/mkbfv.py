@@ -23,7 +23,7 @@ class RelinearizationKey:
     """mkbfv.RelinearizationKey{Value [2]*mkrlwe.RelinearizationKey} (mkbfv/keys.go:6-9); only
     Value[0].Value[2] (= v) of the third slot is used (mkbfv/keyswitch_hoisted.go:191)."""
 
-    def __init__(self, ctx, id, b1, d1, v, b2, d2):
+    def __init__(self, ctx, id, b1=None, d1=None, v=None, b2=None, d2=None):
         self.ID = id
         self.b1, self.d1, self.v = SwitchingKey(ctx, b1), SwitchingKey(ctx, d1), SwitchingKey(ctx, v)
         self.b2, self.d2 = SwitchingKey(ctx, b2), SwitchingKey(ctx, d2)
@@ -40,6 +40,18 @@ class RelinearizationKeySet:
         if id not in self.Value:
             raise RuntimeError("cannot GetRelinearizationKey: there is no relinearization key for given id")
         return self.Value[id]
+
+
+class KeyGenerator(mkrlwe.KeyGenerator):
+    """mkbfv.KeyGenerator (mkbfv/keygen.go:8-162) on the device"""
+
+    def GenRelinearizationKey(self, sk, r):
+        """mkbfv/keygen.go:24-88 with GenBFVSwitchingKey (:91-162)"""
+        rlk = RelinearizationKey(self.ctx, sk.ID)
+        crs = self.params.CRS
+        self.ctx.keygen_bfv_relin(self.seed, self._take(5 * self.ctx.beta_max), sk.h, r.h, crs[0].h, crs[-3].h, crs[-1].h,
+                                  rlk.b1.h, rlk.b2.h, rlk.d1.h, rlk.d2.h, rlk.v.h)
+        return rlk
 
 
 class FastBasisExtender:

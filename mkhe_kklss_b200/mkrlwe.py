@@ -5,8 +5,9 @@ keys.go, idset.go); a Go `panic(msg)` becomes `raise RuntimeError(msg)` with the
 Everything heavy lives on the device: `Poly` / `SwitchingKey` are handles, a `Ciphertext` is a
 `map id -> Poly` exactly like `Ciphertext.Value map[string]*ring.Poly` (elements.go:17-19).
 
-Key generation, encryption and decryption are client-side and out of scope:
-keys and ciphertexts arrive as host arrays with the reference's byte layout and are uploaded once.
+Keys and ciphertexts made elsewhere arrive as host arrays with the reference's byte layout and are uploaded once; `KeyGenerator`,
+`Encryptor` and `Decryptor` below make / use them on the device from the documented counter-based
+streams of include/mkhe_prng.h, so a key set never crosses PCIe.
 """
 from __future__ import annotations
 
@@ -230,8 +231,18 @@ class Parameters:
         return self.gamma
 
     def SetCRS(self, idx, arr):
-        """upload CRS[idx] (params.go:37-58; generation itself stays with the caller)"""
+        """upload a CRS[idx] made elsewhere (params.go:37-58)"""
         self.CRS[idx] = SwitchingKey(self.ctx, arr)
+
+    CRS_STREAM_STRIDE = 1 << 20          # streams of CRS[idx] start at (idx mod 2^32) * 2^20: disjoint for every index
+
+    def AddCRS(self, idx, seed):
+        """params.go:77-99 on the device: beta uniform QP polys in Montgomery form from (seed, streams of idx).  Every party
+        that uses the same seed obtains the same CRS -- which is what a common reference string is."""
+        swk = SwitchingKey(self.ctx)
+        self.ctx.sample_crs(seed, (idx & 0xFFFFFFFF) * self.CRS_STREAM_STRIDE, swk.h)
+        self.CRS[idx] = swk
+        return swk
 
 
 class KeySwitcher:
@@ -327,3 +338,110 @@ class Decryptor:
         pt = Poly(self.ctx, level + 1)
         self.ctx.decrypt(level, ciphertext.handles(ids), [skSet[i].h for i in ids], pt.h)
         return pt
+
+
+class SecretKey:
+    """mkrlwe.SecretKey{Value rlwe.PolyQP, ID} (keys.go:10-13) on the device: one poly of nQ + nP limbs (Q limbs then P limbs),
+    NTT domain, Montgomery form.  `.h` is what Decryptor / the key generator take."""
+
+    def __init__(self, ctx, id, poly=None):
+        self.ID = id
+        self.Value = poly if poly is not None else Poly(ctx, ctx.D)
+        self.h = self.Value.h
+
+
+class PublicKey:
+    """mkrlwe.PublicKey{Value [2]rlwe.PolyQP, ID} (keys.go:15-19)"""
+
+    def __init__(self, ctx, id):
+        self.ID = id
+        self.Value = [Poly(ctx, ctx.D), Poly(ctx, ctx.D)]
+
+
+class KeyGenerator:
+    """mkrlwe.KeyGenerator (keygen.go) on the device.  The reference seeds a Blake2b PRNG from crypto/rand per generator; here the
+    caller gives (seed, first stream) of the counter-based generator "mkhe-ctr-1" (include/mkhe_prng.h) and every call consumes
+    the number of streams include/mkhe.h documents, in the order the Go methods draw their polynomials -- so the oracle's
+    KeyGenerator over oracle.CtrPRNG(seed, stream) makes the same keys bit for bit."""
+
+    def __init__(self, params: Parameters, seed: int, stream: int = 0):
+        self.params, self.ctx = params, params.ctx
+        self.seed, self.stream = int(seed), int(stream)
+
+    def _take(self, n):
+        s = self.stream
+        self.stream += n
+        return s
+
+    def GenSecretKey(self, id):
+        """keygen.go:58-60"""
+        return self.GenSecretKeyWithDistrib(0.5, id)
+
+    def GenSecretKeyWithDistrib(self, p, id):
+        """keygen.go:68-76"""
+        sk = SecretKey(self.ctx, id)
+        self.ctx.keygen_secret(self.seed, self._take(1), p, sk.h)
+        return sk
+
+    def GenPublicKey(self, sk: SecretKey):
+        """keygen.go:88-109"""
+        pk = PublicKey(self.ctx, sk.ID)
+        self.ctx.keygen_public(self.seed, self._take(1), sk.h, self.params.CRS[0].h, pk.Value[0].h, pk.Value[1].h)
+        return pk
+
+    def GenKeyPair(self, id):
+        sk = self.GenSecretKey(id)
+        return sk, self.GenPublicKey(sk)
+
+    def GenSwitchingKey(self, skIn: SecretKey, swk: SwitchingKey):
+        """keygen.go:269-327"""
+        self.ctx.keygen_switching_key(self.seed, self._take(self.ctx.beta_max), skIn.h, swk.h)
+
+    def GenRelinearizationKey(self, sk: SecretKey, r: SecretKey):
+        """keygen.go:137-187"""
+        if self.params.PCount() == 0:
+            raise RuntimeError("modulus P is empty")
+        rlk = RelinearizationKey(self.ctx, sk.ID, None, None, None)
+        self.ctx.keygen_relin(self.seed, self._take(3 * self.ctx.beta_max), sk.h, r.h, self.params.CRS[0].h, self.params.CRS[-1].h,
+                              rlk.Value[0].h, rlk.Value[1].h, rlk.Value[2].h)
+        return rlk
+
+    def GenRotationKey(self, rotidx, sk: SecretKey):
+        """keygen.go:190-229"""
+        if rotidx not in self.params.CRS:
+            raise RuntimeError("Cannot GenRotationKey: CRS for given rot idx is not generated")
+        rk = SwitchingKey(self.ctx)
+        self.ctx.keygen_rotation(self.seed, self._take(self.ctx.beta_max), rotidx, sk.h, self.params.CRS[rotidx].h, rk.h)
+        return rk
+
+    def GenDefaultRotationKeys(self, sk: SecretKey, rtkSet: RotationKeySet):
+        """keygen.go:232-237: the powers of two"""
+        for i in range(self.params.logN - 1):
+            rtkSet.AddRotationKey(sk.ID, 1 << i, self.GenRotationKey(1 << i, sk))
+
+    def GenConjugationKey(self, sk: SecretKey):
+        """keygen.go:240-266"""
+        ck = SwitchingKey(self.ctx)
+        self.ctx.keygen_conjugation(self.seed, self._take(self.ctx.beta_max), sk.h, self.params.CRS[-2].h, ck.h)
+        return ck
+
+
+class Encryptor:
+    """mkrlwe.Encryptor.Encrypt (encryptor.go:55-118), coefficient-domain ciphertexts (what mkckks / mkbfv make), on the device.
+    Each call takes three streams (w, e0, e1) of (seed, stream)."""
+
+    def __init__(self, params: Parameters, seed: int, stream: int = 0):
+        self.params, self.ctx = params, params.ctx
+        self.seed, self.stream = int(seed), int(stream)
+
+    def Encrypt(self, plaintext: Poly, pk: PublicKey, ctOut: Ciphertext):
+        """plaintext: coefficient-domain rlwe.Plaintext.Value on the device (or None: an encryption of zero)"""
+        levelQ = ctOut.Level() if plaintext is None else min(plaintext.nlimbs() - 1, ctOut.Level())
+        if pk.ID not in ctOut.Value:
+            ctOut.Value[pk.ID] = Poly(self.ctx, levelQ + 1)
+        s = self.stream
+        self.stream += 3
+        self.ctx.encrypt(self.seed, s, levelQ, None if plaintext is None else plaintext.h, pk.Value[0].h, pk.Value[1].h,
+                         ctOut.Value["0"].h, ctOut.Value[pk.ID].h)
+        ctOut.Value["0"].set_nlimbs(levelQ + 1)
+        ctOut.Value[pk.ID].set_nlimbs(levelQ + 1)

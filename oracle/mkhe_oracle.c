@@ -6,6 +6,7 @@
  * restated from its published algorithm; the reference call sites are given instead).
  */
 #include "mkhe_oracle.h"
+#include "../include/mkhe_prng.h"
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -504,6 +505,19 @@ void ork_sample_gaussian(ork_prng *p, int N, double sigma, int bound, int64_t *o
             break;
         }
     }
+}
+/* ---- the counter-based samplers of include/mkhe_prng.h ("mkhe-ctr-1"): what the device-side key generation and encryption
+ * draw from; the oracle's KeyGenerator / Encryptor run unchanged on top of them (oracle.CtrPRNG), so a key made on the GPU can be
+ * compared with the oracle's bit for bit.  Limb i of a uniform poly is stream `stream + i`. */
+void ork_ctr_uniform(uint64_t seed, uint64_t stream, const ork_ring *r, int level, uint64_t *out) {
+    for (int i = 0; i <= level; i++)
+        for (int j = 0; j < r->N; j++) out[(size_t)i * r->N + j] = mkhe_sample_uniform(seed, stream + (uint64_t)i, (uint64_t)j, r->q[i]);
+}
+void ork_ctr_ternary(uint64_t seed, uint64_t stream, int N, uint64_t thr53, int64_t *out) {
+    for (int j = 0; j < N; j++) out[j] = mkhe_sample_ternary(seed, stream, (uint64_t)j, thr53);
+}
+void ork_ctr_gaussian(uint64_t seed, uint64_t stream, int N, int64_t *out) {
+    for (int j = 0; j < N; j++) out[j] = mkhe_sample_gaussian(seed, stream, (uint64_t)j);
 }
 /* write a small signed vector into every limb (sampler ReadLvl / ExtendBasisSmallNormAndCenter) */
 void ork_lift_small(const ork_ring *r, int level, const int64_t *small, uint64_t *out) {

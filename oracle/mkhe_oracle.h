@@ -82,6 +82,10 @@ void ork_sample_uniform(ork_prng *p, const ork_ring *r, int level, uint64_t *out
 /* small-norm integer vectors (signed), then lifted to any ring */
 void ork_sample_ternary(ork_prng *p, int N, double pzero, int64_t *out);
 void ork_sample_gaussian(ork_prng *p, int N, double sigma, int bound, int64_t *out);
+/* counter-based samplers (include/mkhe_prng.h) */
+void ork_ctr_uniform(uint64_t seed, uint64_t stream, const ork_ring *r, int level, uint64_t *out);
+void ork_ctr_ternary(uint64_t seed, uint64_t stream, int N, uint64_t thr53, int64_t *out);
+void ork_ctr_gaussian(uint64_t seed, uint64_t stream, int N, int64_t *out);
 void ork_lift_small(const ork_ring *r, int level, const int64_t *small, uint64_t *out);
 
 /* ---------------- FastBasisExtender (mkrlwe/basis_extension.go) ---------------- */

@@ -41,7 +41,8 @@ def build(force: bool = False) -> str:
     """Compile the C oracle (gcc); building the checker is not using it."""
     src = os.path.join(_HERE, "mkhe_oracle.c")
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
-            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "mkhe_oracle.h"))):
+            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "mkhe_oracle.h")),
+            os.path.getmtime(os.path.join(_HERE, "..", "include", "mkhe_prng.h"))):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return _LIB_PATH
 
@@ -248,6 +249,36 @@ class PRNG:
         return out
 
 
+class CtrPRNG:
+    """the counter-based samplers of include/mkhe_prng.h behind the PRNG interface: every sampled polynomial takes the next
+    stream id(s) (a uniform poly: one per limb), in call order -- the order the device-side generators document
+    (include/mkhe.h, mkhe_keygen_*).  Swapping it in for PRNG makes KeyGenerator / Encryptor / MKParams reproduce what the GPU
+    makes from the same (seed, first stream)."""
+
+    def __init__(self, seed: int, stream: int = 0):
+        self.seed, self.stream = int(seed) & (2**64 - 1), int(stream)
+
+    def uniform(self, ring: Ring, level=None):
+        level = ring.nmod - 1 if level is None else level
+        out = np.zeros((level + 1, ring.N), dtype=np.uint64)
+        lib().ork_ctr_uniform(C.c_uint64(self.seed), C.c_uint64(self.stream), ring.ptr, C.c_int(level), _p(out))
+        self.stream += level + 1
+        return out
+
+    def ternary(self, N, pzero=0.5):
+        out = np.zeros(N, dtype=np.int64)
+        lib().ork_ctr_ternary(C.c_uint64(self.seed), C.c_uint64(self.stream), C.c_int(N), C.c_uint64(int(pzero * 2**53)), out.ctypes.data_as(i64p))
+        self.stream += 1
+        return out
+
+    def gaussian(self, N, sigma=3.2, bound=19):
+        assert sigma == 3.2 and bound == 19, "mkhe-ctr-1 fixes sigma = 3.2, bound = 19 (rlwe.DefaultSigma)"
+        out = np.zeros(N, dtype=np.int64)
+        lib().ork_ctr_gaussian(C.c_uint64(self.seed), C.c_uint64(self.stream), C.c_int(N), out.ctypes.data_as(i64p))
+        self.stream += 1
+        return out
+
+
 class BasisExtender:
     """mkrlwe.FastBasisExtender (basis_extension.go:12-357)."""
 
@@ -353,11 +384,11 @@ class MKParams:
     def new_swk(self):
         return np.zeros((self.beta(self.max_level()), self.D, self.N), dtype=np.uint64)
 
-    def add_crs(self, idx):
+    def add_crs(self, idx, prng=None):
         """uniform QP polys, then MForm (params.go:49-58, 77-99); one PRNG stream per index."""
-        if idx in self.CRS:
+        if idx in self.CRS and prng is None:
             return
-        prng = PRNG(self.seed ^ (0xC125 << 20) ^ (idx & 0xFFFFF))
+        prng = prng if prng is not None else PRNG(self.seed ^ (0xC125 << 20) ^ (idx & 0xFFFFF))
         swk = self.new_swk()
         for i in range(swk.shape[0]):
             swk[i, :self.nQ] = self.ringQ.mform(prng.uniform(self.ringQ))
@@ -372,9 +403,9 @@ class MKParams:
 # key generation (mkrlwe/keygen.go)
 # --------------------------------------------------------------------------------------------
 class KeyGenerator:
-    def __init__(self, params: MKParams, seed=1):
+    def __init__(self, params: MKParams, seed=1, prng=None):
         self.params = params
-        self.prng = PRNG(params.seed + 0x1000 + seed)
+        self.prng = prng if prng is not None else PRNG(params.seed + 0x1000 + seed)     # prng=CtrPRNG(..): the device's streams
 
     # QP helpers ---------------------------------------------------------------------------
     def _qp_ntt_mform(self, small):
@@ -448,19 +479,21 @@ class KeyGenerator:
             p.ringP.mul_mont_sub(np.ascontiguousarray(a[i, p.nQ:]), s.P, op)
             out[i, :p.nQ] = oq; out[i, p.nQ:] = op
 
-    def _gen_b(self, a, sk):
-        """b = -s*a + e in MForm (keygen.go:161-167)"""
+    def _gen_b_digit(self, ai, sk):
+        """one digit of b = -s*a + e in MForm (keygen.go:161-167)"""
         p = self.params
-        b = p.new_swk()
+        t = np.concatenate([p.ringQ.mul_mont(np.ascontiguousarray(ai[:p.nQ]), sk.Q),
+                            p.ringP.mul_mont(np.ascontiguousarray(ai[p.nQ:]), sk.P)])
+        t = np.concatenate([p.ringQ.invmform(np.ascontiguousarray(t[:p.nQ])), p.ringP.invmform(np.ascontiguousarray(t[p.nQ:]))])
+        e = self._gaussian_error_ntt()
+        t = np.concatenate([p.ringQ.sub(np.ascontiguousarray(e[:p.nQ]), np.ascontiguousarray(t[:p.nQ])),
+                            p.ringP.sub(np.ascontiguousarray(e[p.nQ:]), np.ascontiguousarray(t[p.nQ:]))])
+        return np.concatenate([p.ringQ.mform(np.ascontiguousarray(t[:p.nQ])), p.ringP.mform(np.ascontiguousarray(t[p.nQ:]))])
+
+    def _gen_b(self, a, sk):
+        b = self.params.new_swk()
         for i in range(b.shape[0]):
-            t = np.concatenate([p.ringQ.mul_mont(np.ascontiguousarray(a[i, :p.nQ]), sk.Q),
-                                p.ringP.mul_mont(np.ascontiguousarray(a[i, p.nQ:]), sk.P)])
-            t = np.concatenate([p.ringQ.invmform(np.ascontiguousarray(t[:p.nQ])), p.ringP.invmform(np.ascontiguousarray(t[p.nQ:]))])
-            e = self._gaussian_error_ntt()
-            t = np.concatenate([p.ringQ.sub(np.ascontiguousarray(e[:p.nQ]), np.ascontiguousarray(t[:p.nQ])),
-                                p.ringP.sub(np.ascontiguousarray(e[p.nQ:]), np.ascontiguousarray(t[p.nQ:]))])
-            b[i, :p.nQ] = p.ringQ.mform(np.ascontiguousarray(t[:p.nQ]))
-            b[i, p.nQ:] = p.ringP.mform(np.ascontiguousarray(t[p.nQ:]))
+            b[i] = self._gen_b_digit(a[i], sk)
         return b
 
     def _gen_v(self, sk, r):
@@ -516,9 +549,9 @@ class KeyGenerator:
 class Encryptor:
     """mkrlwe.Encryptor.Encrypt, coefficient-domain ciphertext branch (encryptor.go:55-118)."""
 
-    def __init__(self, params: MKParams, seed=7):
+    def __init__(self, params: MKParams, seed=7, prng=None):
         self.params = params
-        self.prng = PRNG(params.seed + 0x2000 + seed)
+        self.prng = prng if prng is not None else PRNG(params.seed + 0x2000 + seed)
 
     def encrypt(self, pt: np.ndarray, pk, id, scale=0.0):
         p = self.params
@@ -965,7 +998,10 @@ class BFVKeyGenerator(KeyGenerator):
         """GenRelinearizationKey mkbfv/keygen.go:24-88"""
         p = self.params
         a1, a2 = p.CRS[0], p.CRS[-3]
-        b1, b2 = self._gen_b(a1, sk), self._gen_b(a2, sk)
+        b1, b2 = p.new_swk(), p.new_swk()
+        for i in range(b1.shape[0]):                            # :51-63: e1, e2 drawn alternately, digit by digit
+            b1[i] = self._gen_b_digit(a1[i], sk)
+            b2[i] = self._gen_b_digit(a2[i], sk)
         d1, d2 = self.gen_bfv_switching_keys(sk)
         self._mul_sub_digits(a1, r, d1)
         self._mul_sub_digits(a2, r, d2)

@@ -591,6 +591,147 @@ def check_ckks_semantics(w: CKKSWorld):
     assert np.abs(dec_dev(w.dev.MulPtxtNew(d0, dpt, lit.scale)) - mp * msgs[0]).max() <= bound, "MulPtxtNew precision"
 
 
+# ---- key generation and encryption on the device ----------------------------------
+KG_SEED = 0x6B65795F67656E21
+
+
+def _ctr_crs(op: O.MKParams, dp, idxs):
+    """the same CRS on both sides from the counter-based streams (Parameters.AddCRS); compared bit for bit"""
+    for idx in idxs:
+        op.CRS.pop(idx, None)
+        op.add_crs(idx, prng=O.CtrPRNG(KG_SEED, (idx & 0xFFFFFFFF) * dp.CRS_STREAM_STRIDE))
+        assert_same(dp.AddCRS(idx, KG_SEED).numpy(), op.CRS[idx], f"AddCRS({idx})")
+
+
+def check_keygen(lit: ParamLiteral, lib=None, nparties=2, rots=(1, 2), semantics=True):
+    """every key mkrlwe.KeyGenerator makes + Encryptor.Encrypt, device against the oracle's KeyGenerator / Encryptor drawing from
+    the same streams; then the whole flow on device-made material only: encrypt -> MulRelinNew -> RotateHoistedNew -> Decrypt
+    with the reference's precision thresholds (mkckks_test.go:357-358, 552-598)."""
+    op = O.MKParams(lit.logN, lit.Q, lit.P, lit.gamma, crs_rots=list(rots))
+    dp = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, lib=lib, gamma=lit.gamma)
+    try:
+        _ctr_crs(op, dp, [0, -1, -2] + list(rots))
+        okg = O.KeyGenerator(op, prng=O.CtrPRNG(KG_SEED, 1 << 40))
+        dkg = mkrlwe.KeyGenerator(dp, KG_SEED, 1 << 40)
+        d_rlk, d_rk, d_ck = mkrlwe.RelinearizationKeySet(), mkrlwe.RotationKeySet(), mkrlwe.ConjugationKeySet()
+        o_sk, d_sk, o_pk, d_pk, o_rlk, o_rk = {}, {}, {}, {}, {}, {}
+        for i in range(nparties):
+            osk, orr = okg.gen_secret_key(i), okg.gen_secret_key(i)
+            dsk, drr = dkg.GenSecretKey(i), dkg.GenSecretKey(i)
+            assert_same(dsk.Value.numpy(), okg.sk_qp(osk), f"GenSecretKey({i})")
+            assert_same(drr.Value.numpy(), okg.sk_qp(orr), f"GenSecretKey(r{i})")
+            opk, dpk = okg.gen_public_key(osk), dkg.GenPublicKey(dsk)
+            assert_same(dpk.Value[0].numpy(), opk[0], f"GenPublicKey({i})[0]")
+            assert_same(dpk.Value[1].numpy(), opk[1], f"GenPublicKey({i})[1]")
+            orl, drl = okg.gen_relin_key(osk, orr), dkg.GenRelinearizationKey(dsk, drr)
+            for name, dv, ov in zip("bdv", drl.Value, (orl.b, orl.d, orl.v)):
+                assert_same(dv.numpy(), ov, f"GenRelinearizationKey({i}).{name}")
+            d_rlk.AddRelinearizationKey(drl)
+            o_rk[i] = {}
+            for rot in rots:
+                ork, drk = okg.gen_rotation_key(rot, osk), dkg.GenRotationKey(rot, dsk)
+                assert_same(drk.numpy(), ork, f"GenRotationKey({rot}, {i})")
+                d_rk.AddRotationKey(i, rot, drk)
+                o_rk[i][rot] = ork
+            ock, dck = okg.gen_conjugation_key(osk), dkg.GenConjugationKey(dsk)
+            assert_same(dck.numpy(), ock, f"GenConjugationKey({i})")
+            d_ck.AddConjugationKey(i, dck)
+            oswk, dswk = okg.gen_switching_key(osk), mkrlwe.SwitchingKey(dp.ctx)
+            dkg.GenSwitchingKey(dsk, dswk)
+            assert_same(dswk.numpy(), oswk, f"GenSwitchingKey({i})")
+            o_sk[i], d_sk[i], o_pk[i], d_pk[i], o_rlk[i] = osk, dsk, opk, dpk, orl
+        # Encrypt: fresh ciphertexts at two levels, with and without a plaintext
+        oenc, denc = O.Encryptor(op, prng=O.CtrPRNG(KG_SEED, 1 << 41)), mkrlwe.Encryptor(dp, KG_SEED, 1 << 41)
+        n = op.N // 2
+        rng = np.random.default_rng(5)
+        msgs, octs, dcts = [], [], []
+        for i in range(nparties):
+            level = op.max_level() if i == 0 or semantics else max(op.max_level() - 1, 1)
+            m = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)) / nparties
+            pt = O.ckks_encode(op, m, lit.scale, level)
+            oc = oenc.encrypt(pt, o_pk[i], i, lit.scale)
+            dc = mkckks.Ciphertext.new(dp, [i], level, lit.scale)
+            denc.Encrypt(mkrlwe.Poly.from_numpy(dp.ctx, pt), d_pk[i], dc)
+            for kk in oc.value:
+                assert_same(dc.Value[kk].numpy(), oc.value[kk], f"Encrypt(party {i})[{kk}]")
+            msgs.append(m); octs.append(oc); dcts.append(dc)
+        zero_pt = np.zeros((op.max_level() + 1, op.N), dtype=np.uint64)
+        oz = oenc.encrypt(zero_pt, o_pk[0], 0)
+        dz = mkckks.Ciphertext.new(dp, [0], op.max_level(), lit.scale)
+        denc.Encrypt(None, d_pk[0], dz)
+        for kk in oz.value:
+            assert_same(dz.Value[kk].numpy(), oz.value[kk], f"Encrypt(zero)[{kk}]")
+        if not semantics:
+            return
+        # the flow on device-made material only
+        dev = mkckks.Evaluator(dp)
+        acc = dcts[0]
+        for c in dcts[1:]:
+            acc = dev.AddNew(acc, c)
+        msum = sum(msgs)
+        dres = dev.MulRelinNew(acc, acc, d_rlk)
+        ddec = mkrlwe.Decryptor(dp)
+        got = O.ckks_decode(op, ddec.Decrypt(dres, d_sk).numpy(), dres.Scale)
+        err, bound = np.abs(got - msum * msum).max(), 2.0 ** (-np.log2(lit.scale) + np.log2(n) + 12)
+        assert err <= bound, f"MulRelin precision on device-made keys {np.log2(err):.1f} > {np.log2(bound):.1f}"
+        drot = dev.RotateHoistedNew(acc, rots[-1], dev.HoistedForm(acc), d_rk)
+        got = O.ckks_decode(op, ddec.Decrypt(drot, d_sk).numpy(), drot.Scale)
+        err, bound = np.abs(got - np.roll(msum, -rots[-1])).max(), 2.0 ** (-np.log2(lit.scale) + np.log2(n) + 11)
+        assert err <= bound, f"Rotate precision on device-made keys {np.log2(err):.1f} > {np.log2(bound):.1f}"
+        dcj = dev.ConjugateNew(acc, d_ck)
+        got = O.ckks_decode(op, ddec.Decrypt(dcj, d_sk).numpy(), dcj.Scale)
+        err = np.abs(got - np.conj(msum)).max()
+        assert err <= bound, f"Conjugate precision on device-made keys {np.log2(err):.1f} > {np.log2(bound):.1f}"
+    finally:
+        dp.ctx.close()
+
+
+def _negacyclic_mod(a, b, T):
+    N = len(a)
+    full = np.convolve(np.array([int(x) for x in a], dtype=object), np.array([int(x) for x in b], dtype=object))
+    ref = np.zeros(N, dtype=object)
+    ref[:N] += full[:N]
+    ref[:len(full) - N] -= full[N:]
+    return np.array([int(v) % T for v in ref], dtype=np.int64)
+
+
+def check_bfv_keygen(lit: ParamLiteral, lib=None, nparties=2):
+    """mkbfv.KeyGenerator.GenRelinearizationKey (mkbfv/keygen.go:24-162) on the device against the oracle, then an exact BFV product
+    on device-made keys and encryptions (mkbfv_test.go: plaintexts multiply exactly modulo T)"""
+    op = O.BFVParams(lit.logN, lit.Q, lit.QMul, lit.P, lit.T)
+    dp = mkbfv.Parameters(lit.logN, lit.Q, lit.QMul, lit.P, lit.T, lib=lib)
+    try:
+        _ctr_crs(op, dp, [0, -1, -3])
+        okg = O.BFVKeyGenerator(op, prng=O.CtrPRNG(KG_SEED, 1 << 40))
+        dkg = mkbfv.KeyGenerator(dp, KG_SEED, 1 << 40)
+        d_rlk, d_sk, d_pk = mkbfv.RelinearizationKeySet(), {}, {}
+        for i in range(nparties):
+            osk, orr = okg.gen_secret_key(i), okg.gen_secret_key(i)
+            dsk, drr = dkg.GenSecretKey(i), dkg.GenSecretKey(i)
+            opk, dpk = okg.gen_public_key(osk), dkg.GenPublicKey(dsk)
+            assert_same(dpk.Value[0].numpy(), opk[0], f"GenPublicKey({i})[0]")
+            orl, drl = okg.gen_bfv_relin_key(osk, orr), dkg.GenRelinearizationKey(dsk, drr)
+            for name in ("b1", "b2", "d1", "d2", "v"):
+                assert_same(getattr(drl, name).numpy(), getattr(orl, name), f"mkbfv GenRelinearizationKey({i}).{name}")
+            d_rlk.AddRelinearizationKey(drl)
+            d_sk[i], d_pk[i] = dsk, dpk
+        denc = mkrlwe.Encryptor(dp, KG_SEED, 1 << 41)
+        rng = np.random.default_rng(9)
+        ms = [rng.integers(0, lit.T, op.N) for _ in range(2)]
+        cts = []
+        for j in range(2):
+            i = j % nparties
+            c = mkrlwe.Ciphertext.new(dp.ctx, [i], op.max_level())
+            denc.Encrypt(mkrlwe.Poly.from_numpy(dp.ctx, O.bfv_encode(op, ms[j])), d_pk[i], c)
+            cts.append(c)
+        dev = mkbfv.Evaluator(dp)
+        res = dev.MulRelinNew(cts[0], cts[1], d_rlk)
+        got = O.bfv_decode(op, mkrlwe.Decryptor(dp).Decrypt(res, d_sk).numpy())
+        assert np.array_equal(got, _negacyclic_mod(ms[0], ms[1], lit.T)), "BFV product on device-made keys"
+    finally:
+        dp.ctx.close()
+
+
 # ---- BFV --------------------------------------------------------------------------------------------
 class BFVWorld:
     def __init__(self, lit: ParamLiteral, nparties, seed=0xB2000003, lib=None, real_keys=False):

@@ -96,3 +96,11 @@ def test_elementwise_semantics_under_emulation(emu):
 def test_cnn_flow_under_emulation(emu):
     """the reference's CNN op sequence at logN = 12 (rotations beyond N/2 wrap, the ones without a key chain powers of two)"""
     parity.check_cnn_flow(PR.CNN_PN14QP433.at_logn(12), lib=emu)
+
+
+def test_keygen_and_encrypt_under_emulation(emu):
+    """device-side KeyGenerator / Encryptor against the oracle's on the same counter-based streams, then the
+    encrypt -> MulRelin -> Rotate -> Conjugate -> Decrypt flow on device-made material only"""
+    parity.check_keygen(PR.CKKS_PN14QP439.at_logn(12), lib=emu)
+    parity.check_keygen(PR.PN16QP1761_Q7.at_logn(12), lib=emu, rots=(1,), semantics=False)     # alpha = 2: multi-limb gadget digits
+    parity.check_bfv_keygen(PR.BFV_PN14QP439.at_logn(12), lib=emu)

@@ -360,3 +360,19 @@ def test_pn16qp1761_full_limb_count():
     parity.check_mul_relin_new(w, w.ids, w.ids)
     parity.check_rotate(w, w.ids, 1)
     w.close()
+
+
+@pytest.mark.gpu
+def test_keygen_and_encrypt_on_device():
+    """every key of mkrlwe.KeyGenerator / mkbfv.KeyGenerator and Encryptor.Encrypt made on the device,
+    bit for bit against the oracle's generators on the same counter-based streams; then encrypt -> MulRelin -> Rotate ->
+    Conjugate -> Decrypt on device-made material only, with the reference's precision thresholds."""
+    parity.check_keygen(PR.CKKS_PN14QP439.at_logn(13))
+    parity.check_keygen(PR.PN16QP1761_Q7.at_logn(12), rots=(1,), semantics=False)
+    parity.check_bfv_keygen(PR.BFV_PN14QP439.at_logn(12))
+
+
+@pytest.mark.gpu
+def test_keygen_full_size():
+    """PN15QP880 at logN = 15: a party's whole key set made on the device (no 168 MiB upload per party), against the oracle"""
+    parity.check_keygen(PR.CKKS_PN15QP880, nparties=1, rots=(1,), semantics=False)

@@ -253,3 +253,35 @@ def test_golden_fixtures():
         golden = json.load(f)
     got = gen.compute_digests()
     assert got == golden
+
+
+def test_counter_based_samplers_have_the_reference_distributions():
+    """include/mkhe_prng.h ("mkhe-ctr-1"), what the device-side key generation and encryption draw from: the distributions of
+    lattigo's samplers as the reference configures them (keygen.go:35,58-60; params.go:32-33) -- uniform below q, ternary with
+    P(0) = 1/2, rounded Gaussian sigma = 3.2 cut at 19 -- and statelessness (element j of a stream does not depend on the rest)."""
+    lit = PR.CKKS_PN14QP439.at_logn(14)
+    ring = O.Ring(lit.logN, lit.Q[:3])
+    prng = O.CtrPRNG(0x1234, 7)
+    N = ring.N
+    u = prng.uniform(ring)
+    for i, q in enumerate(lit.Q[:3]):
+        assert u[i].max() < q
+        assert abs(float(u[i].astype(np.float64).mean()) / q - 0.5) < 0.02
+    assert prng.stream == 7 + 3
+    assert np.array_equal(O.CtrPRNG(0x1234, 8).uniform(O.Ring(lit.logN, lit.Q[:3]))[0][:8] < np.uint64(lit.Q[0]), np.ones(8, bool))
+    t = np.concatenate([prng.ternary(N) for _ in range(8)])
+    assert set(np.unique(t)) == {-1, 0, 1}
+    assert abs((t == 0).mean() - 0.5) < 0.01 and abs((t == 1).mean() - 0.25) < 0.01
+    t3 = O.CtrPRNG(1, 0).ternary(8 * N, 1.0 / 3)
+    assert abs((t3 == 0).mean() - 1.0 / 3) < 0.01
+    g = np.concatenate([prng.gaussian(N) for _ in range(16)])
+    assert np.abs(g).max() <= 19
+    assert abs(g.mean()) < 0.05 and abs(g.std() - 3.2) < 0.05
+    # counter-based: the same (seed, stream) gives the same polynomial, another stream an unrelated one
+    a, b, c = O.CtrPRNG(5, 100).gaussian(N), O.CtrPRNG(5, 100).gaussian(N), O.CtrPRNG(5, 101).gaussian(N)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    # known answers: the committed constants ARE the specification (tools/gen_cdt.py regenerates the table)
+    assert [int(x) for x in O.CtrPRNG(0, 0).gaussian(16)] == [-1, -1, 0, 4, 4, 1, -1, -4, 4, 0, 1, 4, 1, 2, -1, 0]
+    assert [int(x) for x in O.CtrPRNG(0, 0).ternary(16)] == [0, 0, 0, 1, 1, 0, 0, -1, 1, 0, 0, 1, 0, 0, 0, 0]
+    assert [int(x) for x in O.CtrPRNG(0, 0).uniform(O.Ring(12, [0x10000000006e0001]))[0][:4]] == [
+        0x38275bc38fcbe91, 0xf101fe21496ea20, 0xb91752fd22fb56a, 0xda3e176f37bc9fb]
