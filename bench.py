@@ -520,6 +520,119 @@ def bfv_mul_relin_ops(lit, k, device, steps, warmup, batch, nlanes):
     return batch * steps / (ms * 1e-3)
 
 
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 5: the reference's encrypted-CNN inference (cnn/cnn.go, timed by cnn/cnn_bench_test.go) over a batch of images
+def cnn_host_inputs(lit, nimages, seed=0xB2000005):
+    """synthetic inputs of the flow as host arrays: CRS entries, uniform relinearisation / rotation keys of the model owner and the
+    data owner (24 rotation keys each), model ciphertexts, the mask plaintext and `nimages` image ciphertexts at the top level"""
+    from mkhe_kklss_b200 import cnn
+    rng = np.random.default_rng(seed)
+    mods, beta, L = list(lit.Q) + list(lit.P), len(lit.Q), len(lit.Q) - 1
+    sw = lambda: uniform_limbs(rng, mods, (beta,), lit.N)
+    rots = [r for r in cnn.cnn_rotations(lit.logN) if r < lit.N // 2]
+    ct = lambda ids: {("0" if i < 0 else i): uniform_limbs(rng, lit.Q[:L + 1], (), lit.N) for i in [-1] + list(ids)}
+    M, Dt = cnn.MODEL, cnn.DATA
+    return {"rots": rots, "crs": {idx: sw() for idx in [-1] + rots},
+            "rlk": {i: (sw(), sw(), sw()) for i in (M, Dt)}, "rk": {i: {r: sw() for r in rots} for i in (M, Dt)},
+            "kernels": [ct([M]) for _ in range(4)], "fc1": [ct([M]) for _ in range(8)], "fc2": ct([M]), "b1": ct([M]), "b2": ct([M]),
+            "mask": uniform_limbs(rng, lit.Q[:L + 1], (), lit.N), "images": [ct([Dt]) for _ in range(nimages)]}
+
+
+def cnn_leg(lit, device, nimages, nlanes, rounds=2):
+    """images/s of the whole inference (HoistedForm(image), Convolution, square, FC1Layer, square, FC2Layer; the model's hoisted
+    forms are precomputed like in cnn_bench_test.go:43-52) through the host mirror of the reference API, independent images
+    alternating over the lanes.  Returns (device-resident images/s, end-to-end images/s with the image ciphertext uploaded and the
+    result downloaded per image, the results of image 0 as host arrays, inputs)"""
+    from mkhe_kklss_b200 import cnn, mkckks, mkrlwe
+    inp = cnn_host_inputs(lit, nimages)
+    dp = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, device=device)
+    ctx = dp.ctx
+    for idx, arr in inp["crs"].items():
+        dp.SetCRS(idx, arr)
+    rl, rk = mkrlwe.RelinearizationKeySet(), mkrlwe.RotationKeySet()
+    for i in (cnn.MODEL, cnn.DATA):
+        rl.AddRelinearizationKey(mkrlwe.RelinearizationKey(ctx, i, *inp["rlk"][i]))
+        for r, a in inp["rk"][i].items():
+            rk.AddRotationKey(i, r, mkrlwe.SwitchingKey(ctx, a))
+    up = lambda c: mkckks.Ciphertext.from_numpy(ctx, c, lit.scale)
+    ev0 = mkckks.Evaluator(dp)
+    evs = [ev0] + [ev0.ShallowCopy() for _ in range(nlanes - 1)]
+    Es = [cnn.DeviceFacade(e, rl, rk) for e in evs]
+    kernels, fc1 = [up(c) for c in inp["kernels"]], [up(c) for c in inp["fc1"]]
+    fc2, b1, b2 = up(inp["fc2"]), up(inp["b1"]), up(inp["b2"])
+    mask = mkrlwe.Poly.from_numpy(ctx, inp["mask"])
+    kh, fh = cnn.hoist_model(Es[0], kernels, fc1)
+    images = [up(c) for c in inp["images"]]
+
+    def sync():
+        for e in evs:
+            e.ctx.sync()
+
+    def run(n, image):
+        return cnn.infer(Es[n % nlanes], image, kernels, kh, fc1, fh, fc2, b1, b2, mask, lit.scale)[0]
+
+    first = run(0, images[0])                                   # warm-up (and the parity sample)
+    sync()
+    res0 = first.numpy()
+    l0 = sum(e.ctx.launch_count() for e in evs)
+    t0 = time.perf_counter()
+    for r in range(rounds):
+        keep = [run(n, im) for n, im in enumerate(images)]
+    sync()
+    dt = time.perf_counter() - t0
+    launches = (sum(e.ctx.launch_count() for e in evs) - l0) / (rounds * nimages)
+    t0 = time.perf_counter()
+    for r in range(rounds):
+        outs = [run(n, up(c)) for n, c in enumerate(inp["images"])]     # upload per image (2 polys x 7 limbs)
+        host = [o.numpy() for o in outs]                                 # result download per image (level 0)
+    dt_e2e = time.perf_counter() - t0
+    del keep, outs, host
+    ctx.close()
+    return rounds * nimages / dt, rounds * nimages / dt_e2e, res0, inp, launches
+
+
+def cnn_cpu_run(lit, inp, threads=1):
+    """the oracle port of the same inference on the host (one image; checker + CPU baseline): returns (result arrays, seconds)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cnn_flow as F
+    from oracle import oracle as O
+    from mkhe_kklss_b200 import cnn
+    cores = O.set_threads(threads)
+    op = O.MKParams(lit.logN, lit.Q, lit.P, lit.gamma, crs_rots=[])
+    for idx, arr in inp["crs"].items():
+        op.CRS[idx] = arr
+    rlk = {i: O.RelinKey(i, *inp["rlk"][i]) for i in (cnn.MODEL, cnn.DATA)}
+    E = F.OracleFacade(O.CKKSEvaluator(op, lit.scale), rlk, inp["rk"])
+    oc = lambda c: O.Ciphertext({k: v.copy() for k, v in c.items()}, lit.scale)
+    kernels, fc1 = [oc(c) for c in inp["kernels"]], [oc(c) for c in inp["fc1"]]
+    kh, fh = cnn.hoist_model(E, kernels, fc1)
+    t0 = time.perf_counter()
+    out = cnn.infer(E, oc(inp["images"][0]), kernels, kh, fc1, fh, oc(inp["fc2"]), oc(inp["b1"]), oc(inp["b2"]), inp["mask"], lit.scale)[0]
+    return out.value, time.perf_counter() - t0, cores
+
+
+def keygen_leg(lit, k, device, rots=(1, 2)):
+    """the key set of k parties (secret + public + relinearisation b, d, v + rotation keys) made on the device from
+    the counter-based streams -- seconds and bytes of key material that never cross PCIe"""
+    from mkhe_kklss_b200 import mkckks, mkrlwe
+    dp = mkckks.Parameters(lit.logN, lit.Q, lit.P, lit.scale, device=device)
+    for idx in [0, -1] + list(rots):
+        dp.AddCRS(idx, 0xC125)
+    kg = mkrlwe.KeyGenerator(dp, 0x5EED, 0)
+    dp.ctx.sync()
+    t0 = time.perf_counter()
+    keep = []
+    for i in range(k):
+        sk, r = kg.GenSecretKey(i), kg.GenSecretKey(i)
+        keep.append((kg.GenPublicKey(sk), kg.GenRelinearizationKey(sk, r), [kg.GenRotationKey(rot, sk) for rot in rots]))
+    dp.ctx.sync()
+    dt = time.perf_counter() - t0
+    nbytes = k * (3 + len(rots)) * len(lit.Q) * (len(lit.Q) + len(lit.P)) * lit.N * 8
+    del keep
+    dp.ctx.close()
+    return dt, nbytes
+
+
 def cpu_oracle_run(lit, k, steps, warmup, threads, seed=0xB2000002):
     """times the oracle port of MulRelinNew on the host cores; returns (ops/s, cores used, seconds per op)"""
     from oracle import oracle as O
@@ -803,6 +916,23 @@ def main():
         wl14.ctx.close()
         del wl14
         extra["bfv_mulrelin_PN15QP880_k4_ops_s"] = bfv_mul_relin_ops(PR.BFV_PN15QP880, 4, local_rank, max(args.steps // 2, 2), warmup, 8, args.lanes)
+        # config 5: encrypted CNN inference, PN14QP433 (cnn/cnn_test.go:80-96), two parties, a batch of synthetic images
+        cnn_ips, cnn_e2e, cnn_res0, cnn_inp, cnn_launches = cnn_leg(PR.CNN_PN14QP433, local_rank, 8, args.lanes)
+        extra["cnn_PN14QP433_images_s"] = cnn_ips
+        extra["cnn_PN14QP433_e2e_images_s"] = cnn_e2e
+        extra["cnn_launches_per_image"] = cnn_launches
+        if not args.no_cpu_baseline:
+            want, sec, cores = cnn_cpu_run(PR.CNN_PN14QP433, cnn_inp, 1)
+            extra["cnn_cpu_baseline"] = {"value": 1.0 / sec, "unit": "images/s", "cores": cores, "kind": "port",
+                                         "sample": f"one image through the oracle port of the same op sequence ({sec:.1f} s), single thread"}
+            extra["cnn_parity_check"] = {"equal": bool(set(map(str, want)) == set(map(str, cnn_res0)) and
+                                                       all(np.array_equal(cnn_res0[kk], want[kk]) for kk in want)),
+                                         "what": "fc2Out of image 0 (level 0, every component) against the oracle on the same inputs"}
+        del cnn_inp
+        # key generation on the device
+        kg_s, kg_bytes = keygen_leg(lit, 32, local_rank)
+        extra["keygen_on_device_k32"] = {"seconds": kg_s, "key_bytes": kg_bytes, "gb_per_s": kg_bytes / kg_s / 1e9,
+                                         "what": "32 parties x (sk, r, pk, relin b/d/v, 2 rotation keys), PN15QP880, made in HBM: nothing crosses PCIe"}
 
     if not args.no_extras and world > 1:
         wl.ctx.close()

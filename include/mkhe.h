@@ -116,6 +116,9 @@ int mkhe_intt(mkhe_ctx *ctx, int level, mkhe_poly in, mkhe_poly out);
 /* ---- mkrlwe.KeySwitcher */
 /* Decompose(levelQ, a, ad)                                   mkrlwe/keyswitch.go:49-73 (= HoistedForm body, mkckks/evaluator.go:543-553) */
 int mkhe_decompose(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk ad);
+/* FastBasisExtender.ModDownQPtoQNTT(levelQ, levelP = max, p1Q, p1P, p2Q)      mkrlwe/basis_extension.go:239-290
+ * p1 = one rlwe.PolyQP (nQ + nP limbs: Q limbs, then P limbs) in the NTT domain; p2Q = round(p1 / P), NTT domain */
+int mkhe_moddown_qp_to_q_ntt(mkhe_ctx *ctx, int levelQ, mkhe_poly p1, mkhe_poly p2Q);
 /* ExternalProduct(levelQ, a, bg, c)                          mkrlwe/keyswitch.go:79-118 */
 int mkhe_external_product(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk bg, mkhe_poly c);
 /* ExternalProductHoisted(levelQ, aHoisted, bg, c)            mkrlwe/keyswitch_hoisted.go:10-40 */

@@ -278,6 +278,9 @@ class Context:
     def decompose(self, level, hpoly, hswk):
         self.check(self.dll.mkhe_decompose(self.ptr, C.c_int(level), C.c_uint64(hpoly), C.c_uint64(hswk)))
 
+    def moddown_qp_to_q_ntt(self, level, p1, p2q):
+        self.check(self.dll.mkhe_moddown_qp_to_q_ntt(self.ptr, C.c_int(level), C.c_uint64(p1), C.c_uint64(p2q)))
+
     def external_product(self, level, ha, hbg, hc):
         self.check(self.dll.mkhe_external_product(self.ptr, C.c_int(level), C.c_uint64(ha), C.c_uint64(hbg), C.c_uint64(hc)))
 

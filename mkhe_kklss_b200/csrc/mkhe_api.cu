@@ -1859,6 +1859,62 @@ int mkhe_external_product_hoisted(mkhe_ctx *ctx, int levelQ, mkhe_swk a_hoisted,
     return ext_products(ctx, levelQ, 1, 1, &k->d, &h->d, nullptr, nullptr, &o->d, nullptr, false);
 }
 
+/* FastBasisExtender.ModDownQPtoQNTT (mkrlwe/basis_extension.go:239-290): p1 = one rlwe.PolyQP in the NTT domain (Q limbs, then P
+ * limbs), p2Q = round(p1 / P) in the NTT domain.  The reference brings only the P part out of the NTT domain, lifts it to Q,
+ * transforms the lift and combines in the NTT domain; here the whole QP value goes through the key switch's own tail (inverse pass
+ * A, k_moddown_P / k_moddown_Q) and the quotient is transformed forward: by linearity the same canonical residues. */
+int mkhe_moddown_qp_to_q_ntt(mkhe_ctx *ctx, int levelQ, mkhe_poly p1, mkhe_poly p2Q) {
+    CHECK_CTX();
+    TRY(check_level(ctx, levelQ));
+    POLY_R(in, p1);
+    POLY(out, p2Q);
+    if (in->cap_limbs < ctx->dmax) return fail(ctx, MKHE_ERR_INVALID, "ModDownQPtoQNTT needs a poly of nQ + nP = %d limbs (rlwe.PolyQP)", ctx->dmax);
+    if (out->cap_limbs < levelQ + 1) return fail(ctx, MKHE_ERR_INVALID, "ModDownQPtoQNTT: output has %d limbs", out->cap_limbs);
+    const Slots s = qp_slots(ctx, levelQ);
+    u64 *acc;
+    TRY(get_scratch(ctx, "accqp", (size_t)(ctx->dmax + ctx->nP) * ctx->N * 8, &acc));
+    {   // inverse pass A of the Q limbs up to the level and of the P limbs, into the accumulator
+        InvAArgs a;
+        memset(&a, 0, sizeof a);
+        a.nslots = s.n; a.logN = ctx->logN; a.nbatch = 1;
+        for (int i = 0; i < s.n; i++) { a.slots[i] = s.slot[i]; a.mods[i] = s.mod[i]; }
+        a.in.p[0] = in->d; a.out.p[0] = acc;
+        LAUNCH(k_intt_passA, dim3(ctx->N / MKHE_TILE, s.n, 1), dim3(MKHE_PA_THREADS), MKHE_PA_SMEM, a, ctx->d_mods, ctx->d_twi_tiled);
+    }
+    ModDownPArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.np_limbs = ctx->nP; pa.p_slot0 = ctx->nQ; pa.vslot = ctx->dmax; pa.logN = ctx->logN;
+    for (int i = 0; i < ctx->nP; i++) pa.plist[pa.nplist++] = i;
+    pa.acc[0] = acc;
+    TRY(dispatch_s1(ctx, [&](auto S) -> int {
+        auto k_moddown_P_ = k_moddown_P<decltype(S)::value>;
+        LAUNCH(k_moddown_P_, dim3(COLGROUPS, 1, pa.nplist), dim3(MKHE_NTT_THREADS), 0, pa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi);
+        return MKHE_OK;
+    }));
+    ModDownQArgs qa;
+    memset(&qa, 0, sizeof qa);
+    qa.np_limbs = ctx->nP; qa.logN = ctx->logN;
+    for (int j = 0; j <= levelQ; j++) qa.qlist[qa.nqlist++] = j;
+    qa.split[0] = 1; qa.dst[0] = out->d; qa.src[0] = nullptr; qa.dst_team_off[0] = -1;
+    qa.first[0] = 0; qa.first[1] = 1;
+    qa.acc[0] = acc; qa.pp[0] = acc + (size_t)ctx->nQ * ctx->N;
+    TRY(dispatch_s1(ctx, [&](auto S) -> int {
+        constexpr int s1 = decltype(S)::value;
+        const dim3 grid(COLGROUPS, qa.nqlist, 1);
+        const size_t rowsm = MKHE_MDQ_SMEM(s1);
+        switch (ctx->nP) {
+            case 1: { auto k = k_moddown_Q<s1, 1, false>; LAUNCH(k, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+            case 2: { auto k = k_moddown_Q<s1, 2, false>; LAUNCH(k, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+            case 3: { auto k = k_moddown_Q<s1, 3, false>; LAUNCH(k, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+            case 4: { auto k = k_moddown_Q<s1, 4, false>; LAUNCH(k, grid, dim3(MKHE_NTT_THREADS), rowsm, qa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi); break; }
+            default: return fail(ctx, MKHE_ERR_UNSUPPORTED, "%d special primes (1..4 supported)", ctx->nP);
+        }
+        return MKHE_OK;
+    }));
+    out->nlimbs = levelQ + 1;
+    return ntt_fwd(ctx, q_slots(levelQ), 1, &out->d, &out->d);
+}
+
 int mkhe_external_product(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk bg, mkhe_poly c) {
     CHECK_CTX();
     TRY(check_level(ctx, levelQ));

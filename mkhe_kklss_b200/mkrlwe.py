@@ -245,6 +245,21 @@ class Parameters:
         return swk
 
 
+class FastBasisExtender:
+    """mkrlwe.FastBasisExtender (basis_extension.go:12-357): the conversions the key switch uses are fused into its kernels
+    (k_bcast_ntt_pass1 / k_decomp_lift = ModUp of a digit, k_moddown_P / k_moddown_Q = ModDownQPtoQ); the stand-alone NTT-domain
+    ModDown is exposed for completeness of the type."""
+
+    def __init__(self, params):
+        self.ctx = params.ctx
+
+    def ModDownQPtoQNTT(self, levelQ, levelP, p1QP: Poly, p2Q: Poly):
+        """basis_extension.go:239-290; p1QP = the PolyQP as one device poly (Q limbs then P limbs), levelP = the maximum"""
+        if levelP != self.ctx.nP - 1:
+            raise RuntimeError("ModDownQPtoQNTT: levelP must be the maximum level of P")
+        self.ctx.moddown_qp_to_q_ntt(levelQ, p1QP.h, p2Q.h)
+
+
 class KeySwitcher:
     """mkrlwe.KeySwitcher (keyswitch.go:8-16): method bodies are C-ABI calls, pools live in the context."""
 
@@ -361,8 +376,8 @@ class PublicKey:
 class KeyGenerator:
     """mkrlwe.KeyGenerator (keygen.go) on the device.  The reference seeds a Blake2b PRNG from crypto/rand per generator; here the
     caller gives (seed, first stream) of the counter-based generator "mkhe-ctr-1" (include/mkhe_prng.h) and every call consumes
-    the number of streams include/mkhe.h documents, in the order the Go methods draw their polynomials -- so the oracle's
-    KeyGenerator over oracle.CtrPRNG(seed, stream) makes the same keys bit for bit."""
+    the number of streams include/mkhe.h documents, in the order the Go methods draw their polynomials, so a CPU
+    restatement of keygen.go drawing from the same streams makes the same keys bit for bit (tests/parity.py::check_keygen)."""
 
     def __init__(self, params: Parameters, seed: int, stream: int = 0):
         self.params, self.ctx = params, params.ctx

@@ -660,6 +660,27 @@ void ork_be_moddown_qp_to_q(const ork_basis_extender *be, int levelQ, int levelP
     }
     free(pool);
 }
+/* ModDownQPtoQNTT :239-290: inputs in the NTT domain; p1P is overwritten by its lazy inverse transform like in the reference */
+void ork_be_moddown_qp_to_q_ntt(const ork_basis_extender *be, int levelQ, int levelP, const uint64_t *p1Q, uint64_t *p1P, uint64_t *p2Q) {
+    const ork_ring *ringQ = be->ringQ;
+    int N = ringQ->N;
+    uint64_t *pool = (uint64_t *)xmalloc(sizeof(uint64_t) * (size_t)(levelQ + 1) * N);
+    ork_intt_lazy_lvl(be->ringP, levelP, p1P, p1P);                          /* :247 */
+    ork_be_modup_p_to_q(be, levelP, levelQ, p1P, pool);                      /* :251 */
+    PAR_FOR
+    for (int i = 0; i <= levelQ; i++) {
+        uint64_t qi = ringQ->q[i], twoqi = qi << 1;
+        uint64_t params = qi - be->modDownPtoQ[(size_t)levelP * ringQ->nmod + i];
+        uint64_t qinv = ringQ->qinv[i];
+        uint64_t *p3 = pool + (size_t)i * N;
+        ntt_lazy(p3, p3, N, ringQ->psi + (size_t)i * N, qi, qinv);           /* :268, in place like ring.NTTLazy(p3tmp, p3tmp, ..) */
+        for (int j = 0; j < N; j++) {
+            size_t o = (size_t)i * N + j;
+            p2Q[o] = mred(pool[o] + twoqi - p1Q[o], params, qi, qinv);       /* :277-284 */
+        }
+    }
+    free(pool);
+}
 /* ModDownQPtoP :294-334.  NOTE the reference indexes modDownParams[levelP][i] (not [levelQ][i]); kept. */
 void ork_be_moddown_qp_to_p(const ork_basis_extender *be, int levelQ, int levelP, const uint64_t *p1Q, const uint64_t *p1P, uint64_t *p2P) {
     const ork_ring *ringP = be->ringP;

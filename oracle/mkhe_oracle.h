@@ -109,6 +109,7 @@ void ork_be_free(ork_basis_extender *be);
 void ork_be_modup_q_to_p(const ork_basis_extender *be, int levelQ, int levelP, const uint64_t *polQ, uint64_t *polP);
 void ork_be_modup_p_to_q(const ork_basis_extender *be, int levelP, int levelQ, const uint64_t *polP, uint64_t *polQ);
 void ork_be_moddown_qp_to_q(const ork_basis_extender *be, int levelQ, int levelP, const uint64_t *p1Q, const uint64_t *p1P, uint64_t *p2Q);
+void ork_be_moddown_qp_to_q_ntt(const ork_basis_extender *be, int levelQ, int levelP, const uint64_t *p1Q, uint64_t *p1P, uint64_t *p2Q);
 void ork_be_moddown_qp_to_p(const ork_basis_extender *be, int levelQ, int levelP, const uint64_t *p1Q, const uint64_t *p1P, uint64_t *p2P);
 
 /* ---------------- KeySwitcher (mkrlwe/keyswitch.go, keyswitch_hoisted.go) ---------------- */

@@ -301,6 +301,13 @@ class BasisExtender:
         lib().ork_be_moddown_qp_to_q(self.ptr, C.c_int(levelQ), C.c_int(levelP), _p(p1Q), _p(p1P), _p(out))
         return out
 
+    def moddown_qp_to_q_ntt(self, levelQ, levelP, p1Q, p1P):
+        """ModDownQPtoQNTT (basis_extension.go:239-290); p1P is left untouched here (the reference overwrites it with its lazy INTT)"""
+        out = np.zeros((levelQ + 1, self.ringQ.N), dtype=np.uint64)
+        tmp = np.ascontiguousarray(p1P).copy()
+        lib().ork_be_moddown_qp_to_q_ntt(self.ptr, C.c_int(levelQ), C.c_int(levelP), _p(np.ascontiguousarray(p1Q)), _p(tmp), _p(out))
+        return out
+
     def moddown_qp_to_p(self, levelQ, levelP, p1Q, p1P):
         out = np.zeros((levelP + 1, self.ringQ.N), dtype=np.uint64)
         lib().ork_be_moddown_qp_to_p(self.ptr, C.c_int(levelQ), C.c_int(levelP), _p(p1Q), _p(p1P), _p(out))

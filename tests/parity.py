@@ -126,6 +126,22 @@ def check_decompose(w: CKKSWorld, level=None):
     assert_same(got[:beta, w.op.nQ:], ref[:beta, w.op.nQ:], f"Decompose(level={level}) P limbs")
 
 
+def check_moddown_ntt(w: CKKSWorld, level=None):
+    """FastBasisExtender.ModDownQPtoQNTT (basis_extension.go:239-290)"""
+    level = w.op.max_level() if level is None else level
+    p = w.op
+    a = np.concatenate([uniform_poly(w.prng, p.ringQ, p.max_level()), uniform_poly(w.prng, p.ringP, p.nP - 1)])
+    pin = mkrlwe.Poly.from_numpy(w.ctx, a)
+    pout = mkrlwe.Poly(w.ctx, level + 1)
+    mkrlwe.FastBasisExtender(w.dp).ModDownQPtoQNTT(level, p.nP - 1, pin, pout)
+    be = O.BasisExtender(p.ringQ, p.ringP)
+    ref = be.moddown_qp_to_q_ntt(level, p.nP - 1, a[:level + 1], a[p.nQ:])
+    assert_same(pout.numpy(), ref, f"ModDownQPtoQNTT(level={level})")
+    # ... and it agrees with the coefficient-domain ModDownQPtoQ of the same value
+    coef = be.moddown_qp_to_q(level, p.nP - 1, p.ringQ.intt(np.ascontiguousarray(a[:level + 1]), level), p.ringP.intt(np.ascontiguousarray(a[p.nQ:])))
+    assert_same(p.ringQ.intt(ref, level), coef, "ModDownQPtoQNTT against ModDownQPtoQ")
+
+
 def check_external_product(w: CKKSWorld, level=None):
     level = w.op.max_level() if level is None else level
     a = uniform_poly(w.prng, w.op.ringQ, level)
@@ -882,6 +898,8 @@ def run_ckks_suite(w: CKKSWorld, quick=False):
     check_decompose(w, level=max(L - 2, 1))
     check_external_product(w)
     check_external_product(w, level=1)
+    check_moddown_ntt(w)
+    check_moddown_ntt(w, level=1)
     check_rescale(w)
     ids = w.ids
     check_mul_relin_hoisted(w, ids, ids)

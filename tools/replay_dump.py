@@ -86,6 +86,94 @@ def make(d, logn, parties, seed=0xB2000007):
     json.dump(meta, open(os.path.join(d, "meta.json"), "w"), indent=1)
 
 
+# ---- mkbfv dumps (meta["scheme"] == "bfv": go/dump_golden_bfv_test.go) -------------------------------------------------------
+def load_bfv(d):
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    N, nQ, nP, k, L = 1 << meta["logN"], len(meta["Q"]), len(meta["P"]), len(meta["ids"]), meta["level"]
+    D, M = nQ + nP, 2 * nQ + nP
+    swk = lambda name: _rd(d, name, (nQ, D, N))
+    ct = lambda prefix: {**{"0": _rd(d, f"{prefix}_c0.bin", (L + 1, N))}, **{i: _rd(d, f"{prefix}_p{i}.bin", (L + 1, N)) for i in range(k)}}
+    return {"meta": meta, "N": N, "k": k, "L": L,
+            "psi": [_rd(d, f"psi_{m}.bin", (N,)) for m in range(M)], "psiinv": [_rd(d, f"psiinv_{m}.bin", (N,)) for m in range(M)],
+            "ninv": _rd(d, "ninv.bin", (M,)), "u": swk("crs_u.bin"),
+            "rlk": [{n: swk(f"rlk_{i}_{n}.bin") for n in ("b1", "d1", "v", "b2", "d2")} for i in range(k)],
+            "ct0": ct("ct0"), "ct1": ct("ct1"), "mul": ct("mul")}
+
+
+def make_bfv(d, logn, parties, seed=0xB2000017):
+    """an oracle-made mkbfv dump in the same format (self test of the tool chain; NOT a pin of the reference)"""
+    from oracle import oracle as O
+    from mkhe_kklss_b200 import params as PR
+    import parity
+    lit = PR.BFV_PN14QP439.at_logn(logn)
+    os.makedirs(d, exist_ok=True)
+    p = O.BFVParams(lit.logN, lit.Q, lit.QMul, lit.P, lit.T, seed=seed)
+    prng = O.PRNG(seed ^ 0x5EED)
+    sw = lambda: parity.uniform_swk(prng, p)
+    ids = list(range(parties))
+    rlk = {i: O.BFVRelinKey(i, sw(), sw(), sw(), sw(), sw()) for i in ids}
+    L = p.max_level()
+    mk = lambda: O.Ciphertext({**{"0": prng.uniform(p.ringQ, L)}, **{i: prng.uniform(p.ringQ, L) for i in ids}})
+    c0, c1 = mk(), mk()
+    mul = O.BFVEvaluator(p).mul_relin_new(c0, c1, rlk)
+    rings = [(p.ringQ, i) for i in range(len(lit.Q))] + [(p.ringP, j) for j in range(len(lit.P))] + [(p.ringQMul, i) for i in range(len(lit.QMul))]
+    ninv = []
+    for m, (ring, i) in enumerate(rings):
+        psi, psiinv, ni = ring.tables(i)
+        _wr(d, f"psi_{m}.bin", psi)
+        _wr(d, f"psiinv_{m}.bin", psiinv)
+        ninv.append(ni)
+    _wr(d, "ninv.bin", np.array(ninv, dtype=np.uint64))
+    _wr(d, "crs_u.bin", p.CRS[-1])
+    for i in ids:
+        for n in ("b1", "d1", "v", "b2", "d2"):
+            _wr(d, f"rlk_{i}_{n}.bin", getattr(rlk[i], n))
+    for prefix, c in (("ct0", c0), ("ct1", c1), ("mul", mul)):
+        _wr(d, f"{prefix}_c0.bin", c.value["0"])
+        for i in ids:
+            _wr(d, f"{prefix}_p{i}.bin", c.value[i])
+    meta = {"format": "mkhe-dump-1", "scheme": "bfv", "params": lit.name, "logN": lit.logN, "Q": [int(q) for q in lit.Q],
+            "P": [int(q) for q in lit.P], "QMul": [int(q) for q in lit.QMul], "T": int(lit.T), "gamma": 2,
+            "ids": [f"user{i}" for i in ids], "level": L, "source": "oracle (tool-chain self test, not the Go reference)"}
+    json.dump(meta, open(os.path.join(d, "meta.json"), "w"), indent=1)
+
+
+def replay_bfv_oracle(x, report):
+    from oracle import oracle as O
+    meta, k = x["meta"], x["k"]
+    p = O.BFVParams(meta["logN"], meta["Q"], meta["QMul"], meta["P"], meta["T"], seed=1)
+    nQ, nP = len(meta["Q"]), len(meta["P"])
+    same = True
+    for m in range(2 * nQ + nP):
+        ring, i = (p.ringQ, m) if m < nQ else ((p.ringP, m - nQ) if m < nQ + nP else (p.ringQMul, m - nQ - nP))
+        psi, psiinv, ninv = ring.tables(i)
+        same = same and np.array_equal(psi, x["psi"][m]) and np.array_equal(psiinv, x["psiinv"][m]) and int(ninv) == int(x["ninv"][m])
+    report.append(("oracle NTT tables (Q, P, QMul) == dumped lattigo tables", same, []))
+    p.CRS[-1] = x["u"]
+    rlk = {i: O.BFVRelinKey(i, x["rlk"][i]["b1"], x["rlk"][i]["d1"], x["rlk"][i]["v"], x["rlk"][i]["b2"], x["rlk"][i]["d2"]) for i in range(k)}
+    c0 = O.Ciphertext({kk: v.copy() for kk, v in x["ct0"].items()})
+    c1 = O.Ciphertext({kk: v.copy() for kk, v in x["ct1"].items()})
+    _cmp(O.BFVEvaluator(p).mul_relin_new(c0, c1, rlk).value, x["mul"], "oracle mkbfv MulRelinNew", report)
+
+
+def replay_bfv_device(x, report, lib=None, use_dumped_tables=True):
+    from mkhe_kklss_b200 import mkbfv, mkrlwe
+    meta, k = x["meta"], x["k"]
+    dp = mkbfv.Parameters(meta["logN"], meta["Q"], meta["QMul"], meta["P"], meta["T"], lib=lib)
+    if use_dumped_tables:
+        for m in range(2 * len(meta["Q"]) + len(meta["P"])):
+            dp.ctx.set_ntt_tables(m, x["psi"][m], x["psiinv"][m], int(x["ninv"][m]))
+    dp.SetCRS(-1, x["u"])
+    rl = mkbfv.RelinearizationKeySet()
+    for i in range(k):
+        r = x["rlk"][i]
+        rl.AddRelinearizationKey(mkbfv.RelinearizationKey(dp.ctx, i, r["b1"], r["d1"], r["v"], r["b2"], r["d2"]))
+    c0, c1 = mkrlwe.Ciphertext.from_numpy(dp.ctx, x["ct0"]), mkrlwe.Ciphertext.from_numpy(dp.ctx, x["ct1"])
+    tag = "device" + (" (dumped tables)" if use_dumped_tables else " (own tables)")
+    _cmp(mkbfv.Evaluator(dp).MulRelinNew(c0, c1, rl).numpy(), x["mul"], f"{tag} mkbfv MulRelinNew", report)
+    dp.ctx.close()
+
+
 def _cmp(got, want, what, report):
     ok = set(got) == set(want) and all(np.array_equal(got[k], want[k]) for k in want)
     bad = [str(k) for k in want if k not in got or not np.array_equal(got[k], want[k])]
@@ -152,18 +240,25 @@ def main():
     ap.add_argument("--parties", type=int, default=2)
     ap.add_argument("--oracle-only", action="store_true")
     ap.add_argument("--device-only", action="store_true")
+    ap.add_argument("--bfv", action="store_true", help="with --make: write an mkbfv dump")
+    ap.add_argument("--lib", default=None, help="development: another build of the library")
     args = ap.parse_args()
     if args.make:
-        make(args.dir, args.logn, args.parties)
+        (make_bfv if args.bfv else make)(args.dir, args.logn, args.parties)
         print("wrote", args.dir)
         return 0
-    x = load(args.dir)
+    lib = None
+    if args.lib:
+        from mkhe_kklss_b200 import _lib
+        lib = _lib.Library(os.path.abspath(args.lib))
+    bfv = json.load(open(os.path.join(args.dir, "meta.json"))).get("scheme") == "bfv"
+    x = load_bfv(args.dir) if bfv else load(args.dir)
     report = []
     if not args.device_only:
-        replay_oracle(x, report)
+        (replay_bfv_oracle if bfv else replay_oracle)(x, report)
     if not args.oracle_only:
-        replay_device(x, report, use_dumped_tables=True)
-        replay_device(x, report, use_dumped_tables=False)
+        (replay_bfv_device if bfv else replay_device)(x, report, lib=lib, use_dumped_tables=True)
+        (replay_bfv_device if bfv else replay_device)(x, report, lib=lib, use_dumped_tables=False)
     print("dump source:", x["meta"].get("source"))
     for what, ok, bad in report:
         print(("PASS " if ok else "FAIL ") + what + ("" if ok else f"  mismatching components: {bad}"))
