@@ -30,6 +30,7 @@ __device__ __forceinline__ void prefetch_l2(const void *) {}
 __device__ __forceinline__ void mbar_init(u64 *bar, int count) { emu_mbar_init(bar, count); }
 __device__ __forceinline__ void mbar_arrive(u64 *bar) { emu_mbar_arrive(bar); }
 __device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void fence_proxy_async_smem() {}
 __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) { emu_mbar_expect_tx(bar, bytes); }
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { emu_mbar_wait(bar, parity); }
 __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, u32 bytes, u64 *bar) { memcpy(smem, gmem, bytes); emu_mbar_complete_tx(bar, bytes); }
@@ -54,14 +55,16 @@ __device__ __forceinline__ void mbar_init(u64 *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 }
-// consumer -> producer: one arrival on an "empty" barrier.  The default .release semantics order the thread's earlier
-// shared-memory reads of the stage before the arrival, so a producer that has observed the completed phase (try_wait,
-// .acquire) may let the TMA engine overwrite the stage.
+// consumer -> producer: one arrival on an "empty" barrier.  When the buffer is refilled by the TMA engine (async proxy) the
+// arrival must be preceded by fence_proxy_async() (MKHE_PRE_RELEASE in mkhe_kernels.cuh): the .release of the arrive orders
+// generic-proxy accesses among themselves, not against an async-proxy write (measured, see there).
 __device__ __forceinline__ void mbar_arrive(u64 *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
-// generic-proxy writes (st.global / st.shared) before, async-proxy (TMA) reads of the same bytes after
+// orders this thread's earlier generic-proxy accesses (ld / st) before later async-proxy (TMA) accesses of the same bytes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// the same, restricted to this CTA's shared memory (does not wait for the thread's global stores)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile(

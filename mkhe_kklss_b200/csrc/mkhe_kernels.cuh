@@ -19,6 +19,21 @@
 #include "../../include/mkhe_prng.h"
 
 #define MKHE_TILE 2048
+// Releasing a TMA landing buffer: the consumer's shared-memory reads are generic-proxy accesses, the refill is an async-proxy
+// write.  mbarrier.arrive (.release) alone does NOT keep a read that is merely in flight ahead of that write on B200: measured,
+// 23-33 of 6400 back-to-back MulRelin calls had one 2048-coefficient tile wrong without this fence (L2 hints off; about 1 in 3000
+// with them), 0 of 6400 with it (tools/gpu_race_ab.sh, profiles/r02m_release_fence.txt).  fence.proxy.async orders the thread's
+// earlier generic-proxy accesses before later async-proxy ones; it sits before every arrive on an "empty" barrier.
+#ifndef MKHE_RELEASE_FENCE                 // development: A/B builds override it (0 = none, 1 = fence.proxy.async, 2 = .shared::cta)
+#define MKHE_RELEASE_FENCE 2
+#endif
+#if MKHE_RELEASE_FENCE == 0
+#define MKHE_PRE_RELEASE()
+#elif MKHE_RELEASE_FENCE == 1
+#define MKHE_PRE_RELEASE() fence_proxy_async()
+#else
+#define MKHE_PRE_RELEASE() fence_proxy_async_smem()
+#endif
 #define MKHE_NTT_THREADS 128     // NTT kernels: 16 elements per thread
 #define MKHE_THREADS 256         // element-wise kernels
 #define MKHE_MAX_RANKS 8          // ranks of a multi-GPU team
@@ -487,6 +502,7 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
             u64 v[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = inbuf[k * 128 + tid];
+            MKHE_PRE_RELEASE();
             mbar_arrive(&in_empty[grp]);                    // this thread's last read of the landing buffer
             tile_fwd_A(v, tw, c, big);
             // everybody of the group has left the previous tile's exchange buffer and mail slot
@@ -517,6 +533,7 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
                     st_global_v4(o + 4 * k, canon(v[4 * k], m), canon(v[4 * k + 1], m), canon(v[4 * k + 2], m), canon(v[4 * k + 3], m));
             }
         }
+        MKHE_PRE_RELEASE();
         mbar_arrive(tw_empty);                              // this thread is done with the pair's twiddles
         npairs++;
     }
@@ -650,6 +667,7 @@ __global__ void __launch_bounds__(MKHE_MI_THREADS(G), 1) k_mac_intt(MacInttArgs 
                     mac128w(acc[2 * j], sv.x, pv.x);
                     mac128w(acc[2 * j + 1], sv.y, pv.y);
                 }
+                MKHE_PRE_RELEASE();
                 mbar_arrive(&empty[st]);                         // after this thread's last read of the stage
             }
             // one reduction per coefficient (the same canonical value as the reference's reduce-every-term loop), stored where the
@@ -682,6 +700,7 @@ __global__ void __launch_bounds__(MKHE_MI_THREADS(G), 1) k_mac_intt(MacInttArgs 
             for (int k = 0; k < 16; k++) v[k] = x.c2[k];
             mbar_wait(tw_full, nu & 1);
             tile_inv(v, x, tw, nttc(m), 1 + g);
+            MKHE_PRE_RELEASE();
             mbar_arrive(tw_empty);                               // after this thread's last twiddle read
             if (a.galEl) {
                 // Rotation: X -> X^galEl sends coefficient i = x + 2048 row to (x galEl mod 2048) + 2048 row' (+ a sign): columns go

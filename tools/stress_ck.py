@@ -4,7 +4,8 @@ context (MKHE_DEBUG_CK=2) checksums every scratch buffer after every kernel laun
 every op must be identical: the first row that differs names the kernel after which a buffer first deviates."""
 import ctypes as C
 import os, sys
-os.environ["MKHE_DEBUG_CK"] = "2"
+NCTX = int(os.environ.get("MKHE_STRESS_CTXS", "2"))      # 1: a single context, single stream (the plain back-to-back case)
+os.environ["MKHE_DEBUG_CK"] = str(NCTX)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
@@ -13,7 +14,7 @@ from mkhe_kklss_b200 import params as PR, mkckks
 
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 B = 8
-ws = [parity.CKKSWorld(PR.CKKS_PN15QP880, 2, rots=(2,)) for _ in range(2)]
+ws = [parity.CKKSWorld(PR.CKKS_PN15QP880, 2, rots=(2,)) for _ in range(NCTX)]
 st = []
 for w in ws:
     ids, level = w.ids, w.op.max_level()
@@ -57,14 +58,14 @@ def snap(w, row):
 
 
 run(mul)                       # warm-up: scratch pools get allocated
-fetch(ws[1])
+fetch(ws[-1])
 if os.environ.get("MKHE_DEBUG_SNAP"):
     N = 1 << 15
     for r in range(rounds):
         run(mul)
-        rows, names = fetch(ws[1])
+        rows, names = fetch(ws[-1])
         per = len(names) // B
-        w, ids, level, d0, d1, want, outs, kb, kd, kv, nb = st[1]
+        w, ids, level, d0, d1, want, outs, kb, kd, kv, nb = st[-1]
         ok = [all(np.array_equal(w.ctx.poly_download(outs[i].Value[key].h, level + 1 - nb), want.value[key]) for key in ["0"] + ids) for i in range(B)]
         if all(ok) or not any(ok):
             continue
@@ -91,9 +92,9 @@ if os.environ.get("MKHE_DEBUG_SNAP"):
 ref = None
 for r in range(rounds):
     run(mul)
-    rows, names = fetch(ws[1])
+    rows, names = fetch(ws[-1])
     per = len(rows) // B
-    w, ids, level, d0, d1, want, outs, kb, kd, kv, nb = st[1]
+    w, ids, level, d0, d1, want, outs, kb, kd, kv, nb = st[-1]
     for i in range(B):
         blk = rows[i * per:(i + 1) * per]
         ok_out = all(np.array_equal(w.ctx.poly_download(outs[i].Value[key].h, level + 1 - nb), want.value[key]) for key in ["0"] + ids)
