@@ -295,6 +295,13 @@ int mkhe_profile_begin(mkhe_ctx *ctx);
 int mkhe_profile_end(mkhe_ctx *ctx, char *buf, size_t cap);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t mkhe_launch_count(const mkhe_ctx *ctx);
+/* CUDA graphs (opt-in per lane; MKHE_GRAPHS=1 in the environment turns it on for every new context): an op issued again on the same
+ * lane with the very same operands (device addresses, ids, level) replays the launch sequence captured at its third occurrence --
+ * one graph launch instead of up to 22 kernel launches.  mkhe_launch_count keeps counting the kernels inside replayed graphs.
+ * Off by default: measured on B200 the ops are GPU bound even at logN = 14, k = 2, and two lanes interleave better kernel by
+ * kernel than graph by graph (profiles/r02p_cuda_graphs.txt). */
+int mkhe_ctx_set_graphs(mkhe_ctx *ctx, int on);
+int mkhe_graph_stats(const mkhe_ctx *ctx, uint64_t *captures, uint64_t *replays);
 /* register-resident Shoup-butterfly throughput microbenchmark: butterflies per second on this device
  * (the integer-pipe roofline denominator) */
 int mkhe_bench_butterfly_peak(mkhe_ctx *ctx, double *butterflies_per_s);

@@ -141,6 +141,16 @@ class Context:
     def launch_count(self) -> int:
         return int(self.dll.mkhe_launch_count(self.ptr))
 
+    def set_graphs(self, on: bool):
+        """opt into the CUDA-graph cache of repeated ops on this lane (mkhe_ctx_set_graphs)"""
+        self.check(self.dll.mkhe_ctx_set_graphs(self.ptr, C.c_int(1 if on else 0)))
+
+    def graph_stats(self):
+        """(graphs captured, graph replays) of this lane"""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.dll.mkhe_graph_stats(self.ptr, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_ntt_tables(self, m, psi, psiinv, ninv):
         psi = np.ascontiguousarray(psi, dtype=np.uint64)
         psiinv = np.ascontiguousarray(psiinv, dtype=np.uint64)

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -102,6 +103,14 @@ struct mkhe_ctx {
     cudaEvent_t override_ev = nullptr;    // an asynchronous transfer completes on a copy stream: its event stands for the op
     bool multi() const { return root->lanes.size() > 1; }
     std::map<std::string, Scratch> scratch;
+    // CUDA graphs: an op issued again with the very same operands -- device addresses and scalars -- replays
+    // the launch sequence captured at its third occurrence (one cudaGraphLaunch instead of up to 22 kernel launches).  Per lane.
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; u64 check = 0; uint64_t launches = 0, stamp = 0; int seen = 1; bool bad = false; };
+    std::unordered_map<u64, GraphEntry> graphs;
+    bool graphs_on = false;               // opt-in (mkhe_ctx_set_graphs, or MKHE_GRAPHS=1 in the environment): measured, the cache does not pay
+                                          // for GPU-bound ops -- profiles/r02p_cuda_graphs.txt
+    bool capturing = false;
+    uint64_t graph_stamp = 0, graph_replays = 0, graph_captures = 0;
     std::string err;
     int sticky = 0;
     uint64_t launches = 0;
@@ -300,9 +309,92 @@ Obj *as_obj(mkhe_ctx *ctx, uint64_t h, int kind, int mode = ACC_WRITE) {
 size_t swk_elems(const mkhe_ctx *ctx) { return (size_t)ctx->beta_max * ctx->dmax * ctx->N; }
 int beta_of(const mkhe_ctx *ctx, int levelQ) { return (levelQ + ctx->alpha) / ctx->alpha; }      // ceil((levelQ+1)/alpha)
 
+void drop_graphs(mkhe_ctx *ctx) {
+#ifndef MKHE_EMU
+    for (auto &kv : ctx->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+#endif
+    ctx->graphs.clear();
+}
+// signature of an op: two independent 64-bit hashes over its scalars and device addresses (the second one guards the first)
+struct GraphKey {
+    u64 h1 = 0xcbf29ce484222325ull, h2 = 0x9E3779B97F4A7C15ull;
+    void add(u64 v) {
+        h1 = (h1 ^ v) * 0x100000001b3ull; h1 ^= h1 >> 29;
+        h2 = (h2 + v) * 0xBF58476D1CE4E5B9ull; h2 ^= h2 >> 31;
+    }
+    void ints(int n, const int *p) { add((u64)n); for (int i = 0; i < n; i++) add((u64)(long)p[i]); }
+    template <class T> void ptrs(const std::vector<T *> &v) { add(v.size()); for (T *q : v) add((u64)(uintptr_t)q); }
+    explicit GraphKey(const char *op) { for (const char *c = op; *c; c++) add((u64)*c); }
+};
+#define MKHE_GRAPH_CACHE 256
+// run `body` (the launches of one op on ctx->stream) through the graph cache
+template <class F> int run_graphed(mkhe_ctx *ctx, const GraphKey &k, F &&body) {
+#ifdef MKHE_EMU
+    (void)k;
+    return body();
+#else
+    if (!ctx->graphs_on || ctx->profiling || ctx->debug_sync || ctx->debug_ck || ctx->capturing) return body();
+    auto it = ctx->graphs.find(k.h1);
+    if (it == ctx->graphs.end()) {
+        // first sight: run eagerly (the scratch pools get their sizes) and remember the signature
+        if (ctx->graphs.size() >= MKHE_GRAPH_CACHE) {
+            auto old = ctx->graphs.begin();
+            for (auto j = ctx->graphs.begin(); j != ctx->graphs.end(); ++j)
+                if (j->second.stamp < old->second.stamp) old = j;
+            if (old->second.exec) cudaGraphExecDestroy(old->second.exec);
+            ctx->graphs.erase(old);
+        }
+        mkhe_ctx::GraphEntry e;
+        e.check = k.h2;
+        e.stamp = ++ctx->graph_stamp;
+        ctx->graphs.emplace(k.h1, e);
+        return body();
+    }
+    mkhe_ctx::GraphEntry &e = it->second;
+    if (e.bad || e.check != k.h2) return body();
+    e.stamp = ++ctx->graph_stamp;
+    if (!e.exec && ++e.seen < 3) return body();          // a signature that shows up only twice is not worth an instantiation
+    if (!e.exec) {
+        const uint64_t l0 = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            e.bad = true;
+            return body();
+        }
+        ctx->capturing = true;
+        const int rc = body();
+        ctx->capturing = false;
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        const uint64_t nl = ctx->launches - l0;
+        ctx->launches = l0;
+        bool ok = rc == MKHE_OK && ce == cudaSuccess && g != nullptr;
+        if (ok && cudaGraphInstantiate(&e.exec, g, 0) != cudaSuccess) { ok = false; e.exec = nullptr; }
+        if (g) cudaGraphDestroy(g);
+        if (!ok) {                              // something in this op cannot be captured: it runs eagerly from now on
+            cudaGetLastError();
+            e.bad = true;
+            ctx->sticky = 0;
+            ctx->err.clear();
+            return body();
+        }
+        e.launches = nl;
+        ctx->graph_captures++;
+    }
+    CU(cudaGraphLaunch(e.exec, ctx->stream));
+    ctx->launches += e.launches;
+    ctx->graph_replays++;
+    return MKHE_OK;
+#endif
+}
+
 int get_scratch(mkhe_ctx *ctx, const std::string &name, size_t bytes, u64 **out) {
     Scratch &s = ctx->scratch[name];
     if (s.bytes < bytes) {
+        // a captured graph holds the old address: never reallocate inside a capture, and forget the graphs made so far
+        if (ctx->capturing) return fail(ctx, MKHE_ERR_UNSUPPORTED, "scratch '%s' would grow during a graph capture", name.c_str());
+        drop_graphs(ctx);
         if (s.p) {
             CU(cudaStreamSynchronize(ctx->stream));
             CU(cudaFree(s.p));
@@ -1383,6 +1475,7 @@ int mkhe_ctx_create(int logN, const uint64_t *Q, int nQ, const uint64_t *P, int 
         if (e && atoi(e) == created) ctx->debug_ck = true;
         ctx->debug_nodiag = getenv("MKHE_DEBUG_NODIAG") != nullptr;
         ctx->l2_hints = getenv("MKHE_DEBUG_NO_L2_HINTS") == nullptr;
+        ctx->graphs_on = getenv("MKHE_GRAPHS") != nullptr && atoi(getenv("MKHE_GRAPHS")) != 0;
         if (const char *hd = getenv("MKHE_DEBUG_HOIST_DIGITS")) ctx->hoist_digits = atoi(hd);
     }
     ctx->root = ctx;
@@ -1462,6 +1555,7 @@ int mkhe_ctx_fork(mkhe_ctx *parent, mkhe_ctx **out) {
     f->tables_dirty = false;
     f->debug_nodiag = root->debug_nodiag;
     f->l2_hints = root->l2_hints;
+    f->graphs_on = root->graphs_on;
     f->hoist_digits = root->hoist_digits;
     f->d_conv_PtoQ = root->d_conv_PtoQ; f->d_conv_QtoQMul = root->d_conv_QtoQMul; f->d_conv_QMultoQ = root->d_conv_QMultoQ;
     f->h_mformQMul = root->h_mformQMul;
@@ -1551,6 +1645,7 @@ void mkhe_ctx_destroy(mkhe_ctx *ctx) {
     cudaStreamSynchronize(ctx->h2d);
     cudaStreamSynchronize(ctx->d2h);
     mkhe_comm_destroy(ctx);
+    drop_graphs(ctx);
 #ifndef MKHE_EMU
     for (int r = 0; r < MKHE_MAX_RANKS; r++) {
         if (ctx->peer_stage[r] && ctx->peer_stage[r] != ctx->p2p_stage) cudaIpcCloseMemHandle(ctx->peer_stage[r]);
@@ -1613,6 +1708,18 @@ int mkhe_host_free(mkhe_ctx *ctx, void *p) {
 }
 
 uint64_t mkhe_launch_count(const mkhe_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int mkhe_ctx_set_graphs(mkhe_ctx *ctx, int on) {
+    if (!ctx) return MKHE_ERR_INVALID;
+    ctx->graphs_on = on != 0;
+    if (!on) drop_graphs(ctx);
+    return MKHE_OK;
+}
+int mkhe_graph_stats(const mkhe_ctx *ctx, uint64_t *captures, uint64_t *replays) {
+    if (!ctx) return MKHE_ERR_INVALID;
+    if (captures) *captures = ctx->graph_captures;
+    if (replays) *replays = ctx->graph_replays;
+    return MKHE_OK;
+}
 
 // ---- polys ------------------------------------------------------------------------------------------
 int mkhe_poly_alloc(mkhe_ctx *ctx, int nlimbs, mkhe_poly *out) {
@@ -1846,7 +1953,9 @@ int mkhe_decompose(mkhe_ctx *ctx, int levelQ, mkhe_poly a, mkhe_swk ad) {
     POLY_R(p, a);
     SWK(k, ad);
     if (p->cap_limbs < levelQ + 1) return fail(ctx, MKHE_ERR_INVALID, "Decompose: poly has %d limbs, level %d", p->cap_limbs, levelQ);
-    return decompose_impl(ctx, levelQ, 1, &p->d, &k->d, 0);
+    GraphKey key("decompose");
+    key.add((u64)levelQ); key.add((u64)(uintptr_t)p->d); key.add((u64)(uintptr_t)k->d);
+    return run_graphed(ctx, key, [&]() -> int { return decompose_impl(ctx, levelQ, 1, &p->d, &k->d, 0); });
 }
 
 int mkhe_external_product_hoisted(mkhe_ctx *ctx, int levelQ, mkhe_swk a_hoisted, mkhe_swk bg, mkhe_poly c) {
@@ -1958,17 +2067,24 @@ int mkhe_mul_relin_hoisted(mkhe_ctx *ctx, int level, int n0, const int *ids0, co
     TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v", ACC_READ));
     SWK_R(uk, u);
     if (h0) TRY(swks_of(ctx, n0, h0, vh0, "h0", ACC_READ));
-    else {
-        TRY(swk_pool(ctx, "nil_h0", n0, vh0));
-        TRY(decompose_impl(ctx, level, n0, p0.data() + 1, vh0.data(), 0));
-    }
     if (h1) TRY(swks_of(ctx, n1, h1, vh1, "h1", ACC_READ));
-    else {
-        TRY(swk_pool(ctx, "nil_h1", n1, vh1));
-        TRY(decompose_impl(ctx, level, n1, p1.data() + 1, vh1.data(), 0));
-    }
-    return mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
-                                  vd.data(), vv.data(), uk->d, nOut, idsOut, po.data());
+    GraphKey key("mul_relin_hoisted");
+    key.add((u64)level); key.add((u64)(h0 != nullptr)); key.add((u64)(h1 != nullptr));
+    key.ints(n0, ids0); key.ints(n1, ids1); key.ints(nOut, idsOut);
+    key.ptrs(p0); key.ptrs(p1); key.ptrs(po); key.ptrs(vh0); key.ptrs(vh1); key.ptrs(vb); key.ptrs(vd); key.ptrs(vv);
+    key.add((u64)(uintptr_t)uk->d);
+    return run_graphed(ctx, key, [&]() -> int {
+        if (!h0) {
+            TRY(swk_pool(ctx, "nil_h0", n0, vh0));
+            TRY(decompose_impl(ctx, level, n0, p0.data() + 1, vh0.data(), 0));
+        }
+        if (!h1) {
+            TRY(swk_pool(ctx, "nil_h1", n1, vh1));
+            TRY(decompose_impl(ctx, level, n1, p1.data() + 1, vh1.data(), 0));
+        }
+        return mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
+                                      vd.data(), vv.data(), uk->d, nOut, idsOut, po.data());
+    });
 }
 
 int mkhe_ckks_mul_relin(mkhe_ctx *ctx, int level, int nb_rescales, int same_operand, int n0, const int *ids0,
@@ -1986,13 +2102,19 @@ int mkhe_ckks_mul_relin(mkhe_ctx *ctx, int level, int nb_rescales, int same_oper
     TRY(swks_of(ctx, n0, rlk_d, vd, "rlk_d", ACC_READ));
     TRY(swks_of(ctx, n0, rlk_v, vv, "rlk_v", ACC_READ));
     SWK_R(uk, u);
-    // hoisting into context pools (rlkSet.HoistPool[0|1], mkckks/evaluator.go:419-441), scheduled inside the op
-    TRY(swk_pool(ctx, "hoistpool0", n0, vh0));
-    if (same_operand) vh1 = vh0;
-    else TRY(swk_pool(ctx, "hoistpool1", n1, vh1));
-    TRY(mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
-                               vd.data(), vv.data(), uk->d, nOut, idsOut, po.data(), Shard(), true, !same_operand, true, true));
-    TRY(rescale_impl(ctx, level, nb_rescales, nOut + 1, po.data(), po.data()));
+    GraphKey key("ckks_mul_relin");
+    key.add((u64)level); key.add((u64)nb_rescales); key.add((u64)same_operand);
+    key.ints(n0, ids0); key.ints(n1, ids1); key.ints(nOut, idsOut);
+    key.ptrs(p0); key.ptrs(p1); key.ptrs(po); key.ptrs(vb); key.ptrs(vd); key.ptrs(vv); key.add((u64)(uintptr_t)uk->d);
+    TRY(run_graphed(ctx, key, [&]() -> int {
+        // hoisting into context pools (rlkSet.HoistPool[0|1], mkckks/evaluator.go:419-441), scheduled inside the op
+        TRY(swk_pool(ctx, "hoistpool0", n0, vh0));
+        if (same_operand) vh1 = vh0;
+        else TRY(swk_pool(ctx, "hoistpool1", n1, vh1));
+        TRY(mul_relin_hoisted_impl(ctx, level, n0, ids0, p0.data(), vh0.data(), n1, ids1, p1.data(), vh1.data(), vb.data(),
+                                   vd.data(), vv.data(), uk->d, nOut, idsOut, po.data(), Shard(), true, !same_operand, true, true));
+        return rescale_impl(ctx, level, nb_rescales, nOut + 1, po.data(), po.data());
+    }));
     for (int t = 0; t <= nOut; t++) reinterpret_cast<Obj *>(out[t])->nlimbs = level + 1 - nb_rescales;
     return MKHE_OK;
 }
@@ -2061,7 +2183,10 @@ int mkhe_rotate_hoisted(mkhe_ctx *ctx, int level, int rotidx, int n, const mkhe_
     TRY(swks_of(ctx, n, hoisted, vh, "hoisted", ACC_READ));
     TRY(swks_of(ctx, n, rk, vrk, "rk", ACC_READ));
     SWK_R(ak, a);
-    return rotate_hoisted_impl(ctx, level, rotidx, n, pi.data(), vh.data(), vrk.data(), ak->d, po.data());
+    GraphKey key("rotate_hoisted");
+    key.add((u64)level); key.add((u64)(long)rotidx);
+    key.ptrs(pi); key.ptrs(po); key.ptrs(vh); key.ptrs(vrk); key.add((u64)(uintptr_t)ak->d);
+    return run_graphed(ctx, key, [&]() -> int { return rotate_hoisted_impl(ctx, level, rotidx, n, pi.data(), vh.data(), vrk.data(), ak->d, po.data()); });
 }
 
 int mkhe_rotate(mkhe_ctx *ctx, int level, int rotidx, int n, const mkhe_poly *ct_in, const mkhe_swk *rk, mkhe_swk a,
@@ -2074,9 +2199,14 @@ int mkhe_rotate(mkhe_ctx *ctx, int level, int rotidx, int n, const mkhe_poly *ct
     TRY(polys_of(ctx, n + 1, ct_out, level + 1, po, "ct_out"));
     TRY(swks_of(ctx, n, rk, vrk, "rk", ACC_READ));
     SWK_R(ak, a);
-    TRY(swk_pool(ctx, "rot_h", n, vh));
-    TRY(decompose_impl(ctx, level, n, pi.data() + 1, vh.data(), 0));
-    return rotate_hoisted_impl(ctx, level, rotidx, n, pi.data(), vh.data(), vrk.data(), ak->d, po.data());
+    GraphKey key("rotate");
+    key.add((u64)level); key.add((u64)(long)rotidx);
+    key.ptrs(pi); key.ptrs(po); key.ptrs(vrk); key.add((u64)(uintptr_t)ak->d);
+    return run_graphed(ctx, key, [&]() -> int {
+        TRY(swk_pool(ctx, "rot_h", n, vh));
+        TRY(decompose_impl(ctx, level, n, pi.data() + 1, vh.data(), 0));
+        return rotate_hoisted_impl(ctx, level, rotidx, n, pi.data(), vh.data(), vrk.data(), ak->d, po.data());
+    });
 }
 
 int mkhe_conjugate(mkhe_ctx *ctx, int level, int n, const mkhe_poly *ct_in, const mkhe_swk *ck, mkhe_swk a,
@@ -2089,18 +2219,22 @@ int mkhe_conjugate(mkhe_ctx *ctx, int level, int n, const mkhe_poly *ct_in, cons
     TRY(polys_of(ctx, n + 1, ct_out, level + 1, po, "ct_out"));
     TRY(swks_of(ctx, n, ck, vck, "ck", ACC_READ));
     SWK_R(ak, a);
-    // permute first (keyswitch.go:315-317), then key-switch the permuted components (:320-331)
-    TRY(poly_pool(ctx, "conj_tmp", n + 1, ctx->nQ, tmp));
-    TRY(automorph_impl(ctx, level, ((u64)2 << ctx->logN) - 1, n + 1, pi.data(), tmp.data()));
-    TRY(swk_pool(ctx, "rot_h", n, vh));
-    TRY(decompose_impl(ctx, level, n, tmp.data() + 1, vh.data(), 0));
-    CU(cudaMemcpyAsync(po[0], tmp[0], (size_t)(level + 1) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    std::vector<Prod> pr;
-    for (int t = 0; t < n; t++) {
-        pr.push_back(Prod{{vck[t], nullptr}, {vh[t], nullptr}, po[0], true});
-        pr.push_back(Prod{{ak->d, nullptr}, {vh[t], nullptr}, po[1 + t], false});
-    }
-    return ext_products(ctx, level, 1, pr);
+    GraphKey key("conjugate");
+    key.add((u64)level); key.ptrs(pi); key.ptrs(po); key.ptrs(vck); key.add((u64)(uintptr_t)ak->d);
+    return run_graphed(ctx, key, [&]() -> int {
+        // permute first (keyswitch.go:315-317), then key-switch the permuted components (:320-331)
+        TRY(poly_pool(ctx, "conj_tmp", n + 1, ctx->nQ, tmp));
+        TRY(automorph_impl(ctx, level, ((u64)2 << ctx->logN) - 1, n + 1, pi.data(), tmp.data()));
+        TRY(swk_pool(ctx, "rot_h", n, vh));
+        TRY(decompose_impl(ctx, level, n, tmp.data() + 1, vh.data(), 0));
+        CU(cudaMemcpyAsync(po[0], tmp[0], (size_t)(level + 1) * ctx->N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        std::vector<Prod> pr;
+        for (int t = 0; t < n; t++) {
+            pr.push_back(Prod{{vck[t], nullptr}, {vh[t], nullptr}, po[0], true});
+            pr.push_back(Prod{{ak->d, nullptr}, {vh[t], nullptr}, po[1 + t], false});
+        }
+        return ext_products(ctx, level, 1, pr);
+    });
 }
 
 // ---- mkckks.Evaluator -------------------------------------------------------------------------------

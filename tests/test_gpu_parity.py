@@ -376,3 +376,37 @@ def test_keygen_and_encrypt_on_device():
 def test_keygen_full_size():
     """PN15QP880 at logN = 15: a party's whole key set made on the device (no 168 MiB upload per party), against the oracle"""
     parity.check_keygen(PR.CKKS_PN15QP880, nparties=1, rots=(1,), semantics=False)
+
+
+def test_cuda_graph_replay_matches_the_oracle():
+    """the opt-in graph cache (mkhe_ctx_set_graphs): ops repeated on the same operands replay a captured launch sequence; every
+    replayed result is the oracle's, and a different operand (another signature) is not served from a stale graph"""
+    from mkhe_kklss_b200 import mkckks
+    w = parity.CKKSWorld(PR.CKKS_PN14QP439.at_logn(13), 2, rots=(2,))
+    w.ctx.set_graphs(True)
+    ids, level = w.ids, w.op.max_level()
+    g = w.d_rlk.GetRelinearizationKey
+    kb, kd, kv = ([g(i).Value[j].h for i in ids] for j in range(3))
+    nb, new_scale = w.dev._nb_rescales(w.lit.scale * w.lit.scale, level, w.lit.scale)
+    cts = [w.random_ct(ids, level) for _ in range(3)]
+    wants = [w.oev.mul_relin_new(cts[i][0], cts[(i + 1) % 3][0], w.o_rlk) for i in range(3)]
+    outs = [mkckks.Ciphertext.new(w.dp, ids, level, w.lit.scale) for _ in range(3)]
+    for rep in range(6):
+        for i in range(3):
+            for p_ in outs[i].Value.values():
+                p_.set_nlimbs(level + 1)
+            w.ctx.ckks_mul_relin(level, nb, False, ids, cts[i][1].handles(ids), ids, cts[(i + 1) % 3][1].handles(ids), kb, kd, kv,
+                                 w.dp.CRS[-1].h, ids, outs[i].handles(ids))
+        for i in range(3):
+            outs[i].Scale = new_scale
+            w.compare_ct(outs[i], wants[i], f"graph replay {rep}, signature {i}")
+    hd = w.dev.HoistedForm(cts[0][1])
+    want_r = w.oev.rotate_hoisted_new(cts[0][0], 2, w.oev.hoisted_form(cts[0][0]), w.o_rk)
+    out_r = mkckks.Ciphertext.new(w.dp, ids, level, w.lit.scale)
+    for rep in range(5):
+        w.ctx.rotate_hoisted(level, 2, cts[0][1].handles(ids), [hd[t].h for t in ids], [w.d_rk.GetRotationKey(t, 2).h for t in ids],
+                             w.dp.CRS[2].h, out_r.handles(ids))
+        w.compare_ct(out_r, want_r, f"graph replay of RotateHoisted {rep}")
+    captures, replays = w.ctx.graph_stats()
+    assert captures >= 4 and replays >= 9, (captures, replays)
+    w.close()

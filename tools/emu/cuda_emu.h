@@ -67,6 +67,7 @@ static inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; retur
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 typedef struct emu_event { double t; } *cudaEvent_t;
+typedef void *cudaGraphExec_t;      // the graph cache of mkhe_api.cu is compiled out under emulation; only the type of its entries is needed
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
