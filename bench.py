@@ -165,6 +165,29 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def nvlink_bytes(device):
+    """cumulative NVLink data counters of one GPU: (tx bytes, rx bytes) summed over its links (`nvidia-smi nvlink -gt d`), or None"""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(device)], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    tx = rx = 0
+    found = False
+    for ln in out.splitlines():
+        f = ln.replace(":", " ").split()
+        if "KiB" in f and ("Tx" in ln or "Rx" in ln):
+            try:
+                v = int(f[f.index("KiB") - 1]) * 1024
+            except ValueError:
+                continue
+            found = True
+            if "Tx" in ln:
+                tx += v
+            else:
+                rx += v
+    return (tx, rx) if found else None
+
+
 # ---------------------------------------------------------------------------------------------------
 class DeviceWorkload:
     """keys + ciphertext pool of one GPU"""
@@ -781,9 +804,25 @@ def main():
     wl = DeviceWorkload(lit, k, local_rank, seed=SEED, batch=B, lanes=args.lanes, team=team, npairs=4 if (2 * args.lanes) % 4 == 0 else 2 * args.lanes)
     clocks = ClockSampler(local_rank)
     clocks.start()
+    nv0 = nvlink_bytes(local_rank) if world > 1 else None
     ms = wl.timed(wl.mul_relin_step, args.steps, warmup, barrier)
     launches_timed = wl.last_launches
+    nv1 = nvlink_bytes(local_rank) if world > 1 else None
     clk = clocks.stop()
+    nvlink = None
+    if world > 1:
+        # what the op's three peer-store exchanges move: y_i of the nP special limbs of the 4k products, the k
+        # re-decomposed p_id (level + 1 limbs each) and the k + 1 result components (level limbs after Rescale); every limb goes from its
+        # owner to the other world - 1 ranks.  The NVLink hardware counters are not exposed on this (virtualised) platform.
+        limbs = 4 * k * nP + k * ell + (k + 1) * (ell - 1)
+        nvlink = {"algorithmic_peer_store_bytes_per_op_all_ranks": limbs * 8 * N * (world - 1),
+                  "algorithmic_tx_bytes_per_op_per_rank": limbs * 8 * N * (world - 1) / world, "counters": None}
+    if nv0 and nv1:
+        # the counters also see the warm-up steps of this call: both reads bracket warm-up + timed steps
+        nops = B * (args.steps + warmup)
+        nvlink["counters"] = {"rank0_tx_bytes_per_op": (nv1[0] - nv0[0]) / nops, "rank0_rx_bytes_per_op": (nv1[1] - nv0[1]) / nops,
+                              "ops_between_reads": nops,
+                              "source": "nvidia-smi nvlink -gt d, rank 0's GPU, all links summed, before / after the warm-up + timed steps"}
     gstats = [ln.graph_stats() for ln in wl.lanes]      # the repeated ops of the timed region replay captured CUDA graphs
     cuda_graphs = {"captures": sum(g[0] for g in gstats), "replays": sum(g[1] for g in gstats),
                    "note": "an op issued again with the same operand addresses replays its captured launch sequence; gpu_launches counts "
@@ -1003,7 +1042,7 @@ def main():
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io[0], "d2h_bytes_per_step": bytes_io[1],
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches_timed, "cuda_graphs": cuda_graphs,
+                "gpu_launches": launches_timed, "cuda_graphs": cuda_graphs, "nvlink": nvlink,
                 "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity_check, "sharded_parity": sharded_parity,
                 "kernels": kernels, "extra": extra}
         print(json.dumps(line))
