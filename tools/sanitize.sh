@@ -7,7 +7,7 @@ mkdir -p "$OUT"
 CS=$(command -v compute-sanitizer || echo /usr/local/cuda/bin/compute-sanitizer)
 rc=0
 for tool in memcheck racecheck; do
-  for wl in ckks ckks15 bfv wide; do
+  for wl in ckks ckks15 bfv wide keygen; do
     extra=""
     [ "$tool" = racecheck ] && extra="--racecheck-report all"
     timeout 900 "$CS" --tool $tool $extra --error-exitcode 9 --print-limit 20 python tools/sanitize_workload.py $wl > "$OUT/${tool}_${wl}.txt" 2>&1

@@ -37,4 +37,11 @@ elif which == "wide":
     parity.check_decompose(w)
     parity.check_mul_relin_new(w, w.ids, w.ids)
     w.close()
+elif which == "keygen":
+    # round 2: samplers, key generation, encryption, the stand-alone NTT-domain ModDown
+    parity.check_keygen(PR.CKKS_PN14QP439.at_logn(12), semantics=False)
+    parity.check_bfv_keygen(PR.BFV_PN14QP439.at_logn(12))
+    w = parity.CKKSWorld(PR.CKKS_PN14QP439.at_logn(12), 2)
+    parity.check_moddown_ntt(w)
+    w.close()
 print("sanitize workload", which, "OK")
