@@ -1123,13 +1123,16 @@ struct ModDownQArgs {
                                            // their columns already permuted (k_mac_intt); galInv = galEl^-1 mod 2N
     int logN;
 };
+#ifndef MKHE_MDQ_MINB
+#define MKHE_MDQ_MINB 4               // resident CTAs per SM the register allocation of k_moddown_Q aims at (A/B builds override it)
+#endif
 #define MKHE_MDQ_SMEM(S1) (((size_t)8 << (S1)) * MKHE_NTT_THREADS)
 // grid = (16 * max split, level+1, ntargets).  A target with several products (c_0 of a rotation or of the relinearisation: one
 // product per party) would otherwise be one long serial chain per thread while the single-product targets finish early: its
 // products are dealt over `split` lanes of the CTA (thread = (lane, column), 128 / split columns per CTA), every lane sums its
 // share and the partial sums meet in shared memory (exact modular adds, any order).
 template <int S1, int NP, bool TEAM>
-__global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? 4 : 2)) k_moddown_Q(ModDownQArgs a, const ConvTable *tabp, const ModC *mods, const ulonglong2 *twi) {
+__global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? MKHE_MDQ_MINB : 2)) k_moddown_Q(ModDownQArgs a, const ConvTable *tabp, const ModC *mods, const ulonglong2 *twi) {
     constexpr int E = 1 << S1, HB = E < 8 ? E : 8;
     MKHE_SMEM(smraw);                          // E * 128 * 8 bytes
     u64 (*rowbuf)[MKHE_NTT_THREADS] = reinterpret_cast<u64 (*)[MKHE_NTT_THREADS]>(smraw);
