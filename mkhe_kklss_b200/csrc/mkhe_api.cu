@@ -444,7 +444,7 @@ void preload_kernels(const mkhe_ctx *ctx) {
     preload(k_reduce); preload(k_rescale); preload(k_automorph); preload(k_scale); preload(k_mul_const); preload(k_neg);
     preload(k_mul_mont); preload(k_decrypt_sum); preload(k_mul2); preload(k_checksum); preload(k_bfly_peak);
     preload(k_sample); preload(k_key_fma); preload(k_permute_ntt);
-    preload(k_team_barrier); preload(k_team_signal); preload(k_team_gather); preload(k_copy_limbs);
+    preload(k_moddown_ov); preload(k_team_barrier); preload(k_team_signal); preload(k_team_gather); preload(k_copy_limbs);
 }
 
 int upload_tables(mkhe_ctx *ctx) {
@@ -880,7 +880,14 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
                 LAUNCH(k_moddown_P_, dim3(COLGROUPS, n, pa.nplist), dim3(MKHE_NTT_THREADS), 0, pa, ctx->d_conv_PtoQ, ctx->d_mods, ctx->d_twi);
                 return MKHE_OK;
             }));
-        if (team) TRY(team_barrier(ctx));                     // every rank has every product's P part
+        if (team) {
+            TRY(team_barrier(ctx));                           // every rank has y_i of every product's P part
+            ModDownOvArgs oa;                                 // ... and makes the overflow estimates from them, once per coefficient
+            memset(&oa, 0, sizeof oa);
+            oa.np_limbs = ctx->nP; oa.p_mod0 = ctx->nQ; oa.logN = ctx->logN;
+            for (int k = 0; k < n; k++) oa.pp[k] = ctx->team.mem + ctx->team.off_pp + (size_t)k * pp_elems;
+            LAUNCH(k_moddown_ov, dim3(ctx->N / MKHE_THREADS, n), dim3(MKHE_THREADS), 0, oa, ctx->d_mods);
+        }
         for (size_t t0 = 0; t0 < tg.size(); t0 += MKHE_MD_TARGETS) {
             const int ntg = (int)std::min<size_t>(MKHE_MD_TARGETS, tg.size() - t0);
             ModDownQArgs qa;

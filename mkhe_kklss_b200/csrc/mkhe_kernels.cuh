@@ -1106,6 +1106,27 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS) k_moddown_P(ModDownPArgs a, 
     }
 }
 
+// limb-sharded runs: after the exchange every rank holds y_0 .. y_{nP-1} of every product; the overflow estimate
+//   v = trunc(sum_i fl(fl(y_i) / fl(p_i)))  (reconstructRNS, basis_extension.go:548-556: limb order, RN adds, truncation)
+// is the same for every Q limb, so it is computed ONCE per coefficient here instead of in every (limb, product) CTA of
+// k_moddown_Q (the fp64 divisions were half of that kernel's time on a team).  Stored as a u64 in the first fp64-term slot of the
+// product's P part (pp + nP N).  grid = (N/256, nproducts)
+struct ModDownOvArgs {
+    u64 *pp[MKHE_MD_PRODUCTS];
+    int np_limbs;
+    int p_mod0;              // modulus index of the first special prime
+    int logN;
+};
+__global__ void __launch_bounds__(MKHE_THREADS) k_moddown_ov(ModDownOvArgs a, const ModC *mods) {
+    const long N = 1L << a.logN;
+    const long j = (long)blockIdx.x * MKHE_THREADS + threadIdx.x;
+    u64 *pp = a.pp[blockIdx.y];
+    double vi = 0.0;
+    for (int i = 0; i < a.np_limbs; i++)
+        vi = __dadd_rn(vi, __ddiv_rn(__ull2double_rn(ld_cg(pp + (long)i * N + j)), mods[a.p_mod0 + i].qd));
+    pp[(long)a.np_limbs * N + j] = __double2ull_rz(vi);
+}
+
 struct ModDownQArgs {
     u64 *dst[MKHE_MD_TARGETS];
     const u64 *src[MKHE_MD_TARGETS];       // the sum starts from this poly (AddLvl onto the target or onto another poly); nullptr = zero
@@ -1149,9 +1170,6 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? MKHE_MDQ_MINB : 2
     // canonical reduction instead of multSum's 128-bit accumulation, its Montgomery fold and a full MRed -- the same canonical
     // residue the reference stores (basis_extension.go:203-229)
     u64 sinv[2], nsi[NP][2];
-    double pqd[NP];                            // fl(p_i): limb-sharded runs recompute the fp64 terms from y_i (only y_i is exchanged)
-#pragma unroll
-    for (int i = 0; i < NP; i++) pqd[i] = mods[tab.src_mod[i]].qd;
     sinv[0] = tab.md_sinv[j][0]; sinv[1] = tab.md_sinv[j][1];
 #pragma unroll
     for (int i = 0; i < NP; i++) { nsi[i][0] = tab.md_nsrcinv[j][i][0]; nsi[i][1] = tab.md_nsrcinv[j][i][1]; }
@@ -1180,15 +1198,19 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? MKHE_MDQ_MINB : 2
             u64 y[NP][HB], ov[HB];
 #pragma unroll
             for (int k = 0; k < HB; k++) {
-                double vi = 0.0;                  // reconstructRNS: vi += fl(y_i)/fl(p_i), limb order, RN; then truncation
+                if (TEAM) {                       // the overflow estimate was made once per coefficient by k_moddown_ov
 #pragma unroll
-                for (int i = 0; i < NP; i++) {
-                    y[i][k] = ld_cg(pps + (long)i * N + (long)(h + k) * MKHE_TILE);
-                    const double term = TEAM ? __ddiv_rn(__ull2double_rn(y[i][k]), pqd[i])
-                                             : __longlong_as_double((long long)ld_cg(pps + (long)(a.np_limbs + i) * N + (long)(h + k) * MKHE_TILE));
-                    vi = __dadd_rn(vi, term);
+                    for (int i = 0; i < NP; i++) y[i][k] = ld_cg(pps + (long)i * N + (long)(h + k) * MKHE_TILE);
+                    ov[k] = ld_cg(pps + (long)a.np_limbs * N + (long)(h + k) * MKHE_TILE);
+                } else {
+                    double vi = 0.0;              // reconstructRNS: vi += fl(y_i)/fl(p_i), limb order, RN; then truncation
+#pragma unroll
+                    for (int i = 0; i < NP; i++) {
+                        y[i][k] = ld_cg(pps + (long)i * N + (long)(h + k) * MKHE_TILE);
+                        vi = __dadd_rn(vi, __longlong_as_double((long long)ld_cg(pps + (long)(a.np_limbs + i) * N + (long)(h + k) * MKHE_TILE)));
+                    }
+                    ov[k] = __double2ull_rz(vi);
                 }
-                ov[k] = __double2ull_rz(vi);
             }
 #pragma unroll
             for (int k = 0; k < HB; k++) {
@@ -1219,12 +1241,20 @@ __global__ void __launch_bounds__(MKHE_NTT_THREADS, (S1 <= 4 ? MKHE_MDQ_MINB : 2
     }
     u64 *dst = a.dst[t] + (long)j * N;
     if (TEAM && a.dst_team_off[t] >= 0) {      // limb sharding: limb j of this poly goes to every rank (peer stores)
+        // The CTA's E x cols_per block is staged in shared memory and leaves as 32-byte stores (4 coefficients per thread and
+        // store): an NVLink write carries the same bytes in a quarter of the requests of the 8-byte-per-thread form.
         if (lane == 0) {
-            const long o = a.dst_team_off[t] + (long)j * N + col;
-            for (int rk = 0; rk < a.team.nranks; rk++) {
 #pragma unroll
-                for (int k = 0; k < E; k++) a.team.peer[rk][o + (long)k * MKHE_TILE] = r[k];
-            }
+            for (int k = 0; k < E; k++) rowbuf[k][cin] = r[k];
+        }
+        __syncthreads();
+        const int per_row = cols_per >> 2;       // cols_per is 128, 64, 32 or 16
+        const long o = a.dst_team_off[t] + (long)j * N + (long)blockIdx.x * cols_per;
+        for (int c = threadIdx.x; c < E * per_row; c += MKHE_NTT_THREADS) {
+            const int row = c / per_row, q4 = (c - row * per_row) << 2;
+            const u64 v0 = rowbuf[row][q4], v1 = rowbuf[row][q4 + 1], v2 = rowbuf[row][q4 + 2], v3 = rowbuf[row][q4 + 3];
+            const long e = o + (long)row * MKHE_TILE + q4;
+            for (int rk = 0; rk < a.team.nranks; rk++) st_global_v4(a.team.peer[rk] + e, v0, v1, v2, v3);
         }
     } else if (a.galEl == 0) {
         if (lane == 0) {
