@@ -738,6 +738,8 @@ def main():
         if rank != 0:
             return
         ncpu = os.cpu_count() or 1
+        config = dict(config, ops_per_step=1, lanes_per_gpu=0, parallelism=f"host CPU, {ncpu} threads (OpenMP over limbs)",
+                      l2_policy="n/a (CPU arm)")            # one op per step here; the GPU arm's batch does not apply
         ops, cores, sec = cpu_oracle_run(lit, k, args.steps, args.warmup, ncpu)
         line = {"impl": "reference", "metric": METRIC, "value": ops, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
