@@ -925,7 +925,7 @@ def main():
                     # the ncu capture is ONE launch (the hoisting of 4 polys); its own algorithmic bytes, for a like-for-like ratio
                     "traffic_algorithmic_bytes": (traffic.get(dom) or {}).get("algorithmic_bytes_of_that_launch"),
                     "binding_resource": "integer issue (fmaheavy pipe + ALU), not HBM: see integer_pipe; the HBM-bound kernels of the step are "
-                                        "k_mac_parties / k_mac_digits (hbm_frac under kernels)",
+                                        "k_mac_parties / k_mac_intt (hbm_frac under kernels)",
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
                     "avg_launch_ms": per_launch_s * 1e3,
                     "integer_pipe": {"achieved_butterflies_per_s": d.get("butterflies_per_s"), "peak_butterflies_per_s": bfly_peak,
