@@ -194,16 +194,6 @@ __device__ __forceinline__ u64 shoup4(u64 x, u64 w, u64 wsh, u64 nq) {
     const u64 a = mulwide(x1, s0);
     const u64 b = mulwide(x0, s1);
     const u64 h = madwide(x1, s1, (u64)hi32(a)) + hi32(b);
-#if defined(MKHE_SHOUP_VARIANT) && MKHE_SHOUP_VARIANT == 1
-    {   // development: the four cross terms first, entering the wide multiply-adds as the high word of their addend
-        u32 c = x0 * hi32(w);
-        c = madlo(x1, lo32(w), c);
-        c = madlo(lo32(h), hi32(nq), c);
-        c = madlo(hi32(h), lo32(nq), c);
-        u64 tt = madwide(x0, lo32(w), mk64(0u, c));
-        return madwide(lo32(h), lo32(nq), tt);
-    }
-#endif
     u64 t = mulwide(x0, lo32(w));
     t = madwide(lo32(h), lo32(nq), t);
     u32 th = hi32(t);
