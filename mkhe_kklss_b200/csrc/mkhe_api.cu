@@ -859,8 +859,8 @@ int ext_products(mkhe_ctx *ctx, int levelQ, int nsets, const std::vector<Prod> &
                     }
                 const long nunits = (long)s.n * tiles * ng;
                 const dim3 grid((unsigned)std::min<long>(ctx->num_sms, nunits));
-                if (G == 2) LAUNCH(k_mac_intt<2>, grid, dim3(MKHE_MI_THREADS(2)), MKHE_MI_SMEM(2), a, ctx->d_mods, ctx->d_twi_tiled);
-                else LAUNCH(k_mac_intt<1>, grid, dim3(MKHE_MI_THREADS(1)), MKHE_MI_SMEM(1), a, ctx->d_mods, ctx->d_twi_tiled);
+                if (G == 2) LAUNCH(k_mac_intt<2>, grid, dim3(MKHE_MI_THREADS(2)), MKHE_MI_SMEM(2), a, ctx->d_mods, ctx->d_twi_tiled, ctx->d_twi);
+                else LAUNCH(k_mac_intt<1>, grid, dim3(MKHE_MI_THREADS(1)), MKHE_MI_SMEM(1), a, ctx->d_mods, ctx->d_twi_tiled, ctx->d_twi);
             }
         // ---- pass B fused with ModDown, the accumulation and (rotations) the automorphism
         ModDownPArgs pa;

@@ -102,6 +102,16 @@ struct TwGlobal {          // same interface straight from the global table (sin
     __device__ __forceinline__ ulonglong2 C(int b, int g) const { return at(10 - b, ((size_t)threadIdx.x << (3 - b)) + g); }
 };
 
+struct TwGlobalT {         // TwGlobal for a group that is not the first 128 threads of its CTA (explicit thread index)
+    const ulonglong2 *t;
+    int S1, tile, tid;
+    __device__ __forceinline__ TwGlobalT(const ulonglong2 *tab, int S1_, int tile_, int tid_) : t(tab), S1(S1_), tile(tile_), tid(tid_) {}
+    __device__ __forceinline__ ulonglong2 at(int lv, size_t g) const { return __ldg(t + ((size_t)1 << (S1 + lv)) + ((size_t)tile << lv) + g); }
+    __device__ __forceinline__ ulonglong2 A(int b, int g) const { return at(3 - b, g); }
+    __device__ __forceinline__ ulonglong2 B(int b, int g) const { return at(7 - b, ((size_t)(tid >> 3) << (3 - b)) + g); }
+    __device__ __forceinline__ ulonglong2 C(int b, int g) const { return at(10 - b, ((size_t)tid << (3 - b)) + g); }
+};
+
 // ------------------------------------------------------------------------------------------------
 // tile rounds.  Thread t = hi*8 + low holds 16 elements; their tile-local indices are
 //   layout A:  k*128 + t                 (stages d = 10..7 are register-local, global access coalesced)
@@ -569,10 +579,16 @@ __global__ void __launch_bounds__(MKHE_P2_THREADS, 1) k_ntt_pass2(
 // ------------------------------------------------------------------------------------------------
 #define MKHE_MI_GROUPS 32                                       // product groups per launch
 #define MKHE_MI_BOX (MKHE_TILE * 8)                              // bytes of one operand tile
-#define MKHE_MI_STAGES(G) ((G) == 1 ? 4 : 3)
+// MKHE_MI_TWG (A/B builds): the G = 2 kernel reads the unit's inverse twiddles straight from the global table (L2 resident) instead
+// of staging them in 32 KiB of shared memory, which buys a fourth ring stage (three stages = 144 KiB in flight per SM instead of 96)
+#ifndef MKHE_MI_TWG
+#define MKHE_MI_TWG 0
+#endif
+#define MKHE_MI_TWGLOBAL(G) (MKHE_MI_TWG && (G) == 2)
+#define MKHE_MI_STAGES(G) ((G) == 1 ? 4 : (MKHE_MI_TWG ? 4 : 3))
 #define MKHE_MI_THREADS(G) (2 * (G) * MKHE_NTT_THREADS + 32)
 #define MKHE_MI_NBARS(G) (2 * MKHE_MI_STAGES(G) + 2 + 2 * (G))
-#define MKHE_MI_SMEM(G) (MKHE_TILE * 16 + MKHE_MI_STAGES(G) * ((G) + 1) * MKHE_MI_BOX + (G) * MKHE_XBUF * 8 + 8 * MKHE_MI_NBARS(G))
+#define MKHE_MI_SMEM(G) ((MKHE_MI_TWGLOBAL(G) ? 0 : MKHE_TILE * 16) + MKHE_MI_STAGES(G) * ((G) + 1) * MKHE_MI_BOX + (G) * MKHE_XBUF * 8 + 8 * MKHE_MI_NBARS(G))
 struct MacInttArgs {
     const u64 *shared[2][MKHE_MI_GROUPS];
     const u64 *priv[2][MKHE_MI_GROUPS * 2];
@@ -589,11 +605,12 @@ struct MacInttArgs {
     int logN;
 };
 template <int G>
-__global__ void __launch_bounds__(MKHE_MI_THREADS(G), 1) k_mac_intt(MacInttArgs a, const ModC *mods, const ulonglong2 *tiled_inv) {
+__global__ void __launch_bounds__(MKHE_MI_THREADS(G), 1) k_mac_intt(MacInttArgs a, const ModC *mods, const ulonglong2 *tiled_inv, const ulonglong2 *twi_plain) {
     MKHE_SMEM(smraw);
     constexpr int NS = MKHE_MI_STAGES(G), BOX = MKHE_MI_BOX, STAGE = (G + 1) * BOX, NG = G * MKHE_NTT_THREADS;
+    constexpr bool TWG = MKHE_MI_TWGLOBAL(G);          // twiddles from the global table: no staging buffer, no tw_full / tw_empty traffic
     ulonglong2 *stw = reinterpret_cast<ulonglong2 *>(smraw);                                   // 32 KiB inverse twiddles of the unit
-    unsigned char *ring = smraw + MKHE_TILE * 16;
+    unsigned char *ring = smraw + (TWG ? 0 : MKHE_TILE * 16);
     unsigned char *xb = ring + NS * STAGE;
     u64 *full = reinterpret_cast<u64 *>(xb + G * MKHE_XBUF * 8), *empty = full + NS, *tw_full = empty + NS, *tw_empty = tw_full + 1;
     u64 *ho_full = tw_empty + 1, *ho_empty = ho_full + G;        // hand-over of a product's accumulator tile: MAC group -> transform group
@@ -639,9 +656,11 @@ __global__ void __launch_bounds__(MKHE_MI_THREADS(G), 1) k_mac_intt(MacInttArgs 
             }
             // the unit's twiddles are needed only after its last term; the previous unit's pass A (the last reader of the
             // twiddle buffer) ran beside this unit's terms and is long over, so this wait does not block
-            mbar_wait(tw_empty, (nu & 1) ^ 1);
-            mbar_expect_tx(tw_full, MKHE_TILE * 16);
-            tma_load_1d(stw, tiled_inv + ((long)a.mods[sidx] * ntiles + tile) * MKHE_TILE, MKHE_TILE * 16, tw_full);
+            if (!TWG) {
+                mbar_wait(tw_empty, (nu & 1) ^ 1);
+                mbar_expect_tx(tw_full, MKHE_TILE * 16);
+                tma_load_1d(stw, tiled_inv + ((long)a.mods[sidx] * ntiles + tile) * MKHE_TILE, MKHE_TILE * 16, tw_full);
+            }
         }
         return;
     }
@@ -698,10 +717,15 @@ __global__ void __launch_bounds__(MKHE_MI_THREADS(G), 1) k_mac_intt(MacInttArgs 
             mbar_wait(&ho_full[g], nu & 1);
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = x.c2[k];
-            mbar_wait(tw_full, nu & 1);
-            tile_inv(v, x, tw, nttc(m), 1 + g);
-            MKHE_PRE_RELEASE();
-            mbar_arrive(tw_empty);                               // after this thread's last twiddle read
+            if (TWG) {
+                const TwGlobalT twg(twi_plain + (long)a.mods[sidx] * N, a.logN - 11, tile, tid);
+                tile_inv(v, x, twg, nttc(m), 1 + g);
+            } else {
+                mbar_wait(tw_full, nu & 1);
+                tile_inv(v, x, tw, nttc(m), 1 + g);
+                MKHE_PRE_RELEASE();
+                mbar_arrive(tw_empty);                           // after this thread's last twiddle read
+            }
             if (a.galEl) {
                 // Rotation: X -> X^galEl sends coefficient i = x + 2048 row to (x galEl mod 2048) + 2048 row' (+ a sign): columns go
                 // to columns.  The column part of the permutation is applied here, on chip, so that the ModDown kernel reads AND
