@@ -410,3 +410,13 @@ def test_cuda_graph_replay_matches_the_oracle():
     captures, replays = w.ctx.graph_stats()
     assert captures >= 4 and replays >= 9, (captures, replays)
     w.close()
+
+
+def test_cnn_inference_semantics_on_device_made_material():
+    """BASELINE config 5 end to end on the device: CRS, both parties' key sets (relinearisation + 24 rotation keys each) and every
+    ciphertext are made on the GPU, the reference's CNN op sequence runs there, the result is decrypted there -- and the ten
+    logits equal the plain forward pass of the same network on the same image within CKKS precision (tests/cnn_semantic.py)."""
+    import cnn_semantic as S
+    got, want = S.run(PR.CNN_PN14QP433)
+    assert np.abs(got - want).max() < 1e-4, (got, want)
+    assert got.argmax() == want.argmax()

@@ -285,3 +285,13 @@ def test_counter_based_samplers_have_the_reference_distributions():
     assert [int(x) for x in O.CtrPRNG(0, 0).ternary(16)] == [0, 0, 0, 1, 1, 0, 0, -1, 1, 0, 0, 1, 0, 0, 0, 0]
     assert [int(x) for x in O.CtrPRNG(0, 0).uniform(O.Ring(12, [0x10000000006e0001]))[0][:4]] == [
         0x38275bc38fcbe91, 0xf101fe21496ea20, 0xb91752fd22fb56a, 0xda3e176f37bc9fb]
+
+
+def test_cnn_inference_semantics():
+    """BASELINE config 5, semantically: the oracle's keys, encryptions, evaluator and decryptor run the reference's CNN op sequence
+    (cnn/cnn.go) on the reference's slot packing (cnn/cnn_test.go:345-545) and must reproduce the PLAIN forward pass of the same
+    random network on the same random image -- rotation directions, packing, scale management and all (tests/cnn_semantic.py)."""
+    import cnn_semantic as S
+    got, want = S.run_oracle(PR.CNN_PN14QP433)
+    assert np.abs(got - want).max() < 1e-4, (got, want)
+    assert got.argmax() == want.argmax()
